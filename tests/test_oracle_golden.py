@@ -1,0 +1,172 @@
+"""The oracle against fixtures produced by the unmodified reference (CPU, no GPU).
+
+This is what pins the oracle: every fixture in tests/golden/ was written by
+tests/golden/make_golden.py from /root/reference's own modules.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import local3d as O
+from oracle import vq as OV
+from tests._golden import load, seeded, checksum, state_dict_of, c1_state_dict
+
+RTOL, ATOL = 1e-5, 2e-6      # fp32 parity bar (BASELINE.json north_star: 1e-5 in fp32)
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    a = a.detach().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize('name', ['attn_small.npz', 'attn_noproj.npz'])
+def test_attention_module_forward_backward(name):
+    f = load(name)
+    p = {k: v.requires_grad_(True) for k, v in state_dict_of(f).items()}
+    x = torch.from_numpy(f['x']).requires_grad_(True)
+    q = torch.from_numpy(f['q']).requires_grad_(True)
+    out = O.local3d_attention_module(p, '', x, q, int(f['heads']), tuple(f['ext']))
+    close(out, f['out'])
+    out.backward(torch.from_numpy(f['dout']))
+    close(x.grad, f['dx'], atol=1e-5)
+    close(q.grad, f['dq'], atol=1e-5)
+    for k, v in p.items():
+        if 'grad/' + k in f:
+            close(v.grad, f['grad/' + k], atol=2e-5)
+
+
+def test_attention_closed_form_backward_matches_autograd():
+    f = load('attn_small.npz')
+    heads, ext = int(f['heads']), tuple(f['ext'])
+    g = torch.Generator().manual_seed(0)
+    q, k, v, do = (torch.randn(2, 3, 5, 4, 32, generator=g) for _ in range(4))
+    leaves = [t.clone().requires_grad_(True) for t in (q, k, v)]
+    O.attention_core(*leaves, heads, ext).backward(do)
+    dq, dk, dv = O.attention_core_backward(q, k, v, do, heads, ext, chunk=17)
+    close(dq, leaves[0].grad.numpy(), atol=1e-5)
+    close(dk, leaves[1].grad.numpy(), atol=1e-5)
+    close(dv, leaves[2].grad.numpy(), atol=1e-5)
+
+
+def test_attention_config1_subsample():
+    f = load('attn_c1.npz')
+    x = seeded(7, 2, 8, 16, 16, 256)
+    dout = seeded(8, 2, 8, 16, 16, 256)
+    if not (np.allclose(checksum(x), f['x_sum'], rtol=1e-12) and np.allclose(checksum(dout), f['dout_sum'], rtol=1e-12)):
+        pytest.skip('seeded inputs differ from the fixture (different torch RNG stream)')
+    p = {k: v.requires_grad_(True) for k, v in c1_state_dict().items()}
+    x.requires_grad_(True)
+    out = O.local3d_attention_module(p, '', x, x, 8, (1, 2, 2))
+    tok = slice(5, None, 16)
+    close(out.reshape(-1, 256)[tok], f['out'], atol=1e-5)
+    out.backward(dout)
+    close(x.grad.reshape(-1, 256)[tok], f['dx'], rtol=1e-4, atol=2e-5)
+    for k, v in p.items():
+        close(v.grad.flatten()[::97], f['grad/' + k], rtol=1e-4, atol=3e-4)
+
+
+def test_attention_core_config4_reduced_grid():
+    f = load('core_c4_reduced.npz')
+    shape = tuple(int(s) for s in f['shape'])
+    q = seeded(11, *shape) * 0.5
+    k = seeded(12, *shape) * 0.5
+    v = seeded(13, *shape)
+    dout = seeded(14, *shape)
+    if not np.allclose(checksum(q), f['q_sum'], rtol=1e-12):
+        pytest.skip('seeded inputs differ from the fixture')
+    heads, ext = int(f['heads']), tuple(f['ext'])
+    out = O.attention_core(q, k, v, heads, ext, chunk=100)
+    close(out[0, ::2, ::3, ::3], f['out'], atol=1e-5)
+    dq, dk, dv = O.attention_core_backward(q, k, v, dout, heads, ext, chunk=100)
+    close(dq[0, ::2, ::3, ::3], f['dq'], rtol=1e-4, atol=2e-5)
+    close(dk[0, ::2, ::3, ::3], f['dk'], rtol=1e-4, atol=2e-5)
+    close(dv[0, ::2, ::3, ::3], f['dv'], rtol=1e-4, atol=2e-5)
+
+
+def _small_cfg(f):
+    c = [int(v) for v in f['cfg']]
+    return O.DenoiserConfig(data_shape=tuple(c[0:3]), dim=c[3], num_classes=c[4], extents=tuple(c[5:8]),
+                            depth=c[8], heads=c[9], dim_head=c[10], mlp_dim=c[11])
+
+
+def test_denoiser_forward_and_grads():
+    f = load('denoiser_small.npz')
+    cfg = _small_cfg(f)
+    p = {k: v.requires_grad_(True) for k, v in state_dict_of(f).items()}
+    tokens = torch.from_numpy(f['tokens'])
+    target = torch.from_numpy(f['target'])
+    close(O.transformer_forward(p, tokens, cfg), f['feats'], atol=1e-5)
+    close(O.denoiser_forward(p, tokens, cfg), f['logits'], atol=1e-5)
+    loss = O.denoiser_loss(p, tokens, target, cfg)
+    assert abs(loss.item() - float(f['loss'])) < 1e-5
+    loss.backward()
+    for k, v in p.items():
+        close(v.grad, f['grad/' + k], rtol=1e-4, atol=2e-6)
+
+
+def test_init_params_match_reference_state_dict_layout():
+    f = load('denoiser_small.npz')
+    cfg = _small_cfg(f)
+    ours = O.init_denoiser_params(cfg)
+    ref = state_dict_of(f)
+    assert set(ours) == set(ref)
+    for k in ref:
+        assert tuple(ours[k].shape) == tuple(ref[k].shape), k
+
+
+# ------------------------------------------------------------------------------ VQ
+def test_vq_eval_and_train_forward():
+    f = load('vq_c2.npz')
+    st = OV.VQState(f['embedding0'].copy(), np.ones((1, 512), np.float32))
+    q, onehot, loss, ppl, idx = OV.forward(st, f['x'], training=False)
+    assert np.array_equal(idx.reshape(f['idx_eval'].shape), f['idx_eval'])       # bit-exact indices
+    assert np.array_equal(OV.encode(f['x'], st.embedding), f['encode'])
+    assert np.array_equal(q, f['q_eval'])                                          # gathered code vectors
+    assert onehot.sum() == f['enc_sum'] and onehot.shape == (512, 1, 512)
+    assert abs(loss - f['loss_eval']) < 1e-6 * max(1, abs(f['loss_eval']))
+    assert abs(ppl - f['ppl_eval']) < 1e-4 * f['ppl_eval']
+    np.testing.assert_allclose(st.accumulated_error, f['acc_err_eval'], rtol=1e-5)
+    np.testing.assert_allclose(OV.distances(f['x'], st.embedding)[::37] / 64, f['dist'], rtol=2e-6)
+    st = OV.VQState(f['embedding0'].copy(), np.ones((1, 512), np.float32))
+    q, onehot, loss, ppl, idx = OV.forward(st, f['x'], training=True)
+    assert abs(loss - f['loss_train']) < 1e-6 * max(1, abs(f['loss_train']))
+    assert abs(ppl - f['ppl_train']) < 1e-4 * f['ppl_train']
+    np.testing.assert_allclose(st.embedding, f['embedding1'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(st.cluster_size, f['cluster_size1'], rtol=1e-6)
+    np.testing.assert_array_equal(st.activation_count, f['activation_count1'])
+    np.testing.assert_allclose(st.accumulated_error, f['acc_err1'], rtol=1e-5)
+
+
+def test_vq_tie_break_lowest_index():
+    f = load('vq_ties.npz')
+    idx = OV.encode(f['x'], f['embedding'])
+    assert np.array_equal(idx, f['encode'])
+    assert idx[0, 0] == 3 and idx[1, 0] == 20      # duplicated codes {3,7,30} and {20,21}
+
+
+def test_vq_multilatent():
+    f = load('vq_multilatent.npz')
+    st = OV.VQState(f['embedding0'].copy(), np.ones((3, 12), np.float32))
+    q, onehot, loss, ppl, idx = OV.forward(st, f['x'], training=True)
+    assert np.array_equal(idx, f['idx'])
+    assert np.array_equal(q, f['q'])
+    assert abs(loss - f['loss']) < 1e-6 and abs(ppl - f['ppl']) < 1e-4 * f['ppl']
+    np.testing.assert_allclose(st.embedding, f['embedding1'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(st.cluster_size, f['cluster_size1'], rtol=1e-6)
+    assert np.array_equal(OV.decode(idx.reshape(5, 7, 3), f['embedding1']), f['decode'])
+
+
+def test_vq_64k_indices_bit_exact():
+    f = load('vq_64k.npz')
+    x = seeded(22, 65536, 64)
+    if not np.allclose(checksum(x), f['x_sum'], rtol=1e-12):
+        pytest.skip('seeded inputs differ from the fixture')
+    emb = seeded(21, 1, 512, 64).numpy()
+    idx = OV.encode(x.numpy(), emb)[:, 0]
+    assert np.array_equal(idx, f['idx'].astype(np.int64))
+
+
+def test_vq_config2_latents():
+    f = load('vq_c2_latents.npz')
+    idx = OV.encode(f['latents'], f['embedding']).reshape(2, 16, 16)
+    assert np.array_equal(idx, f['encode'])
