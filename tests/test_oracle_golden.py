@@ -163,7 +163,7 @@ def test_vq_64k_indices_bit_exact():
         pytest.skip('seeded inputs differ from the fixture')
     emb = seeded(21, 1, 512, 64).numpy()
     idx = OV.encode(x.numpy(), emb)[:, 0]
-    assert np.array_equal(idx, f['idx'].astype(np.int64))
+    assert np.array_equal(idx, f['idx'].astype(np.int64).reshape(-1))
 
 
 def test_vq_config2_latents():
