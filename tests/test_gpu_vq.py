@@ -1,0 +1,126 @@
+"""VQ nearest-neighbour kernel through the C ABI: bit-exact indices against the reference
+fixtures and the oracle, plus size-independent properties at larger sizes."""
+import numpy as np
+import pytest
+import torch
+
+import world_modelz_b200 as wm
+from world_modelz_b200 import ops
+from oracle import vq as OV
+from tests._golden import load, seeded, checksum
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _module(emb, **kw):
+    L, K, D = emb.shape
+    vq = wm.VectorQuantizerEMA(D, K, num_latents=L, **kw).to(DEV)
+    vq.embedding.copy_(torch.as_tensor(emb))
+    return vq
+
+
+def test_forward_eval_and_train_against_reference_fixture():
+    f = load('vq_c2.npz')
+    x = torch.from_numpy(f['x']).to(DEV)
+    vq = _module(f['embedding0']).eval()
+    q, enc, loss, ppl = vq(x)
+    assert np.array_equal(enc.argmax(-1).cpu().numpy(), f['idx_eval'])          # bit-exact indices
+    assert np.array_equal(vq.encode(x).cpu().numpy(), f['encode'])
+    assert np.array_equal(q.cpu().numpy(), f['q_eval'])                          # x + (e - x), bitwise
+    assert enc.shape == (512, 1, 512) and enc.dtype == torch.float32 and enc.sum().item() == f['enc_sum']
+    assert abs(loss.item() - f['loss_eval']) < 1e-6 * max(1, f['loss_eval'])
+    assert abs(ppl.item() - f['ppl_eval']) < 1e-4 * f['ppl_eval']
+    np.testing.assert_allclose(vq.accumulated_error.cpu().numpy(), f['acc_err_eval'], rtol=1e-5)
+    np.testing.assert_allclose(vq.codebook_distance(x)[::37].cpu().numpy(), f['dist'], rtol=1e-5)
+    vq = _module(f['embedding0']).train()
+    q, enc, loss, ppl = vq(x)
+    assert abs(loss.item() - f['loss_train']) < 1e-6 * max(1, f['loss_train'])
+    assert abs(ppl.item() - f['ppl_train']) < 1e-4 * f['ppl_train']
+    np.testing.assert_allclose(vq.embedding.cpu().numpy(), f['embedding1'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(vq.cluster_size.cpu().numpy(), f['cluster_size1'], rtol=1e-6)
+    np.testing.assert_array_equal(vq.activation_count.cpu().numpy(), f['activation_count1'])
+    np.testing.assert_allclose(vq.accumulated_error.cpu().numpy(), f['acc_err1'], rtol=1e-5)
+
+
+def test_straight_through_gradients():
+    f = load('vq_c2.npz')
+    x = torch.from_numpy(f['x'][:1]).to(DEV).requires_grad_(True)
+    vq = _module(f['embedding0']).eval()
+    q, _, loss, _ = vq(x)
+    w = torch.randn_like(q)
+    (q * w).sum().backward(retain_graph=True)
+    assert torch.equal(x.grad, w)                       # identity through the quantiser (vq.py:70)
+    x.grad = None
+    loss.backward()
+    codes = vq.decode(vq.encode(x.detach())).reshape(x.shape)
+    torch.testing.assert_close(x.grad, 2 * (x.detach() - codes) / x.numel(), rtol=1e-5, atol=1e-8)
+
+
+def test_tie_break_lowest_index():
+    f = load('vq_ties.npz')
+    vq = _module(f['embedding'])
+    idx = vq.encode(torch.from_numpy(f['x']).to(DEV)).cpu().numpy()
+    assert np.array_equal(idx, f['encode'])
+    assert idx[0, 0] == 3 and idx[1, 0] == 20
+
+
+def test_multilatent_fixture():
+    f = load('vq_multilatent.npz')
+    vq = _module(f['embedding0']).train()
+    q, enc, loss, ppl = vq(torch.from_numpy(f['x']).to(DEV))
+    assert np.array_equal(enc.argmax(-1).cpu().numpy(), f['idx'])
+    assert np.array_equal(q.cpu().numpy(), f['q'])
+    assert abs(loss.item() - f['loss']) < 1e-6 and abs(ppl.item() - f['ppl']) < 1e-4 * f['ppl']
+    np.testing.assert_allclose(vq.embedding.cpu().numpy(), f['embedding1'], rtol=1e-5, atol=1e-6)
+
+
+def test_64k_indices_bit_exact_against_reference():
+    f = load('vq_64k.npz')
+    x = seeded(22, 65536, 64)
+    if not np.allclose(checksum(x), f['x_sum'], rtol=1e-12):
+        pytest.skip('seeded inputs differ from the fixture')
+    vq = _module(seeded(21, 1, 512, 64).numpy())
+    idx = vq.encode(x.to(DEV)).cpu().numpy().reshape(-1)
+    assert np.array_equal(idx, f['idx'].astype(np.int64).reshape(-1))
+
+
+def test_config2_latents_fixture():
+    f = load('vq_c2_latents.npz')
+    vq = _module(f['embedding'])
+    idx = vq.encode(torch.from_numpy(f['latents']).to(DEV)).view(2, 16, 16).cpu().numpy()
+    assert np.array_equal(idx, f['encode'])
+
+
+@pytest.mark.parametrize('N,L,K,D', [(1, 1, 1, 4), (63, 2, 65, 12), (129, 1, 7, 256), (1000, 3, 130, 36)])
+def test_ragged_shapes_against_oracle(N, L, K, D):
+    g = torch.Generator().manual_seed(N + K)
+    x = torch.randn(N, L, D, generator=g)
+    cb = torch.randn(L, K, D, generator=g)
+    idx, ste, err = ops.vq_nearest(x.to(DEV), cb.to(DEV))
+    ref = OV.encode(x.numpy(), cb.numpy())
+    assert np.array_equal(idx.cpu().numpy(), ref)
+    codes = OV.decode(ref, cb.numpy()).reshape(N, L, D)
+    assert np.array_equal(ste.cpu().numpy(), x.numpy() + (codes - x.numpy()))
+    np.testing.assert_allclose(err.cpu().numpy(), ((codes - x.numpy()) ** 2).sum(-1), rtol=1e-5)
+
+
+def test_empty_input():
+    idx, ste, err = ops.vq_nearest(torch.zeros(0, 1, 8, device=DEV), torch.randn(1, 5, 8, device=DEV))
+    assert idx.shape == (0, 1) and ste.shape == (0, 1, 8)
+
+
+def test_full_size_properties():
+    """1M latents (4096 frames of 16x16): idempotence (codes quantise to themselves, error
+    0), index range, and agreement with a brute-force fp64 torch argmin on the device."""
+    g = torch.Generator().manual_seed(9)
+    cb = torch.randn(1, 512, 64, generator=g).to(DEV)
+    x = torch.randn(1 << 20, 1, 64, generator=g).to(DEV)
+    idx, ste, err = ops.vq_nearest(x, cb)
+    assert idx.min().item() >= 0 and idx.max().item() < 512
+    d = torch.cdist(x[:65536, 0].double(), cb[0].double())
+    assert torch.equal(d.argmin(-1), idx[:65536, 0])
+    codes = cb[0][idx[:, 0]].unsqueeze(1)
+    idx2, ste2, err2 = ops.vq_nearest(codes.contiguous(), cb)
+    assert torch.equal(idx2, idx) and err2.abs().max().item() == 0.0
+    assert torch.equal(ste2, codes)

@@ -1,0 +1,243 @@
+"""Denoiser wrapper, data-parallel training step and iterative sampler.
+
+* ``VqVideoDiffusionModel`` -- drop-in for ``vq-video-diffusion/main.py:25-36`` (same
+  constructor keywords, ``transformer`` / ``logit_proj`` sub-modules and state_dict keys).
+* ``corrupt_last_frame`` -- the noise + mask corruption of ``main.py:246-259`` on the
+  device, without the ``[B, HW, K]`` one-hot / uniform temporaries.
+* ``DenoiserTrainer`` -- one optimisation step (forward, CE, backward, gradient
+  all-reduce, AdamW) as in ``main.py:266-283``; batch-sharded data parallel, one process
+  per GPU, one NCCL all-reduce of a flat gradient buffer per step; the whole step is
+  captured in a CUDA graph.  The reference has no distributed code.
+* ``sample_next_frame`` -- the 30-iteration mask/replace sampler of ``main.py:71-111``;
+  clips are independent, so multi-GPU sampling is batch-sharded with no collective.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+from .local_3d_attention import Local3dAttentionTransformer
+
+
+class VqVideoDiffusionModel(nn.Module):
+    def __init__(self, *, data_shape, dim, num_classes, extents, depth, dim_head, mlp_dim, heads=1, dropout=.0):
+        super().__init__()
+        self.num_classes = num_classes
+        self.transformer = Local3dAttentionTransformer(
+            data_shape=data_shape, dim=dim, num_classes=num_classes + 1,      # +1: the mask token
+            extents=extents, depth=depth, heads=heads, dim_head=dim_head, mlp_dim=mlp_dim, dropout=dropout)
+        self.logit_proj = nn.Linear(dim, num_classes)
+
+    def forward(self, x):
+        feats = self.transformer(x)
+        return self.logit_proj(feats[:, -1])                                  # last frame only
+
+
+def corrupt_last_frame(tokens: torch.Tensor, r: torch.Tensor, num_embeddings: int,
+                       p_max_uniform: float = 0.1) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``tokens [B,S,H,W]`` int64 on the device, ``r [B]`` in [0,1) -> (corrupted, target).
+
+    The reference draws from ``lerp(onehot(z), 1/K, r*0.1)`` with ``multinomial``
+    (``main.py:251-255``); that distribution is "keep z with probability 1-r*0.1, else a
+    uniform code", sampled here directly.  Then each position becomes the mask token
+    ``K`` with probability ``r`` (``:249,258``).
+    """
+    B = tokens.shape[0]
+    last = tokens[:, -1]
+    target = last.clone()
+    rr = r.view(B, 1, 1).to(torch.float32)
+    u = torch.rand(3, *last.shape, device=tokens.device)
+    uniform_code = (u[0] * num_embeddings).long().clamp_(max=num_embeddings - 1)
+    draw = torch.where(u[1] < rr * p_max_uniform, uniform_code, last)
+    draw = torch.where(u[2] < rr, torch.full_like(draw, num_embeddings), draw)
+    out = tokens.clone()
+    out[:, -1] = draw
+    return out, target
+
+
+class LossAwareSamplerEma:
+    """Loss-aware diffusion-time sampler (``importance_sampling.py:5-47``): a 100-bucket
+    EMA histogram of per-sample losses.  Host-side like the reference, but the loss
+    feedback is consumed asynchronously (one step late) so that it never stalls the GPU.
+    """
+
+    def __init__(self, num_histogram_buckets=100, uniform_p=0.01, alpha=0.9, warmup=10, jitter=True, seed=0):
+        self.n = num_histogram_buckets
+        self.uniform_p, self.alpha, self.warmup, self.jitter = uniform_p, alpha, warmup, jitter
+        self._weights = torch.ones(self.n)
+        self._counts = torch.zeros(self.n, dtype=torch.long)
+        self._gen = torch.Generator().manual_seed(seed)
+        self._pending = None
+
+    def warmed_up(self) -> bool:
+        return bool((self._counts > self.warmup).all())
+
+    def weights(self) -> torch.Tensor:
+        if not self.warmed_up():
+            return torch.ones(self.n)
+        w = self._weights / self._weights.sum()
+        return (1 - self.uniform_p) * w + self.uniform_p / self.n
+
+    def sample(self, batch_size: int) -> torch.Tensor:
+        self._drain()
+        b = torch.multinomial(self.weights(), batch_size, replacement=True, generator=self._gen).float()
+        if self.jitter:
+            return (b + torch.rand(batch_size, generator=self._gen)) / self.n
+        return b / (self.n - 1)
+
+    def update_with_losses(self, ts: torch.Tensor, losses: torch.Tensor) -> None:
+        idx = (ts.view(-1) * self.n).long().clamp_(0, self.n - 1)
+        self._counts.scatter_add_(0, idx, torch.ones_like(idx))
+        for i, j in enumerate(idx.tolist()):
+            self._weights[j] = self._weights[j] * self.alpha + float(losses[i]) * (1 - self.alpha)
+
+    def update_async(self, ts_host: torch.Tensor, losses_pinned: torch.Tensor, ready: torch.cuda.Event) -> None:
+        self._drain()
+        self._pending = (ts_host, losses_pinned, ready)
+
+    def _drain(self) -> None:
+        if self._pending is not None:
+            ts, losses, ev = self._pending
+            ev.synchronize()
+            self.update_with_losses(ts, losses)
+            self._pending = None
+
+
+class DenoiserTrainer:
+    """One training step of the denoiser, batch-sharded over ``world_size`` GPUs.
+
+    Parameters live in three flat buffers: fp32 master weights, a compute-dtype shadow the
+    modules read (``param.data`` are views into it) and a flat gradient buffer the autograd
+    engine accumulates into (``param.grad`` are views).  A step is: zero grads, corruption,
+    forward, mean CE, backward, ONE all-reduce(SUM) of the flat gradients over NCCL, ONE
+    fused AdamW launch (``wm_adamw_step``) that also refreshes the shadow copy.
+    """
+
+    def __init__(self, model: VqVideoDiffusionModel, *, lr=1e-4, weight_decay=1e-7, betas=(0.9, 0.999), eps=1e-8,
+                 compute_dtype=torch.bfloat16, process_group=None, use_cuda_graph=True):
+        params = [p for p in model.parameters() if p.requires_grad]
+        if not params or not params[0].is_cuda:
+            raise RuntimeError('DenoiserTrainer needs the model on a CUDA device')
+        self.model = model
+        self.device = params[0].device
+        self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        n = sum(p.numel() for p in params)
+        self.n_params = n
+        pad = (-n) % 8
+        self.master = torch.empty(n + pad, device=self.device, dtype=torch.float32)
+        self.shadow = torch.zeros(n + pad, device=self.device, dtype=compute_dtype) if compute_dtype != torch.float32 else None
+        self.grad = torch.zeros(n + pad, device=self.device, dtype=compute_dtype)
+        self.exp_avg = torch.zeros_like(self.master)
+        self.exp_avg_sq = torch.zeros_like(self.master)
+        self.master.zero_()
+        off = 0
+        for p in params:
+            k = p.numel()
+            self.master[off:off + k].copy_(p.detach().reshape(-1).float())
+            store = self.shadow if self.shadow is not None else self.master
+            store[off:off + k].copy_(p.detach().reshape(-1))
+            p.data = store[off:off + k].view_as(p)
+            p.grad = self.grad[off:off + k].view_as(p)
+            off += k
+        if self.world > 1:   # identical replicas: rank 0's weights win
+            dist.broadcast(self.master, src=dist.get_global_rank(self.pg, 0) if self.pg else 0, group=self.pg)
+            if self.shadow is not None:
+                self.shadow.copy_(self.master)
+        self.dyn = torch.tensor([1.0, lr], device=self.device, dtype=torch.float32)      # {step, lr}
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self._static = None
+        self.K = model.num_classes
+
+    # -- the step body (capturable) ------------------------------------------------------
+    def _step_body(self, tokens, r):
+        self.grad.zero_()
+        corrupted, target = corrupt_last_frame(tokens, r, self.K)
+        logits = self.model(corrupted)
+        ce = F.cross_entropy(logits.reshape(-1, self.K).float(), target.reshape(-1), reduction='none')
+        per_sample = ce.view(tokens.shape[0], -1).mean(dim=1)
+        loss = ce.mean()
+        loss.backward()
+        if self.world > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)
+        store = self.shadow
+        ops.adamw_step(self.master, store, self.grad, self.exp_avg, self.exp_avg_sq, self.dyn, self.betas[0],
+                       self.betas[1], self.eps, self.weight_decay, 1.0 / self.world)
+        self.dyn[0:1] += 1.0
+        return loss.detach(), per_sample.detach()
+
+    def set_lr(self, lr: float) -> None:
+        self.dyn[1:2].fill_(lr)
+
+    def step(self, tokens: torch.Tensor, r: torch.Tensor):
+        """``tokens [b,S,H,W]`` int64 and ``r [b]`` on the device -> (loss, per-sample loss) tensors."""
+        if not self.use_cuda_graph:
+            return self._step_body(tokens, r)
+        if self._graph is None:
+            self._capture(tokens, r)
+        st_tokens, st_r, st_loss, st_ps = self._static
+        st_tokens.copy_(tokens, non_blocking=True)
+        st_r.copy_(r, non_blocking=True)
+        self._graph.replay()
+        return st_loss, st_ps
+
+    def _capture(self, tokens, r):
+        st_tokens, st_r = tokens.clone(), r.clone().float()
+        saved = (self.master.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.dyn.clone(),
+                 None if self.shadow is None else self.shadow.clone())
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):                 # warm-up on a side stream (allocator, cuBLAS handles, NCCL)
+                self._step_body(st_tokens, st_r)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            st_loss, st_ps = self._step_body(st_tokens, st_r)
+        # undo the warm-up / capture updates so that step 1 is step 1
+        self.master.copy_(saved[0]); self.exp_avg.copy_(saved[1]); self.exp_avg_sq.copy_(saved[2])
+        self.dyn.copy_(saved[3])
+        if self.shadow is not None:
+            self.shadow.copy_(saved[4])
+        self._graph, self._static = graph, (st_tokens, st_r, st_loss, st_ps)
+
+    def launches_per_step(self) -> int:
+        """Kernels of libwm_b200 per step: depth x (attention fwd 1 + bwd 2) + AdamW."""
+        depth = len(self.model.transformer.layers)
+        return depth * 3 + 1
+
+
+@torch.no_grad()
+def sample_next_frame(model: VqVideoDiffusionModel, tokens: torch.Tensor, iterations: int = 30,
+                      sample_topk: int = -1) -> torch.Tensor:
+    """Iteratively denoise the last frame (reference ``main.py:71-111``).
+
+    ``tokens [B,S,H,W]`` with the last frame set to the mask token.  Each iteration draws
+    every position from the current logits, re-masks a ``1 - (i+1)/iterations`` fraction
+    and runs one denoiser forward.  Returns the final draw ``[B,H,W]`` (what the reference
+    hands to ``decoder_model.decode``).
+    """
+    B, _, H, W = tokens.shape
+    K = model.num_classes
+    work = tokens.clone()
+    logits = torch.zeros(B * H * W, K, device=tokens.device)
+    sample = None
+    for i in range(iterations):
+        if sample_topk > 0:
+            kth = torch.topk(logits, sample_topk, dim=-1).values[:, -1:]
+            logits = logits.masked_fill(logits < kth, float('-inf'))
+        probs = torch.softmax(logits.float(), dim=-1)
+        sample = torch.multinomial(probs, 1, replacement=True).view(B, H, W)
+        alpha = min(max((i + 1) / iterations, 0.0), 1.0)
+        remask = torch.rand(B, H, W, device=tokens.device) > alpha
+        work[:, -1] = torch.where(remask, torch.full_like(sample, K), sample)
+        logits = model(work).reshape(B * H * W, K)
+    return sample

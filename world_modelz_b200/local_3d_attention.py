@@ -1,0 +1,110 @@
+"""Drop-in ``local_3d_attention`` module: same classes, constructor arguments, forward
+signatures and ``state_dict`` keys as ``vq-video-diffusion/local_3d_attention.py``; the
+attention core runs in the fused sm_100a kernels behind ``ops.local3d_attention``.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import ops
+
+
+class PreNorm(nn.Module):
+    """LayerNorm on the positional input only; keyword inputs (``q=``) bypass the norm
+    (reference ``local_3d_attention.py:11-17``)."""
+
+    def __init__(self, dim, fn):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.fn = fn
+
+    def forward(self, x, **kwargs):
+        return self.fn(self.norm(x), **kwargs)
+
+
+class FeedForward(nn.Module):
+    """Linear-GELU-Linear with the reference's Sequential indices (``net.0`` / ``net.3``)."""
+
+    def __init__(self, dim, hidden_dim, dropout=0.):
+        super().__init__()
+        stages = [nn.Linear(dim, hidden_dim), nn.GELU(), nn.Dropout(dropout),
+                  nn.Linear(hidden_dim, dim), nn.Dropout(dropout)]
+        self.net = nn.Sequential(*stages)
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class Local3dAttention(nn.Module):
+    """NUWA-style "nearby" attention over a (S,H,W) token grid.
+
+    ``forward(x, q)``: K and V are projected from ``x``, Q from ``q``; each query attends to
+    the ``(2e+1)^3`` window around it, neighbours outside the grid excluded.  Parameters:
+    ``to_q/to_k`` (no bias), ``to_v`` (bias), ``to_out.0`` unless ``heads == 1 and
+    dim_head == dim`` (reference ``:35-55``).  fp32 tensors take the exact SIMT kernels,
+    bf16 tensors the tcgen05 kernels.  ``use_checkpointing`` is accepted for API
+    compatibility; the fused kernels keep only O and the LSE, so there is nothing to
+    recompute.
+    """
+
+    def __init__(self, extents, dim, heads=8, dim_head=64, dropout=.0, use_checkpointing=True):
+        super().__init__()
+        if len(extents) != 3:
+            raise ValueError('extents must be (S, H, W)')
+        self.extents = extents
+        self.heads = heads
+        self.scale = dim_head ** -0.5
+        inner_dim = heads * dim_head
+        self.to_q = nn.Linear(dim, inner_dim, bias=False)
+        self.to_k = nn.Linear(dim, inner_dim, bias=False)
+        self.to_v = nn.Linear(dim, inner_dim, bias=True)
+        if heads == 1 and dim_head == dim:
+            self.to_out = nn.Identity()
+        else:
+            self.to_out = nn.Sequential(nn.Linear(inner_dim, dim), nn.Dropout(dropout))
+        self.use_checkpointing = use_checkpointing
+        self.kernel_flags = 0          # ops.FLAG_SIMT forces the SIMT kernels for bf16 (device cross-check)
+
+    def local_attention(self, k, v, q):
+        """Reference-shaped core: ``[B,S,H,W,heads*d]`` in, ``[(B S H W), heads, 1, d]`` out."""
+        out = ops.local3d_attention(q, k, v, self.heads, self.extents, self.scale, self.kernel_flags)
+        return out.reshape(-1, self.heads, 1, out.shape[-1] // self.heads)
+
+    def forward(self, x, q):
+        if x.dim() != 5 or q.shape[:-1] != x.shape[:-1]:
+            raise ValueError(f'expected x, q of shape [B,S,H,W,dim], got {tuple(x.shape)} and {tuple(q.shape)}')
+        core = ops.local3d_attention(self.to_q(q), self.to_k(x), self.to_v(x), self.heads, self.extents,
+                                     self.scale, self.kernel_flags)
+        return self.to_out(core).reshape(q.shape)
+
+
+class Local3dAttentionTransformer(nn.Module):
+    """Token embedding + three axis position embeddings + ``depth`` x (attention, MLP)
+    residual blocks (reference ``local_3d_attention.py:121-163``)."""
+
+    def __init__(self, *, data_shape, dim, num_classes, extents, depth, heads, dim_head, mlp_dim, dropout=.0):
+        super().__init__()
+        self.num_classes = num_classes
+        self.embedding = nn.Embedding(num_classes, dim)
+        self.pos_emb_s = nn.Embedding(data_shape[0], dim)
+        self.pos_emb_h = nn.Embedding(data_shape[1], dim)
+        self.pos_emb_w = nn.Embedding(data_shape[2], dim)
+        self.layers = nn.ModuleList(
+            nn.ModuleList([
+                PreNorm(dim, Local3dAttention(extents, dim, heads=heads, dim_head=dim_head, dropout=dropout)),
+                PreNorm(dim, FeedForward(dim, mlp_dim, dropout=dropout)),
+            ]) for _ in range(depth))
+
+    def get_pos_embedding(self, batch_shape):
+        _, s, h, w = batch_shape
+        pos = (self.pos_emb_s.weight[:s, None, None, :] + self.pos_emb_h.weight[None, :h, None, :]
+               + self.pos_emb_w.weight[None, None, :w, :])
+        return pos.unsqueeze(0).expand(batch_shape[0], -1, -1, -1, -1)
+
+    def forward(self, img_z):
+        x = self.embedding(img_z) + self.get_pos_embedding(img_z.shape)
+        for attn, ff in self.layers:
+            x = attn(x, q=x) + x
+            x = ff(x) + x
+        return x
