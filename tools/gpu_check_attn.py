@@ -1,0 +1,56 @@
+"""Device-side diagnostics: tcgen05 kernels vs the exact SIMT kernels and the CPU oracle.
+Prints error summaries for every case instead of stopping at the first failure."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from world_modelz_b200 import ops
+from oracle import local3d as O
+
+dev = 'cuda'
+CASES = [
+    ((1, 2, 8, 8, 32), 1, (1, 2, 2)),
+    ((1, 4, 16, 16, 64), 2, (1, 2, 2)),
+    ((2, 8, 16, 16, 256), 8, (1, 2, 2)),
+    ((1, 4, 8, 8, 64), 1, (1, 1, 1)),
+    ((1, 6, 10, 10, 256), 2, (2, 3, 3)),
+    ((1, 3, 9, 7, 64), 1, (1, 1, 2)),
+    ((1, 8, 8, 8, 32), 1, (3, 1, 1)),
+    ((1, 5, 12, 20, 96), 3, (0, 2, 1)),
+    ((1, 8, 16, 16, 512), 4, (2, 3, 3)),
+]
+if len(sys.argv) > 1:
+    CASES = CASES[:int(sys.argv[1])]
+
+
+def stats(name, a, b):
+    a, b = a.float(), b.float()
+    diff = (a - b).abs()
+    bad = diff > (4e-3 * b.abs().max() + 2e-2 * b.abs())
+    print(f'    {name:8s} max|diff|={diff.max().item():.3e} scale={b.abs().max().item():.3e} '
+          f'bad={int(bad.sum())}/{bad.numel()} nan={int(torch.isnan(a).sum())}', flush=True)
+    return int(bad.sum()) + int(torch.isnan(a).sum())
+
+
+total_bad = 0
+for shape, heads, ext in CASES:
+    g = torch.Generator().manual_seed(0)
+    q, k, v, do = (torch.randn(shape, generator=g).bfloat16() for _ in range(4))
+    d = shape[-1] // heads
+    print(f'case shape={shape} heads={heads} d={d} ext={ext} tc={ops.uses_tensor_cores(*shape[1:4], heads, d, ext)}', flush=True)
+    qd, kd, vd, dod = (t.to(dev) for t in (q, k, v, do))
+    scale = d ** -0.5
+    o_si, l_si = ops.attn_forward(qd, kd, vd, heads, ext, scale, ops.FLAG_SIMT)
+    torch.cuda.synchronize()
+    o_tc, l_tc = ops.attn_forward(qd, kd, vd, heads, ext, scale, 0)
+    torch.cuda.synchronize()
+    total_bad += stats('out', o_tc, o_si)
+    total_bad += stats('lse', l_tc, l_si)
+    g_si = ops.attn_backward(qd, kd, vd, o_si, l_si, dod, heads, ext, scale, ops.FLAG_SIMT)
+    g_tc = ops.attn_backward(qd, kd, vd, o_tc, l_tc, dod, heads, ext, scale, 0)
+    torch.cuda.synchronize()
+    for n, a, b_ in zip(('dq', 'dk', 'dv'), g_tc, g_si):
+        total_bad += stats(n, a, b_)
+    if shape[1] * shape[2] * shape[3] * shape[0] <= 4096:
+        ref = O.attention_core(q.float(), k.float(), v.float(), heads, ext)
+        stats('out/cpu', o_tc.cpu(), ref)
+print('TOTAL_BAD', total_bad)

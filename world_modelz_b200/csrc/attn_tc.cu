@@ -1,12 +1,501 @@
-// placeholder until the tcgen05 kernels land
+// Local windowed 3D attention on the 5th-generation tensor cores (bf16, fp32 accumulate).
+//
+// Tiling.  A CTA owns a query tile of 128 tokens, a tS x tH x tW brick of the (S,H,W)
+// grid, for one (batch, head).  The keys any of its queries can see form the brick's halo
+// (tS+2eS) x (tH+2eH) x (tW+2eW).  The halo is walked in BLOCKS: one s-plane of the halo,
+// restricted to `ch` consecutive h-rows, i.e. ch*hW keys (<= 256).  K and V blocks are
+// fetched with ONE 5-D TMA box each straight out of the [B,S,H,W,C] activation tensor:
+// the box may start at negative coordinates or run past the grid, and TMA zero-fills
+// those keys -- the reference's F.pad (local_3d_attention.py:57-63) for free.
+//
+// Per block (flash-attention style, accumulators in TMEM):
+//   S = Q K^T          tcgen05.mma, A = Q tile (K-major), B = K block (K-major), N = block
+//   softmax            one thread per query row: tcgen05.ld the row, mask by window /
+//                      grid-border geometry, running max / sum, P in bf16 -> smem
+//   O += P V           tcgen05.mma, A = P (K-major), B = V block (MN-major), N = dim_head
+// Masking (reference :92-94) is a per-thread column bitmask built from coordinates: a
+// key column is live iff it lies inside this query's window AND inside the grid.  Warps
+// skip whole planes / 16-column groups that none of their 32 queries can see.
+//
+// Replaces Local3dAttention.local_attention (local_3d_attention.py:78-99).
+#include "tc_common.cuh"
 #include "wm_common.cuh"
+
+#include <math.h>
+#include <mutex>
+
 namespace wm {
-bool attn_tc_supported(const AttnShape&) { return false; }
-int attn_fwd_tc(const void*, const void*, const void*, void*, float*, const AttnShape&, cudaStream_t) {
-    return fail(WM_EUNSUPPORTED, "tcgen05 attention forward not built");
+namespace tc {
+
+// --------------------------------------------------------------------- host: tensor map
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
 }
-int attn_bwd_tc(const void*, const void*, const void*, const void*, const float*, const void*, void*, void*, void*,
-                float*, const AttnShape&, cudaStream_t) {
-    return fail(WM_EUNSUPPORTED, "tcgen05 attention backward not built");
+
+int make_tensor_map_5d(CUtensorMap* out, const void* base, int B, int S, int H, int W, int C, int box_c, int box_w,
+                       int box_h, int box_s, int swizzle_bytes) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (fn == nullptr) return fail(WM_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)S, (cuuint64_t)B};
+    const cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H,
+                                   (cuuint64_t)C * 2 * W * H * S};
+    const cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_s, 1u};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(WM_ECUDA, "cuTensorMapEncodeTiled failed (%d) for box (%d,%d,%d,%d) of [%d,%d,%d,%d,%d]", (int)r,
+                    box_c, box_w, box_h, box_s, B, S, H, W, C);
+    return WM_OK;
 }
+
+// ------------------------------------------------------------------------------- plan
+struct Plan {
+    int tS, tH, tW;            // query brick, tS*tH*tW == 128
+    int hS, hH, hW;            // halo = brick + 2*extent
+    int ch;                    // halo h-rows per block
+    int nchunk;                // ceil(hH / ch)
+    int ncols;                 // ch*hW: key columns per block that TMA writes
+    int ncols_pad;             // rounded up to 16 (MMA K granularity of P V)
+    int tilesS, tilesH, tilesW;
+    int smem_bytes;
+    int tmem_cols;             // power of two >= D + ncols_pad
+    float scale_log2;
+};
+
+constexpr int kThreads = 128;
+constexpr int kSmemLimit = 227 * 1024;
+
+template <int D> struct Geo {
+    static constexpr int kRowBytes = (D == 32) ? 64 : 128;        // one smem row of one channel slab
+    static constexpr int kSlabs = (D == 128) ? 2 : 1;             // 64-channel slabs
+    static constexpr int kSlabCh = (D == 32) ? 32 : 64;
+    static constexpr int kSwizzleBytes = kRowBytes;
+    static constexpr uint32_t kSwizzleCode = (D == 32) ? 4u : 2u;  // UMMA layout type
+    static constexpr int kAtomBytes = 8 * kRowBytes;               // 8-row swizzle atom
+};
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+static int next_pow2(int v) { int p = 32; while (p < v) p <<= 1; return p; }
+
+template <int D>
+static size_t fwd_smem_bytes(int ncols_pad) {
+    using G = Geo<D>;
+    const size_t q = (size_t)G::kSlabs * 128 * G::kRowBytes;
+    const size_t kv = (size_t)2 /*stages*/ * 2 /*K,V*/ * G::kSlabs * ncols_pad * G::kRowBytes;
+    const size_t p = (size_t)round_up(ncols_pad, 64) / 64 * 128 * 128;
+    return 1024 /*alignment slack*/ + q + kv + p + 8 * kThreads * 4 /*masks*/ + 256 /*barriers*/;
+}
+
+static size_t fwd_smem_bytes_d(int d, int ncols_pad) {
+    return d == 32 ? fwd_smem_bytes<32>(ncols_pad) : d == 64 ? fwd_smem_bytes<64>(ncols_pad) : fwd_smem_bytes<128>(ncols_pad);
+}
+
+// Choose the brick and block shape: minimise the dense MMA columns executed per clip.
+static bool make_plan(const AttnShape& s, Plan& best) {
+    if (s.d != 32 && s.d != 64 && s.d != 128) return false;
+    static const int bricks[][3] = {{2, 8, 8}, {4, 4, 8}, {4, 8, 4}, {1, 8, 16}, {1, 16, 8}, {2, 4, 16}, {2, 16, 4}};
+    double best_cost = 1e300;
+    bool found = false;
+    for (const auto& b : bricks) {
+        Plan p{};
+        p.tS = b[0]; p.tH = b[1]; p.tW = b[2];
+        if (p.tS * p.tH * p.tW != 128 || (p.tH * p.tW) % 32 != 0) continue;
+        p.hS = p.tS + 2 * s.eS; p.hH = p.tH + 2 * s.eH; p.hW = p.tW + 2 * s.eW;
+        if (p.hW > 32 || p.hW > 256 || p.hH > 256) continue;
+        for (int nchunk = 1; nchunk <= p.hH; ++nchunk) {
+            p.nchunk = nchunk;
+            p.ch = (p.hH + nchunk - 1) / nchunk;
+            p.nchunk = (p.hH + p.ch - 1) / p.ch;
+            p.ncols = p.ch * p.hW;
+            p.ncols_pad = round_up(p.ncols, 16);
+            if (p.ncols_pad > 256 || s.d + p.ncols_pad > 512) continue;
+            if (fwd_smem_bytes_d(s.d, p.ncols_pad) > (size_t)kSmemLimit) continue;
+            p.tilesS = (s.S + p.tS - 1) / p.tS; p.tilesH = (s.H + p.tH - 1) / p.tH; p.tilesW = (s.W + p.tW - 1) / p.tW;
+            const double tiles = (double)p.tilesS * p.tilesH * p.tilesW;
+            const double cost = tiles * p.hS * p.nchunk * (p.ncols_pad + 24.0 /*per-block sync overhead*/);
+            if (cost < best_cost) {
+                best_cost = cost;
+                p.smem_bytes = (int)fwd_smem_bytes_d(s.d, p.ncols_pad);
+                p.tmem_cols = next_pow2(s.d + p.ncols_pad);
+                p.scale_log2 = s.scale * 1.4426950408889634f;
+                best = p;
+                found = true;
+            }
+            break;   // the smallest feasible nchunk for this brick
+        }
+    }
+    return found;
+}
+
+// ------------------------------------------------------------------------------ kernel
+struct FwdParams {
+    AttnShape sh;
+    Plan pl;
+    __nv_bfloat16* o;
+    float* lse;
+};
+
+// swizzled byte offset of 16-byte chunk `chunk16` of row `row` inside a 128B-row tile
+__device__ __forceinline__ uint32_t sw128_offset(int row, int chunk16) {
+    return (uint32_t)row * 128u + (uint32_t)((chunk16 ^ (row & 7)) << 4);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads, 1)
+l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv_k,
+                  const __grid_constant__ CUtensorMap map_kv_v, const FwdParams prm) {
+    using G = Geo<D>;
+    const AttnShape& sh = prm.sh;
+    const Plan& pl = prm.pl;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ncols = pl.ncols, ncols_pad = pl.ncols_pad;
+    const int q_slab_bytes = 128 * G::kRowBytes;
+    const int kv_slab_bytes = ncols_pad * G::kRowBytes;
+    const int kv_tile_bytes = G::kSlabs * kv_slab_bytes;
+
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + G::kSlabs * q_slab_bytes;                 // [2 stages][slabs][ncols_pad rows]
+    uint8_t* sV = sK + 2 * kv_tile_bytes;
+    uint8_t* sP = sV + 2 * kv_tile_bytes;                        // [ceil(ncols_pad/64)][128 rows][128 B]
+    const int p_slabs = (ncols_pad + 63) / 64;
+    uint32_t* sMask = reinterpret_cast<uint32_t*>(sP + p_slabs * 128 * 128);   // [8 words][128 threads]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + 8 * kThreads);
+    uint64_t* bar_q = bars;
+    uint64_t* bar_kv = bars + 1;      // [2]
+    uint64_t* bar_mma = bars + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+    // ---- which brick -------------------------------------------------------------------
+    int bid = blockIdx.x;
+    const int tw_i = bid % pl.tilesW; bid /= pl.tilesW;
+    const int th_i = bid % pl.tilesH; bid /= pl.tilesH;
+    const int ts_i = bid % pl.tilesS; bid /= pl.tilesS;
+    const int head = bid % sh.heads;
+    const int b = bid / sh.heads;
+    const int s0 = ts_i * pl.tS, h0 = th_i * pl.tH, w0 = tw_i * pl.tW;
+    const int c_base = head * D;
+
+    // ---- this thread's query row ---------------------------------------------------------
+    const int plane_sz = pl.tH * pl.tW;
+    const int qs = tid / plane_sz, qh = (tid % plane_sz) / pl.tW, qw = tid % pl.tW;
+    const bool q_valid = (s0 + qs < sh.S) && (h0 + qh < sh.H) && (w0 + qw < sh.W);
+    // live key range of this row in halo coordinates (window AND grid), per axis
+    const int kh_lo = max(qh, sh.eH - h0), kh_hi = min(qh + 2 * sh.eH, sh.H - 1 - h0 + sh.eH);
+    const int kw_lo = max(qw, sh.eW - w0), kw_hi = min(qw + 2 * sh.eW, sh.W - 1 - w0 + sh.eW);
+    const uint32_t wbits = (q_valid && kw_hi >= kw_lo) ? ((kw_hi - kw_lo == 31) ? 0xffffffffu : ((1u << (kw_hi - kw_lo + 1)) - 1u)) << kw_lo : 0u;
+    // warp-uniform ranges
+    const int w_qs = (warp * 32) / plane_sz;
+    const int w_qh_lo = ((warp * 32) % plane_sz) / pl.tW, w_qh_hi = ((warp * 32 + 31) % plane_sz) / pl.tW;
+    // block iteration space: planes and h-chunks that intersect the grid
+    const int ks_first = max(0, sh.eS - s0), ks_last = min(pl.hS - 1, sh.S - 1 - s0 + sh.eS);
+    const int khg_lo = max(0, sh.eH - h0), khg_hi = min(pl.hH - 1, sh.H - 1 - h0 + sh.eH);
+    const int chunk_first = khg_lo / pl.ch, chunk_last = khg_hi / pl.ch;
+    const int nplanes = ks_last - ks_first + 1;
+    const int nblocks = nplanes * (chunk_last - chunk_first + 1);
+
+    // ---- one-time setup ----------------------------------------------------------------------
+    if (tid == 0) {
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_kv_k);
+        tma_prefetch_desc(&map_kv_v);
+        mbar_init(bar_q, 1);
+        mbar_init(&bar_kv[0], 1);
+        mbar_init(&bar_kv[1], 1);
+        mbar_init(bar_mma, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        // power-of-two TMEM allocation: O at column 0, S at column D
+        if (pl.tmem_cols <= 64) tmem_alloc<64>(tmem_slot);
+        else if (pl.tmem_cols <= 128) tmem_alloc<128>(tmem_slot);
+        else if (pl.tmem_cols <= 256) tmem_alloc<256>(tmem_slot);
+        else tmem_alloc<512>(tmem_slot);
+    }
+    // rows [ncols, ncols_pad) of every K / V stage are never written by TMA: keep them zero
+    if (ncols_pad > ncols) {
+        const int pad_bytes = (ncols_pad - ncols) * G::kRowBytes;
+        for (int t = 0; t < 2 * 2 * G::kSlabs; ++t) {
+            uint8_t* base = sK + t * kv_slab_bytes + ncols * G::kRowBytes;   // sK and sV are contiguous
+            for (int i = tid * 16; i < pad_bytes; i += kThreads * 16) *reinterpret_cast<uint4*>(base + i) = make_uint4(0, 0, 0, 0);
+        }
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_o = tmem_base;             // columns [0, D)
+    const uint32_t tmem_s = tmem_base + D;         // columns [D, D + ncols_pad)
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+
+    auto block_coords = [&](int j, int& ks, int& chunk) {
+        chunk = chunk_first + j / nplanes;
+        ks = ks_first + j % nplanes;
+    };
+    auto issue_kv_load = [&](int j) {               // thread 0 only
+        int ks, chunk;
+        block_coords(j, ks, chunk);
+        const int stage = j & 1;
+        mbar_expect_tx(&bar_kv[stage], 2u * G::kSlabs * (uint32_t)ncols * G::kRowBytes);
+#pragma unroll
+        for (int sl = 0; sl < G::kSlabs; ++sl) {
+            tma_load_5d(sK + stage * kv_tile_bytes + sl * kv_slab_bytes, &map_kv_k, &bar_kv[stage], c_base + sl * G::kSlabCh,
+                        w0 - sh.eW, h0 - sh.eH + chunk * pl.ch, s0 - sh.eS + ks, b);
+            tma_load_5d(sV + stage * kv_tile_bytes + sl * kv_slab_bytes, &map_kv_v, &bar_kv[stage], c_base + sl * G::kSlabCh,
+                        w0 - sh.eW, h0 - sh.eH + chunk * pl.ch, s0 - sh.eS + ks, b);
+        }
+    };
+    const uint32_t idesc_s = make_idesc_bf16(ncols_pad, false, false);
+    const uint32_t idesc_o = make_idesc_bf16(D, false, true);
+    auto issue_s_mma = [&](int j) {                 // S = Q K_j^T   (thread 0 only)
+        const int stage = j & 1;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+            const int sl = (kk * 16) / G::kSlabCh;
+            const int koff = ((kk * 16) % G::kSlabCh) * 2;
+            const uint64_t da = make_smem_desc(smem_u32(sQ + sl * q_slab_bytes + koff), 16, G::kAtomBytes, G::kSwizzleCode);
+            const uint64_t db = make_smem_desc(smem_u32(sK + stage * kv_tile_bytes + sl * kv_slab_bytes + koff), 16,
+                                               G::kAtomBytes, G::kSwizzleCode);
+            umma_bf16_ss(tmem_s, da, db, idesc_s, kk > 0);
+        }
+    };
+    auto issue_o_mma = [&](int j, bool accumulate) { // O += P V_j    (thread 0 only)
+        const int stage = j & 1;
+        for (int kk = 0; kk < ncols_pad / 16; ++kk) {
+            const uint64_t da = make_smem_desc(smem_u32(sP + (kk >> 2) * (128 * 128) + (kk & 3) * 32), 16, 1024, 2u);
+            const uint64_t db = make_smem_desc(smem_u32(sV + stage * kv_tile_bytes + kk * 16 * G::kRowBytes),
+                                               (uint32_t)kv_slab_bytes, G::kAtomBytes, G::kSwizzleCode);
+            umma_bf16_ss(tmem_o, da, db, idesc_o, (accumulate || kk > 0) ? 1u : 0u);
+        }
+    };
+
+    if (tid == 0) {
+        mbar_expect_tx(bar_q, (uint32_t)G::kSlabs * q_slab_bytes);
+#pragma unroll
+        for (int sl = 0; sl < G::kSlabs; ++sl)
+            tma_load_5d(sQ + sl * q_slab_bytes, &map_q, bar_q, c_base + sl * G::kSlabCh, w0, h0, s0, b);
+        issue_kv_load(0);
+        if (nblocks > 1) issue_kv_load(1);
+        mbar_wait(bar_q, 0);
+        mbar_wait(&bar_kv[0], 0);
+        tc_fence_after();
+        issue_s_mma(0);
+        umma_commit(bar_mma);
+    }
+
+    // ---- main loop ------------------------------------------------------------------------------
+    float m_used = -INFINITY;      // running max (log2 domain, scaled) the row's P values are relative to
+    float l_run = 0.f;             // running sum of P
+    bool p_zero = false;           // this warp's P rows are known to be all zero
+    int mask_chunk = -1;
+    const int nwords = (ncols_pad + 31) / 32;
+
+    for (int j = 0; j < nblocks; ++j) {
+        int ks, chunk;
+        block_coords(j, ks, chunk);
+        mbar_wait(bar_mma, j & 1);                   // S_j ready; P V_{j-1} done (P buffer, stage (j-1)&1 free)
+        tc_fence_after();
+        if (tid == 0 && j >= 1 && j + 1 < nblocks) issue_kv_load(j + 1);
+
+        const int kh0 = chunk * pl.ch;
+        if (chunk != mask_chunk) {                   // per-thread live-column bitmask for this h-chunk
+            mask_chunk = chunk;
+            for (int w = 0; w < nwords; ++w) sMask[w * kThreads + tid] = 0u;
+            if (wbits != 0u) {
+                const int ra = max(kh_lo, kh0), rb = min(kh_hi, kh0 + pl.ch - 1);
+                for (int kh = ra; kh <= rb; ++kh) {
+                    const int pos = (kh - kh0) * pl.hW;
+                    const int w = pos >> 5, sft = pos & 31;
+                    sMask[w * kThreads + tid] |= wbits << sft;
+                    if (sft != 0 && (wbits >> (32 - sft)) != 0u) sMask[(w + 1) * kThreads + tid] |= wbits >> (32 - sft);
+                }
+            }
+        }
+
+        // warp-uniform: can any of this warp's queries see this block?
+        const bool plane_live = (ks >= w_qs) && (ks <= w_qs + 2 * sh.eS);
+        const int ua = max(w_qh_lo, kh0), ub = min(w_qh_hi + 2 * sh.eH, kh0 + pl.ch - 1);
+        const bool live = plane_live && (ub >= ua);
+        if (live) {
+            const int g_lo = ((ua - kh0) * pl.hW) >> 4;                              // 16-column groups
+            const int g_hi = min(((ub - kh0 + 1) * pl.hW + 15) >> 4, ncols_pad >> 4);
+            // pass 1: row maximum over live columns
+            float mx = -INFINITY;
+            for (int g = g_lo; g < g_hi; ++g) {
+                const uint32_t mword = sMask[(g >> 1) * kThreads + tid] >> ((g & 1) * 16);
+                uint32_t r[16];
+                tmem_ld16(tmem_s + lane_sel + g * 16, r);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (mword & (1u << i)) mx = fmaxf(mx, __uint_as_float(r[i]));
+            }
+            const float m_blk = mx * pl.scale_log2;          // scale > 0
+            // lazy rescale: keep the old reference max unless the new one is > 2^8 larger
+            float alpha = 1.f;
+            const bool bump = m_blk > m_used + 8.f;
+            if (bump) {
+                alpha = ex2(m_used - m_blk);                 // 0 when this is the row's first live block
+                m_used = m_blk;
+            }
+            const bool fix_o = bump && (l_run > 0.f);
+            l_run *= alpha;
+            if (j > 0 && __any_sync(0xffffffffu, fix_o)) {  // O rows already hold earlier blocks: rescale
+#pragma unroll
+                for (int c = 0; c < D; c += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(tmem_o + lane_sel + c, r);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                    tmem_st16(tmem_o + lane_sel + c, r);
+                }
+                tmem_wait_st();
+            }
+            // pass 2: P = 2^(s*scale*log2e - m) on live columns, 0 elsewhere -> bf16 -> smem (K-major, 128B swizzle)
+            const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
+            float lsum = 0.f;
+            for (int g = 0; g < (ncols_pad >> 4); ++g) {
+                uint32_t packed[8];
+                if (g >= g_lo && g < g_hi) {
+                    const uint32_t mword = sMask[(g >> 1) * kThreads + tid] >> ((g & 1) * 16);
+                    uint32_t r[16];
+                    tmem_ld16(tmem_s + lane_sel + g * 16, r);
+                    tmem_wait_ld();
+                    float p[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float e = ex2(fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m));
+                        p[i] = (mword & (1u << i)) ? e : 0.f;
+                        lsum += p[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) packed[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) packed[i] = 0u;
+                }
+                uint8_t* slab = sP + (g >> 2) * (128 * 128);
+                const int c16 = (g & 3) * 2;
+                *reinterpret_cast<uint4*>(slab + sw128_offset(tid, c16)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                *reinterpret_cast<uint4*>(slab + sw128_offset(tid, c16 + 1)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            }
+            l_run += lsum;
+            p_zero = false;
+        } else if (!p_zero) {
+            for (int g = 0; g < (ncols_pad >> 4); ++g) {
+                uint8_t* slab = sP + (g >> 2) * (128 * 128);
+                const int c16 = (g & 3) * 2;
+                *reinterpret_cast<uint4*>(slab + sw128_offset(tid, c16)) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(slab + sw128_offset(tid, c16 + 1)) = make_uint4(0, 0, 0, 0);
+            }
+            p_zero = true;
+        }
+        fence_proxy_async();          // P (generic proxy) -> visible to tcgen05.mma (async proxy)
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_o_mma(j, j > 0);
+            if (j + 1 < nblocks) {
+                mbar_wait(&bar_kv[(j + 1) & 1], ((j + 1) >> 1) & 1);
+                tc_fence_after();
+                issue_s_mma(j + 1);
+            }
+            umma_commit(bar_mma);
+        }
+    }
+
+    // ---- epilogue: O / l -> bf16, LSE ---------------------------------------------------------
+    mbar_wait(bar_mma, nblocks & 1);
+    tc_fence_after();
+    const long tok = (((long)b * sh.S + (s0 + qs)) * sh.H + (h0 + qh)) * sh.W + (w0 + qw);
+    const float inv_l = 1.f / l_run;
+    __nv_bfloat16* orow = prm.o + tok * (long)sh.inner() + c_base;
+#pragma unroll
+    for (int c = 0; c < D; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_o + lane_sel + c, r);       // warp-collective: every lane takes part
+        tmem_wait_ld();
+        if (q_valid) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                pk[i] = pack_bf16(__uint_as_float(r[2 * i]) * inv_l, __uint_as_float(r[2 * i + 1]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(orow + c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+    }
+    if (q_valid) prm.lse[tok * sh.heads + head] = (m_used + lg2(l_run)) * 0.6931471805599453f;
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        if (pl.tmem_cols <= 64) tmem_dealloc<64>(tmem_base);
+        else if (pl.tmem_cols <= 128) tmem_dealloc<128>(tmem_base);
+        else if (pl.tmem_cols <= 256) tmem_dealloc<256>(tmem_base);
+        else tmem_dealloc<512>(tmem_base);
+    }
+}
+
+template <int D>
+static int launch_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const AttnShape& s,
+                      const Plan& pl, cudaStream_t st) {
+    using G = Geo<D>;
+    CUtensorMap mq, mk, mv;
+    const int C = s.inner();
+    if (int rc = make_tensor_map_5d(&mq, q, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.tW, pl.tH, pl.tS, G::kSwizzleBytes)) return rc;
+    if (int rc = make_tensor_map_5d(&mk, k, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
+    if (int rc = make_tensor_map_5d(&mv, v, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
+    FwdParams prm{s, pl, static_cast<__nv_bfloat16*>(o), lse};
+    WM_CUDA_CHECK(cudaFuncSetAttribute(l3d_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
+    const long grid = (long)s.B * s.heads * pl.tilesS * pl.tilesH * pl.tilesW;
+    l3d_fwd_tc_kernel<D><<<(unsigned)grid, kThreads, pl.smem_bytes, st>>>(mq, mk, mv, prm);
+    WM_CUDA_CHECK(cudaGetLastError());
+    return WM_OK;
+}
+
+}  // namespace tc
+
+bool attn_tc_supported(const AttnShape& s) {
+    tc::Plan pl;
+    if ((long)s.B * s.heads * 1L > 0x7fffffffL) return false;
+    return tc::make_plan(s, pl);
+}
+
+int attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse, const AttnShape& s, cudaStream_t st) {
+    tc::Plan pl;
+    if (!tc::make_plan(s, pl)) return fail(WM_EUNSUPPORTED, "no tensor-core tiling for this shape");
+    switch (s.d) {
+        case 32: return tc::launch_fwd<32>(q, k, v, o, lse, s, pl, st);
+        case 64: return tc::launch_fwd<64>(q, k, v, o, lse, s, pl, st);
+        default: return tc::launch_fwd<128>(q, k, v, o, lse, s, pl, st);
+    }
+}
+
+int attn_bwd_tc(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout,
+                void* dq, void* dk, void* dv, float* delta, const AttnShape& s, cudaStream_t st) {
+    // the tcgen05 backward kernels are not written yet: exact SIMT kernels on bf16 data
+    return attn_bwd_simt(q, k, v, o, lse, dout, dq, dk, dv, delta, s, WM_DTYPE_BF16, st);
+}
+
 }  // namespace wm
