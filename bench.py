@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the local-3D-attention / VQ denoiser hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+A *step* is one denoiser training step (corruption, forward, CE, backward, gradient
+all-reduce, AdamW) over one batch of synthetic clips of BASELINE config 3: 16 frames x
+16x16 VQ tokens, dim 256, 8 heads x 32, window 3x5x5, depth 4, mlp 256, K=512, bf16.
+Weak scaling: every GPU gets `--clips-per-gpu` clips; `value` is whole-job clips/s.
+The same JSON line carries the attention-core fwd+bwd tokens/s (the other half of the
+metric), its roofline, the VQ kernel's latents/s and a CPU baseline from the oracle.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+C3 = dict(data_shape=(16, 16, 16), dim=256, num_classes=512, extents=(1, 2, 2), depth=4, heads=8, dim_head=32,
+          mlp_dim=256)
+METRIC = 'denoiser_train_clips_per_s'
+UNIT = 'clips/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--clips-per-gpu', type=int, default=32)
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-micro', action='store_true', help='skip the attention / VQ kernel timings')
+    return ap.parse_args()
+
+
+def config_dict(n_gpus, clips_per_gpu):
+    return {'workload': 'config3: denoiser train step, 16x16x16-token clips, dim 256, 8 heads x 32, window 3x5x5, '
+                        'depth 4, mlp 256, K=512',
+            'global_batch': n_gpus * clips_per_gpu, 'clips_per_gpu': clips_per_gpu, 'tokens_per_clip': 4096,
+            'parallelism': f'dp{n_gpus}', 'l2': 'working set per step (activations >1 GB) exceeds the 126 MB L2'}
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return p.get('hbm_gbs', 6650.0), p.get('bf16_tflops_sustained', 1400.0), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 1400.0, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------ CPU reference arm
+def cpu_train_sample(steps, warmup, clips):
+    """Reference CPU path: the oracle's train_step (fp32, all host threads) on `clips` clips."""
+    from oracle import local3d as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.DenoiserConfig(**C3)
+    p = O.init_denoiser_params(cfg, seed=42)
+    state = {}
+    g = torch.Generator().manual_seed(42)
+    times = []
+    for it in range(warmup + steps):
+        tokens = torch.randint(0, cfg.num_classes, (clips, *cfg.data_shape), generator=g)
+        r = torch.rand(clips, generator=g)
+        t0 = time.perf_counter()
+        corrupted, target = O.corrupt_last_frame(tokens, r, cfg.num_classes, gen=g)
+        O.train_step(p, state, it + 1, corrupted, target, cfg)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return sum(times), len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    clips = 1
+    total, n = cpu_train_sample(args.steps, min(args.warmup, 1), clips)
+    value = clips * n / total
+    cores = os.cpu_count() or 1
+    sample = f'{n} steps x {clips} clip(s) of config 3, fp32, oracle port of the reference modules on {cores} host threads'
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': n,
+            'warmup': min(args.warmup, 1), 'ms_per_step': 1e3 * total / n, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic', 'config': config_dict(args.gpus, clips),
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# -------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={index}', f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.1] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], None, set()
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------- kernel timings
+def time_kernel(fn, iters, stream=None):
+    """Average device time of fn() in ms over `iters` calls (CUDA events on the current stream)."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def micro_benchmarks(dev, clips, hbm_gbs, tf_peak):
+    """Attention core fwd / bwd on the config-3 shape and the VQ search on config-2 widths."""
+    from world_modelz_b200 import ops
+    out = {}
+    S, H, W = C3['data_shape']
+    heads, d, ext = C3['heads'], C3['dim_head'], C3['extents']
+    inner = heads * d
+    g = torch.Generator(device=dev).manual_seed(1)
+    q, k, v, do = (torch.randn(clips, S, H, W, inner, device=dev, generator=g).bfloat16() for _ in range(4))
+    scale = d ** -0.5
+    o, lse = ops.attn_forward(q, k, v, heads, ext, scale)
+    t_f = time_kernel(lambda: ops.attn_forward(q, k, v, heads, ext, scale), 20)
+    t_b = time_kernel(lambda: ops.attn_backward(q, k, v, o, lse, do, heads, ext, scale), 10)
+    tokens = clips * S * H * W
+    wn = (2 * ext[0] + 1) * (2 * ext[1] + 1) * (2 * ext[2] + 1)
+    bytes_f = tokens * (4 * inner * 2 + heads * 4)
+    bytes_fb = tokens * (12 * inner * 2 + 3 * heads * 4)
+    flops_f = 4.0 * wn * inner * tokens
+    out['attn'] = {'shape': f'{clips}x{S}x{H}x{W}x({heads}x{d}) window {wn}', 'fwd_ms': t_f, 'bwd_ms': t_b,
+                   'fwd_bwd_tokens_per_s': tokens / ((t_f + t_b) * 1e-3), 'fwd_tokens_per_s': tokens / (t_f * 1e-3),
+                   'fwd_algorithmic_gbs': bytes_f / (t_f * 1e-3) / 1e9,
+                   'fwd_bwd_algorithmic_gbs': bytes_fb / ((t_f + t_b) * 1e-3) / 1e9,
+                   'fwd_algorithmic_tflops': flops_f / (t_f * 1e-3) / 1e12,
+                   'fwd_bwd_algorithmic_tflops': 3.5 * flops_f / ((t_f + t_b) * 1e-3) / 1e12,
+                   'tensor_cores': ops.uses_tensor_cores(S, H, W, heads, d, ext)}
+    # roofline of the dominant kernel of the path: attention forward+backward, HBM-bound algorithmically
+    ach = bytes_fb / ((t_f + t_b) * 1e-3) / 1e9
+    out['roofline'] = {'kernel': 'local-3D attention core fwd+bwd (3 launches)', 'bound': 'hbm', 'achieved': ach,
+                       'peak': hbm_gbs, 'unit': 'GB/s', 'frac': ach / hbm_gbs, 'traffic': None,
+                       'algorithmic_bytes_per_launch_set': bytes_fb,
+                       'note': 'algorithmic bytes = 12*inner*2 B + 12*heads B per token (q,k,v,o,dO read; o,dq,dk,dv written)'}
+    # VQ nearest: 4096 frames of 16x16 latents (D=64) against 512 codes
+    n = 1 << 20
+    x = torch.randn(n, 1, 64, device=dev, generator=g)
+    cb = torch.randn(1, 512, 64, device=dev, generator=g)
+    t_v = time_kernel(lambda: ops.vq_nearest(x, cb), 5)
+    out['vq'] = {'shape': f'{n} latents x 64 vs 512 codes (fp32, bit-exact indices)', 'ms': t_v,
+                 'latents_per_s': n / (t_v * 1e-3), 'algorithmic_gbs': n * 520 / (t_v * 1e-3) / 1e9}
+    return out
+
+
+# ---------------------------------------------------------------------------------- main
+def run_b200(args):
+    import torch.distributed as dist
+    import world_modelz_b200 as wm
+    from world_modelz_b200 import ops, parallel
+    from world_modelz_b200.denoiser import LossAwareSamplerEma
+
+    rank, local_rank, world = parallel.init_from_env('nccl')
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py --impl b200 needs a CUDA device: there is no CPU fallback')
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(42 + rank)
+    hbm_gbs, tf_peak, peak_src = peaks()
+    B = args.clips_per_gpu
+    K = C3['num_classes']
+
+    model = wm.VqVideoDiffusionModel(**C3).to(dev)
+    trainer = wm.DenoiserTrainer(model, lr=1e-4, weight_decay=1e-7, compute_dtype=torch.bfloat16,
+                                 use_cuda_graph=not args.no_graph)
+    sampler = LossAwareSamplerEma(seed=42 + rank)
+    gen = torch.Generator().manual_seed(1234 + rank)
+    n_batches = 4
+    host_tokens = [torch.randint(0, K, (B, *C3['data_shape']), generator=gen).pin_memory() for _ in range(n_batches)]
+    dev_tokens = [t.to(dev) for t in host_tokens]
+    dev_r = [torch.rand(B, device=dev) for _ in range(n_batches)]
+    host_r = torch.empty(B).pin_memory()
+    host_loss = torch.empty(1 + B).pin_memory()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        sync_all()
+        t1 = time.perf_counter()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), t0, t1
+
+    # --- device-resident arm: inputs already in HBM ------------------------------------------
+    def step_resident(i):
+        trainer.step(dev_tokens[i % n_batches], dev_r[i % n_batches])
+
+    # --- end-to-end arm: pinned host tokens + r in, loss + per-sample losses out, every step ---
+    dst_tokens = torch.empty_like(dev_tokens[0])
+    dst_r = torch.empty(B, device=dev)
+    copied = torch.cuda.Event()
+
+    def step_e2e(i):
+        host_r.copy_(sampler.sample(B))
+        dst_tokens.copy_(host_tokens[i % n_batches], non_blocking=True)
+        dst_r.copy_(host_r, non_blocking=True)
+        loss, per_sample = trainer.step(dst_tokens, dst_r)
+        host_loss[:1].copy_(loss.reshape(1), non_blocking=True)
+        host_loss[1:].copy_(per_sample, non_blocking=True)
+        copied.record()
+        copied.synchronize()                      # the step's result is on the host before the next step starts
+        sampler.update_with_losses(host_r, host_loss[1:])
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = ops.launch_count()
+    ms, t0, t1 = timed(step_resident, args.steps)
+    launches = args.steps * trainer.launches_per_step() if not args.no_graph else ops.launch_count() - launches0
+    clock_info = clocks.stop(t0, t1) if clocks else None
+    for i in range(3):
+        step_e2e(i)
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    global_clips = world * B
+    value = global_clips * args.steps / (ms * 1e-3)
+    e2e_value = global_clips * args.steps / (ms_e2e * 1e-3)
+    h2d = B * 4096 * 8 + B * 4
+    d2h = (1 + B) * 4
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': config_dict(world, B), 'clocks': clock_info,
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': launches, 'cuda_graph': not args.no_graph, 'peaks': peak_src,
+            'train_tokens_per_s': value * 4096,
+            'train_model_tflops': value * 42.6e9 / 1e12}
+    if not args.no_micro:
+        micro = micro_benchmarks(dev, B, hbm_gbs, tf_peak)
+        line['roofline'] = micro.pop('roofline')
+        line.update(micro)
+    else:
+        line['roofline'] = None
+    if world == 1 and not args.no_cpu_baseline:
+        total, n = cpu_train_sample(2, 1, 1)
+        cores = os.cpu_count() or 1
+        line['cpu_baseline'] = {'value': n / total, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                'sample': f'{n} steps x 1 clip of config 3, fp32, oracle port on {cores} host threads'}
+    else:
+        line['cpu_baseline'] = None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -297,7 +297,7 @@ def train_step(p: Dict[str, torch.Tensor], opt_state: Dict[str, Dict[str, torch.
             st['v'].mul_(b2).addcmul_(g, g, value=1 - b2)
             denom = (st['v'].sqrt() / math.sqrt(1 - b2 ** step)).add_(eps)
             w.addcdiv_(st['m'], denom, value=-lr / (1 - b1 ** step))
-    return float(loss)
+    return float(loss.detach())
 
 
 @torch.no_grad()

@@ -18,8 +18,7 @@
 // skip whole planes / 16-column groups that none of their 32 queries can see.
 //
 // Replaces Local3dAttention.local_attention (local_3d_attention.py:78-99).
-#include "tc_common.cuh"
-#include "wm_common.cuh"
+#include "attn_tc.cuh"
 
 #include <math.h>
 #include <mutex>
@@ -65,49 +64,31 @@ int make_tensor_map_5d(CUtensorMap* out, const void* base, int B, int S, int H, 
 }
 
 // ------------------------------------------------------------------------------- plan
-struct Plan {
-    int tS, tH, tW;            // query brick, tS*tH*tW == 128
-    int hS, hH, hW;            // halo = brick + 2*extent
-    int ch;                    // halo h-rows per block
-    int nchunk;                // ceil(hH / ch)
-    int ncols;                 // ch*hW: key columns per block that TMA writes
-    int ncols_pad;             // rounded up to 16 (MMA K granularity of P V)
-    int tilesS, tilesH, tilesW;
-    int smem_bytes;
-    int tmem_cols;             // power of two >= D + ncols_pad
-    float scale_log2;
-};
+static int row_bytes_of(int d) { return d == 32 ? 64 : 128; }
+static int slabs_of(int d) { return d == 128 ? 2 : 1; }
 
-constexpr int kThreads = 128;
-constexpr int kSmemLimit = 227 * 1024;
-
-template <int D> struct Geo {
-    static constexpr int kRowBytes = (D == 32) ? 64 : 128;        // one smem row of one channel slab
-    static constexpr int kSlabs = (D == 128) ? 2 : 1;             // 64-channel slabs
-    static constexpr int kSlabCh = (D == 32) ? 32 : 64;
-    static constexpr int kSwizzleBytes = kRowBytes;
-    static constexpr uint32_t kSwizzleCode = (D == 32) ? 4u : 2u;  // UMMA layout type
-    static constexpr int kAtomBytes = 8 * kRowBytes;               // 8-row swizzle atom
-};
-
-static int round_up(int a, int b) { return (a + b - 1) / b * b; }
-static int next_pow2(int v) { int p = 32; while (p < v) p <<= 1; return p; }
-
-template <int D>
-static size_t fwd_smem_bytes(int ncols_pad) {
-    using G = Geo<D>;
-    const size_t q = (size_t)G::kSlabs * 128 * G::kRowBytes;
-    const size_t kv = (size_t)2 /*stages*/ * 2 /*K,V*/ * G::kSlabs * ncols_pad * G::kRowBytes;
-    const size_t p = (size_t)round_up(ncols_pad, 64) / 64 * 128 * 128;
-    return 1024 /*alignment slack*/ + q + kv + p + 8 * kThreads * 4 /*masks*/ + 256 /*barriers*/;
+size_t smem_bytes_for(Mode mode, int d, int ncols_pad) {
+    const size_t row_tile = (size_t)slabs_of(d) * 128 * row_bytes_of(d);
+    const size_t blk = (size_t)slabs_of(d) * ncols_pad * row_bytes_of(d);
+    const size_t ptile = (size_t)round_up(ncols_pad, 64) / 64 * 128 * 128;
+    const size_t fixed = 1024 /*alignment slack*/ + 8 * kThreads * 4 /*masks*/ + 256 /*barriers*/;
+    switch (mode) {
+        case kFwd: return fixed + row_tile + 4 * blk + ptile;                       // Q | 2x(K,V) | P
+        case kBwdDQ: return fixed + 2 * row_tile + 4 * blk + ptile;                 // Q,dO | 2x(K,V) | dS
+        default: return fixed + 2 * row_tile + 4 * blk + 2 * ptile + 4 * ncols_pad * 4;   // K,V | 2x(Q,dO) | P,dS | lse,delta
+    }
 }
 
-static size_t fwd_smem_bytes_d(int d, int ncols_pad) {
-    return d == 32 ? fwd_smem_bytes<32>(ncols_pad) : d == 64 ? fwd_smem_bytes<64>(ncols_pad) : fwd_smem_bytes<128>(ncols_pad);
+int tmem_cols_for(Mode mode, int d, int ncols_pad) {
+    switch (mode) {
+        case kFwd: return d + ncols_pad;                 // O | S
+        case kBwdDQ: return d + 2 * ncols_pad;           // dQ | S | dP
+        default: return 2 * d + 2 * ncols_pad;           // dV | dK | S^T | dP^T
+    }
 }
 
 // Choose the brick and block shape: minimise the dense MMA columns executed per clip.
-static bool make_plan(const AttnShape& s, Plan& best) {
+bool make_plan(const AttnShape& s, Mode mode, Plan& best) {
     if (s.d != 32 && s.d != 64 && s.d != 128) return false;
     static const int bricks[][3] = {{2, 8, 8}, {4, 4, 8}, {4, 8, 4}, {1, 8, 16}, {1, 16, 8}, {2, 4, 16}, {2, 16, 4}};
     double best_cost = 1e300;
@@ -117,22 +98,21 @@ static bool make_plan(const AttnShape& s, Plan& best) {
         p.tS = b[0]; p.tH = b[1]; p.tW = b[2];
         if (p.tS * p.tH * p.tW != 128 || (p.tH * p.tW) % 32 != 0) continue;
         p.hS = p.tS + 2 * s.eS; p.hH = p.tH + 2 * s.eH; p.hW = p.tW + 2 * s.eW;
-        if (p.hW > 32 || p.hW > 256 || p.hH > 256) continue;
+        if (p.hW > 32 || p.hH > 256) continue;
         for (int nchunk = 1; nchunk <= p.hH; ++nchunk) {
-            p.nchunk = nchunk;
             p.ch = (p.hH + nchunk - 1) / nchunk;
             p.nchunk = (p.hH + p.ch - 1) / p.ch;
             p.ncols = p.ch * p.hW;
             p.ncols_pad = round_up(p.ncols, 16);
-            if (p.ncols_pad > 256 || s.d + p.ncols_pad > 512) continue;
-            if (fwd_smem_bytes_d(s.d, p.ncols_pad) > (size_t)kSmemLimit) continue;
+            if (p.ncols_pad > 256 || tmem_cols_for(mode, s.d, p.ncols_pad) > 512) continue;
+            if (smem_bytes_for(mode, s.d, p.ncols_pad) > (size_t)kSmemLimit) continue;
             p.tilesS = (s.S + p.tS - 1) / p.tS; p.tilesH = (s.H + p.tH - 1) / p.tH; p.tilesW = (s.W + p.tW - 1) / p.tW;
             const double tiles = (double)p.tilesS * p.tilesH * p.tilesW;
             const double cost = tiles * p.hS * p.nchunk * (p.ncols_pad + 24.0 /*per-block sync overhead*/);
             if (cost < best_cost) {
                 best_cost = cost;
-                p.smem_bytes = (int)fwd_smem_bytes_d(s.d, p.ncols_pad);
-                p.tmem_cols = next_pow2(s.d + p.ncols_pad);
+                p.smem_bytes = (int)smem_bytes_for(mode, s.d, p.ncols_pad);
+                p.tmem_cols = next_pow2(tmem_cols_for(mode, s.d, p.ncols_pad));
                 p.scale_log2 = s.scale * 1.4426950408889634f;
                 best = p;
                 found = true;
@@ -150,11 +130,6 @@ struct FwdParams {
     __nv_bfloat16* o;
     float* lse;
 };
-
-// swizzled byte offset of 16-byte chunk `chunk16` of row `row` inside a 128B-row tile
-__device__ __forceinline__ uint32_t sw128_offset(int row, int chunk16) {
-    return (uint32_t)row * 128u + (uint32_t)((chunk16 ^ (row & 7)) << 4);
-}
 
 template <int D>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -478,13 +453,12 @@ static int launch_fwd(const void* q, const void* k, const void* v, void* o, floa
 
 bool attn_tc_supported(const AttnShape& s) {
     tc::Plan pl;
-    if ((long)s.B * s.heads * 1L > 0x7fffffffL) return false;
-    return tc::make_plan(s, pl);
+    return tc::make_plan(s, tc::kFwd, pl) && tc::make_plan(s, tc::kBwdDQ, pl) && tc::make_plan(s, tc::kBwdDKV, pl);
 }
 
 int attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse, const AttnShape& s, cudaStream_t st) {
     tc::Plan pl;
-    if (!tc::make_plan(s, pl)) return fail(WM_EUNSUPPORTED, "no tensor-core tiling for this shape");
+    if (!tc::make_plan(s, tc::kFwd, pl)) return fail(WM_EUNSUPPORTED, "no tensor-core tiling for this shape");
     switch (s.d) {
         case 32: return tc::launch_fwd<32>(q, k, v, o, lse, s, pl, st);
         case 64: return tc::launch_fwd<64>(q, k, v, o, lse, s, pl, st);
@@ -494,8 +468,7 @@ int attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse
 
 int attn_bwd_tc(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout,
                 void* dq, void* dk, void* dv, float* delta, const AttnShape& s, cudaStream_t st) {
-    // the tcgen05 backward kernels are not written yet: exact SIMT kernels on bf16 data
-    return attn_bwd_simt(q, k, v, o, lse, dout, dq, dk, dv, delta, s, WM_DTYPE_BF16, st);
+    return tc::launch_bwd_tc(q, k, v, o, lse, dout, dq, dk, dv, delta, s, st);
 }
 
 }  // namespace wm

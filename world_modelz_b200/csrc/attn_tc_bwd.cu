@@ -1,0 +1,459 @@
+// Backward of the local windowed 3D attention on tcgen05 tensor cores (bf16, fp32 accumulate).
+//
+// Same brick / halo-block tiling as the forward kernel (attn_tc.cu).  Two kernels, both
+// deterministic (no atomics):
+//
+//   dQ kernel   (query-stationary)  rows = 128 queries of a brick, blocks = K/V halo
+//       S  = Q K_j^T, dP = dO V_j^T              (two tcgen05.mma chains into TMEM)
+//       dS = exp2(S*c - lse) * (dP - delta) * scale   (one thread per query row)
+//       dQ += dS K_j                              (K_j read MN-major from the same smem)
+//   dK/dV kernel (key-stationary)   rows = 128 keys of a brick, blocks = Q/dO halo.  The
+//       queries that see a key are exactly the keys that key would see (the window is
+//       symmetric), so the halo geometry and the masks are the forward's, transposed:
+//       S^T = K Q_j^T, dP^T = V dO_j^T
+//       P^T = exp2(S^T*c - lse_col), dS^T = P^T * (dP^T - delta_col) * scale
+//       dV += P^T dO_j,  dK += dS^T Q_j
+//   plus a small pre-pass delta = rowsum(dO * O).
+//
+// Replaces the autograd graph of Local3dAttention.local_attention
+// (local_3d_attention.py:78-99; recomputed under checkpoint at :110-111).
+#include "attn_tc.cuh"
+
+#include <math.h>
+
+namespace wm {
+namespace tc {
+
+struct BwdParams {
+    AttnShape sh;
+    Plan pl;
+    const float* lse;        // [B,S,H,W,heads] natural-log LSE from the forward
+    const float* delta;      // [B,S,H,W,heads] rowsum(dO*O)
+    __nv_bfloat16* out1;     // dQ kernel: dq.   dK/dV kernel: dv
+    __nv_bfloat16* out2;     //                  dK/dV kernel: dk
+};
+
+// ---------------------------------------------------------------------------- delta
+__global__ void __launch_bounds__(256)
+l3d_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                 float* __restrict__ delta, long items, int d) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;       // (token, head)
+    if (i >= items) return;
+    const uint4* po = reinterpret_cast<const uint4*>(o + i * d);
+    const uint4* pg = reinterpret_cast<const uint4*>(dout + i * d);
+    float acc = 0.f;
+    for (int c = 0; c < d / 8; ++c) {
+        const uint4 a = __ldg(po + c), g = __ldg(pg + c);
+        const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+        const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 fa = __bfloat1622float2(ha[j]), fg = __bfloat1622float2(hg[j]);
+            acc = fmaf(fa.x, fg.x, acc);
+            acc = fmaf(fa.y, fg.y, acc);
+        }
+    }
+    delta[i] = acc;
+}
+
+// --------------------------------------------------------------------------- kernel
+template <int D, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
+                  const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
+                  const BwdParams prm) {
+    using G = Geo<D>;
+    constexpr bool kDKV = (MODE == kBwdDKV);
+    const AttnShape& sh = prm.sh;
+    const Plan& pl = prm.pl;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int ncols = pl.ncols, ncols_pad = pl.ncols_pad;
+    const int row_slab_bytes = 128 * G::kRowBytes;
+    const int row_tile_bytes = G::kSlabs * row_slab_bytes;
+    const int blk_slab_bytes = ncols_pad * G::kRowBytes;
+    const int blk_tile_bytes = G::kSlabs * blk_slab_bytes;
+    const int p_slabs = (ncols_pad + 63) / 64;
+    const int p_tile_bytes = p_slabs * 128 * 128;
+
+    uint8_t* sA1 = smem;                                   // row brick operand 1 (Q | K)
+    uint8_t* sA2 = sA1 + row_tile_bytes;                   // row brick operand 2 (dO | V)
+    uint8_t* sB = sA2 + row_tile_bytes;                    // [stage][operand][slab][ncols_pad rows]
+    uint8_t* sDS = sB + 4 * blk_tile_bytes;                // dS (or dS^T), bf16, K-major 128B swizzle
+    uint8_t* sPT = sDS + p_tile_bytes;                     // P^T (dK/dV kernel only)
+    uint32_t* sMask = reinterpret_cast<uint32_t*>(sPT + (kDKV ? p_tile_bytes : 0));
+    float* sCol = reinterpret_cast<float*>(sMask + 8 * kThreads);          // [2 bufs][lse2|delta][ncols_pad]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + (kDKV ? 4 * ncols_pad : 0));
+    uint64_t* bar_a = bars;
+    uint64_t* bar_b = bars + 1;       // [2]
+    uint64_t* bar_mma = bars + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+    int bid = blockIdx.x;
+    const int tw_i = bid % pl.tilesW; bid /= pl.tilesW;
+    const int th_i = bid % pl.tilesH; bid /= pl.tilesH;
+    const int ts_i = bid % pl.tilesS; bid /= pl.tilesS;
+    const int head = bid % sh.heads;
+    const int b = bid / sh.heads;
+    const int s0 = ts_i * pl.tS, h0 = th_i * pl.tH, w0 = tw_i * pl.tW;
+    const int c_base = head * D;
+
+    // ---- this thread's row (a query in the dQ kernel, a key in the dK/dV kernel) --------------
+    const int plane_sz = pl.tH * pl.tW;
+    const int rs = tid / plane_sz, rh = (tid % plane_sz) / pl.tW, rw = tid % pl.tW;
+    const bool row_valid = (s0 + rs < sh.S) && (h0 + rh < sh.H) && (w0 + rw < sh.W);
+    const int kh_lo = max(rh, sh.eH - h0), kh_hi = min(rh + 2 * sh.eH, sh.H - 1 - h0 + sh.eH);
+    const int kw_lo = max(rw, sh.eW - w0), kw_hi = min(rw + 2 * sh.eW, sh.W - 1 - w0 + sh.eW);
+    const uint32_t wbits = (row_valid && kw_hi >= kw_lo) ? ((kw_hi - kw_lo == 31) ? 0xffffffffu : ((1u << (kw_hi - kw_lo + 1)) - 1u)) << kw_lo : 0u;
+    const int w_rs = (warp * 32) / plane_sz;
+    const int w_rh_lo = ((warp * 32) % plane_sz) / pl.tW, w_rh_hi = ((warp * 32 + 31) % plane_sz) / pl.tW;
+    const int ks_first = max(0, sh.eS - s0), ks_last = min(pl.hS - 1, sh.S - 1 - s0 + sh.eS);
+    const int khg_lo = max(0, sh.eH - h0), khg_hi = min(pl.hH - 1, sh.H - 1 - h0 + sh.eH);
+    const int chunk_first = khg_lo / pl.ch, chunk_last = khg_hi / pl.ch;
+    const int nplanes = ks_last - ks_first + 1;
+    const int nblocks = nplanes * (chunk_last - chunk_first + 1);
+    const long row_tok = (((long)b * sh.S + (s0 + rs)) * sh.H + (h0 + rh)) * sh.W + (w0 + rw);
+    constexpr float kLog2e = 1.4426950408889634f;
+
+    if (tid == 0) {
+        tma_prefetch_desc(&map_a1); tma_prefetch_desc(&map_a2); tma_prefetch_desc(&map_b1); tma_prefetch_desc(&map_b2);
+        mbar_init(bar_a, 1);
+        mbar_init(&bar_b[0], 1);
+        mbar_init(&bar_b[1], 1);
+        mbar_init(bar_mma, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        if (pl.tmem_cols <= 128) tmem_alloc<128>(tmem_slot);
+        else if (pl.tmem_cols <= 256) tmem_alloc<256>(tmem_slot);
+        else tmem_alloc<512>(tmem_slot);
+    }
+    if (ncols_pad > ncols) {      // rows TMA never writes must stay finite (they meet zero dS / P columns)
+        const int pad_bytes = (ncols_pad - ncols) * G::kRowBytes;
+        for (int t = 0; t < 4 * G::kSlabs; ++t) {
+            uint8_t* base = sB + t * blk_slab_bytes + ncols * G::kRowBytes;
+            for (int i = tid * 16; i < pad_bytes; i += kThreads * 16) *reinterpret_cast<uint4*>(base + i) = make_uint4(0, 0, 0, 0);
+        }
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_acc1 = tmem_base;                                   // dQ | dV
+    const uint32_t tmem_acc2 = tmem_base + D;                               //      dK
+    const uint32_t tmem_t1 = tmem_base + (kDKV ? 2 * D : D);                // S   | S^T
+    const uint32_t tmem_t2 = tmem_t1 + ncols_pad;                           // dP  | dP^T
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+
+    auto block_coords = [&](int j, int& ks, int& chunk) {
+        chunk = chunk_first + j / nplanes;
+        ks = ks_first + j % nplanes;
+    };
+    auto issue_block_load = [&](int j) {            // thread 0 only
+        int ks, chunk;
+        block_coords(j, ks, chunk);
+        const int stage = j & 1;
+        uint8_t* dst = sB + stage * 2 * blk_tile_bytes;
+        mbar_expect_tx(&bar_b[stage], 2u * G::kSlabs * (uint32_t)ncols * G::kRowBytes);
+#pragma unroll
+        for (int sl = 0; sl < G::kSlabs; ++sl) {
+            tma_load_5d(dst + sl * blk_slab_bytes, &map_b1, &bar_b[stage], c_base + sl * G::kSlabCh, w0 - sh.eW,
+                        h0 - sh.eH + chunk * pl.ch, s0 - sh.eS + ks, b);
+            tma_load_5d(dst + blk_tile_bytes + sl * blk_slab_bytes, &map_b2, &bar_b[stage], c_base + sl * G::kSlabCh,
+                        w0 - sh.eW, h0 - sh.eH + chunk * pl.ch, s0 - sh.eS + ks, b);
+        }
+    };
+    const uint32_t idesc_t = make_idesc_bf16(ncols_pad, false, false);
+    const uint32_t idesc_acc = make_idesc_bf16(D, false, true);
+    auto issue_t_mma = [&](int j) {                 // T1 = A1 B1_j^T, T2 = A2 B2_j^T   (thread 0 only)
+        uint8_t* blk = sB + (j & 1) * 2 * blk_tile_bytes;
+#pragma unroll
+        for (int op = 0; op < 2; ++op) {
+#pragma unroll
+            for (int kk = 0; kk < D / 16; ++kk) {
+                const int sl = (kk * 16) / G::kSlabCh;
+                const int koff = ((kk * 16) % G::kSlabCh) * 2;
+                const uint64_t da = make_smem_desc(smem_u32((op ? sA2 : sA1) + sl * row_slab_bytes + koff), 16,
+                                                   G::kAtomBytes, G::kSwizzleCode);
+                const uint64_t db = make_smem_desc(smem_u32(blk + op * blk_tile_bytes + sl * blk_slab_bytes + koff), 16,
+                                                   G::kAtomBytes, G::kSwizzleCode);
+                umma_bf16_ss(op ? tmem_t2 : tmem_t1, da, db, idesc_t, kk > 0);
+            }
+        }
+    };
+    auto issue_acc_mma = [&](int j, bool accumulate) {   // (thread 0 only)
+        uint8_t* blk = sB + (j & 1) * 2 * blk_tile_bytes;
+        for (int kk = 0; kk < ncols_pad / 16; ++kk) {
+            const uint32_t a_off = (kk >> 2) * (128 * 128) + (kk & 3) * 32;
+            const uint32_t acc = (accumulate || kk > 0) ? 1u : 0u;
+            const uint64_t d_ds = make_smem_desc(smem_u32(sDS + a_off), 16, 1024, 2u);
+            const uint64_t d_b1 = make_smem_desc(smem_u32(blk + kk * 16 * G::kRowBytes), (uint32_t)blk_slab_bytes,
+                                                 G::kAtomBytes, G::kSwizzleCode);
+            if constexpr (kDKV) {
+                const uint64_t d_pt = make_smem_desc(smem_u32(sPT + a_off), 16, 1024, 2u);
+                const uint64_t d_b2 = make_smem_desc(smem_u32(blk + blk_tile_bytes + kk * 16 * G::kRowBytes),
+                                                     (uint32_t)blk_slab_bytes, G::kAtomBytes, G::kSwizzleCode);
+                umma_bf16_ss(tmem_acc1, d_pt, d_b2, idesc_acc, acc);      // dV += P^T dO_j
+                umma_bf16_ss(tmem_acc2, d_ds, d_b1, idesc_acc, acc);      // dK += dS^T Q_j
+            } else {
+                umma_bf16_ss(tmem_acc1, d_ds, d_b1, idesc_acc, acc);      // dQ += dS K_j
+            }
+        }
+    };
+    // per-column lse / delta of a block's queries (dK/dV kernel): two columns per thread
+    auto load_colvec = [&](int j, float (&lse2)[2], float (&dl)[2]) {
+        int ks, chunk;
+        block_coords(j, ks, chunk);
+        const int gs = s0 - sh.eS + ks;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int c = tid + t * kThreads;
+            lse2[t] = 0.f;
+            dl[t] = 0.f;
+            if (c < ncols) {
+                const int khl = c / pl.hW, kw = c - khl * pl.hW;
+                const int gh = h0 - sh.eH + chunk * pl.ch + khl, gw = w0 - sh.eW + kw;
+                if (gs >= 0 && gs < sh.S && gh >= 0 && gh < sh.H && gw >= 0 && gw < sh.W) {
+                    const long idx = ((((long)b * sh.S + gs) * sh.H + gh) * sh.W + gw) * sh.heads + head;
+                    lse2[t] = __ldg(prm.lse + idx) * kLog2e;
+                    dl[t] = __ldg(prm.delta + idx);
+                }
+            }
+        }
+    };
+    auto store_colvec = [&](int buf, const float (&lse2)[2], const float (&dl)[2]) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int c = tid + t * kThreads;
+            if (c < ncols_pad) {
+                sCol[(buf * 2 + 0) * ncols_pad + c] = lse2[t];
+                sCol[(buf * 2 + 1) * ncols_pad + c] = dl[t];
+            }
+        }
+    };
+
+    if (tid == 0) {
+        mbar_expect_tx(bar_a, 2u * (uint32_t)row_tile_bytes);
+#pragma unroll
+        for (int sl = 0; sl < G::kSlabs; ++sl) {
+            tma_load_5d(sA1 + sl * row_slab_bytes, &map_a1, bar_a, c_base + sl * G::kSlabCh, w0, h0, s0, b);
+            tma_load_5d(sA2 + sl * row_slab_bytes, &map_a2, bar_a, c_base + sl * G::kSlabCh, w0, h0, s0, b);
+        }
+        issue_block_load(0);
+        if (nblocks > 1) issue_block_load(1);
+        mbar_wait(bar_a, 0);
+        mbar_wait(&bar_b[0], 0);
+        tc_fence_after();
+        issue_t_mma(0);
+        umma_commit(bar_mma);
+    }
+    float row_lse2 = 0.f, row_delta = 0.f;
+    if constexpr (kDKV) {
+        float a[2], c[2];
+        load_colvec(0, a, c);
+        store_colvec(0, a, c);
+        __syncthreads();
+    } else if (row_valid) {
+        row_lse2 = __ldg(prm.lse + row_tok * sh.heads + head) * kLog2e;
+        row_delta = __ldg(prm.delta + row_tok * sh.heads + head);
+    }
+
+    bool p_zero = false;
+    int mask_chunk = -1;
+    const int nwords = (ncols_pad + 31) / 32;
+    const int ngroups = ncols_pad >> 4;
+
+    for (int j = 0; j < nblocks; ++j) {
+        int ks, chunk;
+        block_coords(j, ks, chunk);
+        float nxt_lse2[2] = {0.f, 0.f}, nxt_dl[2] = {0.f, 0.f};
+        if constexpr (kDKV) {
+            if (j + 1 < nblocks) load_colvec(j + 1, nxt_lse2, nxt_dl);     // global loads in flight during the wait
+        }
+        mbar_wait(bar_mma, j & 1);                  // T_j ready; accumulations of block j-1 retired
+        tc_fence_after();
+        if (tid == 0 && j >= 1 && j + 1 < nblocks) issue_block_load(j + 1);
+
+        const int kh0 = chunk * pl.ch;
+        if (chunk != mask_chunk) {
+            mask_chunk = chunk;
+            for (int w = 0; w < nwords; ++w) sMask[w * kThreads + tid] = 0u;
+            if (wbits != 0u) {
+                const int ra = max(kh_lo, kh0), rb = min(kh_hi, kh0 + pl.ch - 1);
+                for (int kh = ra; kh <= rb; ++kh) {
+                    const int pos = (kh - kh0) * pl.hW;
+                    const int w = pos >> 5, sft = pos & 31;
+                    sMask[w * kThreads + tid] |= wbits << sft;
+                    if (sft != 0 && (wbits >> (32 - sft)) != 0u) sMask[(w + 1) * kThreads + tid] |= wbits >> (32 - sft);
+                }
+            }
+        }
+
+        const bool plane_live = (ks >= w_rs) && (ks <= w_rs + 2 * sh.eS);
+        const int ua = max(w_rh_lo, kh0), ub = min(w_rh_hi + 2 * sh.eH, kh0 + pl.ch - 1);
+        const bool live = plane_live && (ub >= ua);
+        if (live) {
+            const int g_lo = ((ua - kh0) * pl.hW) >> 4;
+            const int g_hi = min(((ub - kh0 + 1) * pl.hW + 15) >> 4, ngroups);
+            const float* col_lse2 = sCol + ((j & 1) * 2 + 0) * ncols_pad;
+            const float* col_dl = sCol + ((j & 1) * 2 + 1) * ncols_pad;
+            for (int g = 0; g < ngroups; ++g) {
+                uint32_t pk_ds[8], pk_p[8];
+                if (g >= g_lo && g < g_hi) {
+                    const uint32_t mword = sMask[(g >> 1) * kThreads + tid] >> ((g & 1) * 16);
+                    uint32_t s[16], dp[16];
+                    tmem_ld16(tmem_t1 + lane_sel + g * 16, s);
+                    tmem_ld16(tmem_t2 + lane_sel + g * 16, dp);
+                    float l2[16], dl[16];
+                    if constexpr (kDKV) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 a = *reinterpret_cast<const float4*>(col_lse2 + g * 16 + 4 * i);
+                            const float4 c = *reinterpret_cast<const float4*>(col_dl + g * 16 + 4 * i);
+                            l2[4 * i] = a.x; l2[4 * i + 1] = a.y; l2[4 * i + 2] = a.z; l2[4 * i + 3] = a.w;
+                            dl[4 * i] = c.x; dl[4 * i + 1] = c.y; dl[4 * i + 2] = c.z; dl[4 * i + 3] = c.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { l2[i] = row_lse2; dl[i] = row_delta; }
+                    }
+                    tmem_wait_ld();
+                    float pv[16], dsv[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const bool on = (mword >> i) & 1u;
+                        const float p = ex2(fmaf(__uint_as_float(s[i]), pl.scale_log2, -l2[i]));
+                        const float ds = p * (__uint_as_float(dp[i]) - dl[i]) * sh.scale;
+                        pv[i] = on ? p : 0.f;
+                        dsv[i] = on ? ds : 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        pk_ds[i] = pack_bf16(dsv[2 * i], dsv[2 * i + 1]);
+                        pk_p[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { pk_ds[i] = 0u; pk_p[i] = 0u; }
+                }
+                const uint32_t slab_off = (g >> 2) * (128 * 128);
+                const int c16 = (g & 3) * 2;
+                const uint32_t o0 = slab_off + sw128_offset(tid, c16), o1 = slab_off + sw128_offset(tid, c16 + 1);
+                *reinterpret_cast<uint4*>(sDS + o0) = make_uint4(pk_ds[0], pk_ds[1], pk_ds[2], pk_ds[3]);
+                *reinterpret_cast<uint4*>(sDS + o1) = make_uint4(pk_ds[4], pk_ds[5], pk_ds[6], pk_ds[7]);
+                if constexpr (kDKV) {
+                    *reinterpret_cast<uint4*>(sPT + o0) = make_uint4(pk_p[0], pk_p[1], pk_p[2], pk_p[3]);
+                    *reinterpret_cast<uint4*>(sPT + o1) = make_uint4(pk_p[4], pk_p[5], pk_p[6], pk_p[7]);
+                }
+            }
+            p_zero = false;
+        } else if (!p_zero) {
+            for (int g = 0; g < ngroups; ++g) {
+                const uint32_t slab_off = (g >> 2) * (128 * 128);
+                const int c16 = (g & 3) * 2;
+                const uint32_t o0 = slab_off + sw128_offset(tid, c16), o1 = slab_off + sw128_offset(tid, c16 + 1);
+                *reinterpret_cast<uint4*>(sDS + o0) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(sDS + o1) = make_uint4(0, 0, 0, 0);
+                if constexpr (kDKV) {
+                    *reinterpret_cast<uint4*>(sPT + o0) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4*>(sPT + o1) = make_uint4(0, 0, 0, 0);
+                }
+            }
+            p_zero = true;
+        }
+        if constexpr (kDKV) {
+            if (j + 1 < nblocks) store_colvec((j + 1) & 1, nxt_lse2, nxt_dl);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_acc_mma(j, j > 0);
+            if (j + 1 < nblocks) {
+                mbar_wait(&bar_b[(j + 1) & 1], ((j + 1) >> 1) & 1);
+                tc_fence_after();
+                issue_t_mma(j + 1);
+            }
+            umma_commit(bar_mma);
+        }
+    }
+
+    // ---- epilogue ------------------------------------------------------------------------------
+    mbar_wait(bar_mma, nblocks & 1);
+    tc_fence_after();
+    const long row_off = row_tok * (long)sh.inner() + c_base;
+#pragma unroll
+    for (int which = 0; which < (kDKV ? 2 : 1); ++which) {
+        __nv_bfloat16* dst = (which == 0 ? prm.out1 : prm.out2) + row_off;
+        const uint32_t src = (which == 0 ? tmem_acc1 : tmem_acc2) + lane_sel;
+#pragma unroll
+        for (int c = 0; c < D; c += 16) {
+            uint32_t r[16];
+            tmem_ld16(src + c, r);
+            tmem_wait_ld();
+            if (row_valid) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+                *reinterpret_cast<uint4*>(dst + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(dst + c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        if (pl.tmem_cols <= 128) tmem_dealloc<128>(tmem_base);
+        else if (pl.tmem_cols <= 256) tmem_dealloc<256>(tmem_base);
+        else tmem_dealloc<512>(tmem_base);
+    }
+}
+
+template <int D, int MODE>
+static int launch_one(const void* a1, const void* a2, const void* b1, const void* b2, const float* lse,
+                      const float* delta, void* out1, void* out2, const AttnShape& s, cudaStream_t st) {
+    using G = Geo<D>;
+    Plan pl;
+    if (!make_plan(s, (Mode)MODE, pl)) return fail(WM_EUNSUPPORTED, "no tensor-core backward tiling for this shape");
+    CUtensorMap ma1, ma2, mb1, mb2;
+    const int C = s.inner();
+    if (int rc = make_tensor_map_5d(&ma1, a1, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.tW, pl.tH, pl.tS, G::kSwizzleBytes)) return rc;
+    if (int rc = make_tensor_map_5d(&ma2, a2, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.tW, pl.tH, pl.tS, G::kSwizzleBytes)) return rc;
+    if (int rc = make_tensor_map_5d(&mb1, b1, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
+    if (int rc = make_tensor_map_5d(&mb2, b2, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
+    BwdParams prm{s, pl, lse, delta, static_cast<__nv_bfloat16*>(out1), static_cast<__nv_bfloat16*>(out2)};
+    WM_CUDA_CHECK(cudaFuncSetAttribute(l3d_bwd_tc_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
+    const long grid = (long)s.B * s.heads * pl.tilesS * pl.tilesH * pl.tilesW;
+    l3d_bwd_tc_kernel<D, MODE><<<(unsigned)grid, kThreads, pl.smem_bytes, st>>>(ma1, ma2, mb1, mb2, prm);
+    WM_CUDA_CHECK(cudaGetLastError());
+    return WM_OK;
+}
+
+template <int D>
+static int launch_bwd_d(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout,
+                        void* dq, void* dk, void* dv, float* delta, const AttnShape& s, cudaStream_t st) {
+    const long items = s.tokens() * s.heads;
+    l3d_delta_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(o),
+                                                                      static_cast<const __nv_bfloat16*>(dout), delta,
+                                                                      items, s.d);
+    WM_CUDA_CHECK(cudaGetLastError());
+    if (int rc = launch_one<D, kBwdDQ>(q, dout, k, v, lse, delta, dq, nullptr, s, st)) return rc;
+    return launch_one<D, kBwdDKV>(k, v, q, dout, lse, delta, dv, dk, s, st);
+}
+
+int launch_bwd_tc(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout,
+                  void* dq, void* dk, void* dv, float* delta, const AttnShape& s, cudaStream_t st) {
+    switch (s.d) {
+        case 32: return launch_bwd_d<32>(q, k, v, o, lse, dout, dq, dk, dv, delta, s, st);
+        case 64: return launch_bwd_d<64>(q, k, v, o, lse, dout, dq, dk, dv, delta, s, st);
+        case 128: return launch_bwd_d<128>(q, k, v, o, lse, dout, dq, dk, dv, delta, s, st);
+        default: return fail(WM_EUNSUPPORTED, "dim_head=%d has no tensor-core kernel", s.d);
+    }
+}
+
+}  // namespace tc
+}  // namespace wm
