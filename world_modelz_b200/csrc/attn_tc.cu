@@ -21,6 +21,7 @@
 #include "attn_tc.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <mutex>
 
 namespace wm {
@@ -71,7 +72,7 @@ size_t smem_bytes_for(Mode mode, int d, int ncols_pad) {
     const size_t row_tile = (size_t)slabs_of(d) * 128 * row_bytes_of(d);
     const size_t blk = (size_t)slabs_of(d) * ncols_pad * row_bytes_of(d);
     const size_t ptile = (size_t)round_up(ncols_pad, 64) / 64 * 128 * 128;
-    const size_t fixed = 1024 /*alignment slack*/ + 8 * kThreads * 4 /*masks*/ + 256 /*barriers*/;
+    const size_t fixed = 1024 /*alignment slack*/ + 2 * 8 * 128 * 4 /*masks*/ + 2 * 128 * 4 /*exchange*/ + 256 /*barriers*/;
     switch (mode) {
         case kFwd: return fixed + row_tile + 4 * blk + ptile;                       // Q | 2x(K,V) | P
         case kBwdDQ: return fixed + 2 * row_tile + 4 * blk + ptile;                 // Q,dO | 2x(K,V) | dS
@@ -93,6 +94,13 @@ bool make_plan(const AttnShape& s, Mode mode, Plan& best) {
     static const int bricks[][3] = {{2, 8, 8}, {4, 4, 8}, {4, 8, 4}, {1, 8, 16}, {1, 16, 8}, {2, 4, 16}, {2, 16, 4}};
     double best_cost = 1e300;
     bool found = false;
+    // tuning knob (experiments only): cap the block width, e.g. WM_TC_MAXCOLS="144,80,80" (fwd,dq,dkv)
+    int max_cols = 256;
+    if (const char* env = getenv("WM_TC_MAXCOLS")) {
+        int v[3] = {256, 256, 256};
+        sscanf(env, "%d,%d,%d", &v[0], &v[1], &v[2]);
+        max_cols = v[(int)mode];
+    }
     for (const auto& b : bricks) {
         Plan p{};
         p.tS = b[0]; p.tH = b[1]; p.tW = b[2];
@@ -104,7 +112,7 @@ bool make_plan(const AttnShape& s, Mode mode, Plan& best) {
             p.nchunk = (p.hH + p.ch - 1) / p.ch;
             p.ncols = p.ch * p.hW;
             p.ncols_pad = round_up(p.ncols, 16);
-            if (p.ncols_pad > 256 || tmem_cols_for(mode, s.d, p.ncols_pad) > 512) continue;
+            if (p.ncols_pad > max_cols || tmem_cols_for(mode, s.d, p.ncols_pad) > 512) continue;
             if (smem_bytes_for(mode, s.d, p.ncols_pad) > (size_t)kSmemLimit) continue;
             p.tilesS = (s.S + p.tS - 1) / p.tS; p.tilesH = (s.H + p.tH - 1) / p.tH; p.tilesW = (s.W + p.tW - 1) / p.tW;
             const double tiles = (double)p.tilesS * p.tilesH * p.tilesW;
@@ -131,17 +139,21 @@ struct FwdParams {
     float* lse;
 };
 
+// 256 threads: warps w and w+4 share TMEM lane quadrant w&3 (32 query rows) and split the
+// row's key columns between them ("half" 0 / 1), so every row is worked on by two threads.
 template <int D>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, (D == 128) ? 1 : 2)
 l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv_k,
                   const __grid_constant__ CUtensorMap map_kv_v, const FwdParams prm) {
     using G = Geo<D>;
     const AttnShape& sh = prm.sh;
     const Plan& pl = prm.pl;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays in the shared window
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;              // query row of the brick == TMEM lane
     const int ncols = pl.ncols, ncols_pad = pl.ncols_pad;
     const int q_slab_bytes = 128 * G::kRowBytes;
     const int kv_slab_bytes = ncols_pad * G::kRowBytes;
@@ -152,12 +164,14 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     uint8_t* sV = sK + 2 * kv_tile_bytes;
     uint8_t* sP = sV + 2 * kv_tile_bytes;                        // [ceil(ncols_pad/64)][128 rows][128 B]
     const int p_slabs = (ncols_pad + 63) / 64;
-    uint32_t* sMask = reinterpret_cast<uint32_t*>(sP + p_slabs * 128 * 128);   // [8 words][128 threads]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + 8 * kThreads);
+    uint32_t* sMask = reinterpret_cast<uint32_t*>(sP + p_slabs * 128 * 128);   // [2 halves][8 words][128 rows]
+    float* sX = reinterpret_cast<float*>(sMask + 2 * 8 * 128);                 // [2 halves][128 rows] exchange
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 2 * 128);
     uint64_t* bar_q = bars;
     uint64_t* bar_kv = bars + 1;      // [2]
     uint64_t* bar_mma = bars + 3;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    uint32_t* myMask = sMask + half * 8 * 128;
 
     // ---- which brick -------------------------------------------------------------------
     int bid = blockIdx.x;
@@ -171,15 +185,15 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
     // ---- this thread's query row ---------------------------------------------------------
     const int plane_sz = pl.tH * pl.tW;
-    const int qs = tid / plane_sz, qh = (tid % plane_sz) / pl.tW, qw = tid % pl.tW;
+    const int qs = row / plane_sz, qh = (row % plane_sz) / pl.tW, qw = row % pl.tW;
     const bool q_valid = (s0 + qs < sh.S) && (h0 + qh < sh.H) && (w0 + qw < sh.W);
     // live key range of this row in halo coordinates (window AND grid), per axis
     const int kh_lo = max(qh, sh.eH - h0), kh_hi = min(qh + 2 * sh.eH, sh.H - 1 - h0 + sh.eH);
     const int kw_lo = max(qw, sh.eW - w0), kw_hi = min(qw + 2 * sh.eW, sh.W - 1 - w0 + sh.eW);
     const uint32_t wbits = (q_valid && kw_hi >= kw_lo) ? ((kw_hi - kw_lo == 31) ? 0xffffffffu : ((1u << (kw_hi - kw_lo + 1)) - 1u)) << kw_lo : 0u;
-    // warp-uniform ranges
-    const int w_qs = (warp * 32) / plane_sz;
-    const int w_qh_lo = ((warp * 32) % plane_sz) / pl.tW, w_qh_hi = ((warp * 32 + 31) % plane_sz) / pl.tW;
+    // warp-uniform ranges (identical for the two warps of a quadrant)
+    const int w_qs = (quad * 32) / plane_sz;
+    const int w_qh_lo = ((quad * 32) % plane_sz) / pl.tW, w_qh_hi = ((quad * 32 + 31) % plane_sz) / pl.tW;
     // block iteration space: planes and h-chunks that intersect the grid
     const int ks_first = max(0, sh.eS - s0), ks_last = min(pl.hS - 1, sh.S - 1 - s0 + sh.eS);
     const int khg_lo = max(0, sh.eH - h0), khg_hi = min(pl.hH - 1, sh.H - 1 - h0 + sh.eH);
@@ -220,7 +234,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_o = tmem_base;             // columns [0, D)
     const uint32_t tmem_s = tmem_base + D;         // columns [D, D + ncols_pad)
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
 
     auto block_coords = [&](int j, int& ks, int& chunk) {
         chunk = chunk_first + j / nplanes;
@@ -262,6 +276,12 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             umma_bf16_ss(tmem_o, da, db, idesc_o, (accumulate || kk > 0) ? 1u : 0u);
         }
     };
+    auto store_group = [&](int g, const uint32_t (&pk)[8]) {     // 16 bf16 of this row -> swizzled P tile
+        uint8_t* slab = sP + (g >> 2) * (128 * 128);
+        const int c16 = (g & 3) * 2;
+        *reinterpret_cast<uint4*>(slab + sw128_offset(row, c16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(slab + sw128_offset(row, c16 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    };
 
     if (tid == 0) {
         mbar_expect_tx(bar_q, (uint32_t)G::kSlabs * q_slab_bytes);
@@ -278,11 +298,13 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
 
     // ---- main loop ------------------------------------------------------------------------------
-    float m_used = -INFINITY;      // running max (log2 domain, scaled) the row's P values are relative to
-    float l_run = 0.f;             // running sum of P
-    bool p_zero = false;           // this warp's P rows are known to be all zero
+    float m_used = -INFINITY;      // reference max (log2 domain, scaled) this row's P values are relative to
+    float l_part = 0.f;            // this thread's share of the running sum of P
+    bool p_zero = false;           // this thread's share of the P row is known to be all zero
     int mask_chunk = -1;
     const int nwords = (ncols_pad + 31) / 32;
+    const int ngroups = ncols_pad >> 4;
+    const uint32_t zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
     for (int j = 0; j < nblocks; ++j) {
         int ks, chunk;
@@ -292,31 +314,34 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         if (tid == 0 && j >= 1 && j + 1 < nblocks) issue_kv_load(j + 1);
 
         const int kh0 = chunk * pl.ch;
-        if (chunk != mask_chunk) {                   // per-thread live-column bitmask for this h-chunk
+        if (chunk != mask_chunk) {                   // live-column bitmask of this row for this h-chunk (own copy)
             mask_chunk = chunk;
-            for (int w = 0; w < nwords; ++w) sMask[w * kThreads + tid] = 0u;
+            for (int w = 0; w < nwords; ++w) myMask[w * 128 + row] = 0u;
             if (wbits != 0u) {
                 const int ra = max(kh_lo, kh0), rb = min(kh_hi, kh0 + pl.ch - 1);
                 for (int kh = ra; kh <= rb; ++kh) {
                     const int pos = (kh - kh0) * pl.hW;
                     const int w = pos >> 5, sft = pos & 31;
-                    sMask[w * kThreads + tid] |= wbits << sft;
-                    if (sft != 0 && (wbits >> (32 - sft)) != 0u) sMask[(w + 1) * kThreads + tid] |= wbits >> (32 - sft);
+                    myMask[w * 128 + row] |= wbits << sft;
+                    if (sft != 0 && (wbits >> (32 - sft)) != 0u) myMask[(w + 1) * 128 + row] |= wbits >> (32 - sft);
                 }
             }
         }
 
-        // warp-uniform: can any of this warp's queries see this block?
+        // warp-uniform: can any of this quadrant's queries see this block?
         const bool plane_live = (ks >= w_qs) && (ks <= w_qs + 2 * sh.eS);
         const int ua = max(w_qh_lo, kh0), ub = min(w_qh_hi + 2 * sh.eH, kh0 + pl.ch - 1);
         const bool live = plane_live && (ub >= ua);
         if (live) {
             const int g_lo = ((ua - kh0) * pl.hW) >> 4;                              // 16-column groups
-            const int g_hi = min(((ub - kh0 + 1) * pl.hW + 15) >> 4, ncols_pad >> 4);
-            // pass 1: row maximum over live columns
+            const int g_hi = min(((ub - kh0 + 1) * pl.hW + 15) >> 4, ngroups);
+            const int g_mid = (g_lo + g_hi + 1) >> 1;
+            const int ga = half ? g_mid : g_lo, gb = half ? g_hi : g_mid;            // live groups of this thread
+            const int za = half ? g_hi : 0, zb = half ? ngroups : g_lo;              // groups this thread zero-fills
+            // pass 1: row maximum over this thread's live columns
             float mx = -INFINITY;
-            for (int g = g_lo; g < g_hi; ++g) {
-                const uint32_t mword = sMask[(g >> 1) * kThreads + tid] >> ((g & 1) * 16);
+            for (int g = ga; g < gb; ++g) {
+                const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
                 uint32_t r[16];
                 tmem_ld16(tmem_s + lane_sel + g * 16, r);
                 tmem_wait_ld();
@@ -324,65 +349,57 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 for (int i = 0; i < 16; ++i)
                     if (mword & (1u << i)) mx = fmaxf(mx, __uint_as_float(r[i]));
             }
+            sX[half * 128 + row] = mx;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+            mx = fmaxf(mx, sX[(half ^ 1) * 128 + row]);
             const float m_blk = mx * pl.scale_log2;          // scale > 0
             // lazy rescale: keep the old reference max unless the new one is > 2^8 larger
             float alpha = 1.f;
             const bool bump = m_blk > m_used + 8.f;
+            const bool fix_o = bump && (m_used != -INFINITY);  // the row already holds earlier blocks
             if (bump) {
                 alpha = ex2(m_used - m_blk);                 // 0 when this is the row's first live block
                 m_used = m_blk;
             }
-            const bool fix_o = bump && (l_run > 0.f);
-            l_run *= alpha;
-            if (j > 0 && __any_sync(0xffffffffu, fix_o)) {  // O rows already hold earlier blocks: rescale
+            l_part *= alpha;
+            if (__any_sync(0xffffffffu, fix_o)) {            // rescale this thread's half of the O row
 #pragma unroll
-                for (int c = 0; c < D; c += 16) {
+                for (int c = 0; c < D / 2; c += 16) {
                     uint32_t r[16];
-                    tmem_ld16(tmem_o + lane_sel + c, r);
+                    tmem_ld16(tmem_o + lane_sel + half * (D / 2) + c, r);
                     tmem_wait_ld();
 #pragma unroll
                     for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-                    tmem_st16(tmem_o + lane_sel + c, r);
+                    tmem_st16(tmem_o + lane_sel + half * (D / 2) + c, r);
                 }
                 tmem_wait_st();
             }
             // pass 2: P = 2^(s*scale*log2e - m) on live columns, 0 elsewhere -> bf16 -> smem (K-major, 128B swizzle)
             const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
             float lsum = 0.f;
-            for (int g = 0; g < (ncols_pad >> 4); ++g) {
-                uint32_t packed[8];
-                if (g >= g_lo && g < g_hi) {
-                    const uint32_t mword = sMask[(g >> 1) * kThreads + tid] >> ((g & 1) * 16);
-                    uint32_t r[16];
-                    tmem_ld16(tmem_s + lane_sel + g * 16, r);
-                    tmem_wait_ld();
-                    float p[16];
+            for (int g = ga; g < gb; ++g) {
+                const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
+                uint32_t r[16];
+                tmem_ld16(tmem_s + lane_sel + g * 16, r);
+                tmem_wait_ld();
+                float p[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float e = ex2(fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m));
-                        p[i] = (mword & (1u << i)) ? e : 0.f;
-                        lsum += p[i];
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) packed[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) packed[i] = 0u;
+                for (int i = 0; i < 16; ++i) {
+                    const float e = ex2(fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m));
+                    p[i] = (mword & (1u << i)) ? e : 0.f;
+                    lsum += p[i];
                 }
-                uint8_t* slab = sP + (g >> 2) * (128 * 128);
-                const int c16 = (g & 3) * 2;
-                *reinterpret_cast<uint4*>(slab + sw128_offset(tid, c16)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                *reinterpret_cast<uint4*>(slab + sw128_offset(tid, c16 + 1)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                uint32_t packed[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) packed[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
+                store_group(g, packed);
             }
-            l_run += lsum;
+            for (int g = za; g < zb; ++g) store_group(g, zero8);
+            l_part += lsum;
             p_zero = false;
         } else if (!p_zero) {
-            for (int g = 0; g < (ncols_pad >> 4); ++g) {
-                uint8_t* slab = sP + (g >> 2) * (128 * 128);
-                const int c16 = (g & 3) * 2;
-                *reinterpret_cast<uint4*>(slab + sw128_offset(tid, c16)) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(slab + sw128_offset(tid, c16 + 1)) = make_uint4(0, 0, 0, 0);
-            }
+            const int za = half ? (ngroups >> 1) : 0, zb = half ? ngroups : (ngroups >> 1);
+            for (int g = za; g < zb; ++g) store_group(g, zero8);
             p_zero = true;
         }
         fence_proxy_async();          // P (generic proxy) -> visible to tcgen05.mma (async proxy)
@@ -403,13 +420,16 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     // ---- epilogue: O / l -> bf16, LSE ---------------------------------------------------------
     mbar_wait(bar_mma, nblocks & 1);
     tc_fence_after();
+    sX[half * 128 + row] = l_part;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+    const float l_run = l_part + sX[(half ^ 1) * 128 + row];
     const long tok = (((long)b * sh.S + (s0 + qs)) * sh.H + (h0 + qh)) * sh.W + (w0 + qw);
     const float inv_l = 1.f / l_run;
-    __nv_bfloat16* orow = prm.o + tok * (long)sh.inner() + c_base;
+    __nv_bfloat16* orow = prm.o + tok * (long)sh.inner() + c_base + half * (D / 2);
 #pragma unroll
-    for (int c = 0; c < D; c += 16) {
+    for (int c = 0; c < D / 2; c += 16) {
         uint32_t r[16];
-        tmem_ld16(tmem_o + lane_sel + c, r);       // warp-collective: every lane takes part
+        tmem_ld16(tmem_o + lane_sel + half * (D / 2) + c, r);       // warp-collective: every lane takes part
         tmem_wait_ld();
         if (q_valid) {
             uint32_t pk[8];
@@ -420,7 +440,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             *reinterpret_cast<uint4*>(orow + c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
     }
-    if (q_valid) prm.lse[tok * sh.heads + head] = (m_used + lg2(l_run)) * 0.6931471805599453f;
+    if (q_valid && half == 0) prm.lse[tok * sh.heads + head] = (m_used + lg2(l_run)) * 0.6931471805599453f;
 
     tc_fence_before();
     __syncthreads();

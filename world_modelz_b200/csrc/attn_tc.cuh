@@ -22,7 +22,7 @@ struct Plan {
     float scale_log2;
 };
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;   // 2 threads per brick row (column halves)
 constexpr int kSmemLimit = 227 * 1024;
 
 template <int D> struct Geo {

@@ -58,7 +58,7 @@ l3d_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __res
 
 // --------------------------------------------------------------------------- kernel
 template <int D, int MODE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, (D == 128) ? 1 : 2)
 l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                   const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
                   const BwdParams prm) {
@@ -66,10 +66,13 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     constexpr bool kDKV = (MODE == kBwdDKV);
     const AttnShape& sh = prm.sh;
     const Plan& pl = prm.pl;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays in the shared window
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    // 256 threads: warps w and w+4 share TMEM lane quadrant w&3 and split the row's columns
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;
     const int ncols = pl.ncols, ncols_pad = pl.ncols_pad;
     const int row_slab_bytes = 128 * G::kRowBytes;
     const int row_tile_bytes = G::kSlabs * row_slab_bytes;
@@ -84,12 +87,13 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     uint8_t* sDS = sB + 4 * blk_tile_bytes;                // dS (or dS^T), bf16, K-major 128B swizzle
     uint8_t* sPT = sDS + p_tile_bytes;                     // P^T (dK/dV kernel only)
     uint32_t* sMask = reinterpret_cast<uint32_t*>(sPT + (kDKV ? p_tile_bytes : 0));
-    float* sCol = reinterpret_cast<float*>(sMask + 8 * kThreads);          // [2 bufs][lse2|delta][ncols_pad]
+    float* sCol = reinterpret_cast<float*>(sMask + 2 * 8 * 128);           // [2 bufs][lse2|delta][ncols_pad]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + (kDKV ? 4 * ncols_pad : 0));
     uint64_t* bar_a = bars;
     uint64_t* bar_b = bars + 1;       // [2]
     uint64_t* bar_mma = bars + 3;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    uint32_t* myMask = sMask + half * 8 * 128;                              // [8 words][128 rows], own copy
 
     int bid = blockIdx.x;
     const int tw_i = bid % pl.tilesW; bid /= pl.tilesW;
@@ -102,13 +106,13 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
 
     // ---- this thread's row (a query in the dQ kernel, a key in the dK/dV kernel) --------------
     const int plane_sz = pl.tH * pl.tW;
-    const int rs = tid / plane_sz, rh = (tid % plane_sz) / pl.tW, rw = tid % pl.tW;
+    const int rs = row / plane_sz, rh = (row % plane_sz) / pl.tW, rw = row % pl.tW;
     const bool row_valid = (s0 + rs < sh.S) && (h0 + rh < sh.H) && (w0 + rw < sh.W);
     const int kh_lo = max(rh, sh.eH - h0), kh_hi = min(rh + 2 * sh.eH, sh.H - 1 - h0 + sh.eH);
     const int kw_lo = max(rw, sh.eW - w0), kw_hi = min(rw + 2 * sh.eW, sh.W - 1 - w0 + sh.eW);
     const uint32_t wbits = (row_valid && kw_hi >= kw_lo) ? ((kw_hi - kw_lo == 31) ? 0xffffffffu : ((1u << (kw_hi - kw_lo + 1)) - 1u)) << kw_lo : 0u;
-    const int w_rs = (warp * 32) / plane_sz;
-    const int w_rh_lo = ((warp * 32) % plane_sz) / pl.tW, w_rh_hi = ((warp * 32 + 31) % plane_sz) / pl.tW;
+    const int w_rs = (quad * 32) / plane_sz;
+    const int w_rh_lo = ((quad * 32) % plane_sz) / pl.tW, w_rh_hi = ((quad * 32 + 31) % plane_sz) / pl.tW;
     const int ks_first = max(0, sh.eS - s0), ks_last = min(pl.hS - 1, sh.S - 1 - s0 + sh.eS);
     const int khg_lo = max(0, sh.eH - h0), khg_hi = min(pl.hH - 1, sh.H - 1 - h0 + sh.eH);
     const int chunk_first = khg_lo / pl.ch, chunk_last = khg_hi / pl.ch;
@@ -146,7 +150,7 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     const uint32_t tmem_acc2 = tmem_base + D;                               //      dK
     const uint32_t tmem_t1 = tmem_base + (kDKV ? 2 * D : D);                // S   | S^T
     const uint32_t tmem_t2 = tmem_t1 + ncols_pad;                           // dP  | dP^T
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
 
     auto block_coords = [&](int j, int& ks, int& chunk) {
         chunk = chunk_first + j / nplanes;
@@ -203,36 +207,35 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             }
         }
     };
-    // per-column lse / delta of a block's queries (dK/dV kernel): two columns per thread
-    auto load_colvec = [&](int j, float (&lse2)[2], float (&dl)[2]) {
+    // per-column lse / delta of a block's queries (dK/dV kernel): one column per thread
+    auto load_colvec = [&](int j, float& lse2, float& dl) {
         int ks, chunk;
         block_coords(j, ks, chunk);
         const int gs = s0 - sh.eS + ks;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const int c = tid + t * kThreads;
-            lse2[t] = 0.f;
-            dl[t] = 0.f;
-            if (c < ncols) {
-                const int khl = c / pl.hW, kw = c - khl * pl.hW;
-                const int gh = h0 - sh.eH + chunk * pl.ch + khl, gw = w0 - sh.eW + kw;
-                if (gs >= 0 && gs < sh.S && gh >= 0 && gh < sh.H && gw >= 0 && gw < sh.W) {
-                    const long idx = ((((long)b * sh.S + gs) * sh.H + gh) * sh.W + gw) * sh.heads + head;
-                    lse2[t] = __ldg(prm.lse + idx) * kLog2e;
-                    dl[t] = __ldg(prm.delta + idx);
-                }
+        const int c = tid;
+        lse2 = 0.f;
+        dl = 0.f;
+        if (c < ncols) {
+            const int khl = c / pl.hW, kw = c - khl * pl.hW;
+            const int gh = h0 - sh.eH + chunk * pl.ch + khl, gw = w0 - sh.eW + kw;
+            if (gs >= 0 && gs < sh.S && gh >= 0 && gh < sh.H && gw >= 0 && gw < sh.W) {
+                const long idx = ((((long)b * sh.S + gs) * sh.H + gh) * sh.W + gw) * sh.heads + head;
+                lse2 = __ldg(prm.lse + idx) * kLog2e;
+                dl = __ldg(prm.delta + idx);
             }
         }
     };
-    auto store_colvec = [&](int buf, const float (&lse2)[2], const float (&dl)[2]) {
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const int c = tid + t * kThreads;
-            if (c < ncols_pad) {
-                sCol[(buf * 2 + 0) * ncols_pad + c] = lse2[t];
-                sCol[(buf * 2 + 1) * ncols_pad + c] = dl[t];
-            }
+    auto store_colvec = [&](int buf, float lse2, float dl) {
+        if (tid < ncols_pad) {
+            sCol[(buf * 2 + 0) * ncols_pad + tid] = lse2;
+            sCol[(buf * 2 + 1) * ncols_pad + tid] = dl;
         }
+    };
+    auto store_group = [&](uint8_t* tile, int g, const uint32_t (&pk)[8]) {    // 16 bf16 of this row -> swizzled tile
+        const uint32_t slab_off = (g >> 2) * (128 * 128);
+        const int c16 = (g & 3) * 2;
+        *reinterpret_cast<uint4*>(tile + slab_off + sw128_offset(row, c16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(tile + slab_off + sw128_offset(row, c16 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     };
 
     if (tid == 0) {
@@ -252,7 +255,7 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     }
     float row_lse2 = 0.f, row_delta = 0.f;
     if constexpr (kDKV) {
-        float a[2], c[2];
+        float a, c;
         load_colvec(0, a, c);
         store_colvec(0, a, c);
         __syncthreads();
@@ -265,11 +268,12 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     int mask_chunk = -1;
     const int nwords = (ncols_pad + 31) / 32;
     const int ngroups = ncols_pad >> 4;
+    const uint32_t zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
     for (int j = 0; j < nblocks; ++j) {
         int ks, chunk;
         block_coords(j, ks, chunk);
-        float nxt_lse2[2] = {0.f, 0.f}, nxt_dl[2] = {0.f, 0.f};
+        float nxt_lse2 = 0.f, nxt_dl = 0.f;
         if constexpr (kDKV) {
             if (j + 1 < nblocks) load_colvec(j + 1, nxt_lse2, nxt_dl);     // global loads in flight during the wait
         }
@@ -280,14 +284,14 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         const int kh0 = chunk * pl.ch;
         if (chunk != mask_chunk) {
             mask_chunk = chunk;
-            for (int w = 0; w < nwords; ++w) sMask[w * kThreads + tid] = 0u;
+            for (int w = 0; w < nwords; ++w) myMask[w * 128 + row] = 0u;
             if (wbits != 0u) {
                 const int ra = max(kh_lo, kh0), rb = min(kh_hi, kh0 + pl.ch - 1);
                 for (int kh = ra; kh <= rb; ++kh) {
                     const int pos = (kh - kh0) * pl.hW;
                     const int w = pos >> 5, sft = pos & 31;
-                    sMask[w * kThreads + tid] |= wbits << sft;
-                    if (sft != 0 && (wbits >> (32 - sft)) != 0u) sMask[(w + 1) * kThreads + tid] |= wbits >> (32 - sft);
+                    myMask[w * 128 + row] |= wbits << sft;
+                    if (sft != 0 && (wbits >> (32 - sft)) != 0u) myMask[(w + 1) * 128 + row] |= wbits >> (32 - sft);
                 }
             }
         }
@@ -298,69 +302,59 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         if (live) {
             const int g_lo = ((ua - kh0) * pl.hW) >> 4;
             const int g_hi = min(((ub - kh0 + 1) * pl.hW + 15) >> 4, ngroups);
+            const int g_mid = (g_lo + g_hi + 1) >> 1;
+            const int ga = half ? g_mid : g_lo, gb = half ? g_hi : g_mid;            // live groups of this thread
+            const int za = half ? g_hi : 0, zb = half ? ngroups : g_lo;              // groups this thread zero-fills
             const float* col_lse2 = sCol + ((j & 1) * 2 + 0) * ncols_pad;
             const float* col_dl = sCol + ((j & 1) * 2 + 1) * ncols_pad;
-            for (int g = 0; g < ngroups; ++g) {
-                uint32_t pk_ds[8], pk_p[8];
-                if (g >= g_lo && g < g_hi) {
-                    const uint32_t mword = sMask[(g >> 1) * kThreads + tid] >> ((g & 1) * 16);
-                    uint32_t s[16], dp[16];
-                    tmem_ld16(tmem_t1 + lane_sel + g * 16, s);
-                    tmem_ld16(tmem_t2 + lane_sel + g * 16, dp);
-                    float l2[16], dl[16];
-                    if constexpr (kDKV) {
+            for (int g = ga; g < gb; ++g) {
+                const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
+                uint32_t s[16], dp[16];
+                tmem_ld16(tmem_t1 + lane_sel + g * 16, s);
+                tmem_ld16(tmem_t2 + lane_sel + g * 16, dp);
+                float l2[16], dl[16];
+                if constexpr (kDKV) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float4 a = *reinterpret_cast<const float4*>(col_lse2 + g * 16 + 4 * i);
-                            const float4 c = *reinterpret_cast<const float4*>(col_dl + g * 16 + 4 * i);
-                            l2[4 * i] = a.x; l2[4 * i + 1] = a.y; l2[4 * i + 2] = a.z; l2[4 * i + 3] = a.w;
-                            dl[4 * i] = c.x; dl[4 * i + 1] = c.y; dl[4 * i + 2] = c.z; dl[4 * i + 3] = c.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) { l2[i] = row_lse2; dl[i] = row_delta; }
-                    }
-                    tmem_wait_ld();
-                    float pv[16], dsv[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const bool on = (mword >> i) & 1u;
-                        const float p = ex2(fmaf(__uint_as_float(s[i]), pl.scale_log2, -l2[i]));
-                        const float ds = p * (__uint_as_float(dp[i]) - dl[i]) * sh.scale;
-                        pv[i] = on ? p : 0.f;
-                        dsv[i] = on ? ds : 0.f;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        pk_ds[i] = pack_bf16(dsv[2 * i], dsv[2 * i + 1]);
-                        pk_p[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 a = *reinterpret_cast<const float4*>(col_lse2 + g * 16 + 4 * i);
+                        const float4 c = *reinterpret_cast<const float4*>(col_dl + g * 16 + 4 * i);
+                        l2[4 * i] = a.x; l2[4 * i + 1] = a.y; l2[4 * i + 2] = a.z; l2[4 * i + 3] = a.w;
+                        dl[4 * i] = c.x; dl[4 * i + 1] = c.y; dl[4 * i + 2] = c.z; dl[4 * i + 3] = c.w;
                     }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) { pk_ds[i] = 0u; pk_p[i] = 0u; }
+                    for (int i = 0; i < 16; ++i) { l2[i] = row_lse2; dl[i] = row_delta; }
                 }
-                const uint32_t slab_off = (g >> 2) * (128 * 128);
-                const int c16 = (g & 3) * 2;
-                const uint32_t o0 = slab_off + sw128_offset(tid, c16), o1 = slab_off + sw128_offset(tid, c16 + 1);
-                *reinterpret_cast<uint4*>(sDS + o0) = make_uint4(pk_ds[0], pk_ds[1], pk_ds[2], pk_ds[3]);
-                *reinterpret_cast<uint4*>(sDS + o1) = make_uint4(pk_ds[4], pk_ds[5], pk_ds[6], pk_ds[7]);
+                tmem_wait_ld();
+                float pv[16], dsv[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const bool on = (mword >> i) & 1u;
+                    const float p = ex2(fmaf(__uint_as_float(s[i]), pl.scale_log2, -l2[i]));
+                    const float ds = p * (__uint_as_float(dp[i]) - dl[i]) * sh.scale;
+                    pv[i] = on ? p : 0.f;
+                    dsv[i] = on ? ds : 0.f;
+                }
+                uint32_t pk[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(dsv[2 * i], dsv[2 * i + 1]);
+                store_group(sDS, g, pk);
                 if constexpr (kDKV) {
-                    *reinterpret_cast<uint4*>(sPT + o0) = make_uint4(pk_p[0], pk_p[1], pk_p[2], pk_p[3]);
-                    *reinterpret_cast<uint4*>(sPT + o1) = make_uint4(pk_p[4], pk_p[5], pk_p[6], pk_p[7]);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
+                    store_group(sPT, g, pk);
                 }
+            }
+            for (int g = za; g < zb; ++g) {
+                store_group(sDS, g, zero8);
+                if constexpr (kDKV) store_group(sPT, g, zero8);
             }
             p_zero = false;
         } else if (!p_zero) {
-            for (int g = 0; g < ngroups; ++g) {
-                const uint32_t slab_off = (g >> 2) * (128 * 128);
-                const int c16 = (g & 3) * 2;
-                const uint32_t o0 = slab_off + sw128_offset(tid, c16), o1 = slab_off + sw128_offset(tid, c16 + 1);
-                *reinterpret_cast<uint4*>(sDS + o0) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(sDS + o1) = make_uint4(0, 0, 0, 0);
-                if constexpr (kDKV) {
-                    *reinterpret_cast<uint4*>(sPT + o0) = make_uint4(0, 0, 0, 0);
-                    *reinterpret_cast<uint4*>(sPT + o1) = make_uint4(0, 0, 0, 0);
-                }
+            const int za = half ? (ngroups >> 1) : 0, zb = half ? ngroups : (ngroups >> 1);
+            for (int g = za; g < zb; ++g) {
+                store_group(sDS, g, zero8);
+                if constexpr (kDKV) store_group(sPT, g, zero8);
             }
             p_zero = true;
         }
@@ -385,13 +379,13 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     // ---- epilogue ------------------------------------------------------------------------------
     mbar_wait(bar_mma, nblocks & 1);
     tc_fence_after();
-    const long row_off = row_tok * (long)sh.inner() + c_base;
+    const long row_off = row_tok * (long)sh.inner() + c_base + half * (D / 2);
 #pragma unroll
     for (int which = 0; which < (kDKV ? 2 : 1); ++which) {
         __nv_bfloat16* dst = (which == 0 ? prm.out1 : prm.out2) + row_off;
-        const uint32_t src = (which == 0 ? tmem_acc1 : tmem_acc2) + lane_sel;
+        const uint32_t src = (which == 0 ? tmem_acc1 : tmem_acc2) + lane_sel + half * (D / 2);
 #pragma unroll
-        for (int c = 0; c < D; c += 16) {
+        for (int c = 0; c < D / 2; c += 16) {
             uint32_t r[16];
             tmem_ld16(src + c, r);
             tmem_wait_ld();
