@@ -72,9 +72,9 @@ size_t smem_bytes_for(Mode mode, int d, int ncols_pad) {
     const size_t row_tile = (size_t)slabs_of(d) * 128 * row_bytes_of(d);
     const size_t blk = (size_t)slabs_of(d) * ncols_pad * row_bytes_of(d);
     const size_t ptile = (size_t)round_up(ncols_pad, 64) / 64 * 128 * 128;
-    const size_t fixed = 1024 /*alignment slack*/ + 2 * 8 * 128 * 4 /*masks*/ + 2 * 128 * 4 /*exchange*/ + 256 /*barriers*/;
+    const size_t fixed = 1024 /*alignment slack*/ + 2 * 8 * 128 * 4 /*masks*/ + 3 * 2 * 128 * 4 /*exchange*/ + 256 /*barriers*/;
     switch (mode) {
-        case kFwd: return fixed + row_tile + 4 * blk + ptile;                       // Q | 2x(K,V) | P
+        case kFwd: return fixed + 2 * row_tile + 4 * blk + ptile;                   // 2xQ | 2x(K,V) | P
         case kBwdDQ: return fixed + 2 * row_tile + 4 * blk + ptile;                 // Q,dO | 2x(K,V) | dS
         default: return fixed + 2 * row_tile + 4 * blk + 2 * ptile + 4 * ncols_pad * 4;   // K,V | 2x(Q,dO) | P,dS | lse,delta
     }
@@ -122,6 +122,12 @@ bool make_plan(const AttnShape& s, Mode mode, Plan& best) {
                 p.smem_bytes = (int)smem_bytes_for(mode, s.d, p.ncols_pad);
                 p.tmem_cols = next_pow2(tmem_cols_for(mode, s.d, p.ncols_pad));
                 p.scale_log2 = s.scale * 1.4426950408889634f;
+                p.lgTW = 0; while ((1 << p.lgTW) < p.tW) ++p.lgTW;
+                p.lgPlane = 0; while ((1 << p.lgPlane) < p.tH * p.tW) ++p.lgPlane;
+                // heads per CTA: walk as many heads as possible while keeping >= 3 CTAs per SM slot pair busy
+                p.hpc = 1;
+                for (int h = s.heads; h >= 1; --h)
+                    if (s.heads % h == 0 && (double)s.B * tiles * (s.heads / h) >= 4.0 * 148) { p.hpc = h; break; }
                 best = p;
                 found = true;
             }
@@ -141,6 +147,8 @@ struct FwdParams {
 
 // 256 threads: warps w and w+4 share TMEM lane quadrant w&3 (32 query rows) and split the
 // row's key columns between them ("half" 0 / 1), so every row is worked on by two threads.
+// A CTA walks `hpc` heads of its brick back to back: the geometry (masks, live ranges) is
+// per brick, not per head, and the TMA / MMA pipeline runs straight across head boundaries.
 template <int D>
 __global__ void __launch_bounds__(kThreads, (D == 128) ? 1 : 2)
 l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv_k,
@@ -156,57 +164,63 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const int row = quad * 32 + lane;              // query row of the brick == TMEM lane
     const int ncols = pl.ncols, ncols_pad = pl.ncols_pad;
     const int q_slab_bytes = 128 * G::kRowBytes;
+    const int q_tile_bytes = G::kSlabs * q_slab_bytes;
     const int kv_slab_bytes = ncols_pad * G::kRowBytes;
     const int kv_tile_bytes = G::kSlabs * kv_slab_bytes;
 
-    uint8_t* sQ = smem;
-    uint8_t* sK = sQ + G::kSlabs * q_slab_bytes;                 // [2 stages][slabs][ncols_pad rows]
+    uint8_t* sQ = smem;                                          // [2 head buffers][slabs][128 rows]
+    uint8_t* sK = sQ + 2 * q_tile_bytes;                         // [2 stages][slabs][ncols_pad rows]
     uint8_t* sV = sK + 2 * kv_tile_bytes;
     uint8_t* sP = sV + 2 * kv_tile_bytes;                        // [ceil(ncols_pad/64)][128 rows][128 B]
     const int p_slabs = (ncols_pad + 63) / 64;
     uint32_t* sMask = reinterpret_cast<uint32_t*>(sP + p_slabs * 128 * 128);   // [2 halves][8 words][128 rows]
-    float* sX = reinterpret_cast<float*>(sMask + 2 * 8 * 128);                 // [2 halves][128 rows] exchange
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 2 * 128);
-    uint64_t* bar_q = bars;
-    uint64_t* bar_kv = bars + 1;      // [2]
-    uint64_t* bar_mma = bars + 3;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    float* sX = reinterpret_cast<float*>(sMask + 2 * 8 * 128);                 // [3 uses][2 halves][128 rows]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 3 * 2 * 128);
+    uint64_t* bar_q = bars;           // [2]
+    uint64_t* bar_kv = bars + 2;      // [2]
+    uint64_t* bar_mma = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
     uint32_t* myMask = sMask + half * 8 * 128;
 
-    // ---- which brick -------------------------------------------------------------------
-    int bid = blockIdx.x;
-    const int tw_i = bid % pl.tilesW; bid /= pl.tilesW;
-    const int th_i = bid % pl.tilesH; bid /= pl.tilesH;
-    const int ts_i = bid % pl.tilesS; bid /= pl.tilesS;
-    const int head = bid % sh.heads;
-    const int b = bid / sh.heads;
+    // ---- which brick / head group ----------------------------------------------------------
+    const int tw_i = blockIdx.x % pl.tilesW, th_i = blockIdx.x / pl.tilesW;
+    const int ts_i = blockIdx.y;
+    const int hgroups = sh.heads / pl.hpc;
+    const int hg = blockIdx.z % hgroups, b = blockIdx.z / hgroups;
+    const int head0 = hg * pl.hpc;
     const int s0 = ts_i * pl.tS, h0 = th_i * pl.tH, w0 = tw_i * pl.tW;
-    const int c_base = head * D;
 
     // ---- this thread's query row ---------------------------------------------------------
-    const int plane_sz = pl.tH * pl.tW;
-    const int qs = row / plane_sz, qh = (row % plane_sz) / pl.tW, qw = row % pl.tW;
+    const int plane_mask = (1 << pl.lgPlane) - 1;
+    const int qs = row >> pl.lgPlane, qh = (row & plane_mask) >> pl.lgTW, qw = row & (pl.tW - 1);
     const bool q_valid = (s0 + qs < sh.S) && (h0 + qh < sh.H) && (w0 + qw < sh.W);
     // live key range of this row in halo coordinates (window AND grid), per axis
     const int kh_lo = max(qh, sh.eH - h0), kh_hi = min(qh + 2 * sh.eH, sh.H - 1 - h0 + sh.eH);
     const int kw_lo = max(qw, sh.eW - w0), kw_hi = min(qw + 2 * sh.eW, sh.W - 1 - w0 + sh.eW);
     const uint32_t wbits = (q_valid && kw_hi >= kw_lo) ? ((kw_hi - kw_lo == 31) ? 0xffffffffu : ((1u << (kw_hi - kw_lo + 1)) - 1u)) << kw_lo : 0u;
     // warp-uniform ranges (identical for the two warps of a quadrant)
-    const int w_qs = (quad * 32) / plane_sz;
-    const int w_qh_lo = ((quad * 32) % plane_sz) / pl.tW, w_qh_hi = ((quad * 32 + 31) % plane_sz) / pl.tW;
+    const int w_qs = (quad * 32) >> pl.lgPlane;
+    const int w_qh_lo = ((quad * 32) & plane_mask) >> pl.lgTW, w_qh_hi = ((quad * 32 + 31) & plane_mask) >> pl.lgTW;
     // block iteration space: planes and h-chunks that intersect the grid
     const int ks_first = max(0, sh.eS - s0), ks_last = min(pl.hS - 1, sh.S - 1 - s0 + sh.eS);
     const int khg_lo = max(0, sh.eH - h0), khg_hi = min(pl.hH - 1, sh.H - 1 - h0 + sh.eH);
-    const int chunk_first = khg_lo / pl.ch, chunk_last = khg_hi / pl.ch;
+    int chunk_first = 0, chunk_last = 0;
+    for (int c = 0; c < pl.nchunk; ++c) {           // nchunk is tiny; avoids integer divisions
+        if (khg_lo >= (c + 1) * pl.ch) chunk_first = c + 1;
+        if (khg_hi >= c * pl.ch) chunk_last = c;
+    }
     const int nplanes = ks_last - ks_first + 1;
     const int nblocks = nplanes * (chunk_last - chunk_first + 1);
+    const int nsteps = nblocks * pl.hpc;
+    const long tok = (((long)b * sh.S + (s0 + qs)) * sh.H + (h0 + qh)) * sh.W + (w0 + qw);
 
     // ---- one-time setup ----------------------------------------------------------------------
     if (tid == 0) {
         tma_prefetch_desc(&map_q);
         tma_prefetch_desc(&map_kv_k);
         tma_prefetch_desc(&map_kv_v);
-        mbar_init(bar_q, 1);
+        mbar_init(&bar_q[0], 1);
+        mbar_init(&bar_q[1], 1);
         mbar_init(&bar_kv[0], 1);
         mbar_init(&bar_kv[1], 1);
         mbar_init(bar_mma, 1);
@@ -236,39 +250,51 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const uint32_t tmem_s = tmem_base + D;         // columns [D, D + ncols_pad)
     const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
 
-    auto block_coords = [&](int j, int& ks, int& chunk) {
-        chunk = chunk_first + j / nplanes;
-        ks = ks_first + j % nplanes;
+    // a step = (head, plane, h-chunk); steps run head-major, then chunk, then plane
+    struct Cursor { int hd, ks, chunk; };
+    auto advance = [&](Cursor& c) {
+        if (++c.ks > ks_last) {
+            c.ks = ks_first;
+            if (++c.chunk > chunk_last) { c.chunk = chunk_first; ++c.hd; }
+        }
     };
-    auto issue_kv_load = [&](int j) {               // thread 0 only
-        int ks, chunk;
-        block_coords(j, ks, chunk);
-        const int stage = j & 1;
+    auto issue_q_load = [&](int hd) {               // thread 0 only
+        uint64_t* bar = &bar_q[hd & 1];
+        mbar_expect_tx(bar, (uint32_t)q_tile_bytes);
+#pragma unroll
+        for (int sl = 0; sl < G::kSlabs; ++sl)
+            tma_load_5d(sQ + (hd & 1) * q_tile_bytes + sl * q_slab_bytes, &map_q, bar,
+                        (head0 + hd) * D + sl * G::kSlabCh, w0, h0, s0, b);
+    };
+    auto issue_kv_load = [&](int t, const Cursor& c) {   // thread 0 only
+        const int stage = t & 1;
+        const int cb = (head0 + c.hd) * D;
         mbar_expect_tx(&bar_kv[stage], 2u * G::kSlabs * (uint32_t)ncols * G::kRowBytes);
 #pragma unroll
         for (int sl = 0; sl < G::kSlabs; ++sl) {
-            tma_load_5d(sK + stage * kv_tile_bytes + sl * kv_slab_bytes, &map_kv_k, &bar_kv[stage], c_base + sl * G::kSlabCh,
-                        w0 - sh.eW, h0 - sh.eH + chunk * pl.ch, s0 - sh.eS + ks, b);
-            tma_load_5d(sV + stage * kv_tile_bytes + sl * kv_slab_bytes, &map_kv_v, &bar_kv[stage], c_base + sl * G::kSlabCh,
-                        w0 - sh.eW, h0 - sh.eH + chunk * pl.ch, s0 - sh.eS + ks, b);
+            tma_load_5d(sK + stage * kv_tile_bytes + sl * kv_slab_bytes, &map_kv_k, &bar_kv[stage], cb + sl * G::kSlabCh,
+                        w0 - sh.eW, h0 - sh.eH + c.chunk * pl.ch, s0 - sh.eS + c.ks, b);
+            tma_load_5d(sV + stage * kv_tile_bytes + sl * kv_slab_bytes, &map_kv_v, &bar_kv[stage], cb + sl * G::kSlabCh,
+                        w0 - sh.eW, h0 - sh.eH + c.chunk * pl.ch, s0 - sh.eS + c.ks, b);
         }
     };
     const uint32_t idesc_s = make_idesc_bf16(ncols_pad, false, false);
     const uint32_t idesc_o = make_idesc_bf16(D, false, true);
-    auto issue_s_mma = [&](int j) {                 // S = Q K_j^T   (thread 0 only)
-        const int stage = j & 1;
+    auto issue_s_mma = [&](int t, int hd) {         // S = Q_hd K_t^T   (thread 0 only)
+        const int stage = t & 1;
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
             const int sl = (kk * 16) / G::kSlabCh;
             const int koff = ((kk * 16) % G::kSlabCh) * 2;
-            const uint64_t da = make_smem_desc(smem_u32(sQ + sl * q_slab_bytes + koff), 16, G::kAtomBytes, G::kSwizzleCode);
+            const uint64_t da = make_smem_desc(smem_u32(sQ + (hd & 1) * q_tile_bytes + sl * q_slab_bytes + koff), 16,
+                                               G::kAtomBytes, G::kSwizzleCode);
             const uint64_t db = make_smem_desc(smem_u32(sK + stage * kv_tile_bytes + sl * kv_slab_bytes + koff), 16,
                                                G::kAtomBytes, G::kSwizzleCode);
             umma_bf16_ss(tmem_s, da, db, idesc_s, kk > 0);
         }
     };
-    auto issue_o_mma = [&](int j, bool accumulate) { // O += P V_j    (thread 0 only)
-        const int stage = j & 1;
+    auto issue_o_mma = [&](int t, bool accumulate) { // O += P V_t    (thread 0 only)
+        const int stage = t & 1;
         for (int kk = 0; kk < ncols_pad / 16; ++kk) {
             const uint64_t da = make_smem_desc(smem_u32(sP + (kk >> 2) * (128 * 128) + (kk & 3) * 32), 16, 1024, 2u);
             const uint64_t db = make_smem_desc(smem_u32(sV + stage * kv_tile_bytes + kk * 16 * G::kRowBytes),
@@ -283,42 +309,76 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         *reinterpret_cast<uint4*>(slab + sw128_offset(row, c16 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     };
 
-    if (tid == 0) {
-        mbar_expect_tx(bar_q, (uint32_t)G::kSlabs * q_slab_bytes);
+    float m_used = -INFINITY;      // reference max (log2 domain, scaled) this row's P values are relative to
+    float l_part = 0.f;            // this thread's share of the running sum of P
+    // O / l -> bf16 and the LSE of head `hd`; called by all threads once that head's last P V has retired
+    auto finish_head = [&](int hd) {
+        float* x = sX + 2 * 2 * 128;
+        x[half * 128 + row] = l_part;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+        const float l_run = l_part + x[(half ^ 1) * 128 + row];
+        const float inv_l = 1.f / l_run;
+        const int cb = (head0 + hd) * D;
+        __nv_bfloat16* orow = prm.o + tok * (long)sh.inner() + cb + half * (D / 2);
 #pragma unroll
-        for (int sl = 0; sl < G::kSlabs; ++sl)
-            tma_load_5d(sQ + sl * q_slab_bytes, &map_q, bar_q, c_base + sl * G::kSlabCh, w0, h0, s0, b);
-        issue_kv_load(0);
-        if (nblocks > 1) issue_kv_load(1);
-        mbar_wait(bar_q, 0);
+        for (int c = 0; c < D / 2; c += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem_o + lane_sel + half * (D / 2) + c, r);       // warp-collective: every lane takes part
+            tmem_wait_ld();
+            if (q_valid) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    pk[i] = pack_bf16(__uint_as_float(r[2 * i]) * inv_l, __uint_as_float(r[2 * i + 1]) * inv_l);
+                *reinterpret_cast<uint4*>(orow + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(orow + c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+        }
+        if (q_valid && half == 0) prm.lse[tok * sh.heads + head0 + hd] = (m_used + lg2(l_run)) * 0.6931471805599453f;
+        m_used = -INFINITY;
+        l_part = 0.f;
+    };
+
+    Cursor cur{0, ks_first, chunk_first};           // step t
+    Cursor nxt = cur;                               // step t + 1
+    advance(nxt);
+    if (tid == 0) {
+        issue_q_load(0);
+        issue_kv_load(0, cur);
+        if (nsteps > 1) issue_kv_load(1, nxt);
+        mbar_wait(&bar_q[0], 0);
         mbar_wait(&bar_kv[0], 0);
         tc_fence_after();
-        issue_s_mma(0);
+        issue_s_mma(0, 0);
         umma_commit(bar_mma);
     }
 
     // ---- main loop ------------------------------------------------------------------------------
-    float m_used = -INFINITY;      // reference max (log2 domain, scaled) this row's P values are relative to
-    float l_part = 0.f;            // this thread's share of the running sum of P
     bool p_zero = false;           // this thread's share of the P row is known to be all zero
     int mask_chunk = -1;
+    int g_lo = 0, g_hi = 0;        // live 16-column groups of this quadrant in the current h-chunk
+    bool chunk_live = false, row_has_cols = false;
     const int nwords = (ncols_pad + 31) / 32;
     const int ngroups = ncols_pad >> 4;
     const uint32_t zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
-    for (int j = 0; j < nblocks; ++j) {
-        int ks, chunk;
-        block_coords(j, ks, chunk);
-        mbar_wait(bar_mma, j & 1);                   // S_j ready; P V_{j-1} done (P buffer, stage (j-1)&1 free)
+    for (int t = 0; t < nsteps; ++t) {
+        mbar_wait(bar_mma, t & 1);                   // S_t ready; P V_{t-1} done (P buffer, stage (t-1)&1 free)
         tc_fence_after();
-        if (tid == 0 && j >= 1 && j + 1 < nblocks) issue_kv_load(j + 1);
+        const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
+        if (tid == 0) {
+            if (head_start && cur.hd + 1 < pl.hpc) issue_q_load(cur.hd + 1);   // buffer last read by head hd-1
+            if (t >= 1 && t + 1 < nsteps) issue_kv_load(t + 1, nxt);
+        }
+        if (head_start && t > 0) finish_head(cur.hd - 1);
 
-        const int kh0 = chunk * pl.ch;
-        if (chunk != mask_chunk) {                   // live-column bitmask of this row for this h-chunk (own copy)
-            mask_chunk = chunk;
+        const int kh0 = cur.chunk * pl.ch;
+        if (cur.chunk != mask_chunk) {               // live-column bitmask of this row for this h-chunk (own copy)
+            mask_chunk = cur.chunk;
             for (int w = 0; w < nwords; ++w) myMask[w * 128 + row] = 0u;
-            if (wbits != 0u) {
-                const int ra = max(kh_lo, kh0), rb = min(kh_hi, kh0 + pl.ch - 1);
+            const int ra = max(kh_lo, kh0), rb = min(kh_hi, kh0 + pl.ch - 1);
+            row_has_cols = (wbits != 0u) && (rb >= ra);
+            if (row_has_cols) {
                 for (int kh = ra; kh <= rb; ++kh) {
                     const int pos = (kh - kh0) * pl.hW;
                     const int w = pos >> 5, sft = pos & 31;
@@ -326,76 +386,110 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     if (sft != 0 && (wbits >> (32 - sft)) != 0u) myMask[(w + 1) * 128 + row] |= wbits >> (32 - sft);
                 }
             }
+            const int ua = max(w_qh_lo, kh0), ub = min(w_qh_hi + 2 * sh.eH, kh0 + pl.ch - 1);
+            chunk_live = ub >= ua;
+            g_lo = ((ua - kh0) * pl.hW) >> 4;
+            g_hi = min(((ub - kh0 + 1) * pl.hW + 15) >> 4, ngroups);
         }
 
         // warp-uniform: can any of this quadrant's queries see this block?
-        const bool plane_live = (ks >= w_qs) && (ks <= w_qs + 2 * sh.eS);
-        const int ua = max(w_qh_lo, kh0), ub = min(w_qh_hi + 2 * sh.eH, kh0 + pl.ch - 1);
-        const bool live = plane_live && (ub >= ua);
+        const bool live = chunk_live && (cur.ks >= w_qs) && (cur.ks <= w_qs + 2 * sh.eS);
         if (live) {
-            const int g_lo = ((ua - kh0) * pl.hW) >> 4;                              // 16-column groups
-            const int g_hi = min(((ub - kh0 + 1) * pl.hW + 15) >> 4, ngroups);
             const int g_mid = (g_lo + g_hi + 1) >> 1;
             const int ga = half ? g_mid : g_lo, gb = half ? g_hi : g_mid;            // live groups of this thread
             const int za = half ? g_hi : 0, zb = half ? ngroups : g_lo;              // groups this thread zero-fills
-            // pass 1: row maximum over this thread's live columns
-            float mx = -INFINITY;
-            for (int g = ga; g < gb; ++g) {
-                const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
-                uint32_t r[16];
-                tmem_ld16(tmem_s + lane_sel + g * 16, r);
-                tmem_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (mword & (1u << i)) mx = fmaxf(mx, __uint_as_float(r[i]));
-            }
-            sX[half * 128 + row] = mx;
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-            mx = fmaxf(mx, sX[(half ^ 1) * 128 + row]);
-            const float m_blk = mx * pl.scale_log2;          // scale > 0
-            // lazy rescale: keep the old reference max unless the new one is > 2^8 larger
-            float alpha = 1.f;
-            const bool bump = m_blk > m_used + 8.f;
-            const bool fix_o = bump && (m_used != -INFINITY);  // the row already holds earlier blocks
-            if (bump) {
-                alpha = ex2(m_used - m_blk);                 // 0 when this is the row's first live block
-                m_used = m_blk;
-            }
-            l_part *= alpha;
-            if (__any_sync(0xffffffffu, fix_o)) {            // rescale this thread's half of the O row
-#pragma unroll
-                for (int c = 0; c < D / 2; c += 16) {
+            // Single pass against the stale reference max when every row that has live columns
+            // here already owns one; P may then exceed 1, which is fine up to 2^8.
+            bool two_pass = __any_sync(0xffffffffu, row_has_cols && m_used == -INFINITY);
+            if (!two_pass) {
+                const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
+                float lsum = 0.f, pmax = 0.f;
+                for (int g = ga; g < gb; ++g) {
+                    const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
                     uint32_t r[16];
-                    tmem_ld16(tmem_o + lane_sel + half * (D / 2) + c, r);
+                    tmem_ld16(tmem_s + lane_sel + g * 16, r);
+                    tmem_wait_ld();
+                    float p[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float e = ex2(fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m));
+                        p[i] = (mword & (1u << i)) ? e : 0.f;
+                        lsum += p[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) pmax = fmaxf(pmax, fmaxf(p[i], p[i + 1]));
+                    uint32_t packed[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) packed[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
+                    store_group(g, packed);
+                }
+                float* x = sX + 0 * 2 * 128;
+                x[half * 128 + row] = pmax;
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+                pmax = fmaxf(pmax, x[(half ^ 1) * 128 + row]);
+                two_pass = __any_sync(0xffffffffu, !(pmax <= 256.f));     // also catches inf / NaN
+                if (!two_pass) l_part += lsum;
+            }
+            if (two_pass) {
+                // pass 1: row maximum over this thread's live columns
+                float mx = -INFINITY;
+                for (int g = ga; g < gb; ++g) {
+                    const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
+                    uint32_t r[16];
+                    tmem_ld16(tmem_s + lane_sel + g * 16, r);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-                    tmem_st16(tmem_o + lane_sel + half * (D / 2) + c, r);
+                    for (int i = 0; i < 16; ++i)
+                        if (mword & (1u << i)) mx = fmaxf(mx, __uint_as_float(r[i]));
                 }
-                tmem_wait_st();
-            }
-            // pass 2: P = 2^(s*scale*log2e - m) on live columns, 0 elsewhere -> bf16 -> smem (K-major, 128B swizzle)
-            const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
-            float lsum = 0.f;
-            for (int g = ga; g < gb; ++g) {
-                const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
-                uint32_t r[16];
-                tmem_ld16(tmem_s + lane_sel + g * 16, r);
-                tmem_wait_ld();
-                float p[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float e = ex2(fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m));
-                    p[i] = (mword & (1u << i)) ? e : 0.f;
-                    lsum += p[i];
+                float* x = sX + 1 * 2 * 128;
+                x[half * 128 + row] = mx;
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+                mx = fmaxf(mx, x[(half ^ 1) * 128 + row]);
+                const float m_blk = mx * pl.scale_log2;          // scale > 0
+                float alpha = 1.f;
+                const bool bump = m_blk > m_used;
+                const bool fix_o = bump && (m_used != -INFINITY);  // the row already holds earlier blocks
+                if (bump) {
+                    alpha = ex2(m_used - m_blk);                 // 0 when this is the row's first live block
+                    m_used = m_blk;
                 }
-                uint32_t packed[8];
+                l_part *= alpha;
+                if (__any_sync(0xffffffffu, fix_o)) {            // rescale this thread's half of the O row
 #pragma unroll
-                for (int i = 0; i < 8; ++i) packed[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
-                store_group(g, packed);
+                    for (int c = 0; c < D / 2; c += 16) {
+                        uint32_t r[16];
+                        tmem_ld16(tmem_o + lane_sel + half * (D / 2) + c, r);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                        tmem_st16(tmem_o + lane_sel + half * (D / 2) + c, r);
+                    }
+                    tmem_wait_st();
+                }
+                // pass 2: P = 2^(s*scale*log2e - m) on live columns -> bf16 -> smem (K-major, 128B swizzle)
+                const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
+                float lsum = 0.f;
+                for (int g = ga; g < gb; ++g) {
+                    const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
+                    uint32_t r[16];
+                    tmem_ld16(tmem_s + lane_sel + g * 16, r);
+                    tmem_wait_ld();
+                    float p[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float e = ex2(fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m));
+                        p[i] = (mword & (1u << i)) ? e : 0.f;
+                        lsum += p[i];
+                    }
+                    uint32_t packed[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) packed[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
+                    store_group(g, packed);
+                }
+                l_part += lsum;
             }
             for (int g = za; g < zb; ++g) store_group(g, zero8);
-            l_part += lsum;
             p_zero = false;
         } else if (!p_zero) {
             const int za = half ? (ngroups >> 1) : 0, zb = half ? ngroups : (ngroups >> 1);
@@ -407,40 +501,22 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            issue_o_mma(j, j > 0);
-            if (j + 1 < nblocks) {
-                mbar_wait(&bar_kv[(j + 1) & 1], ((j + 1) >> 1) & 1);
+            issue_o_mma(t, !head_start);
+            if (t + 1 < nsteps) {
+                mbar_wait(&bar_kv[(t + 1) & 1], ((t + 1) >> 1) & 1);
+                if (nxt.hd != cur.hd) mbar_wait(&bar_q[nxt.hd & 1], (nxt.hd >> 1) & 1);
                 tc_fence_after();
-                issue_s_mma(j + 1);
+                issue_s_mma(t + 1, nxt.hd);
             }
             umma_commit(bar_mma);
         }
+        cur = nxt;
+        advance(nxt);
     }
 
-    // ---- epilogue: O / l -> bf16, LSE ---------------------------------------------------------
-    mbar_wait(bar_mma, nblocks & 1);
+    mbar_wait(bar_mma, nsteps & 1);
     tc_fence_after();
-    sX[half * 128 + row] = l_part;
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-    const float l_run = l_part + sX[(half ^ 1) * 128 + row];
-    const long tok = (((long)b * sh.S + (s0 + qs)) * sh.H + (h0 + qh)) * sh.W + (w0 + qw);
-    const float inv_l = 1.f / l_run;
-    __nv_bfloat16* orow = prm.o + tok * (long)sh.inner() + c_base + half * (D / 2);
-#pragma unroll
-    for (int c = 0; c < D / 2; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(tmem_o + lane_sel + half * (D / 2) + c, r);       // warp-collective: every lane takes part
-        tmem_wait_ld();
-        if (q_valid) {
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                pk[i] = pack_bf16(__uint_as_float(r[2 * i]) * inv_l, __uint_as_float(r[2 * i + 1]) * inv_l);
-            *reinterpret_cast<uint4*>(orow + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(orow + c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
-    }
-    if (q_valid && half == 0) prm.lse[tok * sh.heads + head] = (m_used + lg2(l_run)) * 0.6931471805599453f;
+    finish_head(pl.hpc - 1);
 
     tc_fence_before();
     __syncthreads();
@@ -463,8 +539,9 @@ static int launch_fwd(const void* q, const void* k, const void* v, void* o, floa
     if (int rc = make_tensor_map_5d(&mv, v, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
     FwdParams prm{s, pl, static_cast<__nv_bfloat16*>(o), lse};
     WM_CUDA_CHECK(cudaFuncSetAttribute(l3d_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
-    const long grid = (long)s.B * s.heads * pl.tilesS * pl.tilesH * pl.tilesW;
-    l3d_fwd_tc_kernel<D><<<(unsigned)grid, kThreads, pl.smem_bytes, st>>>(mq, mk, mv, prm);
+    const dim3 grid((unsigned)(pl.tilesW * pl.tilesH), (unsigned)pl.tilesS, (unsigned)(s.B * (s.heads / pl.hpc)));
+    if (grid.y > 65535u || grid.z > 65535u) return fail(WM_EUNSUPPORTED, "grid too large for the tensor-core kernel");
+    l3d_fwd_tc_kernel<D><<<grid, kThreads, pl.smem_bytes, st>>>(mq, mk, mv, prm);
     WM_CUDA_CHECK(cudaGetLastError());
     return WM_OK;
 }

@@ -17,6 +17,8 @@ struct Plan {
     int ncols;                 // ch*hW: halo columns per block that TMA writes
     int ncols_pad;             // rounded up to 16 (MMA K granularity of the second GEMM)
     int tilesS, tilesH, tilesW;
+    int lgTW, lgPlane;         // log2(tW), log2(tH*tW): brick dims are powers of two
+    int hpc;                   // heads walked by one CTA (divides heads)
     int smem_bytes;
     int tmem_cols;             // power of two
     float scale_log2;
