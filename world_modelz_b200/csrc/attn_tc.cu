@@ -67,22 +67,22 @@ int make_tensor_map_5d(CUtensorMap* out, const void* base, int B, int S, int H, 
 // ------------------------------------------------------------------------------- plan
 static int row_bytes_of(int d) { return d == 32 ? 64 : 128; }
 static int slabs_of(int d) { return d == 128 ? 2 : 1; }
+static const size_t kFixedSmem = 1024 /*alignment slack*/ + 2 * 8 * 128 * 4 /*masks*/ + 3 * 2 * 128 * 4 /*exchange*/ + 256 /*barriers*/;
 
-size_t smem_bytes_for(Mode mode, int d, int ncols_pad) {
+size_t smem_bytes_for(Mode mode, int d, int ncols_pad, int nstage, int rowbuf) {
     const size_t row_tile = (size_t)slabs_of(d) * 128 * row_bytes_of(d);
     const size_t blk = (size_t)slabs_of(d) * ncols_pad * row_bytes_of(d);
     const size_t ptile = (size_t)round_up(ncols_pad, 64) / 64 * 128 * 128;
-    const size_t fixed = 1024 /*alignment slack*/ + 2 * 8 * 128 * 4 /*masks*/ + 3 * 2 * 128 * 4 /*exchange*/ + 256 /*barriers*/;
     switch (mode) {
-        case kFwd: return fixed + 2 * row_tile + 4 * blk + ptile;                   // 2xQ | 2x(K,V) | P
-        case kBwdDQ: return fixed + 2 * row_tile + 4 * blk + ptile;                 // Q,dO | 2x(K,V) | dS
-        default: return fixed + 2 * row_tile + 4 * blk + 2 * ptile + 4 * ncols_pad * 4;   // K,V | 2x(Q,dO) | P,dS | lse,delta
+        case kFwd: return kFixedSmem + rowbuf * row_tile + nstage * 2 * blk + 2 * ptile;       // Q | (K,V) stages | 2xP
+        case kBwdDQ: return kFixedSmem + 2 * row_tile + nstage * 2 * blk + ptile;              // Q,dO | (K,V) stages | dS
+        default: return kFixedSmem + 2 * row_tile + nstage * 2 * blk + 2 * ptile + 4 * ncols_pad * 4;   // K,V | (Q,dO) | P,dS | lse,delta
     }
 }
 
 int tmem_cols_for(Mode mode, int d, int ncols_pad) {
     switch (mode) {
-        case kFwd: return d + ncols_pad;                 // O | S
+        case kFwd: return 2 * d + 2 * ncols_pad;         // O x2 (per head parity) | S x2 (double buffered)
         case kBwdDQ: return d + 2 * ncols_pad;           // dQ | S | dP
         default: return 2 * d + 2 * ncols_pad;           // dV | dK | S^T | dP^T
     }
@@ -107,27 +107,40 @@ bool make_plan(const AttnShape& s, Mode mode, Plan& best) {
         if (p.tS * p.tH * p.tW != 128 || (p.tH * p.tW) % 32 != 0) continue;
         p.hS = p.tS + 2 * s.eS; p.hH = p.tH + 2 * s.eH; p.hW = p.tW + 2 * s.eW;
         if (p.hW > 32 || p.hH > 256) continue;
+        p.tilesS = (s.S + p.tS - 1) / p.tS; p.tilesH = (s.H + p.tH - 1) / p.tH; p.tilesW = (s.W + p.tW - 1) / p.tW;
+        const double tiles = (double)p.tilesS * p.tilesH * p.tilesW;
+        // heads per CTA (forward kernel): walk as many heads as possible while keeping the grid >= 4 CTAs per SM
+        int hpc = 1;
+        if (mode == kFwd)
+            for (int h = s.heads; h >= 1; --h)
+                if (s.heads % h == 0 && (double)s.B * tiles * (s.heads / h) >= 4.0 * 148) { hpc = h; break; }
         for (int nchunk = 1; nchunk <= p.hH; ++nchunk) {
             p.ch = (p.hH + nchunk - 1) / nchunk;
             p.nchunk = (p.hH + p.ch - 1) / p.ch;
             p.ncols = p.ch * p.hW;
             p.ncols_pad = round_up(p.ncols, 16);
             if (p.ncols_pad > max_cols || tmem_cols_for(mode, s.d, p.ncols_pad) > 512) continue;
-            if (smem_bytes_for(mode, s.d, p.ncols_pad) > (size_t)kSmemLimit) continue;
-            p.tilesS = (s.S + p.tS - 1) / p.tS; p.tilesH = (s.H + p.tH - 1) / p.tH; p.tilesW = (s.W + p.tW - 1) / p.tW;
-            const double tiles = (double)p.tilesS * p.tilesH * p.tilesW;
-            const double cost = tiles * p.hS * p.nchunk * (p.ncols_pad + 24.0 /*per-block sync overhead*/);
+            // shared-memory variants, best first
+            bool fits = false;
+            const int opts[4][3] = {{3, 2, hpc}, {2, 2, hpc}, {3, 1, 1}, {2, 1, 1}};    // {nstage, rowbuf, hpc}
+            for (const auto& o : opts) {
+                if (mode != kFwd && !(o[0] == 2 && o[1] == 1)) continue;               // bwd kernels: 2 stages, 1 row buffer
+                if (mode == kFwd && o[1] == 2 && hpc == 1) continue;
+                if (smem_bytes_for(mode, s.d, p.ncols_pad, o[0], o[1]) <= (size_t)kSmemLimit) {
+                    p.nstage = o[0]; p.rowbuf = o[1]; p.hpc = o[2];
+                    fits = true;
+                    break;
+                }
+            }
+            if (!fits) continue;
+            const double cost = tiles * p.hS * p.nchunk * (p.ncols_pad + 24.0 /*per-block overhead*/);
             if (cost < best_cost) {
                 best_cost = cost;
-                p.smem_bytes = (int)smem_bytes_for(mode, s.d, p.ncols_pad);
+                p.smem_bytes = (int)smem_bytes_for(mode, s.d, p.ncols_pad, p.nstage, p.rowbuf);
                 p.tmem_cols = next_pow2(tmem_cols_for(mode, s.d, p.ncols_pad));
                 p.scale_log2 = s.scale * 1.4426950408889634f;
                 p.lgTW = 0; while ((1 << p.lgTW) < p.tW) ++p.lgTW;
                 p.lgPlane = 0; while ((1 << p.lgPlane) < p.tH * p.tW) ++p.lgPlane;
-                // heads per CTA: walk as many heads as possible while keeping >= 3 CTAs per SM slot pair busy
-                p.hpc = 1;
-                for (int h = s.heads; h >= 1; --h)
-                    if (s.heads % h == 0 && (double)s.B * tiles * (s.heads / h) >= 4.0 * 148) { p.hpc = h; break; }
                 best = p;
                 found = true;
             }
@@ -145,12 +158,16 @@ struct FwdParams {
     float* lse;
 };
 
-// 256 threads: warps w and w+4 share TMEM lane quadrant w&3 (32 query rows) and split the
-// row's key columns between them ("half" 0 / 1), so every row is worked on by two threads.
-// A CTA walks `hpc` heads of its brick back to back: the geometry (masks, live ranges) is
-// per brick, not per head, and the TMA / MMA pipeline runs straight across head boundaries.
+// Warp-specialised forward kernel.
+//   warps 0-7  compute: warps w and w+4 share TMEM lane quadrant w&3 (32 query rows) and split
+//              the row's key columns ("half" 0 / 1): softmax, P -> smem, epilogue.
+//   warp  8    driver (one lane): TMA loads of Q / K / V blocks and every tcgen05.mma.
+// S lives in two TMEM buffers and P in two smem buffers, so S_{t+1} = Q K_{t+1}^T is
+// computed while the compute warps are still in the softmax of step t, and O += P_t V_t
+// runs while they are already in step t+1.  All hand-offs are mbarriers; there is no
+// CTA-wide barrier inside the loop.  A CTA walks `hpc` heads of its brick back to back.
 template <int D>
-__global__ void __launch_bounds__(kThreads, (D == 128) ? 1 : 2)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv_k,
                   const __grid_constant__ CUtensorMap map_kv_v, const FwdParams prm) {
     using G = Geo<D>;
@@ -160,27 +177,27 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays in the shared window
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int quad = warp & 3, half = warp >> 2;
-    const int row = quad * 32 + lane;              // query row of the brick == TMEM lane
     const int ncols = pl.ncols, ncols_pad = pl.ncols_pad;
+    const int nstage = pl.nstage;
     const int q_slab_bytes = 128 * G::kRowBytes;
     const int q_tile_bytes = G::kSlabs * q_slab_bytes;
     const int kv_slab_bytes = ncols_pad * G::kRowBytes;
     const int kv_tile_bytes = G::kSlabs * kv_slab_bytes;
-
-    uint8_t* sQ = smem;                                          // [2 head buffers][slabs][128 rows]
-    uint8_t* sK = sQ + 2 * q_tile_bytes;                         // [2 stages][slabs][ncols_pad rows]
-    uint8_t* sV = sK + 2 * kv_tile_bytes;
-    uint8_t* sP = sV + 2 * kv_tile_bytes;                        // [ceil(ncols_pad/64)][128 rows][128 B]
     const int p_slabs = (ncols_pad + 63) / 64;
-    uint32_t* sMask = reinterpret_cast<uint32_t*>(sP + p_slabs * 128 * 128);   // [2 halves][8 words][128 rows]
+    const int p_tile_bytes = p_slabs * 128 * 128;
+
+    uint8_t* sQ = smem;                                          // [rowbuf][slabs][128 rows]
+    uint8_t* sKV = sQ + pl.rowbuf * q_tile_bytes;                // [nstage][K|V][slabs][ncols_pad rows]
+    uint8_t* sP = sKV + nstage * 2 * kv_tile_bytes;              // [2][ceil(ncols_pad/64)][128 rows][128 B]
+    uint32_t* sMask = reinterpret_cast<uint32_t*>(sP + 2 * p_tile_bytes);      // [2 halves][8 words][128 rows]
     float* sX = reinterpret_cast<float*>(sMask + 2 * 8 * 128);                 // [3 uses][2 halves][128 rows]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 3 * 2 * 128);
-    uint64_t* bar_q = bars;           // [2]
-    uint64_t* bar_kv = bars + 2;      // [2]
-    uint64_t* bar_mma = bars + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-    uint32_t* myMask = sMask + half * 8 * 128;
+    uint64_t* bar_q = bars;           // [2]  Q tile of a head landed
+    uint64_t* bar_kv = bars + 2;      // [3]  K/V block landed
+    uint64_t* bar_s = bars + 5;       // [2]  S buffer computed            (tcgen05.commit)
+    uint64_t* bar_p = bars + 7;       // [2]  P buffer written, S buffer drained (256 compute threads)
+    uint64_t* bar_o = bars + 9;       // [2]  O += P V of a step retired   (tcgen05.commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
     // ---- which brick / head group ----------------------------------------------------------
     const int tw_i = blockIdx.x % pl.tilesW, th_i = blockIdx.x / pl.tilesW;
@@ -190,17 +207,6 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const int head0 = hg * pl.hpc;
     const int s0 = ts_i * pl.tS, h0 = th_i * pl.tH, w0 = tw_i * pl.tW;
 
-    // ---- this thread's query row ---------------------------------------------------------
-    const int plane_mask = (1 << pl.lgPlane) - 1;
-    const int qs = row >> pl.lgPlane, qh = (row & plane_mask) >> pl.lgTW, qw = row & (pl.tW - 1);
-    const bool q_valid = (s0 + qs < sh.S) && (h0 + qh < sh.H) && (w0 + qw < sh.W);
-    // live key range of this row in halo coordinates (window AND grid), per axis
-    const int kh_lo = max(qh, sh.eH - h0), kh_hi = min(qh + 2 * sh.eH, sh.H - 1 - h0 + sh.eH);
-    const int kw_lo = max(qw, sh.eW - w0), kw_hi = min(qw + 2 * sh.eW, sh.W - 1 - w0 + sh.eW);
-    const uint32_t wbits = (q_valid && kw_hi >= kw_lo) ? ((kw_hi - kw_lo == 31) ? 0xffffffffu : ((1u << (kw_hi - kw_lo + 1)) - 1u)) << kw_lo : 0u;
-    // warp-uniform ranges (identical for the two warps of a quadrant)
-    const int w_qs = (quad * 32) >> pl.lgPlane;
-    const int w_qh_lo = ((quad * 32) & plane_mask) >> pl.lgTW, w_qh_hi = ((quad * 32 + 31) & plane_mask) >> pl.lgTW;
     // block iteration space: planes and h-chunks that intersect the grid
     const int ks_first = max(0, sh.eS - s0), ks_last = min(pl.hS - 1, sh.S - 1 - s0 + sh.eS);
     const int khg_lo = max(0, sh.eH - h0), khg_hi = min(pl.hH - 1, sh.H - 1 - h0 + sh.eH);
@@ -212,7 +218,6 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const int nplanes = ks_last - ks_first + 1;
     const int nblocks = nplanes * (chunk_last - chunk_first + 1);
     const int nsteps = nblocks * pl.hpc;
-    const long tok = (((long)b * sh.S + (s0 + qs)) * sh.H + (h0 + qh)) * sh.W + (w0 + qw);
 
     // ---- one-time setup ----------------------------------------------------------------------
     if (tid == 0) {
@@ -221,24 +226,26 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         tma_prefetch_desc(&map_kv_v);
         mbar_init(&bar_q[0], 1);
         mbar_init(&bar_q[1], 1);
-        mbar_init(&bar_kv[0], 1);
-        mbar_init(&bar_kv[1], 1);
-        mbar_init(bar_mma, 1);
+        for (int i = 0; i < 3; ++i) mbar_init(&bar_kv[i], 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_s[i], 1);
+            mbar_init(&bar_p[i], 256);
+            mbar_init(&bar_o[i], 1);
+        }
         fence_barrier_init();
     }
-    if (warp == 0) {
-        // power-of-two TMEM allocation: O at column 0, S at column D
-        if (pl.tmem_cols <= 64) tmem_alloc<64>(tmem_slot);
-        else if (pl.tmem_cols <= 128) tmem_alloc<128>(tmem_slot);
+    if (warp == 8) {
+        // power-of-two TMEM allocation
+        if (pl.tmem_cols <= 128) tmem_alloc<128>(tmem_slot);
         else if (pl.tmem_cols <= 256) tmem_alloc<256>(tmem_slot);
         else tmem_alloc<512>(tmem_slot);
     }
     // rows [ncols, ncols_pad) of every K / V stage are never written by TMA: keep them zero
     if (ncols_pad > ncols) {
         const int pad_bytes = (ncols_pad - ncols) * G::kRowBytes;
-        for (int t = 0; t < 2 * 2 * G::kSlabs; ++t) {
-            uint8_t* base = sK + t * kv_slab_bytes + ncols * G::kRowBytes;   // sK and sV are contiguous
-            for (int i = tid * 16; i < pad_bytes; i += kThreads * 16) *reinterpret_cast<uint4*>(base + i) = make_uint4(0, 0, 0, 0);
+        for (int t = 0; t < nstage * 2 * G::kSlabs; ++t) {
+            uint8_t* base = sKV + t * kv_slab_bytes + ncols * G::kRowBytes;
+            for (int i = tid * 16; i < pad_bytes; i += kFwdThreads * 16) *reinterpret_cast<uint4*>(base + i) = make_uint4(0, 0, 0, 0);
         }
         fence_proxy_async();
     }
@@ -246,9 +253,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_o = tmem_base;             // columns [0, D)
-    const uint32_t tmem_s = tmem_base + D;         // columns [D, D + ncols_pad)
-    const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
+    // TMEM columns: O of even heads [0, D), O of odd heads [D, 2D), S buffers at 2D and 2D + ncols_pad
 
     // a step = (head, plane, h-chunk); steps run head-major, then chunk, then plane
     struct Cursor { int hd, ks, chunk; };
@@ -258,271 +263,362 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             if (++c.chunk > chunk_last) { c.chunk = chunk_first; ++c.hd; }
         }
     };
-    auto issue_q_load = [&](int hd) {               // thread 0 only
-        uint64_t* bar = &bar_q[hd & 1];
-        mbar_expect_tx(bar, (uint32_t)q_tile_bytes);
-#pragma unroll
-        for (int sl = 0; sl < G::kSlabs; ++sl)
-            tma_load_5d(sQ + (hd & 1) * q_tile_bytes + sl * q_slab_bytes, &map_q, bar,
-                        (head0 + hd) * D + sl * G::kSlabCh, w0, h0, s0, b);
-    };
-    auto issue_kv_load = [&](int t, const Cursor& c) {   // thread 0 only
-        const int stage = t & 1;
-        const int cb = (head0 + c.hd) * D;
-        mbar_expect_tx(&bar_kv[stage], 2u * G::kSlabs * (uint32_t)ncols * G::kRowBytes);
-#pragma unroll
-        for (int sl = 0; sl < G::kSlabs; ++sl) {
-            tma_load_5d(sK + stage * kv_tile_bytes + sl * kv_slab_bytes, &map_kv_k, &bar_kv[stage], cb + sl * G::kSlabCh,
-                        w0 - sh.eW, h0 - sh.eH + c.chunk * pl.ch, s0 - sh.eS + c.ks, b);
-            tma_load_5d(sV + stage * kv_tile_bytes + sl * kv_slab_bytes, &map_kv_v, &bar_kv[stage], cb + sl * G::kSlabCh,
-                        w0 - sh.eW, h0 - sh.eH + c.chunk * pl.ch, s0 - sh.eS + c.ks, b);
-        }
-    };
-    const uint32_t idesc_s = make_idesc_bf16(ncols_pad, false, false);
-    const uint32_t idesc_o = make_idesc_bf16(D, false, true);
-    auto issue_s_mma = [&](int t, int hd) {         // S = Q_hd K_t^T   (thread 0 only)
-        const int stage = t & 1;
-#pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-            const int sl = (kk * 16) / G::kSlabCh;
-            const int koff = ((kk * 16) % G::kSlabCh) * 2;
-            const uint64_t da = make_smem_desc(smem_u32(sQ + (hd & 1) * q_tile_bytes + sl * q_slab_bytes + koff), 16,
-                                               G::kAtomBytes, G::kSwizzleCode);
-            const uint64_t db = make_smem_desc(smem_u32(sK + stage * kv_tile_bytes + sl * kv_slab_bytes + koff), 16,
-                                               G::kAtomBytes, G::kSwizzleCode);
-            umma_bf16_ss(tmem_s, da, db, idesc_s, kk > 0);
-        }
-    };
-    auto issue_o_mma = [&](int t, bool accumulate) { // O += P V_t    (thread 0 only)
-        const int stage = t & 1;
-        for (int kk = 0; kk < ncols_pad / 16; ++kk) {
-            const uint64_t da = make_smem_desc(smem_u32(sP + (kk >> 2) * (128 * 128) + (kk & 3) * 32), 16, 1024, 2u);
-            const uint64_t db = make_smem_desc(smem_u32(sV + stage * kv_tile_bytes + kk * 16 * G::kRowBytes),
-                                               (uint32_t)kv_slab_bytes, G::kAtomBytes, G::kSwizzleCode);
-            umma_bf16_ss(tmem_o, da, db, idesc_o, (accumulate || kk > 0) ? 1u : 0u);
-        }
-    };
-    auto store_group = [&](int g, const uint32_t (&pk)[8]) {     // 16 bf16 of this row -> swizzled P tile
-        uint8_t* slab = sP + (g >> 2) * (128 * 128);
-        const int c16 = (g & 3) * 2;
-        *reinterpret_cast<uint4*>(slab + sw128_offset(row, c16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(slab + sw128_offset(row, c16 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-    };
 
-    float m_used = -INFINITY;      // reference max (log2 domain, scaled) this row's P values are relative to
-    float l_part = 0.f;            // this thread's share of the running sum of P
-    // O / l -> bf16 and the LSE of head `hd`; called by all threads once that head's last P V has retired
-    auto finish_head = [&](int hd) {
-        float* x = sX + 2 * 2 * 128;
-        x[half * 128 + row] = l_part;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-        const float l_run = l_part + x[(half ^ 1) * 128 + row];
-        const float inv_l = 1.f / l_run;
-        const int cb = (head0 + hd) * D;
-        __nv_bfloat16* orow = prm.o + tok * (long)sh.inner() + cb + half * (D / 2);
+    if (warp == 8) {
+        // =============================== driver ===============================================
+        if (lane == 0) {
+            auto q_buf = [&](int hd) { return sQ + (pl.rowbuf == 2 ? (hd & 1) : 0) * q_tile_bytes; };
+            auto issue_q_load = [&](int hd) {
+                uint64_t* bar = &bar_q[hd & 1];
+                mbar_expect_tx(bar, (uint32_t)q_tile_bytes);
 #pragma unroll
-        for (int c = 0; c < D / 2; c += 16) {
-            uint32_t r[16];
-            tmem_ld16(tmem_o + lane_sel + half * (D / 2) + c, r);       // warp-collective: every lane takes part
-            tmem_wait_ld();
-            if (q_valid) {
-                uint32_t pk[8];
+                for (int sl = 0; sl < G::kSlabs; ++sl)
+                    tma_load_5d(q_buf(hd) + sl * q_slab_bytes, &map_q, bar, (head0 + hd) * D + sl * G::kSlabCh, w0, h0, s0, b);
+            };
+            auto issue_kv_load = [&](int stage, const Cursor& c) {
+                const int cb = (head0 + c.hd) * D;
+                uint8_t* dst = sKV + stage * 2 * kv_tile_bytes;
+                mbar_expect_tx(&bar_kv[stage], 2u * G::kSlabs * (uint32_t)ncols * G::kRowBytes);
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    pk[i] = pack_bf16(__uint_as_float(r[2 * i]) * inv_l, __uint_as_float(r[2 * i + 1]) * inv_l);
-                *reinterpret_cast<uint4*>(orow + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                *reinterpret_cast<uint4*>(orow + c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            }
-        }
-        if (q_valid && half == 0) prm.lse[tok * sh.heads + head0 + hd] = (m_used + lg2(l_run)) * 0.6931471805599453f;
-        m_used = -INFINITY;
-        l_part = 0.f;
-    };
-
-    Cursor cur{0, ks_first, chunk_first};           // step t
-    Cursor nxt = cur;                               // step t + 1
-    advance(nxt);
-    if (tid == 0) {
-        issue_q_load(0);
-        issue_kv_load(0, cur);
-        if (nsteps > 1) issue_kv_load(1, nxt);
-        mbar_wait(&bar_q[0], 0);
-        mbar_wait(&bar_kv[0], 0);
-        tc_fence_after();
-        issue_s_mma(0, 0);
-        umma_commit(bar_mma);
-    }
-
-    // ---- main loop ------------------------------------------------------------------------------
-    bool p_zero = false;           // this thread's share of the P row is known to be all zero
-    int mask_chunk = -1;
-    int g_lo = 0, g_hi = 0;        // live 16-column groups of this quadrant in the current h-chunk
-    bool chunk_live = false, row_has_cols = false;
-    const int nwords = (ncols_pad + 31) / 32;
-    const int ngroups = ncols_pad >> 4;
-    const uint32_t zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-
-    for (int t = 0; t < nsteps; ++t) {
-        mbar_wait(bar_mma, t & 1);                   // S_t ready; P V_{t-1} done (P buffer, stage (t-1)&1 free)
-        tc_fence_after();
-        const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
-        if (tid == 0) {
-            if (head_start && cur.hd + 1 < pl.hpc) issue_q_load(cur.hd + 1);   // buffer last read by head hd-1
-            if (t >= 1 && t + 1 < nsteps) issue_kv_load(t + 1, nxt);
-        }
-        if (head_start && t > 0) finish_head(cur.hd - 1);
-
-        const int kh0 = cur.chunk * pl.ch;
-        if (cur.chunk != mask_chunk) {               // live-column bitmask of this row for this h-chunk (own copy)
-            mask_chunk = cur.chunk;
-            for (int w = 0; w < nwords; ++w) myMask[w * 128 + row] = 0u;
-            const int ra = max(kh_lo, kh0), rb = min(kh_hi, kh0 + pl.ch - 1);
-            row_has_cols = (wbits != 0u) && (rb >= ra);
-            if (row_has_cols) {
-                for (int kh = ra; kh <= rb; ++kh) {
-                    const int pos = (kh - kh0) * pl.hW;
-                    const int w = pos >> 5, sft = pos & 31;
-                    myMask[w * 128 + row] |= wbits << sft;
-                    if (sft != 0 && (wbits >> (32 - sft)) != 0u) myMask[(w + 1) * 128 + row] |= wbits >> (32 - sft);
+                for (int sl = 0; sl < G::kSlabs; ++sl) {
+                    tma_load_5d(dst + sl * kv_slab_bytes, &map_kv_k, &bar_kv[stage], cb + sl * G::kSlabCh, w0 - sh.eW,
+                                h0 - sh.eH + c.chunk * pl.ch, s0 - sh.eS + c.ks, b);
+                    tma_load_5d(dst + kv_tile_bytes + sl * kv_slab_bytes, &map_kv_v, &bar_kv[stage], cb + sl * G::kSlabCh,
+                                w0 - sh.eW, h0 - sh.eH + c.chunk * pl.ch, s0 - sh.eS + c.ks, b);
                 }
-            }
-            const int ua = max(w_qh_lo, kh0), ub = min(w_qh_hi + 2 * sh.eH, kh0 + pl.ch - 1);
-            chunk_live = ub >= ua;
-            g_lo = ((ua - kh0) * pl.hW) >> 4;
-            g_hi = min(((ub - kh0 + 1) * pl.hW + 15) >> 4, ngroups);
-        }
-
-        // warp-uniform: can any of this quadrant's queries see this block?
-        const bool live = chunk_live && (cur.ks >= w_qs) && (cur.ks <= w_qs + 2 * sh.eS);
-        if (live) {
-            const int g_mid = (g_lo + g_hi + 1) >> 1;
-            const int ga = half ? g_mid : g_lo, gb = half ? g_hi : g_mid;            // live groups of this thread
-            const int za = half ? g_hi : 0, zb = half ? ngroups : g_lo;              // groups this thread zero-fills
-            // Single pass against the stale reference max when every row that has live columns
-            // here already owns one; P may then exceed 1, which is fine up to 2^8.
-            bool two_pass = __any_sync(0xffffffffu, row_has_cols && m_used == -INFINITY);
-            if (!two_pass) {
-                const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
-                float lsum = 0.f, pmax = 0.f;
-                for (int g = ga; g < gb; ++g) {
-                    const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
-                    uint32_t r[16];
-                    tmem_ld16(tmem_s + lane_sel + g * 16, r);
-                    tmem_wait_ld();
-                    float p[16];
+            };
+            const uint32_t idesc_s = make_idesc_bf16(ncols_pad, false, false);
+            const uint32_t idesc_o = make_idesc_bf16(D, false, true);
+            auto issue_s_mma = [&](int t, int stage, int hd) {     // S[t&1] = Q_hd K_t^T
+                const uint32_t tmem_s = tmem_base + 2 * D + (t & 1) * ncols_pad;
+                uint8_t* kblk = sKV + stage * 2 * kv_tile_bytes;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float e = ex2(fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m));
-                        p[i] = (mword & (1u << i)) ? e : 0.f;
-                        lsum += p[i];
+                for (int kk = 0; kk < D / 16; ++kk) {
+                    const int sl = (kk * 16) / G::kSlabCh;
+                    const int koff = ((kk * 16) % G::kSlabCh) * 2;
+                    const uint64_t da = make_smem_desc(smem_u32(q_buf(hd) + sl * q_slab_bytes + koff), 16, G::kAtomBytes, G::kSwizzleCode);
+                    const uint64_t db = make_smem_desc(smem_u32(kblk + sl * kv_slab_bytes + koff), 16, G::kAtomBytes, G::kSwizzleCode);
+                    umma_bf16_ss(tmem_s, da, db, idesc_s, kk > 0);
+                }
+                umma_commit(&bar_s[t & 1]);
+            };
+            auto issue_o_mma = [&](int t, int stage, int hd, bool accumulate) {   // O[hd&1] += P[t&1] V_t
+                const uint32_t tmem_o = tmem_base + (hd & 1) * D;
+                uint8_t* vblk = sKV + stage * 2 * kv_tile_bytes + kv_tile_bytes;
+                uint8_t* pbuf = sP + (t & 1) * p_tile_bytes;
+                for (int kk = 0; kk < ncols_pad / 16; ++kk) {
+                    const uint64_t da = make_smem_desc(smem_u32(pbuf + (kk >> 2) * (128 * 128) + (kk & 3) * 32), 16, 1024, 2u);
+                    const uint64_t db = make_smem_desc(smem_u32(vblk + kk * 16 * G::kRowBytes), (uint32_t)kv_slab_bytes,
+                                                       G::kAtomBytes, G::kSwizzleCode);
+                    umma_bf16_ss(tmem_o, da, db, idesc_o, (accumulate || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(&bar_o[t & 1]);
+            };
+
+            // stage of step t is t % nstage; its n-th use has parity n & 1
+            int stage_of[3] = {0, 0, 0};   // unused; stages are tracked with running counters below
+            (void)stage_of;
+            Cursor ld = {0, ks_first, chunk_first};      // next block to load
+            int ld_t = 0;                                // its step index
+            issue_q_load(0);
+            for (; ld_t < nstage && ld_t < nsteps; ++ld_t) {
+                issue_kv_load(ld_t % nstage, ld);
+                advance(ld);
+            }
+            Cursor cur = {0, ks_first, chunk_first}, nxt = cur;
+            advance(nxt);
+            mbar_wait(&bar_q[0], 0);
+            mbar_wait(&bar_kv[0], 0);
+            tc_fence_after();
+            issue_s_mma(0, 0, 0);
+            int st_cur = 0, use_cur = 0;                 // stage / use count of step t
+            int st_nxt = (nstage > 1) ? 1 : 0, use_nxt = 0;
+            for (int t = 0; t < nsteps; ++t) {
+                const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
+                // (a) Q of the next head: its buffer was last read by the S MMAs of head hd-1 (rowbuf 2)
+                //     or is being read by this head (rowbuf 1: loaded at the head switch instead)
+                if (head_start && pl.rowbuf == 2 && cur.hd + 1 < pl.hpc) issue_q_load(cur.hd + 1);
+                // (b) refill the stage freed by step t-1 once its P V has retired
+                if (t >= 1 && ld_t < nsteps) {
+                    mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);
+                    issue_kv_load(ld_t % nstage, ld);     // == stage of step t-1
+                    advance(ld);
+                    ++ld_t;
+                }
+                // (c) S of step t+1 into the other TMEM buffer, as soon as its K block is in
+                if (t + 1 < nsteps) {
+                    if (nxt.hd != cur.hd && pl.rowbuf == 1) {
+                        // single Q buffer: every S MMA of this head has been issued (S_t was) and retired (bar_s of t)
+                        mbar_wait(&bar_s[t & 1], (t >> 1) & 1);
+                        issue_q_load(nxt.hd);
                     }
-#pragma unroll
-                    for (int i = 0; i < 16; i += 2) pmax = fmaxf(pmax, fmaxf(p[i], p[i + 1]));
-                    uint32_t packed[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) packed[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
-                    store_group(g, packed);
+                    mbar_wait(&bar_kv[st_nxt], use_nxt & 1);
+                    if (nxt.hd != cur.hd) mbar_wait(&bar_q[nxt.hd & 1], (nxt.hd >> 1) & 1);
+                    if (t >= 1) mbar_wait(&bar_p[(t + 1) & 1], ((t - 1) >> 1) & 1);   // S buffer drained by step t-1
+                    tc_fence_after();
+                    issue_s_mma(t + 1, st_nxt, nxt.hd);
                 }
-                float* x = sX + 0 * 2 * 128;
-                x[half * 128 + row] = pmax;
-                asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-                pmax = fmaxf(pmax, x[(half ^ 1) * 128 + row]);
-                two_pass = __any_sync(0xffffffffu, !(pmax <= 256.f));     // also catches inf / NaN
-                if (!two_pass) l_part += lsum;
+                // (d) O += P_t V_t once the compute warps have written P_t
+                mbar_wait(&bar_p[t & 1], (t >> 1) & 1);
+                tc_fence_after();
+                issue_o_mma(t, st_cur, cur.hd, !head_start);
+                cur = nxt;
+                advance(nxt);
+                st_cur = st_nxt; use_cur = use_nxt;
+                if (++st_nxt == nstage) { st_nxt = 0; }
+                use_nxt = (t + 2) / nstage;
             }
-            if (two_pass) {
-                // pass 1: row maximum over this thread's live columns
-                float mx = -INFINITY;
-                for (int g = ga; g < gb; ++g) {
-                    const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
-                    uint32_t r[16];
-                    tmem_ld16(tmem_s + lane_sel + g * 16, r);
-                    tmem_wait_ld();
+            (void)use_cur;
+        }
+    } else {
+        // =============================== compute warps ==========================================
+        const int quad = warp & 3, half = warp >> 2;
+        const int row = quad * 32 + lane;              // query row of the brick == TMEM lane
+        const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
+        uint32_t* myMask = sMask + half * 8 * 128;
+        const int plane_mask = (1 << pl.lgPlane) - 1;
+        const int qs = row >> pl.lgPlane, qh = (row & plane_mask) >> pl.lgTW, qw = row & (pl.tW - 1);
+        const bool q_valid = (s0 + qs < sh.S) && (h0 + qh < sh.H) && (w0 + qw < sh.W);
+        // live key range of this row in halo coordinates (window AND grid), per axis
+        const int kh_lo = max(qh, sh.eH - h0), kh_hi = min(qh + 2 * sh.eH, sh.H - 1 - h0 + sh.eH);
+        const int kw_lo = max(qw, sh.eW - w0), kw_hi = min(qw + 2 * sh.eW, sh.W - 1 - w0 + sh.eW);
+        const uint32_t wbits = (q_valid && kw_hi >= kw_lo) ? ((kw_hi - kw_lo == 31) ? 0xffffffffu : ((1u << (kw_hi - kw_lo + 1)) - 1u)) << kw_lo : 0u;
+        // warp-uniform ranges (identical for the two warps of a quadrant)
+        const int w_qs = (quad * 32) >> pl.lgPlane;
+        const int w_qh_lo = ((quad * 32) & plane_mask) >> pl.lgTW, w_qh_hi = ((quad * 32 + 31) & plane_mask) >> pl.lgTW;
+        const long tok = (((long)b * sh.S + (s0 + qs)) * sh.H + (h0 + qh)) * sh.W + (w0 + qw);
+
+        float m_used = -INFINITY;      // reference max (log2 domain, scaled) this row's P values are relative to
+        float l_part = 0.f;            // this thread's share of the running sum of P
+        // O / l -> bf16 and the LSE of head `hd`; called once that head's last P V has retired
+        auto finish_head = [&](int hd) {
+            const uint32_t tmem_o = tmem_base + (hd & 1) * D;
+            float* x = sX + 2 * 2 * 128;
+            x[half * 128 + row] = l_part;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+            const float l_run = l_part + x[(half ^ 1) * 128 + row];
+            const float inv_l = 1.f / l_run;
+            const int cb = (head0 + hd) * D;
+            __nv_bfloat16* orow = prm.o + tok * (long)sh.inner() + cb + half * (D / 2);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (mword & (1u << i)) mx = fmaxf(mx, __uint_as_float(r[i]));
-                }
-                float* x = sX + 1 * 2 * 128;
-                x[half * 128 + row] = mx;
-                asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-                mx = fmaxf(mx, x[(half ^ 1) * 128 + row]);
-                const float m_blk = mx * pl.scale_log2;          // scale > 0
-                float alpha = 1.f;
-                const bool bump = m_blk > m_used;
-                const bool fix_o = bump && (m_used != -INFINITY);  // the row already holds earlier blocks
-                if (bump) {
-                    alpha = ex2(m_used - m_blk);                 // 0 when this is the row's first live block
-                    m_used = m_blk;
-                }
-                l_part *= alpha;
-                if (__any_sync(0xffffffffu, fix_o)) {            // rescale this thread's half of the O row
+            for (int c = 0; c < D / 2; c += 16) {
+                uint32_t r[16];
+                tmem_ld16(tmem_o + lane_sel + half * (D / 2) + c, r);       // warp-collective: every lane takes part
+                tmem_wait_ld();
+                if (q_valid) {
+                    uint32_t pk[8];
 #pragma unroll
-                    for (int c = 0; c < D / 2; c += 16) {
+                    for (int i = 0; i < 8; ++i)
+                        pk[i] = pack_bf16(__uint_as_float(r[2 * i]) * inv_l, __uint_as_float(r[2 * i + 1]) * inv_l);
+                    *reinterpret_cast<uint4*>(orow + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4*>(orow + c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
+            }
+            if (q_valid && half == 0) prm.lse[tok * sh.heads + head0 + hd] = (m_used + lg2(l_run)) * 0.6931471805599453f;
+        };
+
+        Cursor cur{0, ks_first, chunk_first};
+        bool p_zero[2] = {false, false};   // this thread's share of P buffer i is known to be all zero
+        int mask_chunk = -1;
+        int g_lo = 0, g_hi = 0;            // live 16-column groups of this quadrant in the current h-chunk
+        bool chunk_live = false, row_has_cols = false;
+        const int nwords = (ncols_pad + 31) / 32;
+        const int ngroups = ncols_pad >> 4;
+        const uint32_t zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+        for (int t = 0; t < nsteps; ++t) {
+            const int buf = t & 1;
+            const uint32_t tmem_s = tmem_base + 2 * D + buf * ncols_pad;
+            const uint32_t tmem_o = tmem_base + (cur.hd & 1) * D;
+            uint8_t* pbuf = sP + buf * p_tile_bytes;
+            auto store_group = [&](int g, const uint32_t (&pk)[8]) {     // 16 bf16 of this row -> swizzled P tile
+                uint8_t* slab = pbuf + (g >> 2) * (128 * 128);
+                const int c16 = (g & 3) * 2;
+                *reinterpret_cast<uint4*>(slab + sw128_offset(row, c16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(slab + sw128_offset(row, c16 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            };
+            const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
+            float prev_m = 0.f, prev_l = 0.f;
+            if (head_start && t > 0) {               // the previous head is finished AFTER this step (its O buffer is not reused yet)
+                prev_m = m_used; prev_l = l_part;
+                m_used = -INFINITY; l_part = 0.f;
+            }
+            const int kh0 = cur.chunk * pl.ch;
+            if (cur.chunk != mask_chunk) {               // live-column bitmask of this row for this h-chunk (own copy)
+                mask_chunk = cur.chunk;
+                for (int w = 0; w < nwords; ++w) myMask[w * 128 + row] = 0u;
+                const int ra = max(kh_lo, kh0), rb = min(kh_hi, kh0 + pl.ch - 1);
+                row_has_cols = (wbits != 0u) && (rb >= ra);
+                if (row_has_cols) {
+                    for (int kh = ra; kh <= rb; ++kh) {
+                        const int pos = (kh - kh0) * pl.hW;
+                        const int w = pos >> 5, sft = pos & 31;
+                        myMask[w * 128 + row] |= wbits << sft;
+                        if (sft != 0 && (wbits >> (32 - sft)) != 0u) myMask[(w + 1) * 128 + row] |= wbits >> (32 - sft);
+                    }
+                }
+                const int ua = max(w_qh_lo, kh0), ub = min(w_qh_hi + 2 * sh.eH, kh0 + pl.ch - 1);
+                chunk_live = ub >= ua;
+                g_lo = ((ua - kh0) * pl.hW) >> 4;
+                g_hi = min(((ub - kh0 + 1) * pl.hW + 15) >> 4, ngroups);
+            }
+            // P buffer `buf` is free once the P V of step t-2 has retired
+            if (t >= 2) mbar_wait(&bar_o[buf], ((t - 2) >> 1) & 1);
+
+            // warp-uniform: can any of this quadrant's queries see this block?
+            const bool live = chunk_live && (cur.ks >= w_qs) && (cur.ks <= w_qs + 2 * sh.eS);
+            if (live) {
+                mbar_wait(&bar_s[buf], (t >> 1) & 1);    // S_t computed
+                tc_fence_after();
+                const int g_mid = (g_lo + g_hi + 1) >> 1;
+                const int ga = half ? g_mid : g_lo, gb = half ? g_hi : g_mid;            // live groups of this thread
+                const int za = half ? g_hi : 0, zb = half ? ngroups : g_lo;              // groups this thread zero-fills
+                // Single pass against the stale reference max when every row that has live columns
+                // here already owns one; P may then exceed 1, which is fine up to 2^8.
+                bool two_pass = __any_sync(0xffffffffu, row_has_cols && m_used == -INFINITY);
+                if (!two_pass) {
+                    const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
+                    float ls[4] = {0.f, 0.f, 0.f, 0.f}, pm[4] = {0.f, 0.f, 0.f, 0.f};   // independent chains
+                    int g = ga;
+                    for (; g + 2 <= gb; g += 2) {        // two 16-column groups per TMEM load: 32 independent exps
+                        const uint32_t w0m = myMask[(g >> 1) * 128 + row], w1m = myMask[((g + 1) >> 1) * 128 + row];
+                        const uint32_t mword = ((w0m >> ((g & 1) * 16)) & 0xffffu) | ((w1m >> (((g + 1) & 1) * 16)) << 16);
+                        uint32_t r[32];
+                        tmem_ld32(tmem_s + lane_sel + g * 16, r);
+                        tmem_wait_ld();
+                        float p[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float e = ex2(fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m));
+                            p[i] = (mword & (1u << i)) ? e : 0.f;
+                            ls[i & 3] += p[i];
+                            pm[i & 3] = fmaxf(pm[i & 3], p[i]);
+                        }
+                        uint32_t packed[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) packed[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
+                        store_group(g, packed);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) packed[i] = pack_bf16(p[16 + 2 * i], p[17 + 2 * i]);
+                        store_group(g + 1, packed);
+                    }
+                    if (g < gb) {
+                        const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
                         uint32_t r[16];
-                        tmem_ld16(tmem_o + lane_sel + half * (D / 2) + c, r);
+                        tmem_ld16(tmem_s + lane_sel + g * 16, r);
+                        tmem_wait_ld();
+                        float p[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float e = ex2(fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m));
+                            p[i] = (mword & (1u << i)) ? e : 0.f;
+                            ls[i & 3] += p[i];
+                            pm[i & 3] = fmaxf(pm[i & 3], p[i]);
+                        }
+                        uint32_t packed[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) packed[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
+                        store_group(g, packed);
+                    }
+                    const float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+                    float pmax = fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3]));
+                    float* x = sX + 0 * 2 * 128;
+                    x[half * 128 + row] = pmax;
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+                    pmax = fmaxf(pmax, x[(half ^ 1) * 128 + row]);
+                    two_pass = __any_sync(0xffffffffu, !(pmax <= 256.f));     // also catches inf / NaN
+                    if (!two_pass) l_part += lsum;
+                }
+                if (two_pass) {
+                    // pass 1: row maximum over this thread's live columns
+                    float mx = -INFINITY;
+                    for (int g = ga; g < gb; ++g) {
+                        const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
+                        uint32_t r[16];
+                        tmem_ld16(tmem_s + lane_sel + g * 16, r);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-                        tmem_st16(tmem_o + lane_sel + half * (D / 2) + c, r);
+                        for (int i = 0; i < 16; ++i)
+                            if (mword & (1u << i)) mx = fmaxf(mx, __uint_as_float(r[i]));
                     }
-                    tmem_wait_st();
-                }
-                // pass 2: P = 2^(s*scale*log2e - m) on live columns -> bf16 -> smem (K-major, 128B swizzle)
-                const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
-                float lsum = 0.f;
-                for (int g = ga; g < gb; ++g) {
-                    const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
-                    uint32_t r[16];
-                    tmem_ld16(tmem_s + lane_sel + g * 16, r);
-                    tmem_wait_ld();
-                    float p[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float e = ex2(fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m));
-                        p[i] = (mword & (1u << i)) ? e : 0.f;
-                        lsum += p[i];
+                    float* x = sX + 1 * 2 * 128;
+                    x[half * 128 + row] = mx;
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+                    mx = fmaxf(mx, x[(half ^ 1) * 128 + row]);
+                    const float m_blk = mx * pl.scale_log2;          // scale > 0
+                    float alpha = 1.f;
+                    const bool bump = m_blk > m_used;
+                    const bool fix_o = bump && (m_used != -INFINITY);  // the row already holds earlier blocks
+                    if (bump) {
+                        alpha = ex2(m_used - m_blk);                 // 0 when this is the row's first live block
+                        m_used = m_blk;
                     }
-                    uint32_t packed[8];
+                    l_part *= alpha;
+                    if (__any_sync(0xffffffffu, fix_o)) {            // rescale this thread's half of the O row
+                        mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);     // every earlier P V has retired
+                        tc_fence_after();
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) packed[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
-                    store_group(g, packed);
+                        for (int c = 0; c < D / 2; c += 16) {
+                            uint32_t r[16];
+                            tmem_ld16(tmem_o + lane_sel + half * (D / 2) + c, r);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                            tmem_st16(tmem_o + lane_sel + half * (D / 2) + c, r);
+                        }
+                        tmem_wait_st();
+                    }
+                    // pass 2: P = 2^(s*scale*log2e - m) on live columns -> bf16 -> smem (K-major, 128B swizzle)
+                    const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
+                    float lsum = 0.f;
+                    for (int g = ga; g < gb; ++g) {
+                        const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
+                        uint32_t r[16];
+                        tmem_ld16(tmem_s + lane_sel + g * 16, r);
+                        tmem_wait_ld();
+                        float p[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float e = ex2(fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m));
+                            p[i] = (mword & (1u << i)) ? e : 0.f;
+                            lsum += p[i];
+                        }
+                        uint32_t packed[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) packed[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
+                        store_group(g, packed);
+                    }
+                    l_part += lsum;
                 }
-                l_part += lsum;
+                for (int g = za; g < zb; ++g) store_group(g, zero8);
+                p_zero[buf] = false;
+            } else if (!p_zero[buf]) {
+                const int za = half ? (ngroups >> 1) : 0, zb = half ? ngroups : (ngroups >> 1);
+                for (int g = za; g < zb; ++g) store_group(g, zero8);
+                p_zero[buf] = true;
             }
-            for (int g = za; g < zb; ++g) store_group(g, zero8);
-            p_zero = false;
-        } else if (!p_zero) {
-            const int za = half ? (ngroups >> 1) : 0, zb = half ? ngroups : (ngroups >> 1);
-            for (int g = za; g < zb; ++g) store_group(g, zero8);
-            p_zero = true;
-        }
-        fence_proxy_async();          // P (generic proxy) -> visible to tcgen05.mma (async proxy)
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            issue_o_mma(t, !head_start);
-            if (t + 1 < nsteps) {
-                mbar_wait(&bar_kv[(t + 1) & 1], ((t + 1) >> 1) & 1);
-                if (nxt.hd != cur.hd) mbar_wait(&bar_q[nxt.hd & 1], (nxt.hd >> 1) & 1);
+            fence_proxy_async();          // P (generic proxy) -> visible to tcgen05.mma (async proxy)
+            tc_fence_before();            // our tcgen05.ld of S_t are complete before the driver reuses the buffer
+            mbar_arrive(&bar_p[buf]);
+            if (head_start && t > 0) {               // epilogue of the previous head, off the critical path
+                mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);     // its last P V has retired
                 tc_fence_after();
-                issue_s_mma(t + 1, nxt.hd);
+                const float keep_m = m_used, keep_l = l_part;
+                m_used = prev_m; l_part = prev_l;
+                finish_head(cur.hd - 1);
+                m_used = keep_m; l_part = keep_l;
             }
-            umma_commit(bar_mma);
+            advance(cur);
         }
-        cur = nxt;
-        advance(nxt);
+        mbar_wait(&bar_o[(nsteps - 1) & 1], ((nsteps - 1) >> 1) & 1);
+        tc_fence_after();
+        finish_head(pl.hpc - 1);
     }
-
-    mbar_wait(bar_mma, nsteps & 1);
-    tc_fence_after();
-    finish_head(pl.hpc - 1);
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
-        if (pl.tmem_cols <= 64) tmem_dealloc<64>(tmem_base);
-        else if (pl.tmem_cols <= 128) tmem_dealloc<128>(tmem_base);
+    if (warp == 8) {
+        if (pl.tmem_cols <= 128) tmem_dealloc<128>(tmem_base);
         else if (pl.tmem_cols <= 256) tmem_dealloc<256>(tmem_base);
         else tmem_dealloc<512>(tmem_base);
     }
@@ -541,7 +637,7 @@ static int launch_fwd(const void* q, const void* k, const void* v, void* o, floa
     WM_CUDA_CHECK(cudaFuncSetAttribute(l3d_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
     const dim3 grid((unsigned)(pl.tilesW * pl.tilesH), (unsigned)pl.tilesS, (unsigned)(s.B * (s.heads / pl.hpc)));
     if (grid.y > 65535u || grid.z > 65535u) return fail(WM_EUNSUPPORTED, "grid too large for the tensor-core kernel");
-    l3d_fwd_tc_kernel<D><<<grid, kThreads, pl.smem_bytes, st>>>(mq, mk, mv, prm);
+    l3d_fwd_tc_kernel<D><<<grid, kFwdThreads, pl.smem_bytes, st>>>(mq, mk, mv, prm);
     WM_CUDA_CHECK(cudaGetLastError());
     return WM_OK;
 }

@@ -19,12 +19,15 @@ struct Plan {
     int tilesS, tilesH, tilesW;
     int lgTW, lgPlane;         // log2(tW), log2(tH*tW): brick dims are powers of two
     int hpc;                   // heads walked by one CTA (divides heads)
+    int nstage;                // halo-block stages in shared memory (2 or 3)
+    int rowbuf;                // row-brick buffers (2 when the CTA walks several heads)
     int smem_bytes;
     int tmem_cols;             // power of two
     float scale_log2;
 };
 
-constexpr int kThreads = 256;   // 2 threads per brick row (column halves)
+constexpr int kThreads = 256;        // bwd kernels: 2 threads per brick row (column halves)
+constexpr int kFwdThreads = 288;     // fwd: 8 compute warps + 1 driver warp (TMA + MMA issue)
 constexpr int kSmemLimit = 227 * 1024;
 
 template <int D> struct Geo {
@@ -40,7 +43,7 @@ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 inline int next_pow2(int v) { int p = 32; while (p < v) p <<= 1; return p; }
 
 // shared memory / tensor memory needed by a kernel family for a given block width
-size_t smem_bytes_for(Mode mode, int d, int ncols_pad);
+size_t smem_bytes_for(Mode mode, int d, int ncols_pad, int nstage, int rowbuf);
 int tmem_cols_for(Mode mode, int d, int ncols_pad);
 bool make_plan(const AttnShape& s, Mode mode, Plan& best);
 
