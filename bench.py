@@ -201,6 +201,11 @@ def micro_benchmarks(dev, clips, hbm_gbs, tf_peak):
 
 
 # ---------------------------------------------------------------------------------- main
+def dbg(msg):
+    if os.environ.get('WM_BENCH_DEBUG'):
+        print(f'[bench rank {os.environ.get("RANK", "0")} t={time.perf_counter():.1f}] {msg}', file=sys.stderr, flush=True)
+
+
 def run_b200(args):
     import torch.distributed as dist
     import world_modelz_b200 as wm
@@ -208,6 +213,7 @@ def run_b200(args):
     from world_modelz_b200.denoiser import LossAwareSamplerEma
 
     rank, local_rank, world = parallel.init_from_env('nccl')
+    dbg(f'process group up: world={world}')
     if not torch.cuda.is_available():
         raise RuntimeError('bench.py --impl b200 needs a CUDA device: there is no CPU fallback')
     dev = torch.device('cuda', local_rank)
@@ -220,6 +226,7 @@ def run_b200(args):
     model = wm.VqVideoDiffusionModel(**C3).to(dev)
     trainer = wm.DenoiserTrainer(model, lr=1e-4, weight_decay=1e-7, compute_dtype=torch.bfloat16,
                                  use_cuda_graph=not args.no_graph)
+    dbg('trainer built')
     sampler = LossAwareSamplerEma(seed=42 + rank)
     gen = torch.Generator().manual_seed(1234 + rank)
     n_batches = 4
@@ -272,14 +279,17 @@ def run_b200(args):
 
     for i in range(max(args.warmup, 3)):
         step_resident(i)
+    dbg('warm-up done')
     clocks = ClockSampler(local_rank) if rank == 0 else None
     launches0 = ops.launch_count()
     ms, t0, t1 = timed(step_resident, args.steps)
     launches = args.steps * trainer.launches_per_step() if not args.no_graph else ops.launch_count() - launches0
     clock_info = clocks.stop(t0, t1) if clocks else None
+    dbg(f'timed resident arm: {ms:.1f} ms')
     for i in range(3):
         step_e2e(i)
     ms_e2e, _, _ = timed(step_e2e, args.steps)
+    dbg(f'timed e2e arm: {ms_e2e:.1f} ms')
 
     if rank != 0:
         if world > 1:

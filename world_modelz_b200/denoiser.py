@@ -6,8 +6,8 @@
   device, without the ``[B, HW, K]`` one-hot / uniform temporaries.
 * ``DenoiserTrainer`` -- one optimisation step (forward, CE, backward, gradient
   all-reduce, AdamW) as in ``main.py:266-283``; batch-sharded data parallel, one process
-  per GPU, one NCCL all-reduce of a flat gradient buffer per step; the whole step is
-  captured in a CUDA graph.  The reference has no distributed code.
+  per GPU, one NCCL all-reduce of a flat gradient buffer per step; forward+backward and
+  the optimiser update are two CUDA graphs with the (eager) all-reduce between them.  The reference has no distributed code.
 * ``sample_next_frame`` -- the 30-iteration mask/replace sampler of ``main.py:71-111``;
   clips are independent, so multi-GPU sampling is batch-sharded with no collective.
 """
@@ -157,8 +157,8 @@ class DenoiserTrainer:
         self._static = None
         self.K = model.num_classes
 
-    # -- the step body (capturable) ------------------------------------------------------
-    def _step_body(self, tokens, r):
+    # -- the step, in three pieces: graph A | one NCCL all-reduce | graph B ------------------------
+    def _forward_backward(self, tokens, r):
         self.grad.zero_()
         corrupted, target = corrupt_last_frame(tokens, r, self.K)
         logits = self.model(corrupted)
@@ -166,13 +166,23 @@ class DenoiserTrainer:
         per_sample = ce.view(tokens.shape[0], -1).mean(dim=1)
         loss = ce.mean()
         loss.backward()
+        return loss.detach(), per_sample.detach()
+
+    def _exchange(self):
+        """The path's only collective: SUM all-reduce of the flat gradient buffer (NCCL over NVLink)."""
         if self.world > 1:
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)
-        store = self.shadow
-        ops.adamw_step(self.master, store, self.grad, self.exp_avg, self.exp_avg_sq, self.dyn, self.betas[0],
+
+    def _update(self):
+        ops.adamw_step(self.master, self.shadow, self.grad, self.exp_avg, self.exp_avg_sq, self.dyn, self.betas[0],
                        self.betas[1], self.eps, self.weight_decay, 1.0 / self.world)
         self.dyn[0:1] += 1.0
-        return loss.detach(), per_sample.detach()
+
+    def _step_body(self, tokens, r):
+        out = self._forward_backward(tokens, r)
+        self._exchange()
+        self._update()
+        return out
 
     def set_lr(self, lr: float) -> None:
         self.dyn[1:2].fill_(lr)
@@ -186,7 +196,10 @@ class DenoiserTrainer:
         st_tokens, st_r, st_loss, st_ps = self._static
         st_tokens.copy_(tokens, non_blocking=True)
         st_r.copy_(r, non_blocking=True)
-        self._graph.replay()
+        graph_a, graph_b = self._graph
+        graph_a.replay()
+        self._exchange()          # eager, between the two graphs: the collective is never captured
+        graph_b.replay()
         return st_loss, st_ps
 
     def _capture(self, tokens, r):
@@ -196,18 +209,23 @@ class DenoiserTrainer:
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(3):                 # warm-up on a side stream (allocator, cuBLAS handles, NCCL)
-                self._step_body(st_tokens, st_r)
+            for _ in range(3):                 # warm-up on a side stream (allocator, cuBLAS handles, autograd)
+                self._forward_backward(st_tokens, st_r)
+                self._update()
         torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            st_loss, st_ps = self._step_body(st_tokens, st_r)
-        # undo the warm-up / capture updates so that step 1 is step 1
+        torch.cuda.synchronize()
+        graph_a = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph_a):
+            st_loss, st_ps = self._forward_backward(st_tokens, st_r)
+        graph_b = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph_b, pool=graph_a.pool()):
+            self._update()
+        # undo the warm-up updates so that step 1 is step 1 (capture itself executes nothing)
         self.master.copy_(saved[0]); self.exp_avg.copy_(saved[1]); self.exp_avg_sq.copy_(saved[2])
         self.dyn.copy_(saved[3])
         if self.shadow is not None:
             self.shadow.copy_(saved[4])
-        self._graph, self._static = graph, (st_tokens, st_r, st_loss, st_ps)
+        self._graph, self._static = (graph_a, graph_b), (st_tokens, st_r, st_loss, st_ps)
 
     def launches_per_step(self) -> int:
         """Kernels of libwm_b200 per step: depth x (attention fwd 1 + bwd 2) + AdamW."""
