@@ -54,3 +54,19 @@ for shape, heads, ext in CASES:
         ref = O.attention_core(q.float(), k.float(), v.float(), heads, ext)
         stats('out/cpu', o_tc.cpu(), ref)
 print('TOTAL_BAD', total_bad)
+
+# extreme logits: exercises the re-centring (two-pass) path of the tensor-core softmax
+for sc, tag in ((12.0, 'large'), (40.0, 'huge')):
+    shape, heads, ext = (1, 4, 16, 16, 64), 2, (1, 2, 2)
+    g = torch.Generator().manual_seed(5)
+    q, k, v = (torch.randn(shape, generator=g).bfloat16() for _ in range(3))
+    q = (q.float() * sc).bfloat16()
+    k[:, 2:] = (k[:, 2:].float() * 0.05).bfloat16()     # later planes score far lower than the first ones
+    qd, kd, vd = (t.to(dev) for t in (q, k, v))
+    o_si, l_si = ops.attn_forward(qd, kd, vd, heads, ext, 32 ** -0.5, ops.FLAG_SIMT)
+    o_tc, l_tc = ops.attn_forward(qd, kd, vd, heads, ext, 32 ** -0.5, 0)
+    torch.cuda.synchronize()
+    print(f'extreme logits ({tag}): |lse| up to {l_si.abs().max().item():.1f}')
+    total_bad += stats('out', o_tc, o_si)
+    total_bad += stats('lse', l_tc, l_si)
+print('TOTAL_BAD_WITH_EXTREME', total_bad)

@@ -67,7 +67,7 @@ int make_tensor_map_5d(CUtensorMap* out, const void* base, int B, int S, int H, 
 // ------------------------------------------------------------------------------- plan
 static int row_bytes_of(int d) { return d == 32 ? 64 : 128; }
 static int slabs_of(int d) { return d == 128 ? 2 : 1; }
-static const size_t kFixedSmem = 1024 /*alignment slack*/ + 2 * 8 * 128 * 4 /*masks*/ + 3 * 2 * 128 * 4 /*exchange*/ + 256 /*barriers*/;
+static const size_t kFixedSmem = 1024 /*alignment slack*/ + 2 * 9 * 128 * 4 /*masks*/ + 3 * 2 * 4 * 128 * 4 /*exchange*/ + 256 /*barriers*/;
 
 size_t smem_bytes_for(Mode mode, int d, int ncols_pad, int nstage, int rowbuf) {
     const size_t row_tile = (size_t)slabs_of(d) * 128 * row_bytes_of(d);
@@ -166,8 +166,8 @@ struct FwdParams {
 // computed while the compute warps are still in the softmax of step t, and O += P_t V_t
 // runs while they are already in step t+1.  All hand-offs are mbarriers; there is no
 // CTA-wide barrier inside the loop.  A CTA walks `hpc` heads of its brick back to back.
-template <int D>
-__global__ void __launch_bounds__(kFwdThreads, 1)
+template <int D, int NPART>
+__global__ void __launch_bounds__(32 * (4 * NPART + 1), 1)
 l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv_k,
                   const __grid_constant__ CUtensorMap map_kv_v, const FwdParams prm) {
     using G = Geo<D>;
@@ -189,9 +189,11 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     uint8_t* sQ = smem;                                          // [rowbuf][slabs][128 rows]
     uint8_t* sKV = sQ + pl.rowbuf * q_tile_bytes;                // [nstage][K|V][slabs][ncols_pad rows]
     uint8_t* sP = sKV + nstage * 2 * kv_tile_bytes;              // [2][ceil(ncols_pad/64)][128 rows][128 B]
-    uint32_t* sMask = reinterpret_cast<uint32_t*>(sP + 2 * p_tile_bytes);      // [2 halves][8 words][128 rows]
-    float* sX = reinterpret_cast<float*>(sMask + 2 * 8 * 128);                 // [3 uses][2 halves][128 rows]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 3 * 2 * 128);
+    constexpr int kDriverWarp = 4 * NPART;
+    constexpr int kThreadsAll = 32 * (4 * NPART + 1);
+    uint32_t* sMask = reinterpret_cast<uint32_t*>(sP + 2 * p_tile_bytes);      // [9 words][128 rows] (+ spare copy)
+    float* sX = reinterpret_cast<float*>(sMask + 2 * 9 * 128);                 // [3 uses][2 parities][NPART][128 rows]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 3 * 2 * 4 * 128);
     uint64_t* bar_q = bars;           // [2]  Q tile of a head landed
     uint64_t* bar_kv = bars + 2;      // [3]  K/V block landed
     uint64_t* bar_s = bars + 5;       // [2]  S buffer computed            (tcgen05.commit)
@@ -229,12 +231,12 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int i = 0; i < 3; ++i) mbar_init(&bar_kv[i], 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bar_s[i], 1);
-            mbar_init(&bar_p[i], 256);
+            mbar_init(&bar_p[i], 128 * NPART);
             mbar_init(&bar_o[i], 1);
         }
         fence_barrier_init();
     }
-    if (warp == 8) {
+    if (warp == kDriverWarp) {
         // power-of-two TMEM allocation
         if (pl.tmem_cols <= 128) tmem_alloc<128>(tmem_slot);
         else if (pl.tmem_cols <= 256) tmem_alloc<256>(tmem_slot);
@@ -245,7 +247,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const int pad_bytes = (ncols_pad - ncols) * G::kRowBytes;
         for (int t = 0; t < nstage * 2 * G::kSlabs; ++t) {
             uint8_t* base = sKV + t * kv_slab_bytes + ncols * G::kRowBytes;
-            for (int i = tid * 16; i < pad_bytes; i += kFwdThreads * 16) *reinterpret_cast<uint4*>(base + i) = make_uint4(0, 0, 0, 0);
+            for (int i = tid * 16; i < pad_bytes; i += kThreadsAll * 16) *reinterpret_cast<uint4*>(base + i) = make_uint4(0, 0, 0, 0);
         }
         fence_proxy_async();
     }
@@ -264,7 +266,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         }
     };
 
-    if (warp == 8) {
+    if (warp == kDriverWarp) {
         // =============================== driver ===============================================
         if (lane == 0) {
             auto q_buf = [&](int hd) { return sQ + (pl.rowbuf == 2 ? (hd & 1) : 0) * q_tile_bytes; };
@@ -338,13 +340,15 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 // (a) Q of the next head: its buffer was last read by the S MMAs of head hd-1 (rowbuf 2)
                 //     or is being read by this head (rowbuf 1: loaded at the head switch instead)
                 if (head_start && pl.rowbuf == 2 && cur.hd + 1 < pl.hpc) issue_q_load(cur.hd + 1);
-                // (b) refill the stage freed by step t-1 once its P V has retired
-                if (t >= 1 && ld_t < nsteps) {
-                    mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);
-                    issue_kv_load(ld_t % nstage, ld);     // == stage of step t-1
-                    advance(ld);
-                    ++ld_t;
-                }
+                auto refill = [&]() {        // (b) refill the stage freed by step t-1 once its P V has retired
+                    if (t >= 1 && ld_t < nsteps) {
+                        mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);
+                        issue_kv_load(ld_t % nstage, ld);     // == stage of step t-1
+                        advance(ld);
+                        ++ld_t;
+                    }
+                };
+                if (nstage < 3) refill();    // two stages: the block of step t+1 is the one being refilled
                 // (c) S of step t+1 into the other TMEM buffer, as soon as its K block is in
                 if (t + 1 < nsteps) {
                     if (nxt.hd != cur.hd && pl.rowbuf == 1) {
@@ -358,6 +362,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     tc_fence_after();
                     issue_s_mma(t + 1, st_nxt, nxt.hd);
                 }
+                if (nstage >= 3) refill();
                 // (d) O += P_t V_t once the compute warps have written P_t
                 mbar_wait(&bar_p[t & 1], (t >> 1) & 1);
                 tc_fence_after();
@@ -372,10 +377,14 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         }
     } else {
         // =============================== compute warps ==========================================
-        const int quad = warp & 3, half = warp >> 2;
+        // NPART threads per query row: warps w, w+4, ... share TMEM lane quadrant w&3 and split the
+        // row's live key columns (in groups of 8) between them.
+        constexpr int LOGP = (NPART == 4) ? 2 : 1;
+        constexpr int CP = D / NPART;                  // O columns per thread in rescale / epilogue
+        const int quad = warp & 3, part = warp >> 2;
         const int row = quad * 32 + lane;              // query row of the brick == TMEM lane
         const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
-        uint32_t* myMask = sMask + half * 8 * 128;
+        auto quad_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * NPART) : "memory"); };
         const int plane_mask = (1 << pl.lgPlane) - 1;
         const int qs = row >> pl.lgPlane, qh = (row & plane_mask) >> pl.lgTW, qw = row & (pl.tW - 1);
         const bool q_valid = (s0 + qs < sh.S) && (h0 + qh < sh.H) && (w0 + qw < sh.W);
@@ -383,84 +392,100 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const int kh_lo = max(qh, sh.eH - h0), kh_hi = min(qh + 2 * sh.eH, sh.H - 1 - h0 + sh.eH);
         const int kw_lo = max(qw, sh.eW - w0), kw_hi = min(qw + 2 * sh.eW, sh.W - 1 - w0 + sh.eW);
         const uint32_t wbits = (q_valid && kw_hi >= kw_lo) ? ((kw_hi - kw_lo == 31) ? 0xffffffffu : ((1u << (kw_hi - kw_lo + 1)) - 1u)) << kw_lo : 0u;
-        // warp-uniform ranges (identical for the two warps of a quadrant)
+        // warp-uniform ranges (identical for all warps of a quadrant)
         const int w_qs = (quad * 32) >> pl.lgPlane;
         const int w_qh_lo = ((quad * 32) & plane_mask) >> pl.lgTW, w_qh_hi = ((quad * 32 + 31) & plane_mask) >> pl.lgTW;
         const long tok = (((long)b * sh.S + (s0 + qs)) * sh.H + (h0 + qh)) * sh.W + (w0 + qw);
 
-        float m_used = -INFINITY;      // reference max (log2 domain, scaled) this row's P values are relative to
+        // Reference exponent (log2 domain, scaled) this row's P values are relative to.  It starts at 0 and is
+        // only moved when a block's row maximum leaves [2^-64, 2^64] relative to it: bf16 P and the fp32 sums
+        // keep full precision over that range, so no per-block max pass and (in practice) no O rescale is needed.
+        float m_used = 0.f;
         float l_part = 0.f;            // this thread's share of the running sum of P
+        bool head_has_blocks = false;  // warp-uniform: this quadrant already accumulated a block of the current head
+        bool row_seen = false;         // this row had live columns in an earlier block of the current head
+        // exchange slot: [use][parity][part][row]; parity alternates so that a slot is rewritten only
+        // after a later quad_sync has proven every reader of its previous contents done
+        auto xslot = [&](int use, int parity) { return sX + ((use * 2 + (parity & 1)) * 4) * 128; };
         // O / l -> bf16 and the LSE of head `hd`; called once that head's last P V has retired
         auto finish_head = [&](int hd) {
             const uint32_t tmem_o = tmem_base + (hd & 1) * D;
-            float* x = sX + 2 * 2 * 128;
-            x[half * 128 + row] = l_part;
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-            const float l_run = l_part + x[(half ^ 1) * 128 + row];
+            float* x = xslot(2, hd);
+            x[part * 128 + row] = l_part;
+            quad_sync();
+            float l_run = 0.f;
+#pragma unroll
+            for (int pp = 0; pp < NPART; ++pp) l_run += x[pp * 128 + row];
             const float inv_l = 1.f / l_run;
             const int cb = (head0 + hd) * D;
-            __nv_bfloat16* orow = prm.o + tok * (long)sh.inner() + cb + half * (D / 2);
+            __nv_bfloat16* orow = prm.o + tok * (long)sh.inner() + cb + part * CP;
 #pragma unroll
-            for (int c = 0; c < D / 2; c += 16) {
-                uint32_t r[16];
-                tmem_ld16(tmem_o + lane_sel + half * (D / 2) + c, r);       // warp-collective: every lane takes part
+            for (int c = 0; c < CP; c += 8) {
+                uint32_t r[8];
+                tmem_ld8(tmem_o + lane_sel + part * CP + c, r);       // warp-collective: every lane takes part
                 tmem_wait_ld();
                 if (q_valid) {
-                    uint32_t pk[8];
+                    uint32_t pk[4];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
+                    for (int i = 0; i < 4; ++i)
                         pk[i] = pack_bf16(__uint_as_float(r[2 * i]) * inv_l, __uint_as_float(r[2 * i + 1]) * inv_l);
                     *reinterpret_cast<uint4*>(orow + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    *reinterpret_cast<uint4*>(orow + c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                 }
             }
-            if (q_valid && half == 0) prm.lse[tok * sh.heads + head0 + hd] = (m_used + lg2(l_run)) * 0.6931471805599453f;
+            if (q_valid && part == 0) prm.lse[tok * sh.heads + head0 + hd] = (m_used + lg2(l_run)) * 0.6931471805599453f;
         };
 
         Cursor cur{0, ks_first, chunk_first};
         bool p_zero[2] = {false, false};   // this thread's share of P buffer i is known to be all zero
         int mask_chunk = -1;
-        int g_lo = 0, g_hi = 0;            // live 16-column groups of this quadrant in the current h-chunk
+        int g_lo = 0, g_hi = 0;            // live 8-column groups of this quadrant in the current h-chunk
         bool chunk_live = false, row_has_cols = false;
         const int nwords = (ncols_pad + 31) / 32;
-        const int ngroups = ncols_pad >> 4;
-        const uint32_t zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int ngroups = ncols_pad >> 3;
+        const uint4 zero4 = make_uint4(0, 0, 0, 0);
 
         for (int t = 0; t < nsteps; ++t) {
             const int buf = t & 1;
             const uint32_t tmem_s = tmem_base + 2 * D + buf * ncols_pad;
             const uint32_t tmem_o = tmem_base + (cur.hd & 1) * D;
             uint8_t* pbuf = sP + buf * p_tile_bytes;
-            auto store_group = [&](int g, const uint32_t (&pk)[8]) {     // 16 bf16 of this row -> swizzled P tile
-                uint8_t* slab = pbuf + (g >> 2) * (128 * 128);
-                const int c16 = (g & 3) * 2;
-                *reinterpret_cast<uint4*>(slab + sw128_offset(row, c16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                *reinterpret_cast<uint4*>(slab + sw128_offset(row, c16 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            auto p_addr = [&](int g) {     // 8 bf16 (one 16-byte chunk) of this row in the swizzled P tile
+                return reinterpret_cast<uint4*>(pbuf + (g >> 3) * (128 * 128) + sw128_offset(row, g & 7));
+            };
+            auto mask_bits = [&](int g) -> uint32_t {     // live bits of columns [8g, 8g+16)
+                const uint32_t w0m = sMask[(g >> 2) * 128 + row], w1m = sMask[((g >> 2) + 1) * 128 + row];
+                return (uint32_t)(((((uint64_t)w1m) << 32) | w0m) >> ((g & 3) * 8));
             };
             const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
             float prev_m = 0.f, prev_l = 0.f;
             if (head_start && t > 0) {               // the previous head is finished AFTER this step (its O buffer is not reused yet)
                 prev_m = m_used; prev_l = l_part;
-                m_used = -INFINITY; l_part = 0.f;
+                m_used = 0.f; l_part = 0.f;
+                head_has_blocks = false;
+                row_seen = false;
             }
             const int kh0 = cur.chunk * pl.ch;
-            if (cur.chunk != mask_chunk) {               // live-column bitmask of this row for this h-chunk (own copy)
+            if (cur.chunk != mask_chunk) {               // live-column bitmask of this row for this h-chunk
                 mask_chunk = cur.chunk;
-                for (int w = 0; w < nwords; ++w) myMask[w * 128 + row] = 0u;
                 const int ra = max(kh_lo, kh0), rb = min(kh_hi, kh0 + pl.ch - 1);
                 row_has_cols = (wbits != 0u) && (rb >= ra);
-                if (row_has_cols) {
-                    for (int kh = ra; kh <= rb; ++kh) {
-                        const int pos = (kh - kh0) * pl.hW;
-                        const int w = pos >> 5, sft = pos & 31;
-                        myMask[w * 128 + row] |= wbits << sft;
-                        if (sft != 0 && (wbits >> (32 - sft)) != 0u) myMask[(w + 1) * 128 + row] |= wbits >> (32 - sft);
+                quad_sync();                             // every reader of the old mask is done
+                if (part == 0) {
+                    for (int w = 0; w <= nwords; ++w) sMask[w * 128 + row] = 0u;
+                    if (row_has_cols) {
+                        for (int kh = ra; kh <= rb; ++kh) {
+                            const int pos = (kh - kh0) * pl.hW;
+                            const int w = pos >> 5, sft = pos & 31;
+                            sMask[w * 128 + row] |= wbits << sft;
+                            if (sft != 0 && (wbits >> (32 - sft)) != 0u) sMask[(w + 1) * 128 + row] |= wbits >> (32 - sft);
+                        }
                     }
                 }
+                quad_sync();
                 const int ua = max(w_qh_lo, kh0), ub = min(w_qh_hi + 2 * sh.eH, kh0 + pl.ch - 1);
                 chunk_live = ub >= ua;
-                g_lo = ((ua - kh0) * pl.hW) >> 4;
-                g_hi = min(((ub - kh0 + 1) * pl.hW + 15) >> 4, ngroups);
+                g_lo = ((ua - kh0) * pl.hW) >> 3;
+                g_hi = min(((ub - kh0 + 1) * pl.hW + 7) >> 3, ngroups);
             }
             // P buffer `buf` is free once the P V of step t-2 has retired
             if (t >= 2) mbar_wait(&bar_o[buf], ((t - 2) >> 1) & 1);
@@ -470,42 +495,19 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             if (live) {
                 mbar_wait(&bar_s[buf], (t >> 1) & 1);    // S_t computed
                 tc_fence_after();
-                const int g_mid = (g_lo + g_hi + 1) >> 1;
-                const int ga = half ? g_mid : g_lo, gb = half ? g_hi : g_mid;            // live groups of this thread
-                const int za = half ? g_hi : 0, zb = half ? ngroups : g_lo;              // groups this thread zero-fills
+                const int n8 = g_hi - g_lo;
+                const int ga = g_lo + ((n8 * part) >> LOGP), gb = g_lo + ((n8 * (part + 1)) >> LOGP);
                 // Single pass against the stale reference max when every row that has live columns
                 // here already owns one; P may then exceed 1, which is fine up to 2^8.
-                bool two_pass = __any_sync(0xffffffffu, row_has_cols && m_used == -INFINITY);
-                if (!two_pass) {
-                    const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
+                bool two_pass = false;
+                {
+                    const float neg_m = -m_used;
                     float ls[4] = {0.f, 0.f, 0.f, 0.f}, pm[4] = {0.f, 0.f, 0.f, 0.f};   // independent chains
                     int g = ga;
-                    for (; g + 2 <= gb; g += 2) {        // two 16-column groups per TMEM load: 32 independent exps
-                        const uint32_t w0m = myMask[(g >> 1) * 128 + row], w1m = myMask[((g + 1) >> 1) * 128 + row];
-                        const uint32_t mword = ((w0m >> ((g & 1) * 16)) & 0xffffu) | ((w1m >> (((g + 1) & 1) * 16)) << 16);
-                        uint32_t r[32];
-                        tmem_ld32(tmem_s + lane_sel + g * 16, r);
-                        tmem_wait_ld();
-                        float p[32];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float e = ex2(fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m));
-                            p[i] = (mword & (1u << i)) ? e : 0.f;
-                            ls[i & 3] += p[i];
-                            pm[i & 3] = fmaxf(pm[i & 3], p[i]);
-                        }
-                        uint32_t packed[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) packed[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
-                        store_group(g, packed);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) packed[i] = pack_bf16(p[16 + 2 * i], p[17 + 2 * i]);
-                        store_group(g + 1, packed);
-                    }
-                    if (g < gb) {
-                        const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
+                    for (; g + 2 <= gb; g += 2) {        // two 8-column groups per TMEM load
+                        const uint32_t mword = mask_bits(g);
                         uint32_t r[16];
-                        tmem_ld16(tmem_s + lane_sel + g * 16, r);
+                        tmem_ld16(tmem_s + lane_sel + g * 8, r);
                         tmem_wait_ld();
                         float p[16];
 #pragma unroll
@@ -515,86 +517,104 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                             ls[i & 3] += p[i];
                             pm[i & 3] = fmaxf(pm[i & 3], p[i]);
                         }
-                        uint32_t packed[8];
+                        *p_addr(g) = make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+                        *p_addr(g + 1) = make_uint4(pack_bf16(p[8], p[9]), pack_bf16(p[10], p[11]), pack_bf16(p[12], p[13]), pack_bf16(p[14], p[15]));
+                    }
+                    if (g < gb) {
+                        const uint32_t mword = mask_bits(g);
+                        uint32_t r[8];
+                        tmem_ld8(tmem_s + lane_sel + g * 8, r);
+                        tmem_wait_ld();
+                        float p[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) packed[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
-                        store_group(g, packed);
+                        for (int i = 0; i < 8; ++i) {
+                            const float e = ex2(fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m));
+                            p[i] = (mword & (1u << i)) ? e : 0.f;
+                            ls[i & 3] += p[i];
+                            pm[i & 3] = fmaxf(pm[i & 3], p[i]);
+                        }
+                        *p_addr(g) = make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
                     }
                     const float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
                     float pmax = fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3]));
-                    float* x = sX + 0 * 2 * 128;
-                    x[half * 128 + row] = pmax;
-                    asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-                    pmax = fmaxf(pmax, x[(half ^ 1) * 128 + row]);
-                    two_pass = __any_sync(0xffffffffu, !(pmax <= 256.f));     // also catches inf / NaN
+                    float* x = xslot(0, t);
+                    x[part * 128 + row] = pmax;
+                    quad_sync();
+#pragma unroll
+                    for (int pp = 0; pp < NPART; ++pp) pmax = fmaxf(pmax, x[pp * 128 + row]);
+                    // rows with live columns must land in [2^-64, 2^64]; !(a && b) also catches inf / NaN
+                    const bool out_of_range = row_has_cols && !(pmax <= 1.8446744e19f && pmax >= 5.4210109e-20f);
+                    two_pass = __any_sync(0xffffffffu, out_of_range);
                     if (!two_pass) l_part += lsum;
                 }
                 if (two_pass) {
                     // pass 1: row maximum over this thread's live columns
                     float mx = -INFINITY;
                     for (int g = ga; g < gb; ++g) {
-                        const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
-                        uint32_t r[16];
-                        tmem_ld16(tmem_s + lane_sel + g * 16, r);
+                        const uint32_t mword = mask_bits(g);
+                        uint32_t r[8];
+                        tmem_ld8(tmem_s + lane_sel + g * 8, r);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
+                        for (int i = 0; i < 8; ++i)
                             if (mword & (1u << i)) mx = fmaxf(mx, __uint_as_float(r[i]));
                     }
-                    float* x = sX + 1 * 2 * 128;
-                    x[half * 128 + row] = mx;
-                    asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-                    mx = fmaxf(mx, x[(half ^ 1) * 128 + row]);
-                    const float m_blk = mx * pl.scale_log2;          // scale > 0
+                    float* x = xslot(1, t);
+                    x[part * 128 + row] = mx;
+                    quad_sync();
+#pragma unroll
+                    for (int pp = 0; pp < NPART; ++pp) mx = fmaxf(mx, x[pp * 128 + row]);
+                    const float m_blk = mx * pl.scale_log2;          // scale > 0; -inf for rows without live columns
                     float alpha = 1.f;
-                    const bool bump = m_blk > m_used;
-                    const bool fix_o = bump && (m_used != -INFINITY);  // the row already holds earlier blocks
-                    if (bump) {
-                        alpha = ex2(m_used - m_blk);                 // 0 when this is the row's first live block
+                    // re-centre the reference on this block's maximum: upwards always (alpha < 2^-32), downwards
+                    // only while the row has nothing accumulated yet (alpha would overflow otherwise)
+                    const bool move = (m_blk != -INFINITY) && (m_blk > m_used + 32.f || (!row_seen && m_blk < m_used - 32.f));
+                    if (move) {
+                        alpha = row_seen ? ex2(m_used - m_blk) : 0.f;
                         m_used = m_blk;
                     }
                     l_part *= alpha;
-                    if (__any_sync(0xffffffffu, fix_o)) {            // rescale this thread's half of the O row
+                    if (head_has_blocks && __any_sync(0xffffffffu, move)) {   // rescale this thread's share of the O row
                         mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);     // every earlier P V has retired
                         tc_fence_after();
 #pragma unroll
-                        for (int c = 0; c < D / 2; c += 16) {
-                            uint32_t r[16];
-                            tmem_ld16(tmem_o + lane_sel + half * (D / 2) + c, r);
+                        for (int c = 0; c < CP; c += 8) {
+                            uint32_t r[8];
+                            tmem_ld8(tmem_o + lane_sel + part * CP + c, r);
                             tmem_wait_ld();
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-                            tmem_st16(tmem_o + lane_sel + half * (D / 2) + c, r);
+                            for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                            tmem_st8(tmem_o + lane_sel + part * CP + c, r);
                         }
                         tmem_wait_st();
                     }
                     // pass 2: P = 2^(s*scale*log2e - m) on live columns -> bf16 -> smem (K-major, 128B swizzle)
-                    const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
+                    const float neg_m = -m_used;
                     float lsum = 0.f;
                     for (int g = ga; g < gb; ++g) {
-                        const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
-                        uint32_t r[16];
-                        tmem_ld16(tmem_s + lane_sel + g * 16, r);
+                        const uint32_t mword = mask_bits(g);
+                        uint32_t r[8];
+                        tmem_ld8(tmem_s + lane_sel + g * 8, r);
                         tmem_wait_ld();
-                        float p[16];
+                        float p[8];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
+                        for (int i = 0; i < 8; ++i) {
                             const float e = ex2(fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m));
                             p[i] = (mword & (1u << i)) ? e : 0.f;
                             lsum += p[i];
                         }
-                        uint32_t packed[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) packed[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
-                        store_group(g, packed);
+                        *p_addr(g) = make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
                     }
                     l_part += lsum;
                 }
-                for (int g = za; g < zb; ++g) store_group(g, zero8);
+                // columns outside the quadrant's live range: zero, shared round-robin between the parts
+                for (int g = part; g < g_lo; g += NPART) *p_addr(g) = zero4;
+                for (int g = g_hi + part; g < ngroups; g += NPART) *p_addr(g) = zero4;
                 p_zero[buf] = false;
+                head_has_blocks = true;
+                row_seen = row_seen || row_has_cols;
             } else if (!p_zero[buf]) {
-                const int za = half ? (ngroups >> 1) : 0, zb = half ? ngroups : (ngroups >> 1);
-                for (int g = za; g < zb; ++g) store_group(g, zero8);
+                for (int g = part; g < ngroups; g += NPART) *p_addr(g) = zero4;
                 p_zero[buf] = true;
             }
             fence_proxy_async();          // P (generic proxy) -> visible to tcgen05.mma (async proxy)
@@ -617,7 +637,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == kDriverWarp) {
         if (pl.tmem_cols <= 128) tmem_dealloc<128>(tmem_base);
         else if (pl.tmem_cols <= 256) tmem_dealloc<256>(tmem_base);
         else tmem_dealloc<512>(tmem_base);
@@ -634,10 +654,11 @@ static int launch_fwd(const void* q, const void* k, const void* v, void* o, floa
     if (int rc = make_tensor_map_5d(&mk, k, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
     if (int rc = make_tensor_map_5d(&mv, v, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
     FwdParams prm{s, pl, static_cast<__nv_bfloat16*>(o), lse};
-    WM_CUDA_CHECK(cudaFuncSetAttribute(l3d_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
+    constexpr int NPART = 2;
+    WM_CUDA_CHECK(cudaFuncSetAttribute(l3d_fwd_tc_kernel<D, NPART>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
     const dim3 grid((unsigned)(pl.tilesW * pl.tilesH), (unsigned)pl.tilesS, (unsigned)(s.B * (s.heads / pl.hpc)));
     if (grid.y > 65535u || grid.z > 65535u) return fail(WM_EUNSUPPORTED, "grid too large for the tensor-core kernel");
-    l3d_fwd_tc_kernel<D><<<grid, kFwdThreads, pl.smem_bytes, st>>>(mq, mk, mv, prm);
+    l3d_fwd_tc_kernel<D, NPART><<<grid, 32 * (4 * NPART + 1), pl.smem_bytes, st>>>(mq, mk, mv, prm);
     WM_CUDA_CHECK(cudaGetLastError());
     return WM_OK;
 }
