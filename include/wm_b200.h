@@ -108,6 +108,25 @@ WM_API int wm_adamw_step(float* master, void* shadow, const void* grad, float* e
                          long n, const float* dyn, float beta1, float beta2, float eps, float weight_decay,
                          float grad_scale, int grad_dtype, void* stream);
 
+/* ---- layer-level kernels around the attention core -------------------------------------
+ * Replace the ATen chains of PreNorm + the residual adds of the transformer block
+ * (local_3d_attention.py:11-17,159-161) and the bias gradients of its nn.Linear layers.
+ * Rows are tokens, `dim` channels contiguous (multiple of 8, <= 2048); dtype bf16 or fp32.
+ *
+ * wm_add_layernorm_fwd: sum = res (+ delta, when delta != NULL; written to sum_out when that
+ *   is != NULL); y = LayerNorm(sum) * gamma + beta; mean / rstd [rows] fp32 kept for backward.
+ * wm_add_layernorm_bwd: dx = (dres, when != NULL, +) dLayerNorm(dy; x, mean, rstd, gamma);
+ *   dgamma / dbeta [dim].  workspace: wm_reduce_blocks(rows) * 2 * dim floats.
+ * wm_colsum: out[c] = sum_r a[r, c] (bias gradient).  workspace: wm_reduce_blocks(rows) * cols floats. */
+WM_API int wm_reduce_blocks(long rows);
+WM_API int wm_add_layernorm_fwd(const void* res, const void* delta, const void* gamma, const void* beta,
+                                void* sum_out, void* y, float* mean, float* rstd, long rows, int dim, float eps,
+                                int dtype, void* stream);
+WM_API int wm_add_layernorm_bwd(const void* dy, const void* dres, const void* x, const float* mean,
+                                const float* rstd, const void* gamma, void* dx, void* dgamma, void* dbeta,
+                                float* workspace, long rows, int dim, int dtype, void* stream);
+WM_API int wm_colsum(const void* a, void* out, float* workspace, long rows, int cols, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,60 @@
+"""Layer-level kernels (fused residual-add + LayerNorm, bias-gradient column sums) against
+stock PyTorch fp32 references of the same ops."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from world_modelz_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+@pytest.mark.parametrize('dtype,rtol,atol', [(torch.float32, 1e-5, 1e-5), (torch.bfloat16, 2e-2, 2e-2)])
+@pytest.mark.parametrize('rows,dim,with_delta', [(1000, 32, True), (4096, 256, True), (777, 384, False),
+                                                 (130, 1024, True), (5, 8, True)])
+def test_add_layernorm_forward_backward(dtype, rtol, atol, rows, dim, with_delta):
+    g = torch.Generator().manual_seed(rows + dim)
+    res = torch.randn(3, rows // 3 + 1, dim, generator=g)
+    delta = torch.randn_like(res) if with_delta else None
+    gamma = torch.rand(dim, generator=g) + 0.5
+    beta = torch.randn(dim, generator=g)
+    w_sum, w_y = torch.randn_like(res), torch.randn_like(res)
+    # fp32 reference on the same (rounded) inputs
+    cast = lambda t: None if t is None else t.detach().to(dtype).float().clone().requires_grad_(True)
+    r_res, r_delta, r_gamma, r_beta = cast(res), cast(delta), cast(gamma), cast(beta)
+    total = r_res if r_delta is None else (r_res + r_delta).to(dtype).float()
+    if r_delta is not None:      # keep the graph through the rounding of the sum
+        total = r_res + r_delta + ((r_res + r_delta).to(dtype).float() - (r_res + r_delta)).detach()
+    y = F.layer_norm(total, (dim,), r_gamma, r_beta, 1e-5)
+    (total * w_sum).sum().add((y * w_y).sum()).backward()
+    dev = lambda t: None if t is None else t.detach().to(DEV, dtype).requires_grad_(True)
+    d_res, d_delta, d_gamma, d_beta = dev(res), dev(delta), dev(gamma), dev(beta)
+    o_total, o_y = ops.add_layernorm(d_res, d_delta, d_gamma, d_beta, 1e-5)
+    ((o_total.float() * w_sum.to(DEV)).sum() + (o_y.float() * w_y.to(DEV)).sum()).backward()
+    torch.testing.assert_close(o_total.float().cpu(), total.detach(), rtol=rtol, atol=atol)
+    torch.testing.assert_close(o_y.float().cpu(), y.detach(), rtol=rtol, atol=atol)
+    torch.testing.assert_close(d_res.grad.float().cpu(), r_res.grad, rtol=rtol, atol=atol * 4)
+    if with_delta:
+        torch.testing.assert_close(d_delta.grad.float().cpu(), r_delta.grad, rtol=rtol, atol=atol * 4)
+    scale = max(1.0, (rows ** 0.5))
+    torch.testing.assert_close(d_gamma.grad.float().cpu(), r_gamma.grad, rtol=rtol, atol=atol * scale)
+    torch.testing.assert_close(d_beta.grad.float().cpu(), r_beta.grad, rtol=rtol, atol=atol * scale)
+
+
+@pytest.mark.parametrize('dtype,rtol,atol', [(torch.float32, 1e-5, 1e-4), (torch.bfloat16, 2e-2, 5e-2)])
+@pytest.mark.parametrize('rows,cin,cout', [(4096, 256, 256), (1000, 32, 48), (333, 64, 2048), (64, 16, 8)])
+def test_linear_bias_gradient(dtype, rtol, atol, rows, cin, cout):
+    g = torch.Generator().manual_seed(rows)
+    x = torch.randn(2, rows // 2, cin, generator=g)
+    w = torch.randn(cout, cin, generator=g) / cin ** 0.5
+    b = torch.randn(cout, generator=g)
+    dy = torch.randn(2, rows // 2, cout, generator=g)
+    ref = [t.detach().to(dtype).float().clone().requires_grad_(True) for t in (x, w, b)]
+    F.linear(*ref).backward(dy.to(dtype).float())
+    got = [t.detach().to(DEV, dtype).requires_grad_(True) for t in (x, w, b)]
+    out = ops.linear(*got)
+    out.backward(dy.to(DEV, dtype))
+    torch.testing.assert_close(out.float().cpu(), F.linear(*ref).detach(), rtol=rtol, atol=atol)
+    for a, r in zip(got, ref):
+        torch.testing.assert_close(a.grad.float().cpu(), r.grad, rtol=rtol, atol=atol * max(1.0, rows ** 0.5 / 8))

@@ -47,6 +47,14 @@ def lib() -> ctypes.CDLL:
     L.wm_vq_distance.argtypes = [c_void_p] * 3 + [c_long, c_int, c_int, c_int, c_int, c_void_p]
     L.wm_adamw_step.restype = c_int
     L.wm_adamw_step.argtypes = [c_void_p] * 5 + [c_long, c_void_p] + [c_float] * 5 + [c_int, c_void_p]
+    L.wm_reduce_blocks.restype = c_int
+    L.wm_reduce_blocks.argtypes = [c_long]
+    L.wm_add_layernorm_fwd.restype = c_int
+    L.wm_add_layernorm_fwd.argtypes = [c_void_p] * 8 + [c_long, c_int, c_float, c_int, c_void_p]
+    L.wm_add_layernorm_bwd.restype = c_int
+    L.wm_add_layernorm_bwd.argtypes = [c_void_p] * 10 + [c_long, c_int, c_int, c_void_p]
+    L.wm_colsum.restype = c_int
+    L.wm_colsum.argtypes = [c_void_p] * 3 + [c_long, c_int, c_int, c_void_p]
     _lib = L
     return L
 
@@ -57,4 +65,5 @@ def check(rc: int, what: str) -> None:
 
 
 EXPORTS = ('wm_version', 'wm_last_error', 'wm_l3d_attn_uses_tensor_cores', 'wm_l3d_attn_fwd', 'wm_l3d_attn_bwd',
-           'wm_vq_nearest', 'wm_vq_distance', 'wm_adamw_step')
+           'wm_vq_nearest', 'wm_vq_distance', 'wm_adamw_step', 'wm_reduce_blocks', 'wm_add_layernorm_fwd',
+           'wm_add_layernorm_bwd', 'wm_colsum')

@@ -1,0 +1,348 @@
+// Layer-level kernels around the attention core: fused residual-add + LayerNorm (forward and
+// backward) and column sums (bias gradients).  One warp per token row, 16-byte vector
+// accesses, fp32 statistics.
+//
+// Reference: PreNorm / the residual adds of Local3dAttentionTransformer.forward
+// (vq-video-diffusion/local_3d_attention.py:11-17,159-161) and the bias gradients that autograd
+// derives for its nn.Linear layers (:24-27,46-53).
+#include "wm_common.cuh"
+
+#include <math.h>
+
+namespace wm {
+namespace {
+
+constexpr int kMaxChunks = 8;          // 8 elements per lane per chunk of 256 -> dim <= 2048
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// 8 consecutive elements <-> 8 floats
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __bfloat1622float2(h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+    uint4 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = r;
+}
+__device__ __forceinline__ void store8(float* p, const float (&f)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+__device__ __forceinline__ float round_to(float v, const __nv_bfloat16*) { return __bfloat162float(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ float round_to(float v, const float*) { return v; }
+
+// sum = res (+ delta); y = LayerNorm(sum) * gamma + beta; mean / rstd kept for backward
+template <typename T, int CHUNKS>
+__global__ void __launch_bounds__(256)
+add_layernorm_fwd_kernel(const T* __restrict__ res, const T* __restrict__ delta, const T* __restrict__ gamma,
+                         const T* __restrict__ beta, T* __restrict__ sum_out, T* __restrict__ y,
+                         float* __restrict__ mean_out, float* __restrict__ rstd_out, long rows, int dim, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float x[CHUNKS][8];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int col = c * 256 + lane * 8;
+        if (col < dim) {
+            load8(res + row * dim + col, x[c]);
+            if (delta != nullptr) {
+                float d[8];
+                load8(delta + row * dim + col, d);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[c][i] = round_to(x[c][i] + d[i], res);   // the sum as the next layer reads it
+                if (sum_out != nullptr) store8(sum_out + row * dim + col, x[c]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s += x[c][i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[c][i] = 0.f;
+        }
+    }
+    const float mean = warp_sum(s) / dim;
+    float v = 0.f;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c)
+        if (c * 256 + lane * 8 < dim)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v = fmaf(x[c][i] - mean, x[c][i] - mean, v);
+    const float rstd = rsqrtf(warp_sum(v) / dim + eps);
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int col = c * 256 + lane * 8;
+        if (col < dim) {
+            float g[8], b[8], o[8];
+            load8(gamma + col, g);
+            load8(beta + col, b);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = fmaf((x[c][i] - mean) * rstd, g[i], b[i]);
+            store8(y + row * dim + col, o);
+        }
+    }
+    if (lane == 0) {
+        mean_out[row] = mean;
+        rstd_out[row] = rstd;
+    }
+}
+
+// dx = (dres +) LayerNorm backward(dy); per-block partial sums of dgamma / dbeta
+template <typename T, int CHUNKS>
+__global__ void __launch_bounds__(256)
+add_layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dres, const T* __restrict__ x,
+                         const float* __restrict__ mean, const float* __restrict__ rstd, const T* __restrict__ gamma,
+                         T* __restrict__ dx, float* __restrict__ part, long rows, int dim) {
+    extern __shared__ float red[];          // [8 warps][2][dim]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float g[CHUNKS][8], dg[CHUNKS][8], db[CHUNKS][8];
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int col = c * 256 + lane * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { dg[c][i] = 0.f; db[c][i] = 0.f; g[c][i] = 0.f; }
+        if (col < dim) load8(gamma + col, g[c]);
+    }
+    const float inv_dim = 1.f / dim;
+    for (long row = (long)blockIdx.x * 8 + warp; row < rows; row += (long)gridDim.x * 8) {
+        const float mu = mean[row], rs = rstd[row];
+        float xh[CHUNKS][8], gy[CHUNKS][8];
+        float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+            const int col = c * 256 + lane * 8;
+            if (col < dim) {
+                float d[8], xv[8];
+                load8(dy + row * dim + col, d);
+                load8(x + row * dim + col, xv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    xh[c][i] = (xv[i] - mu) * rs;
+                    gy[c][i] = d[i] * g[c][i];
+                    c1 = fmaf(gy[c][i], xh[c][i], c1);
+                    c2 += gy[c][i];
+                    dg[c][i] = fmaf(d[i], xh[c][i], dg[c][i]);
+                    db[c][i] += d[i];
+                }
+            }
+        }
+        c1 = warp_sum(c1) * inv_dim;
+        c2 = warp_sum(c2) * inv_dim;
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+            const int col = c * 256 + lane * 8;
+            if (col < dim) {
+                float o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = rs * (gy[c][i] - c2 - xh[c][i] * c1);
+                if (dres != nullptr) {
+                    float r[8];
+                    load8(dres + row * dim + col, r);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] += r[i];
+                }
+                store8(dx + row * dim + col, o);
+            }
+        }
+    }
+    // block reduction of the parameter gradients
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int col = c * 256 + lane * 8;
+        if (col < dim)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                red[(warp * 2 + 0) * dim + col + i] = dg[c][i];
+                red[(warp * 2 + 1) * dim + col + i] = db[c][i];
+            }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 2 * dim; e += blockDim.x) {
+        const int which = e / dim, col = e - which * dim;
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a += red[(w * 2 + which) * dim + col];
+        part[((long)blockIdx.x * 2 + which) * dim + col] = a;
+    }
+}
+
+// out[which][col] = sum_b part[b][which][col]   (final stage of the parameter-gradient reduction)
+template <typename T>
+__global__ void reduce_partials_kernel(const float* __restrict__ part, T* __restrict__ out0, T* __restrict__ out1,
+                                       int nblocks, int dim, int nwhich) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nwhich * dim) return;
+    const int which = e / dim, col = e - which * dim;
+    float a = 0.f;
+    for (int b = 0; b < nblocks; ++b) a += part[((long)b * nwhich + which) * dim + col];
+    T* out = which == 0 ? out0 : out1;
+    if constexpr (sizeof(T) == 2) out[col] = __float2bfloat16_rn(a);
+    else out[col] = a;
+}
+
+// per-block column sums of a [rows, C] matrix: thread = (column group of 8, row lane)
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const T* __restrict__ a, float* __restrict__ part, long rows, int C) {
+    extern __shared__ float red[];          // [row lanes][C]
+    const int groups = C / 8;
+    const int lanes = blockDim.x / groups;                 // row lanes per block
+    const int grp = threadIdx.x % groups, rl = threadIdx.x / groups;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    if (rl < lanes) {
+        for (long row = (long)blockIdx.x * lanes + rl; row < rows; row += (long)gridDim.x * lanes) {
+            float v[8];
+            load8(a + row * C + grp * 8, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[rl * C + grp * 8 + i] = acc[i];
+    }
+    __syncthreads();
+    for (int col = threadIdx.x; col < C; col += blockDim.x) {
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += red[l * C + col];
+        part[(long)blockIdx.x * C + col] = s;
+    }
+}
+
+template <typename T>
+int launch_ln_fwd(const void* res, const void* delta, const void* gamma, const void* beta, void* sum_out, void* y,
+                  float* mean, float* rstd, long rows, int dim, float eps, cudaStream_t st) {
+    const int chunks = (dim + 255) / 256;
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+#define WM_LN_FWD(CH)                                                                                           \
+    add_layernorm_fwd_kernel<T, CH><<<grid, 256, 0, st>>>(static_cast<const T*>(res), static_cast<const T*>(delta), \
+                                                         static_cast<const T*>(gamma), static_cast<const T*>(beta), \
+                                                         static_cast<T*>(sum_out), static_cast<T*>(y), mean, rstd, \
+                                                         rows, dim, eps)
+    switch (chunks) {
+        case 1: WM_LN_FWD(1); break;
+        case 2: WM_LN_FWD(2); break;
+        case 3: case 4: WM_LN_FWD(4); break;
+        default: WM_LN_FWD(8); break;
+    }
+#undef WM_LN_FWD
+    WM_CUDA_CHECK(cudaGetLastError());
+    return WM_OK;
+}
+
+template <typename T>
+int launch_ln_bwd(const void* dy, const void* dres, const void* x, const float* mean, const float* rstd,
+                  const void* gamma, void* dx, void* dgamma, void* dbeta, float* part, int nblocks, long rows, int dim,
+                  cudaStream_t st) {
+    const int chunks = (dim + 255) / 256;
+    const size_t smem = (size_t)8 * 2 * dim * sizeof(float);
+#define WM_LN_BWD(CH)                                                                                              \
+    do {                                                                                                           \
+        WM_CUDA_CHECK(cudaFuncSetAttribute(add_layernorm_bwd_kernel<T, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        add_layernorm_bwd_kernel<T, CH><<<nblocks, 256, smem, st>>>(static_cast<const T*>(dy), static_cast<const T*>(dres), \
+                                                                  static_cast<const T*>(x), mean, rstd,              \
+                                                                  static_cast<const T*>(gamma), static_cast<T*>(dx), part, rows, dim); \
+    } while (0)
+    switch (chunks) {
+        case 1: WM_LN_BWD(1); break;
+        case 2: WM_LN_BWD(2); break;
+        case 3: case 4: WM_LN_BWD(4); break;
+        default: WM_LN_BWD(8); break;
+    }
+#undef WM_LN_BWD
+    WM_CUDA_CHECK(cudaGetLastError());
+    reduce_partials_kernel<T><<<(2 * dim + 255) / 256, 256, 0, st>>>(part, static_cast<T*>(dgamma), static_cast<T*>(dbeta),
+                                                                   nblocks, dim, 2);
+    WM_CUDA_CHECK(cudaGetLastError());
+    return WM_OK;
+}
+
+template <typename T>
+int launch_colsum(const void* a, void* out, float* part, int nblocks, long rows, int C, cudaStream_t st) {
+    const size_t smem = (size_t)(256 / (C / 8) > 0 ? 256 / (C / 8) : 1) * C * sizeof(float);
+    WM_CUDA_CHECK(cudaFuncSetAttribute(colsum_partial_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    colsum_partial_kernel<T><<<nblocks, 256, smem, st>>>(static_cast<const T*>(a), part, rows, C);
+    WM_CUDA_CHECK(cudaGetLastError());
+    reduce_partials_kernel<T><<<(C + 255) / 256, 256, 0, st>>>(part, static_cast<T*>(out), static_cast<T*>(out), nblocks, C, 1);
+    WM_CUDA_CHECK(cudaGetLastError());
+    return WM_OK;
+}
+
+int check_rows(const char* what, long rows, int dim, int dtype) {
+    if (dtype != WM_DTYPE_BF16 && dtype != WM_DTYPE_FP32) return fail(WM_EINVAL, "%s: unknown dtype %d", what, dtype);
+    if (rows < 0 || dim <= 0) return fail(WM_EINVAL, "%s: bad sizes rows=%ld dim=%d", what, rows, dim);
+    if (dim % 8 != 0 || dim > 2048) return fail(WM_EUNSUPPORTED, "%s: dim=%d must be a multiple of 8, at most 2048", what, dim);
+    return WM_OK;
+}
+
+}  // namespace
+}  // namespace wm
+
+using namespace wm;
+
+extern "C" int wm_reduce_blocks(long rows) {
+    long b = (rows + 63) / 64;
+    if (b > 148L * 4) b = 148L * 4;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+extern "C" int wm_add_layernorm_fwd(const void* res, const void* delta, const void* gamma, const void* beta,
+                                    void* sum_out, void* y, float* mean, float* rstd, long rows, int dim, float eps,
+                                    int dtype, void* stream) {
+    if (int rc = check_rows("wm_add_layernorm_fwd", rows, dim, dtype)) return rc;
+    if (rows == 0) return WM_OK;
+    if (!res || !gamma || !beta || !y || !mean || !rstd) return fail(WM_EINVAL, "wm_add_layernorm_fwd: null pointer");
+    if (!aligned16(res) || !aligned16(y) || (delta && !aligned16(delta)) || (sum_out && !aligned16(sum_out)) ||
+        !aligned16(gamma) || !aligned16(beta))
+        return fail(WM_EINVAL, "wm_add_layernorm_fwd: pointers must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return dtype == WM_DTYPE_BF16
+               ? launch_ln_fwd<__nv_bfloat16>(res, delta, gamma, beta, sum_out, y, mean, rstd, rows, dim, eps, st)
+               : launch_ln_fwd<float>(res, delta, gamma, beta, sum_out, y, mean, rstd, rows, dim, eps, st);
+}
+
+extern "C" int wm_add_layernorm_bwd(const void* dy, const void* dres, const void* x, const float* mean,
+                                    const float* rstd, const void* gamma, void* dx, void* dgamma, void* dbeta,
+                                    float* workspace, long rows, int dim, int dtype, void* stream) {
+    if (int rc = check_rows("wm_add_layernorm_bwd", rows, dim, dtype)) return rc;
+    if (rows == 0) return WM_OK;
+    if (!dy || !x || !mean || !rstd || !gamma || !dx || !dgamma || !dbeta || !workspace)
+        return fail(WM_EINVAL, "wm_add_layernorm_bwd: null pointer");
+    if (!aligned16(dy) || !aligned16(x) || !aligned16(dx) || (dres && !aligned16(dres)) || !aligned16(gamma))
+        return fail(WM_EINVAL, "wm_add_layernorm_bwd: pointers must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nb = wm_reduce_blocks(rows);
+    return dtype == WM_DTYPE_BF16
+               ? launch_ln_bwd<__nv_bfloat16>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, workspace, nb, rows, dim, st)
+               : launch_ln_bwd<float>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, workspace, nb, rows, dim, st);
+}
+
+extern "C" int wm_colsum(const void* a, void* out, float* workspace, long rows, int cols, int dtype, void* stream) {
+    if (int rc = check_rows("wm_colsum", rows, cols, dtype)) return rc;
+    if (!a || !out || !workspace) return fail(WM_EINVAL, "wm_colsum: null pointer");
+    if (!aligned16(a)) return fail(WM_EINVAL, "wm_colsum: input must be 16-byte aligned");
+    if (cols / 8 > 256) return fail(WM_EUNSUPPORTED, "wm_colsum: at most 2048 columns");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nb = wm_reduce_blocks(rows);
+    return dtype == WM_DTYPE_BF16 ? launch_colsum<__nv_bfloat16>(a, out, workspace, nb, rows, cols, st)
+                                  : launch_colsum<float>(a, out, workspace, nb, rows, cols, st);
+}

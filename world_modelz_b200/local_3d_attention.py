@@ -22,6 +22,11 @@ class PreNorm(nn.Module):
     def forward(self, x, **kwargs):
         return self.fn(self.norm(x), **kwargs)
 
+    def forward_prenormed(self, x_normed, **kwargs):
+        """Run the wrapped module on an input the caller has already normalised with ``self.norm``'s
+        parameters (the transformer fuses that LayerNorm with the preceding residual add)."""
+        return self.fn(x_normed, **kwargs)
+
 
 class FeedForward(nn.Module):
     """Linear-GELU-Linear with the reference's Sequential indices (``net.0`` / ``net.3``)."""
@@ -33,6 +38,9 @@ class FeedForward(nn.Module):
         self.net = nn.Sequential(*stages)
 
     def forward(self, x):
+        if x.is_cuda and (not self.training or (self.net[2].p == 0.0 and self.net[4].p == 0.0)):
+            h = torch.nn.functional.gelu(ops.linear(x, self.net[0].weight, self.net[0].bias))
+            return ops.linear(h, self.net[3].weight, self.net[3].bias)
         return self.net(x)
 
 
@@ -74,9 +82,13 @@ class Local3dAttention(nn.Module):
     def forward(self, x, q):
         if x.dim() != 5 or q.shape[:-1] != x.shape[:-1]:
             raise ValueError(f'expected x, q of shape [B,S,H,W,dim], got {tuple(x.shape)} and {tuple(q.shape)}')
-        core = ops.local3d_attention(self.to_q(q), self.to_k(x), self.to_v(x), self.heads, self.extents,
-                                     self.scale, self.kernel_flags)
-        return self.to_out(core).reshape(q.shape)
+        v = ops.linear(x, self.to_v.weight, self.to_v.bias)
+        core = ops.local3d_attention(self.to_q(q), self.to_k(x), v, self.heads, self.extents, self.scale,
+                                     self.kernel_flags)
+        if isinstance(self.to_out, nn.Identity):
+            return core.reshape(q.shape)
+        out = ops.linear(core, self.to_out[0].weight, self.to_out[0].bias)
+        return self.to_out[1](out).reshape(q.shape)
 
 
 class Local3dAttentionTransformer(nn.Module):
@@ -103,8 +115,13 @@ class Local3dAttentionTransformer(nn.Module):
         return pos.unsqueeze(0).expand(batch_shape[0], -1, -1, -1, -1)
 
     def forward(self, img_z):
+        """``x = attn(LN(x), q=x) + x; x = ff(LN(x)) + x`` per layer (reference ``:159-161``), scheduled so
+        that every residual add is fused with the LayerNorm that follows it (``wm_add_layernorm_*``)."""
         x = self.embedding(img_z) + self.get_pos_embedding(img_z.shape)
+        pending = None                               # branch output not yet added to the residual stream
         for attn, ff in self.layers:
-            x = attn(x, q=x) + x
-            x = ff(x) + x
-        return x
+            x, xn = ops.add_layernorm(x, pending, attn.norm.weight, attn.norm.bias, attn.norm.eps)
+            a = attn.forward_prenormed(xn, q=x)
+            x, xn = ops.add_layernorm(x, a, ff.norm.weight, ff.norm.bias, ff.norm.eps)
+            pending = ff.forward_prenormed(xn)
+        return x + pending if pending is not None else x

@@ -149,3 +149,104 @@ def adamw_step(master, shadow, grad, exp_avg, exp_avg_sq, dyn, beta1, beta2, eps
                                    dyn.data_ptr(), beta1, beta2, eps, weight_decay, grad_scale,
                                    _dtype_code(grad), _stream()), 'wm_adamw_step')
     _count(1)
+
+
+# ------------------------------------------------------- layer-level kernels (LayerNorm, bias grads)
+def _rows(t: torch.Tensor) -> int:
+    return t.numel() // t.shape[-1]
+
+
+class _AddLayerNormFn(torch.autograd.Function):
+    """(res, delta) -> (sum = res + delta, LayerNorm(sum)); ``delta`` may be None (then sum is res)."""
+
+    @staticmethod
+    def forward(ctx, res, delta, gamma, beta, eps):
+        _require_cuda(res)
+        res = res.contiguous()
+        dim = res.shape[-1]
+        rows = _rows(res)
+        y = torch.empty_like(res)
+        mean = torch.empty(rows, device=res.device, dtype=torch.float32)
+        rstd = torch.empty(rows, device=res.device, dtype=torch.float32)
+        if delta is not None:
+            delta = delta.contiguous()
+            total = torch.empty_like(res)
+        else:
+            total = res
+        check(_lib.lib().wm_add_layernorm_fwd(res.data_ptr(), delta.data_ptr() if delta is not None else None,
+                                              gamma.data_ptr(), beta.data_ptr(),
+                                              total.data_ptr() if delta is not None else None, y.data_ptr(),
+                                              mean.data_ptr(), rstd.data_ptr(), rows, dim, float(eps), _dtype_code(res),
+                                              _stream()), 'wm_add_layernorm_fwd')
+        _count(1)
+        ctx.save_for_backward(total, mean, rstd, gamma)
+        ctx.has_delta = delta is not None
+        return total, y
+
+    @staticmethod
+    def backward(ctx, dtotal, dy):
+        total, mean, rstd, gamma = ctx.saved_tensors
+        dim = total.shape[-1]
+        rows = _rows(total)
+        dy = dy.contiguous() if dy is not None else torch.zeros_like(total)
+        dres = dtotal.contiguous() if dtotal is not None else None
+        dx = torch.empty_like(total)
+        dgamma = torch.empty_like(gamma)
+        dbeta = torch.empty_like(gamma)
+        ws = torch.empty(_lib.lib().wm_reduce_blocks(rows) * 2 * dim, device=total.device, dtype=torch.float32)
+        check(_lib.lib().wm_add_layernorm_bwd(dy.data_ptr(), dres.data_ptr() if dres is not None else None,
+                                              total.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                              dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), rows,
+                                              dim, _dtype_code(total), _stream()), 'wm_add_layernorm_bwd')
+        _count(2)
+        return dx, (dx if ctx.has_delta else None), dgamma, dbeta, None
+
+
+def add_layernorm(res: torch.Tensor, delta: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor,
+                  eps: float = 1e-5) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fused ``s = res + delta; y = LayerNorm(s)``; returns ``(s, y)`` (``s is res`` when delta is None).
+
+    One kernel forward, one backward (which also folds the gradient arriving at ``s`` from the
+    residual path into ``dx``).  Reference: PreNorm + residual adds, local_3d_attention.py:11-17,159-161.
+    """
+    dim = res.shape[-1]
+    if dim % 8 != 0 or dim > 2048:      # widths the kernel does not tile: stock CUDA ops (still on the device)
+        total = res if delta is None else res + delta
+        return total, torch.nn.functional.layer_norm(total, (dim,), gamma, beta, eps)
+    return _AddLayerNormFn.apply(res, delta, gamma, beta, eps)
+
+
+class _LinearFn(torch.autograd.Function):
+    """``x @ W^T + b`` on cuBLAS; the bias gradient is a column sum in ``wm_colsum``."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return torch.nn.functional.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        x2 = x.reshape(-1, x.shape[-1])
+        dx = (dy2 @ weight).view(x.shape) if ctx.needs_input_grad[0] else None
+        dw = dy2.t() @ x2
+        db = None
+        if ctx.has_bias:
+            rows, cols = dy2.shape
+            db = torch.empty(cols, device=dy.device, dtype=dy.dtype)
+            ws = torch.empty(_lib.lib().wm_reduce_blocks(rows) * cols, device=dy.device, dtype=torch.float32)
+            check(_lib.lib().wm_colsum(dy2.data_ptr(), db.data_ptr(), ws.data_ptr(), rows, cols, _dtype_code(dy2),
+                                       _stream()), 'wm_colsum')
+            _count(2)
+        return dx, dw, db
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nn.Linear forward on cuBLAS with the bias gradient reduced by ``wm_colsum``."""
+    if bias is None or not x.is_cuda or bias.shape[0] % 8 != 0 or bias.shape[0] > 2048:
+        return torch.nn.functional.linear(x, weight, bias)
+    return _LinearFn.apply(x, weight, bias)
