@@ -75,8 +75,8 @@ size_t smem_bytes_for(Mode mode, int d, int ncols_pad, int nstage, int rowbuf) {
     const size_t ptile = (size_t)round_up(ncols_pad, 64) / 64 * 128 * 128;
     switch (mode) {
         case kFwd: return kFixedSmem + rowbuf * row_tile + nstage * 2 * blk + 2 * ptile;       // Q | (K,V) stages | 2xP
-        case kBwdDQ: return kFixedSmem + 2 * row_tile + nstage * 2 * blk + ptile;              // Q,dO | (K,V) stages | dS
-        default: return kFixedSmem + 2 * row_tile + nstage * 2 * blk + 2 * ptile + 4 * ncols_pad * 4;   // K,V | (Q,dO) | P,dS | lse,delta
+        case kBwdDQ: return kFixedSmem + rowbuf * 2 * row_tile + nstage * 2 * blk + ptile;     // Q,dO | (K,V) stages | dS
+        default: return kFixedSmem + rowbuf * 2 * row_tile + nstage * 2 * blk + 2 * ptile + 4 * ncols_pad * 4;   // K,V | (Q,dO) | P,dS | lse,delta
     }
 }
 
@@ -111,9 +111,8 @@ bool make_plan(const AttnShape& s, Mode mode, Plan& best) {
         const double tiles = (double)p.tilesS * p.tilesH * p.tilesW;
         // heads per CTA (forward kernel): walk as many heads as possible while keeping the grid >= 4 CTAs per SM
         int hpc = 1;
-        if (mode == kFwd)
-            for (int h = s.heads; h >= 1; --h)
-                if (s.heads % h == 0 && (double)s.B * tiles * (s.heads / h) >= 4.0 * 148) { hpc = h; break; }
+        for (int h = s.heads; h >= 1; --h)
+            if (s.heads % h == 0 && (double)s.B * tiles * (s.heads / h) >= 4.0 * 148) { hpc = h; break; }
         for (int nchunk = 1; nchunk <= p.hH; ++nchunk) {
             p.ch = (p.hH + nchunk - 1) / nchunk;
             p.nchunk = (p.hH + p.ch - 1) / p.ch;
@@ -122,10 +121,11 @@ bool make_plan(const AttnShape& s, Mode mode, Plan& best) {
             if (p.ncols_pad > max_cols || tmem_cols_for(mode, s.d, p.ncols_pad) > 512) continue;
             // shared-memory variants, best first
             bool fits = false;
-            const int opts[4][3] = {{3, 2, hpc}, {2, 2, hpc}, {3, 1, 1}, {2, 1, 1}};    // {nstage, rowbuf, hpc}
+            const int opts[5][3] = {{3, 2, hpc}, {2, 2, hpc}, {3, 1, 1}, {2, 1, hpc}, {2, 1, 1}};    // {nstage, rowbuf, hpc}
             for (const auto& o : opts) {
-                if (mode != kFwd && !(o[0] == 2 && o[1] == 1)) continue;               // bwd kernels: 2 stages, 1 row buffer
-                if (mode == kFwd && o[1] == 2 && hpc == 1) continue;
+                if (mode != kFwd && o[0] != 2) continue;                               // bwd kernels: 2 block stages
+                if (mode != kFwd && o[1] == 1 && o[2] != 1) continue;                  // ... and a head loop only with 2 row buffers
+                if (o[1] == 2 && hpc == 1) continue;
                 if (smem_bytes_for(mode, s.d, p.ncols_pad, o[0], o[1]) <= (size_t)kSmemLimit) {
                     p.nstage = o[0]; p.rowbuf = o[1]; p.hpc = o[2];
                     fits = true;

@@ -57,6 +57,9 @@ l3d_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __res
 }
 
 // --------------------------------------------------------------------------- kernel
+// 256 threads: warps w and w+4 share TMEM lane quadrant w&3 and split the row's columns.  A CTA
+// walks `hpc` heads of its brick (row tiles double-buffered when they fit); thread 0 issues TMA
+// and MMA.  Steps are (head, halo plane, h-chunk).
 template <int D, int MODE>
 __global__ void __launch_bounds__(kThreads, (D == 128) ? 1 : 2)
 l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
@@ -69,7 +72,6 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays in the shared window
 
-    // 256 threads: warps w and w+4 share TMEM lane quadrant w&3 and split the row's columns
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int quad = warp & 3, half = warp >> 2;
     const int row = quad * 32 + lane;
@@ -81,49 +83,52 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     const int p_slabs = (ncols_pad + 63) / 64;
     const int p_tile_bytes = p_slabs * 128 * 128;
 
-    uint8_t* sA1 = smem;                                   // row brick operand 1 (Q | K)
-    uint8_t* sA2 = sA1 + row_tile_bytes;                   // row brick operand 2 (dO | V)
-    uint8_t* sB = sA2 + row_tile_bytes;                    // [stage][operand][slab][ncols_pad rows]
+    uint8_t* sA = smem;                                    // [rowbuf][A1 | A2][slabs][128 rows]  (Q,dO | K,V)
+    uint8_t* sB = sA + pl.rowbuf * 2 * row_tile_bytes;     // [stage][operand][slab][ncols_pad rows]
     uint8_t* sDS = sB + 4 * blk_tile_bytes;                // dS (or dS^T), bf16, K-major 128B swizzle
     uint8_t* sPT = sDS + p_tile_bytes;                     // P^T (dK/dV kernel only)
     uint32_t* sMask = reinterpret_cast<uint32_t*>(sPT + (kDKV ? p_tile_bytes : 0));
-    float* sCol = reinterpret_cast<float*>(sMask + 2 * 8 * 128);           // [2 bufs][lse2|delta][ncols_pad]
+    float* sCol = reinterpret_cast<float*>(sMask + 2 * 9 * 128);           // [2 bufs][lse2|delta][ncols_pad]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + (kDKV ? 4 * ncols_pad : 0));
-    uint64_t* bar_a = bars;
-    uint64_t* bar_b = bars + 1;       // [2]
-    uint64_t* bar_mma = bars + 3;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-    uint32_t* myMask = sMask + half * 8 * 128;                              // [8 words][128 rows], own copy
+    uint64_t* bar_a = bars;           // [2]
+    uint64_t* bar_b = bars + 2;       // [2]
+    uint64_t* bar_mma = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    uint32_t* myMask = sMask + half * 9 * 128;                              // [9 words][128 rows], own copy
 
-    int bid = blockIdx.x;
-    const int tw_i = bid % pl.tilesW; bid /= pl.tilesW;
-    const int th_i = bid % pl.tilesH; bid /= pl.tilesH;
-    const int ts_i = bid % pl.tilesS; bid /= pl.tilesS;
-    const int head = bid % sh.heads;
-    const int b = bid / sh.heads;
+    const int tw_i = blockIdx.x % pl.tilesW, th_i = blockIdx.x / pl.tilesW;
+    const int ts_i = blockIdx.y;
+    const int hgroups = sh.heads / pl.hpc;
+    const int hg = blockIdx.z % hgroups, b = blockIdx.z / hgroups;
+    const int head0 = hg * pl.hpc;
     const int s0 = ts_i * pl.tS, h0 = th_i * pl.tH, w0 = tw_i * pl.tW;
-    const int c_base = head * D;
 
     // ---- this thread's row (a query in the dQ kernel, a key in the dK/dV kernel) --------------
-    const int plane_sz = pl.tH * pl.tW;
-    const int rs = row / plane_sz, rh = (row % plane_sz) / pl.tW, rw = row % pl.tW;
+    const int plane_mask = (1 << pl.lgPlane) - 1;
+    const int rs = row >> pl.lgPlane, rh = (row & plane_mask) >> pl.lgTW, rw = row & (pl.tW - 1);
     const bool row_valid = (s0 + rs < sh.S) && (h0 + rh < sh.H) && (w0 + rw < sh.W);
     const int kh_lo = max(rh, sh.eH - h0), kh_hi = min(rh + 2 * sh.eH, sh.H - 1 - h0 + sh.eH);
     const int kw_lo = max(rw, sh.eW - w0), kw_hi = min(rw + 2 * sh.eW, sh.W - 1 - w0 + sh.eW);
     const uint32_t wbits = (row_valid && kw_hi >= kw_lo) ? ((kw_hi - kw_lo == 31) ? 0xffffffffu : ((1u << (kw_hi - kw_lo + 1)) - 1u)) << kw_lo : 0u;
-    const int w_rs = (quad * 32) / plane_sz;
-    const int w_rh_lo = ((quad * 32) % plane_sz) / pl.tW, w_rh_hi = ((quad * 32 + 31) % plane_sz) / pl.tW;
+    const int w_rs = (quad * 32) >> pl.lgPlane;
+    const int w_rh_lo = ((quad * 32) & plane_mask) >> pl.lgTW, w_rh_hi = ((quad * 32 + 31) & plane_mask) >> pl.lgTW;
     const int ks_first = max(0, sh.eS - s0), ks_last = min(pl.hS - 1, sh.S - 1 - s0 + sh.eS);
     const int khg_lo = max(0, sh.eH - h0), khg_hi = min(pl.hH - 1, sh.H - 1 - h0 + sh.eH);
-    const int chunk_first = khg_lo / pl.ch, chunk_last = khg_hi / pl.ch;
+    int chunk_first = 0, chunk_last = 0;
+    for (int c = 0; c < pl.nchunk; ++c) {
+        if (khg_lo >= (c + 1) * pl.ch) chunk_first = c + 1;
+        if (khg_hi >= c * pl.ch) chunk_last = c;
+    }
     const int nplanes = ks_last - ks_first + 1;
     const int nblocks = nplanes * (chunk_last - chunk_first + 1);
+    const int nsteps = nblocks * pl.hpc;
     const long row_tok = (((long)b * sh.S + (s0 + rs)) * sh.H + (h0 + rh)) * sh.W + (w0 + rw);
     constexpr float kLog2e = 1.4426950408889634f;
 
     if (tid == 0) {
         tma_prefetch_desc(&map_a1); tma_prefetch_desc(&map_a2); tma_prefetch_desc(&map_b1); tma_prefetch_desc(&map_b2);
-        mbar_init(bar_a, 1);
+        mbar_init(&bar_a[0], 1);
+        mbar_init(&bar_a[1], 1);
         mbar_init(&bar_b[0], 1);
         mbar_init(&bar_b[1], 1);
         mbar_init(bar_mma, 1);
@@ -152,35 +157,48 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     const uint32_t tmem_t2 = tmem_t1 + ncols_pad;                           // dP  | dP^T
     const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
 
-    auto block_coords = [&](int j, int& ks, int& chunk) {
-        chunk = chunk_first + j / nplanes;
-        ks = ks_first + j % nplanes;
+    struct Cursor { int hd, ks, chunk; };
+    auto advance = [&](Cursor& c) {
+        if (++c.ks > ks_last) {
+            c.ks = ks_first;
+            if (++c.chunk > chunk_last) { c.chunk = chunk_first; ++c.hd; }
+        }
     };
-    auto issue_block_load = [&](int j) {            // thread 0 only
-        int ks, chunk;
-        block_coords(j, ks, chunk);
-        const int stage = j & 1;
+    auto a_buf = [&](int hd) { return sA + (pl.rowbuf == 2 ? (hd & 1) : 0) * 2 * row_tile_bytes; };
+    auto issue_row_load = [&](int hd) {             // thread 0 only
+        uint64_t* bar = &bar_a[hd & 1];
+        const int cb = (head0 + hd) * D;
+        mbar_expect_tx(bar, 2u * (uint32_t)row_tile_bytes);
+#pragma unroll
+        for (int sl = 0; sl < G::kSlabs; ++sl) {
+            tma_load_5d(a_buf(hd) + sl * row_slab_bytes, &map_a1, bar, cb + sl * G::kSlabCh, w0, h0, s0, b);
+            tma_load_5d(a_buf(hd) + row_tile_bytes + sl * row_slab_bytes, &map_a2, bar, cb + sl * G::kSlabCh, w0, h0, s0, b);
+        }
+    };
+    auto issue_block_load = [&](int t, const Cursor& c) {   // thread 0 only
+        const int stage = t & 1;
+        const int cb = (head0 + c.hd) * D;
         uint8_t* dst = sB + stage * 2 * blk_tile_bytes;
         mbar_expect_tx(&bar_b[stage], 2u * G::kSlabs * (uint32_t)ncols * G::kRowBytes);
 #pragma unroll
         for (int sl = 0; sl < G::kSlabs; ++sl) {
-            tma_load_5d(dst + sl * blk_slab_bytes, &map_b1, &bar_b[stage], c_base + sl * G::kSlabCh, w0 - sh.eW,
-                        h0 - sh.eH + chunk * pl.ch, s0 - sh.eS + ks, b);
-            tma_load_5d(dst + blk_tile_bytes + sl * blk_slab_bytes, &map_b2, &bar_b[stage], c_base + sl * G::kSlabCh,
-                        w0 - sh.eW, h0 - sh.eH + chunk * pl.ch, s0 - sh.eS + ks, b);
+            tma_load_5d(dst + sl * blk_slab_bytes, &map_b1, &bar_b[stage], cb + sl * G::kSlabCh, w0 - sh.eW,
+                        h0 - sh.eH + c.chunk * pl.ch, s0 - sh.eS + c.ks, b);
+            tma_load_5d(dst + blk_tile_bytes + sl * blk_slab_bytes, &map_b2, &bar_b[stage], cb + sl * G::kSlabCh,
+                        w0 - sh.eW, h0 - sh.eH + c.chunk * pl.ch, s0 - sh.eS + c.ks, b);
         }
     };
     const uint32_t idesc_t = make_idesc_bf16(ncols_pad, false, false);
     const uint32_t idesc_acc = make_idesc_bf16(D, false, true);
-    auto issue_t_mma = [&](int j) {                 // T1 = A1 B1_j^T, T2 = A2 B2_j^T   (thread 0 only)
-        uint8_t* blk = sB + (j & 1) * 2 * blk_tile_bytes;
+    auto issue_t_mma = [&](int t, int hd) {         // T1 = A1 B1_t^T, T2 = A2 B2_t^T   (thread 0 only)
+        uint8_t* blk = sB + (t & 1) * 2 * blk_tile_bytes;
 #pragma unroll
         for (int op = 0; op < 2; ++op) {
 #pragma unroll
             for (int kk = 0; kk < D / 16; ++kk) {
                 const int sl = (kk * 16) / G::kSlabCh;
                 const int koff = ((kk * 16) % G::kSlabCh) * 2;
-                const uint64_t da = make_smem_desc(smem_u32((op ? sA2 : sA1) + sl * row_slab_bytes + koff), 16,
+                const uint64_t da = make_smem_desc(smem_u32(a_buf(hd) + op * row_tile_bytes + sl * row_slab_bytes + koff), 16,
                                                    G::kAtomBytes, G::kSwizzleCode);
                 const uint64_t db = make_smem_desc(smem_u32(blk + op * blk_tile_bytes + sl * blk_slab_bytes + koff), 16,
                                                    G::kAtomBytes, G::kSwizzleCode);
@@ -188,8 +206,8 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             }
         }
     };
-    auto issue_acc_mma = [&](int j, bool accumulate) {   // (thread 0 only)
-        uint8_t* blk = sB + (j & 1) * 2 * blk_tile_bytes;
+    auto issue_acc_mma = [&](int t, bool accumulate) {   // (thread 0 only)
+        uint8_t* blk = sB + (t & 1) * 2 * blk_tile_bytes;
         for (int kk = 0; kk < ncols_pad / 16; ++kk) {
             const uint32_t a_off = (kk >> 2) * (128 * 128) + (kk & 3) * 32;
             const uint32_t acc = (accumulate || kk > 0) ? 1u : 0u;
@@ -200,26 +218,24 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                 const uint64_t d_pt = make_smem_desc(smem_u32(sPT + a_off), 16, 1024, 2u);
                 const uint64_t d_b2 = make_smem_desc(smem_u32(blk + blk_tile_bytes + kk * 16 * G::kRowBytes),
                                                      (uint32_t)blk_slab_bytes, G::kAtomBytes, G::kSwizzleCode);
-                umma_bf16_ss(tmem_acc1, d_pt, d_b2, idesc_acc, acc);      // dV += P^T dO_j
-                umma_bf16_ss(tmem_acc2, d_ds, d_b1, idesc_acc, acc);      // dK += dS^T Q_j
+                umma_bf16_ss(tmem_acc1, d_pt, d_b2, idesc_acc, acc);      // dV += P^T dO_t
+                umma_bf16_ss(tmem_acc2, d_ds, d_b1, idesc_acc, acc);      // dK += dS^T Q_t
             } else {
-                umma_bf16_ss(tmem_acc1, d_ds, d_b1, idesc_acc, acc);      // dQ += dS K_j
+                umma_bf16_ss(tmem_acc1, d_ds, d_b1, idesc_acc, acc);      // dQ += dS K_t
             }
         }
     };
     // per-column lse / delta of a block's queries (dK/dV kernel): one column per thread
-    auto load_colvec = [&](int j, float& lse2, float& dl) {
-        int ks, chunk;
-        block_coords(j, ks, chunk);
-        const int gs = s0 - sh.eS + ks;
-        const int c = tid;
+    auto load_colvec = [&](const Cursor& c, float& lse2, float& dl) {
+        const int gs = s0 - sh.eS + c.ks;
+        const int col = tid;
         lse2 = 0.f;
         dl = 0.f;
-        if (c < ncols) {
-            const int khl = c / pl.hW, kw = c - khl * pl.hW;
-            const int gh = h0 - sh.eH + chunk * pl.ch + khl, gw = w0 - sh.eW + kw;
+        if (col < ncols) {
+            const int khl = col / pl.hW, kw = col - khl * pl.hW;
+            const int gh = h0 - sh.eH + c.chunk * pl.ch + khl, gw = w0 - sh.eW + kw;
             if (gs >= 0 && gs < sh.S && gh >= 0 && gh < sh.H && gw >= 0 && gw < sh.W) {
-                const long idx = ((((long)b * sh.S + gs) * sh.H + gh) * sh.W + gw) * sh.heads + head;
+                const long idx = ((((long)b * sh.S + gs) * sh.H + gh) * sh.W + gw) * sh.heads + head0 + c.hd;
                 lse2 = __ldg(prm.lse + idx) * kLog2e;
                 dl = __ldg(prm.delta + idx);
             }
@@ -237,54 +253,81 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         *reinterpret_cast<uint4*>(tile + slab_off + sw128_offset(row, c16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *reinterpret_cast<uint4*>(tile + slab_off + sw128_offset(row, c16 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     };
-
-    if (tid == 0) {
-        mbar_expect_tx(bar_a, 2u * (uint32_t)row_tile_bytes);
+    // accumulators of head `hd` -> bf16 -> global; called by all threads once its last step has retired
+    auto finish_head = [&](int hd) {
+        const long row_off = row_tok * (long)sh.inner() + (head0 + hd) * D + half * (D / 2);
 #pragma unroll
-        for (int sl = 0; sl < G::kSlabs; ++sl) {
-            tma_load_5d(sA1 + sl * row_slab_bytes, &map_a1, bar_a, c_base + sl * G::kSlabCh, w0, h0, s0, b);
-            tma_load_5d(sA2 + sl * row_slab_bytes, &map_a2, bar_a, c_base + sl * G::kSlabCh, w0, h0, s0, b);
+        for (int which = 0; which < (kDKV ? 2 : 1); ++which) {
+            __nv_bfloat16* dst = (which == 0 ? prm.out1 : prm.out2) + row_off;
+            const uint32_t src = (which == 0 ? tmem_acc1 : tmem_acc2) + lane_sel + half * (D / 2);
+#pragma unroll
+            for (int c = 0; c < D / 2; c += 16) {
+                uint32_t r[16];
+                tmem_ld16(src + c, r);
+                tmem_wait_ld();
+                if (row_valid) {
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+                    *reinterpret_cast<uint4*>(dst + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4*>(dst + c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
+            }
         }
-        issue_block_load(0);
-        if (nblocks > 1) issue_block_load(1);
-        mbar_wait(bar_a, 0);
+    };
+
+    Cursor cur{0, ks_first, chunk_first};
+    Cursor nxt = cur;
+    advance(nxt);
+    if (tid == 0) {
+        issue_row_load(0);
+        issue_block_load(0, cur);
+        if (nsteps > 1) issue_block_load(1, nxt);
+        mbar_wait(&bar_a[0], 0);
         mbar_wait(&bar_b[0], 0);
         tc_fence_after();
-        issue_t_mma(0);
+        issue_t_mma(0, 0);
         umma_commit(bar_mma);
     }
     float row_lse2 = 0.f, row_delta = 0.f;
     if constexpr (kDKV) {
         float a, c;
-        load_colvec(0, a, c);
+        load_colvec(cur, a, c);
         store_colvec(0, a, c);
         __syncthreads();
-    } else if (row_valid) {
-        row_lse2 = __ldg(prm.lse + row_tok * sh.heads + head) * kLog2e;
-        row_delta = __ldg(prm.delta + row_tok * sh.heads + head);
     }
 
     bool p_zero = false;
     int mask_chunk = -1;
+    int g_lo = 0, g_hi = 0;
+    bool chunk_live = false;
     const int nwords = (ncols_pad + 31) / 32;
     const int ngroups = ncols_pad >> 4;
     const uint32_t zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
-    for (int j = 0; j < nblocks; ++j) {
-        int ks, chunk;
-        block_coords(j, ks, chunk);
+    for (int t = 0; t < nsteps; ++t) {
+        const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
         float nxt_lse2 = 0.f, nxt_dl = 0.f;
         if constexpr (kDKV) {
-            if (j + 1 < nblocks) load_colvec(j + 1, nxt_lse2, nxt_dl);     // global loads in flight during the wait
+            if (t + 1 < nsteps) load_colvec(nxt, nxt_lse2, nxt_dl);        // global loads in flight during the wait
+        } else {
+            if (head_start && row_valid) {
+                row_lse2 = __ldg(prm.lse + row_tok * sh.heads + head0 + cur.hd) * kLog2e;
+                row_delta = __ldg(prm.delta + row_tok * sh.heads + head0 + cur.hd);
+            }
         }
-        mbar_wait(bar_mma, j & 1);                  // T_j ready; accumulations of block j-1 retired
+        mbar_wait(bar_mma, t & 1);                  // T_t ready; accumulations of step t-1 retired
         tc_fence_after();
-        if (tid == 0 && j >= 1 && j + 1 < nblocks) issue_block_load(j + 1);
+        if (tid == 0) {
+            if (head_start && pl.rowbuf == 2 && cur.hd + 1 < pl.hpc) issue_row_load(cur.hd + 1);
+            if (t >= 1 && t + 1 < nsteps) issue_block_load(t + 1, nxt);
+        }
+        if (head_start && t > 0) finish_head(cur.hd - 1);
 
-        const int kh0 = chunk * pl.ch;
-        if (chunk != mask_chunk) {
-            mask_chunk = chunk;
-            for (int w = 0; w < nwords; ++w) myMask[w * 128 + row] = 0u;
+        const int kh0 = cur.chunk * pl.ch;
+        if (cur.chunk != mask_chunk) {
+            mask_chunk = cur.chunk;
+            for (int w = 0; w <= nwords; ++w) myMask[w * 128 + row] = 0u;
             if (wbits != 0u) {
                 const int ra = max(kh_lo, kh0), rb = min(kh_hi, kh0 + pl.ch - 1);
                 for (int kh = ra; kh <= rb; ++kh) {
@@ -294,19 +337,19 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                     if (sft != 0 && (wbits >> (32 - sft)) != 0u) myMask[(w + 1) * 128 + row] |= wbits >> (32 - sft);
                 }
             }
+            const int ua = max(w_rh_lo, kh0), ub = min(w_rh_hi + 2 * sh.eH, kh0 + pl.ch - 1);
+            chunk_live = ub >= ua;
+            g_lo = ((ua - kh0) * pl.hW) >> 4;
+            g_hi = min(((ub - kh0 + 1) * pl.hW + 15) >> 4, ngroups);
         }
 
-        const bool plane_live = (ks >= w_rs) && (ks <= w_rs + 2 * sh.eS);
-        const int ua = max(w_rh_lo, kh0), ub = min(w_rh_hi + 2 * sh.eH, kh0 + pl.ch - 1);
-        const bool live = plane_live && (ub >= ua);
+        const bool live = chunk_live && (cur.ks >= w_rs) && (cur.ks <= w_rs + 2 * sh.eS);
         if (live) {
-            const int g_lo = ((ua - kh0) * pl.hW) >> 4;
-            const int g_hi = min(((ub - kh0 + 1) * pl.hW + 15) >> 4, ngroups);
             const int g_mid = (g_lo + g_hi + 1) >> 1;
             const int ga = half ? g_mid : g_lo, gb = half ? g_hi : g_mid;            // live groups of this thread
             const int za = half ? g_hi : 0, zb = half ? ngroups : g_lo;              // groups this thread zero-fills
-            const float* col_lse2 = sCol + ((j & 1) * 2 + 0) * ncols_pad;
-            const float* col_dl = sCol + ((j & 1) * 2 + 1) * ncols_pad;
+            const float* col_lse2 = sCol + ((t & 1) * 2 + 0) * ncols_pad;
+            const float* col_dl = sCol + ((t & 1) * 2 + 1) * ncols_pad;
             for (int g = ga; g < gb; ++g) {
                 const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
                 uint32_t s[16], dp[16];
@@ -359,45 +402,29 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             p_zero = true;
         }
         if constexpr (kDKV) {
-            if (j + 1 < nblocks) store_colvec((j + 1) & 1, nxt_lse2, nxt_dl);
+            if (t + 1 < nsteps) store_colvec((t + 1) & 1, nxt_lse2, nxt_dl);
         }
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            issue_acc_mma(j, j > 0);
-            if (j + 1 < nblocks) {
-                mbar_wait(&bar_b[(j + 1) & 1], ((j + 1) >> 1) & 1);
+            issue_acc_mma(t, !head_start);
+            if (t + 1 < nsteps) {
+                mbar_wait(&bar_b[(t + 1) & 1], ((t + 1) >> 1) & 1);
+                if (nxt.hd != cur.hd) mbar_wait(&bar_a[nxt.hd & 1], (nxt.hd >> 1) & 1);   // hpc > 1 implies two row buffers
                 tc_fence_after();
-                issue_t_mma(j + 1);
+                issue_t_mma(t + 1, nxt.hd);
             }
             umma_commit(bar_mma);
         }
+        cur = nxt;
+        advance(nxt);
     }
 
-    // ---- epilogue ------------------------------------------------------------------------------
-    mbar_wait(bar_mma, nblocks & 1);
+    mbar_wait(bar_mma, nsteps & 1);
     tc_fence_after();
-    const long row_off = row_tok * (long)sh.inner() + c_base + half * (D / 2);
-#pragma unroll
-    for (int which = 0; which < (kDKV ? 2 : 1); ++which) {
-        __nv_bfloat16* dst = (which == 0 ? prm.out1 : prm.out2) + row_off;
-        const uint32_t src = (which == 0 ? tmem_acc1 : tmem_acc2) + lane_sel + half * (D / 2);
-#pragma unroll
-        for (int c = 0; c < D / 2; c += 16) {
-            uint32_t r[16];
-            tmem_ld16(src + c, r);
-            tmem_wait_ld();
-            if (row_valid) {
-                uint32_t pk[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-                *reinterpret_cast<uint4*>(dst + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                *reinterpret_cast<uint4*>(dst + c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            }
-        }
-    }
+    finish_head(pl.hpc - 1);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -421,8 +448,9 @@ static int launch_one(const void* a1, const void* a2, const void* b1, const void
     if (int rc = make_tensor_map_5d(&mb2, b2, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
     BwdParams prm{s, pl, lse, delta, static_cast<__nv_bfloat16*>(out1), static_cast<__nv_bfloat16*>(out2)};
     WM_CUDA_CHECK(cudaFuncSetAttribute(l3d_bwd_tc_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
-    const long grid = (long)s.B * s.heads * pl.tilesS * pl.tilesH * pl.tilesW;
-    l3d_bwd_tc_kernel<D, MODE><<<(unsigned)grid, kThreads, pl.smem_bytes, st>>>(ma1, ma2, mb1, mb2, prm);
+    const dim3 grid((unsigned)(pl.tilesW * pl.tilesH), (unsigned)pl.tilesS, (unsigned)(s.B * (s.heads / pl.hpc)));
+    if (grid.y > 65535u || grid.z > 65535u) return fail(WM_EUNSUPPORTED, "grid too large for the tensor-core kernel");
+    l3d_bwd_tc_kernel<D, MODE><<<grid, kThreads, pl.smem_bytes, st>>>(ma1, ma2, mb1, mb2, prm);
     WM_CUDA_CHECK(cudaGetLastError());
     return WM_OK;
 }

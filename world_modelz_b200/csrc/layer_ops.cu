@@ -185,17 +185,30 @@ add_layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dres, c
 }
 
 // out[which][col] = sum_b part[b][which][col]   (final stage of the parameter-gradient reduction)
+// block = 32 columns x 8 partial-lanes; the partial index runs across lanes, then shared memory
 template <typename T>
-__global__ void reduce_partials_kernel(const float* __restrict__ part, T* __restrict__ out0, T* __restrict__ out1,
-                                       int nblocks, int dim, int nwhich) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nwhich * dim) return;
-    const int which = e / dim, col = e - which * dim;
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ part, T* __restrict__ out0, T* __restrict__ out1, int nblocks,
+                       int dim, int nwhich) {
+    __shared__ float red[8][33];
+    const int c = threadIdx.x & 31, l = threadIdx.x >> 5;
+    const int e = blockIdx.x * 32 + c;                  // flattened (which, col)
     float a = 0.f;
-    for (int b = 0; b < nblocks; ++b) a += part[((long)b * nwhich + which) * dim + col];
-    T* out = which == 0 ? out0 : out1;
-    if constexpr (sizeof(T) == 2) out[col] = __float2bfloat16_rn(a);
-    else out[col] = a;
+    if (e < nwhich * dim) {
+        const int which = e / dim, col = e - which * dim;
+        for (int b = l; b < nblocks; b += 8) a += part[((long)b * nwhich + which) * dim + col];
+    }
+    red[l][c] = a;
+    __syncthreads();
+    if (l == 0 && e < nwhich * dim) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += red[i][c];
+        const int which = e / dim, col = e - which * dim;
+        T* out = which == 0 ? out0 : out1;
+        if constexpr (sizeof(T) == 2) out[col] = __float2bfloat16_rn(s);
+        else out[col] = s;
+    }
 }
 
 // per-block column sums of a [rows, C] matrix: thread = (column group of 8, row lane)
@@ -269,7 +282,7 @@ int launch_ln_bwd(const void* dy, const void* dres, const void* x, const float* 
     }
 #undef WM_LN_BWD
     WM_CUDA_CHECK(cudaGetLastError());
-    reduce_partials_kernel<T><<<(2 * dim + 255) / 256, 256, 0, st>>>(part, static_cast<T*>(dgamma), static_cast<T*>(dbeta),
+    reduce_partials_kernel<T><<<(2 * dim + 31) / 32, 256, 0, st>>>(part, static_cast<T*>(dgamma), static_cast<T*>(dbeta),
                                                                    nblocks, dim, 2);
     WM_CUDA_CHECK(cudaGetLastError());
     return WM_OK;
@@ -281,7 +294,7 @@ int launch_colsum(const void* a, void* out, float* part, int nblocks, long rows,
     WM_CUDA_CHECK(cudaFuncSetAttribute(colsum_partial_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     colsum_partial_kernel<T><<<nblocks, 256, smem, st>>>(static_cast<const T*>(a), part, rows, C);
     WM_CUDA_CHECK(cudaGetLastError());
-    reduce_partials_kernel<T><<<(C + 255) / 256, 256, 0, st>>>(part, static_cast<T*>(out), static_cast<T*>(out), nblocks, C, 1);
+    reduce_partials_kernel<T><<<(C + 31) / 32, 256, 0, st>>>(part, static_cast<T*>(out), static_cast<T*>(out), nblocks, C, 1);
     WM_CUDA_CHECK(cudaGetLastError());
     return WM_OK;
 }
