@@ -1,0 +1,40 @@
+import sys, os, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from world_modelz_b200 import ops, _lib
+B, S, H, W, heads, d, ext = 32, 16, 16, 16, 8, 32, (1, 2, 2)
+g = torch.Generator(device='cuda').manual_seed(0)
+q, k, v = (torch.randn(B, S, H, W, heads * d, device='cuda', generator=g).bfloat16() for _ in range(3))
+for _ in range(3):
+    ops.attn_forward(q, k, v, heads, ext, d ** -0.5)
+torch.cuda.synchronize()
+buf = (ctypes.c_longlong * (64 * 16))()
+rc = _lib.lib().wm_debug_read(buf)
+import numpy as np
+a = np.array(buf[:], dtype=np.int64).reshape(64, 16)
+t0 = a[0, 0]
+names = {0: 'drv:iter top', 1: 'drv:S deps ok', 2: 'drv:S issued', 3: 'drv:refill done', 4: 'drv:p_full ok', 5: 'drv:PV issued',
+         8: 'cmp:step top', 9: 'cmp:P buf free', 10: 'cmp:S ready', 11: 'cmp:compute done', 12: 'cmp:arrived'}
+print('rc', rc)
+for t in range(0, 14):
+    ev = sorted((a[t, s] - t0, names[s]) for s in names if a[t, s] != 0)
+    print(f'step {t}: ' + '  '.join(f'{n}@{c}' for c, n in ev))
+d0 = np.diff(a[2:30, 0]); print('driver iteration period (cycles):', d0.tolist())
+
+# ---- backward kernels
+do = torch.randn(B, S, H, W, heads * d, device='cuda', generator=g).bfloat16()
+o, lse = ops.attn_forward(q, k, v, heads, ext, d ** -0.5)
+for _ in range(2):
+    ops.attn_backward(q, k, v, o, lse, do, heads, ext, d ** -0.5)
+torch.cuda.synchronize()
+buf2 = (ctypes.c_longlong * (2 * 64 * 16))()
+rc = _lib.lib().wm_debug_read_bwd(buf2)
+b2 = np.array(buf2[:], dtype=np.int64).reshape(2, 64, 16)
+nb = {0: 'top', 1: 'mma ok', 2: 'compute done', 3: 'synced', 4: 'acc issued', 5: 'T issued+commit'}
+for m, name in ((0, 'dQ'), (1, 'dK/dV')):
+    a = b2[m]; t0 = a[0, 0]
+    print('====', name)
+    for t in range(2, 10):
+        ev = [(a[t, s] - a[t, 0], nb[s]) for s in nb if a[t, s] != 0]
+        print(f'step {t} (+{a[t,0]-t0}): ' + '  '.join(f'{n}@{c}' for c, n in ev))
+    print('period:', np.diff(a[2:26, 0]).tolist())

@@ -10,7 +10,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_long, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, '_C', 'libwm_b200.so')
+LIB_PATH = os.environ.get('WM_B200_LIB') or os.path.join(_HERE, '_C', 'libwm_b200.so')   # env override: tuning experiments only
 
 DTYPE_BF16 = 0
 DTYPE_FP32 = 1

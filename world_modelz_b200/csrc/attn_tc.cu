@@ -20,6 +20,10 @@
 // Replaces Local3dAttention.local_attention (local_3d_attention.py:78-99).
 #include "attn_tc.cuh"
 
+#ifndef WM_EXPERIMENT
+#define WM_EXPERIMENT 0
+#endif
+
 #include <math.h>
 #include <stdlib.h>
 #include <mutex>
@@ -150,6 +154,13 @@ bool make_plan(const AttnShape& s, Mode mode, Plan& best) {
     return found;
 }
 
+#if WM_EXPERIMENT == 7
+__device__ long long g_dbg[64 * 16];
+#define DBG(slot) do { if (dbg_on && t < 64) g_dbg[t * 16 + (slot)] = clock64(); } while (0)
+#else
+#define DBG(slot) do { } while (0)
+#endif
+
 // ------------------------------------------------------------------------------ kernel
 struct FwdParams {
     AttnShape sh;
@@ -268,16 +279,21 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
     if (warp == kDriverWarp) {
         // =============================== driver ===============================================
-        if (lane == 0) {
-            auto q_buf = [&](int hd) { return sQ + (pl.rowbuf == 2 ? (hd & 1) : 0) * q_tile_bytes; };
-            auto issue_q_load = [&](int hd) {
+        // The whole warp runs this code so that addresses and descriptors stay warp-uniform (uniform
+        // datapath); only the TMA / tcgen05 instructions themselves are predicated on one lane.
+        const bool leader = (lane == 0);
+        auto q_buf = [&](int hd) { return sQ + (pl.rowbuf == 2 ? (hd & 1) : 0) * q_tile_bytes; };
+        auto issue_q_load = [&](int hd) {
+            if (leader) {
                 uint64_t* bar = &bar_q[hd & 1];
                 mbar_expect_tx(bar, (uint32_t)q_tile_bytes);
 #pragma unroll
                 for (int sl = 0; sl < G::kSlabs; ++sl)
                     tma_load_5d(q_buf(hd) + sl * q_slab_bytes, &map_q, bar, (head0 + hd) * D + sl * G::kSlabCh, w0, h0, s0, b);
-            };
-            auto issue_kv_load = [&](int stage, const Cursor& c) {
+            }
+        };
+        auto issue_kv_load = [&](int stage, const Cursor& c) {
+            if (leader) {
                 const int cb = (head0 + c.hd) * D;
                 uint8_t* dst = sKV + stage * 2 * kv_tile_bytes;
                 mbar_expect_tx(&bar_kv[stage], 2u * G::kSlabs * (uint32_t)ncols * G::kRowBytes);
@@ -288,92 +304,105 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     tma_load_5d(dst + kv_tile_bytes + sl * kv_slab_bytes, &map_kv_v, &bar_kv[stage], cb + sl * G::kSlabCh,
                                 w0 - sh.eW, h0 - sh.eH + c.chunk * pl.ch, s0 - sh.eS + c.ks, b);
                 }
-            };
-            const uint32_t idesc_s = make_idesc_bf16(ncols_pad, false, false);
-            const uint32_t idesc_o = make_idesc_bf16(D, false, true);
-            auto issue_s_mma = [&](int t, int stage, int hd) {     // S[t&1] = Q_hd K_t^T
-                const uint32_t tmem_s = tmem_base + 2 * D + (t & 1) * ncols_pad;
-                uint8_t* kblk = sKV + stage * 2 * kv_tile_bytes;
+            }
+        };
+        const uint32_t idesc_s = make_idesc_bf16(ncols_pad, false, false);
+        const uint32_t idesc_o = make_idesc_bf16(D, false, true);
+        // descriptor bases; a byte offset is added as (offset >> 4) to the low (start address) field
+        const uint64_t dq0 = make_smem_desc(smem_u32(sQ), 16, G::kAtomBytes, G::kSwizzleCode);
+        const uint64_t dk0 = make_smem_desc(smem_u32(sKV), 16, G::kAtomBytes, G::kSwizzleCode);
+        const uint64_t dv0 = make_smem_desc(smem_u32(sKV + kv_tile_bytes), (uint32_t)kv_slab_bytes, G::kAtomBytes, G::kSwizzleCode);
+        const uint64_t dp0 = make_smem_desc(smem_u32(sP), 16, 1024, 2u);
+        const uint32_t q_buf_step = (pl.rowbuf == 2) ? (uint32_t)(q_tile_bytes >> 4) : 0u;
+        const uint32_t stage_step = (uint32_t)((2 * kv_tile_bytes) >> 4);
+        auto issue_s_mma = [&](int t, int stage, int hd) {     // S[t&1] = Q_hd K_t^T
+            const uint32_t tmem_s = tmem_base + 2 * D + (t & 1) * ncols_pad;
+            const uint64_t da0 = dq0 + (hd & 1) * q_buf_step, db0 = dk0 + stage * stage_step;
 #pragma unroll
-                for (int kk = 0; kk < D / 16; ++kk) {
-                    const int sl = (kk * 16) / G::kSlabCh;
-                    const int koff = ((kk * 16) % G::kSlabCh) * 2;
-                    const uint64_t da = make_smem_desc(smem_u32(q_buf(hd) + sl * q_slab_bytes + koff), 16, G::kAtomBytes, G::kSwizzleCode);
-                    const uint64_t db = make_smem_desc(smem_u32(kblk + sl * kv_slab_bytes + koff), 16, G::kAtomBytes, G::kSwizzleCode);
-                    umma_bf16_ss(tmem_s, da, db, idesc_s, kk > 0);
-                }
-                umma_commit(&bar_s[t & 1]);
-            };
-            auto issue_o_mma = [&](int t, int stage, int hd, bool accumulate) {   // O[hd&1] += P[t&1] V_t
-                const uint32_t tmem_o = tmem_base + (hd & 1) * D;
-                uint8_t* vblk = sKV + stage * 2 * kv_tile_bytes + kv_tile_bytes;
-                uint8_t* pbuf = sP + (t & 1) * p_tile_bytes;
-                for (int kk = 0; kk < ncols_pad / 16; ++kk) {
-                    const uint64_t da = make_smem_desc(smem_u32(pbuf + (kk >> 2) * (128 * 128) + (kk & 3) * 32), 16, 1024, 2u);
-                    const uint64_t db = make_smem_desc(smem_u32(vblk + kk * 16 * G::kRowBytes), (uint32_t)kv_slab_bytes,
-                                                       G::kAtomBytes, G::kSwizzleCode);
-                    umma_bf16_ss(tmem_o, da, db, idesc_o, (accumulate || kk > 0) ? 1u : 0u);
-                }
-                umma_commit(&bar_o[t & 1]);
-            };
+            for (int kk = 0; kk < D / 16; ++kk) {
+                const uint32_t off = (uint32_t)(((kk * 16) / G::kSlabCh) * 1 /*slab*/);
+                const uint32_t koff = (uint32_t)((((kk * 16) % G::kSlabCh) * 2) >> 4);
+                if (leader)
+                    umma_bf16_ss(tmem_s, da0 + off * (uint32_t)(q_slab_bytes >> 4) + koff,
+                                 db0 + off * (uint32_t)(kv_slab_bytes >> 4) + koff, idesc_s, kk > 0);
+            }
+            if (leader) umma_commit(&bar_s[t & 1]);
+        };
+        const int nk_o = ncols_pad / 16;
+        auto issue_o_mma = [&](int t, int stage, int hd, bool accumulate) {   // O[hd&1] += P[t&1] V_t
+            const uint32_t tmem_o = tmem_base + (hd & 1) * D;
+            uint64_t da = dp0 + (t & 1) * (uint32_t)(p_tile_bytes >> 4);
+            uint64_t db = dv0 + stage * stage_step;
+            for (int kk = 0; kk < nk_o; ++kk) {
+                if (leader) umma_bf16_ss(tmem_o, da, db, idesc_o, (accumulate || kk > 0) ? 1u : 0u);
+                da += ((kk & 3) == 3) ? (uint32_t)((128 * 128 - 96) >> 4) : 2u;     // next 16 columns of P
+                db += (uint32_t)((16 * G::kRowBytes) >> 4);                          // next 16 keys of V
+            }
+            if (leader) umma_commit(&bar_o[t & 1]);
+        };
 
-            // stage of step t is t % nstage; its n-th use has parity n & 1
-            int stage_of[3] = {0, 0, 0};   // unused; stages are tracked with running counters below
-            (void)stage_of;
-            Cursor ld = {0, ks_first, chunk_first};      // next block to load
-            int ld_t = 0;                                // its step index
-            issue_q_load(0);
-            for (; ld_t < nstage && ld_t < nsteps; ++ld_t) {
-                issue_kv_load(ld_t % nstage, ld);
-                advance(ld);
-            }
-            Cursor cur = {0, ks_first, chunk_first}, nxt = cur;
-            advance(nxt);
-            mbar_wait(&bar_q[0], 0);
-            mbar_wait(&bar_kv[0], 0);
-            tc_fence_after();
-            issue_s_mma(0, 0, 0);
-            int st_cur = 0, use_cur = 0;                 // stage / use count of step t
-            int st_nxt = (nstage > 1) ? 1 : 0, use_nxt = 0;
-            for (int t = 0; t < nsteps; ++t) {
-                const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
-                // (a) Q of the next head: its buffer was last read by the S MMAs of head hd-1 (rowbuf 2)
-                //     or is being read by this head (rowbuf 1: loaded at the head switch instead)
-                if (head_start && pl.rowbuf == 2 && cur.hd + 1 < pl.hpc) issue_q_load(cur.hd + 1);
-                auto refill = [&]() {        // (b) refill the stage freed by step t-1 once its P V has retired
-                    if (t >= 1 && ld_t < nsteps) {
-                        mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);
-                        issue_kv_load(ld_t % nstage, ld);     // == stage of step t-1
-                        advance(ld);
-                        ++ld_t;
-                    }
-                };
-                if (nstage < 3) refill();    // two stages: the block of step t+1 is the one being refilled
-                // (c) S of step t+1 into the other TMEM buffer, as soon as its K block is in
-                if (t + 1 < nsteps) {
-                    if (nxt.hd != cur.hd && pl.rowbuf == 1) {
-                        // single Q buffer: every S MMA of this head has been issued (S_t was) and retired (bar_s of t)
-                        mbar_wait(&bar_s[t & 1], (t >> 1) & 1);
-                        issue_q_load(nxt.hd);
-                    }
-                    mbar_wait(&bar_kv[st_nxt], use_nxt & 1);
-                    if (nxt.hd != cur.hd) mbar_wait(&bar_q[nxt.hd & 1], (nxt.hd >> 1) & 1);
-                    if (t >= 1) mbar_wait(&bar_p[(t + 1) & 1], ((t - 1) >> 1) & 1);   // S buffer drained by step t-1
-                    tc_fence_after();
-                    issue_s_mma(t + 1, st_nxt, nxt.hd);
+        Cursor ld = {0, ks_first, chunk_first};      // next block to load, its step index and stage
+        int ld_t = 0, ld_stage = 0;
+        issue_q_load(0);
+        for (; ld_t < nstage && ld_t < nsteps; ++ld_t) {
+            issue_kv_load(ld_stage, ld);
+            advance(ld);
+            if (++ld_stage == nstage) ld_stage = 0;
+        }
+        Cursor cur = {0, ks_first, chunk_first}, nxt = cur;
+        advance(nxt);
+        mbar_wait(&bar_q[0], 0);
+        mbar_wait(&bar_kv[0], 0);
+        tc_fence_after();
+        issue_s_mma(0, 0, 0);
+        int st_cur = 0;                              // stage of step t
+        int st_nxt = (nstage > 1) ? 1 : 0;           // stage of step t+1 ...
+        uint32_t kv_par = 1u;                        // bit s = parity of stage s's next completion (stage 0 was consumed once)
+        const bool dbg_on = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0) && leader;
+        (void)dbg_on;
+        for (int t = 0; t < nsteps; ++t) {
+            DBG(0);
+            const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
+            // (a) Q of the next head: its buffer was last read by the S MMAs of head hd-1 (rowbuf 2)
+            if (head_start && pl.rowbuf == 2 && cur.hd + 1 < pl.hpc) issue_q_load(cur.hd + 1);
+            auto refill = [&]() {        // (b) refill the stage freed by step t-1 once its P V has retired
+                if (t >= 1 && ld_t < nsteps) {
+                    mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);
+                    issue_kv_load(ld_stage, ld);          // == stage of step t-1
+                    advance(ld);
+                    ++ld_t;
+                    if (++ld_stage == nstage) ld_stage = 0;
                 }
-                if (nstage >= 3) refill();
-                // (d) O += P_t V_t once the compute warps have written P_t
-                mbar_wait(&bar_p[t & 1], (t >> 1) & 1);
+            };
+            if (nstage < 3) refill();    // two stages: the block of step t+1 is the one being refilled
+            // (c) S of step t+1 into the other TMEM buffer, as soon as its K block is in.  That buffer was
+            //     drained by step t-1, which iteration t-1 already waited for (bar_p) before issuing P V.
+            if (t + 1 < nsteps) {
+                if (nxt.hd != cur.hd && pl.rowbuf == 1) {
+                    // single Q buffer: every S MMA of this head has been issued (S_t was) and retired (bar_s of t)
+                    mbar_wait(&bar_s[t & 1], (t >> 1) & 1);
+                    issue_q_load(nxt.hd);
+                }
+                mbar_wait(&bar_kv[st_nxt], (kv_par >> st_nxt) & 1u);
+                kv_par ^= 1u << st_nxt;
+                if (nxt.hd != cur.hd) mbar_wait(&bar_q[nxt.hd & 1], (nxt.hd >> 1) & 1);
                 tc_fence_after();
-                issue_o_mma(t, st_cur, cur.hd, !head_start);
-                cur = nxt;
-                advance(nxt);
-                st_cur = st_nxt; use_cur = use_nxt;
-                if (++st_nxt == nstage) { st_nxt = 0; }
-                use_nxt = (t + 2) / nstage;
+                DBG(1);
+                issue_s_mma(t + 1, st_nxt, nxt.hd);
+                DBG(2);
             }
-            (void)use_cur;
+            if (nstage >= 3) refill();
+            DBG(3);
+            // (d) O += P_t V_t once the compute warps have written P_t
+            mbar_wait(&bar_p[t & 1], (t >> 1) & 1);
+            tc_fence_after();
+            DBG(4);
+            issue_o_mma(t, st_cur, cur.hd, !head_start);
+            DBG(5);
+            cur = nxt;
+            advance(nxt);
+            st_cur = st_nxt;
+            if (++st_nxt == nstage) st_nxt = 0;
         }
     } else {
         // =============================== compute warps ==========================================
@@ -444,7 +473,10 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const int ngroups = ncols_pad >> 3;
         const uint4 zero4 = make_uint4(0, 0, 0, 0);
 
+        const bool dbg_on = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0 && tid == 0);
+        (void)dbg_on;
         for (int t = 0; t < nsteps; ++t) {
+            DBG(8);
             const int buf = t & 1;
             const uint32_t tmem_s = tmem_base + 2 * D + buf * ncols_pad;
             const uint32_t tmem_o = tmem_base + (cur.hd & 1) * D;
@@ -489,12 +521,14 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             }
             // P buffer `buf` is free once the P V of step t-2 has retired
             if (t >= 2) mbar_wait(&bar_o[buf], ((t - 2) >> 1) & 1);
+            DBG(9);
 
             // warp-uniform: can any of this quadrant's queries see this block?
             const bool live = chunk_live && (cur.ks >= w_qs) && (cur.ks <= w_qs + 2 * sh.eS);
             if (live) {
                 mbar_wait(&bar_s[buf], (t >> 1) & 1);    // S_t computed
                 tc_fence_after();
+                DBG(10);
                 const int n8 = g_hi - g_lo;
                 const int ga = g_lo + ((n8 * part) >> LOGP), gb = g_lo + ((n8 * (part + 1)) >> LOGP);
                 // Single pass against the stale reference max when every row that has live columns
@@ -507,18 +541,32 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     for (; g + 2 <= gb; g += 2) {        // two 8-column groups per TMEM load
                         const uint32_t mword = mask_bits(g);
                         uint32_t r[16];
+#if WM_EXPERIMENT == 3
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(neg_m + i + g);
+#else
                         tmem_ld16(tmem_s + lane_sel + g * 8, r);
                         tmem_wait_ld();
+#endif
                         float p[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
+#if WM_EXPERIMENT == 1
+                            const float e = fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m);
+#else
                             const float e = ex2(fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m));
+#endif
                             p[i] = (mword & (1u << i)) ? e : 0.f;
                             ls[i & 3] += p[i];
                             pm[i & 3] = fmaxf(pm[i & 3], p[i]);
                         }
+#if WM_EXPERIMENT == 2
+                        if (pm[0] == 123.456f)
+#endif
+                        {
                         *p_addr(g) = make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
                         *p_addr(g + 1) = make_uint4(pack_bf16(p[8], p[9]), pack_bf16(p[10], p[11]), pack_bf16(p[12], p[13]), pack_bf16(p[14], p[15]));
+                        }
                     }
                     if (g < gb) {
                         const uint32_t mword = mask_bits(g);
@@ -617,9 +665,11 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 for (int g = part; g < ngroups; g += NPART) *p_addr(g) = zero4;
                 p_zero[buf] = true;
             }
+            DBG(11);
             fence_proxy_async();          // P (generic proxy) -> visible to tcgen05.mma (async proxy)
             tc_fence_before();            // our tcgen05.ld of S_t are complete before the driver reuses the buffer
             mbar_arrive(&bar_p[buf]);
+            DBG(12);
             if (head_start && t > 0) {               // epilogue of the previous head, off the critical path
                 mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);     // its last P V has retired
                 tc_fence_after();
@@ -664,6 +714,12 @@ static int launch_fwd(const void* q, const void* k, const void* v, void* o, floa
 }
 
 }  // namespace tc
+
+#if WM_EXPERIMENT == 7
+extern "C" __attribute__((visibility("default"))) int wm_debug_read(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, tc::g_dbg, sizeof(long long) * 64 * 16);
+}
+#endif
 
 bool attn_tc_supported(const AttnShape& s) {
     tc::Plan pl;

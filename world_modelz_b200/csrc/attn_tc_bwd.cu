@@ -19,6 +19,16 @@
 // (local_3d_attention.py:78-99; recomputed under checkpoint at :110-111).
 #include "attn_tc.cuh"
 
+#ifndef WM_EXPERIMENT
+#define WM_EXPERIMENT 0
+#endif
+#if WM_EXPERIMENT == 7
+namespace wm { namespace tc { __device__ long long g_dbg_bwd[2 * 64 * 16]; } }
+#define DBGB(slot) do { if (dbg_on && t < 64) g_dbg_bwd[(MODE - 1) * 1024 + t * 16 + (slot)] = clock64(); } while (0)
+#else
+#define DBGB(slot) do { } while (0)
+#endif
+
 #include <math.h>
 
 namespace wm {
@@ -164,65 +174,79 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             if (++c.chunk > chunk_last) { c.chunk = chunk_first; ++c.hd; }
         }
     };
+    // TMA / MMA issue: executed by the whole of warp 0 so that addresses and descriptors stay warp-uniform
+    // (uniform datapath); only the instructions themselves are predicated on one lane.
+    const bool leader = (lane == 0);
     auto a_buf = [&](int hd) { return sA + (pl.rowbuf == 2 ? (hd & 1) : 0) * 2 * row_tile_bytes; };
-    auto issue_row_load = [&](int hd) {             // thread 0 only
-        uint64_t* bar = &bar_a[hd & 1];
-        const int cb = (head0 + hd) * D;
-        mbar_expect_tx(bar, 2u * (uint32_t)row_tile_bytes);
+    auto issue_row_load = [&](int hd) {
+        if (leader) {
+            uint64_t* bar = &bar_a[hd & 1];
+            const int cb = (head0 + hd) * D;
+            mbar_expect_tx(bar, 2u * (uint32_t)row_tile_bytes);
 #pragma unroll
-        for (int sl = 0; sl < G::kSlabs; ++sl) {
-            tma_load_5d(a_buf(hd) + sl * row_slab_bytes, &map_a1, bar, cb + sl * G::kSlabCh, w0, h0, s0, b);
-            tma_load_5d(a_buf(hd) + row_tile_bytes + sl * row_slab_bytes, &map_a2, bar, cb + sl * G::kSlabCh, w0, h0, s0, b);
+            for (int sl = 0; sl < G::kSlabs; ++sl) {
+                tma_load_5d(a_buf(hd) + sl * row_slab_bytes, &map_a1, bar, cb + sl * G::kSlabCh, w0, h0, s0, b);
+                tma_load_5d(a_buf(hd) + row_tile_bytes + sl * row_slab_bytes, &map_a2, bar, cb + sl * G::kSlabCh, w0, h0, s0, b);
+            }
         }
     };
-    auto issue_block_load = [&](int t, const Cursor& c) {   // thread 0 only
-        const int stage = t & 1;
-        const int cb = (head0 + c.hd) * D;
-        uint8_t* dst = sB + stage * 2 * blk_tile_bytes;
-        mbar_expect_tx(&bar_b[stage], 2u * G::kSlabs * (uint32_t)ncols * G::kRowBytes);
+    auto issue_block_load = [&](int t, const Cursor& c) {
+        if (leader) {
+            const int stage = t & 1;
+            const int cb = (head0 + c.hd) * D;
+            uint8_t* dst = sB + stage * 2 * blk_tile_bytes;
+            mbar_expect_tx(&bar_b[stage], 2u * G::kSlabs * (uint32_t)ncols * G::kRowBytes);
 #pragma unroll
-        for (int sl = 0; sl < G::kSlabs; ++sl) {
-            tma_load_5d(dst + sl * blk_slab_bytes, &map_b1, &bar_b[stage], cb + sl * G::kSlabCh, w0 - sh.eW,
-                        h0 - sh.eH + c.chunk * pl.ch, s0 - sh.eS + c.ks, b);
-            tma_load_5d(dst + blk_tile_bytes + sl * blk_slab_bytes, &map_b2, &bar_b[stage], cb + sl * G::kSlabCh,
-                        w0 - sh.eW, h0 - sh.eH + c.chunk * pl.ch, s0 - sh.eS + c.ks, b);
+            for (int sl = 0; sl < G::kSlabs; ++sl) {
+                tma_load_5d(dst + sl * blk_slab_bytes, &map_b1, &bar_b[stage], cb + sl * G::kSlabCh, w0 - sh.eW,
+                            h0 - sh.eH + c.chunk * pl.ch, s0 - sh.eS + c.ks, b);
+                tma_load_5d(dst + blk_tile_bytes + sl * blk_slab_bytes, &map_b2, &bar_b[stage], cb + sl * G::kSlabCh,
+                            w0 - sh.eW, h0 - sh.eH + c.chunk * pl.ch, s0 - sh.eS + c.ks, b);
+            }
         }
     };
     const uint32_t idesc_t = make_idesc_bf16(ncols_pad, false, false);
     const uint32_t idesc_acc = make_idesc_bf16(D, false, true);
-    auto issue_t_mma = [&](int t, int hd) {         // T1 = A1 B1_t^T, T2 = A2 B2_t^T   (thread 0 only)
-        uint8_t* blk = sB + (t & 1) * 2 * blk_tile_bytes;
+    // descriptor bases; byte offsets are added as (offset >> 4) to the low (start address) field
+    const uint64_t da0 = make_smem_desc(smem_u32(sA), 16, G::kAtomBytes, G::kSwizzleCode);
+    const uint64_t dbk0 = make_smem_desc(smem_u32(sB), 16, G::kAtomBytes, G::kSwizzleCode);                         // block, K-major
+    const uint64_t dbm0 = make_smem_desc(smem_u32(sB), (uint32_t)blk_slab_bytes, G::kAtomBytes, G::kSwizzleCode);   // block, MN-major
+    const uint64_t dds0 = make_smem_desc(smem_u32(sDS), 16, 1024, 2u);
+    const uint64_t dpt0 = make_smem_desc(smem_u32(sPT), 16, 1024, 2u);
+    const uint32_t a_buf_step = (pl.rowbuf == 2) ? (uint32_t)((2 * row_tile_bytes) >> 4) : 0u;
+    const uint32_t stage_step = (uint32_t)((2 * blk_tile_bytes) >> 4);
+    auto issue_t_mma = [&](int t, int hd) {         // T1 = A1 B1_t^T, T2 = A2 B2_t^T
+        const uint64_t da_h = da0 + (hd & 1) * a_buf_step, db_s = dbk0 + (t & 1) * stage_step;
 #pragma unroll
         for (int op = 0; op < 2; ++op) {
 #pragma unroll
             for (int kk = 0; kk < D / 16; ++kk) {
-                const int sl = (kk * 16) / G::kSlabCh;
-                const int koff = ((kk * 16) % G::kSlabCh) * 2;
-                const uint64_t da = make_smem_desc(smem_u32(a_buf(hd) + op * row_tile_bytes + sl * row_slab_bytes + koff), 16,
-                                                   G::kAtomBytes, G::kSwizzleCode);
-                const uint64_t db = make_smem_desc(smem_u32(blk + op * blk_tile_bytes + sl * blk_slab_bytes + koff), 16,
-                                                   G::kAtomBytes, G::kSwizzleCode);
-                umma_bf16_ss(op ? tmem_t2 : tmem_t1, da, db, idesc_t, kk > 0);
+                const uint32_t sl = (uint32_t)((kk * 16) / G::kSlabCh);
+                const uint32_t koff = (uint32_t)((((kk * 16) % G::kSlabCh) * 2) >> 4);
+                const uint64_t da = da_h + op * (uint32_t)(row_tile_bytes >> 4) + sl * (uint32_t)(row_slab_bytes >> 4) + koff;
+                const uint64_t db = db_s + op * (uint32_t)(blk_tile_bytes >> 4) + sl * (uint32_t)(blk_slab_bytes >> 4) + koff;
+                if (leader) umma_bf16_ss(op ? tmem_t2 : tmem_t1, da, db, idesc_t, kk > 0);
             }
         }
     };
-    auto issue_acc_mma = [&](int t, bool accumulate) {   // (thread 0 only)
-        uint8_t* blk = sB + (t & 1) * 2 * blk_tile_bytes;
-        for (int kk = 0; kk < ncols_pad / 16; ++kk) {
-            const uint32_t a_off = (kk >> 2) * (128 * 128) + (kk & 3) * 32;
+    const int nk_acc = ncols_pad / 16;
+    auto issue_acc_mma = [&](int t, bool accumulate) {
+        uint64_t d_ds = dds0, d_pt = dpt0;
+        uint64_t d_b1 = dbm0 + (t & 1) * stage_step;
+        uint64_t d_b2 = d_b1 + (uint32_t)(blk_tile_bytes >> 4);
+        for (int kk = 0; kk < nk_acc; ++kk) {
             const uint32_t acc = (accumulate || kk > 0) ? 1u : 0u;
-            const uint64_t d_ds = make_smem_desc(smem_u32(sDS + a_off), 16, 1024, 2u);
-            const uint64_t d_b1 = make_smem_desc(smem_u32(blk + kk * 16 * G::kRowBytes), (uint32_t)blk_slab_bytes,
-                                                 G::kAtomBytes, G::kSwizzleCode);
             if constexpr (kDKV) {
-                const uint64_t d_pt = make_smem_desc(smem_u32(sPT + a_off), 16, 1024, 2u);
-                const uint64_t d_b2 = make_smem_desc(smem_u32(blk + blk_tile_bytes + kk * 16 * G::kRowBytes),
-                                                     (uint32_t)blk_slab_bytes, G::kAtomBytes, G::kSwizzleCode);
-                umma_bf16_ss(tmem_acc1, d_pt, d_b2, idesc_acc, acc);      // dV += P^T dO_t
-                umma_bf16_ss(tmem_acc2, d_ds, d_b1, idesc_acc, acc);      // dK += dS^T Q_t
+                if (leader) {
+                    umma_bf16_ss(tmem_acc1, d_pt, d_b2, idesc_acc, acc);      // dV += P^T dO_t
+                    umma_bf16_ss(tmem_acc2, d_ds, d_b1, idesc_acc, acc);      // dK += dS^T Q_t
+                }
             } else {
-                umma_bf16_ss(tmem_acc1, d_ds, d_b1, idesc_acc, acc);      // dQ += dS K_t
+                if (leader) umma_bf16_ss(tmem_acc1, d_ds, d_b1, idesc_acc, acc);      // dQ += dS K_t
             }
+            const uint32_t a_step = ((kk & 3) == 3) ? (uint32_t)((128 * 128 - 96) >> 4) : 2u;
+            d_ds += a_step; d_pt += a_step;
+            d_b1 += (uint32_t)((16 * G::kRowBytes) >> 4); d_b2 += (uint32_t)((16 * G::kRowBytes) >> 4);
         }
     };
     // per-column lse / delta of a block's queries (dK/dV kernel): one column per thread
@@ -279,7 +303,7 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     Cursor cur{0, ks_first, chunk_first};
     Cursor nxt = cur;
     advance(nxt);
-    if (tid == 0) {
+    if (warp == 0) {
         issue_row_load(0);
         issue_block_load(0, cur);
         if (nsteps > 1) issue_block_load(1, nxt);
@@ -287,7 +311,7 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         mbar_wait(&bar_b[0], 0);
         tc_fence_after();
         issue_t_mma(0, 0);
-        umma_commit(bar_mma);
+        if (leader) umma_commit(bar_mma);
     }
     float row_lse2 = 0.f, row_delta = 0.f;
     if constexpr (kDKV) {
@@ -305,7 +329,10 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     const int ngroups = ncols_pad >> 4;
     const uint32_t zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
+    const bool dbg_on = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0 && tid == 0);
+    (void)dbg_on;
     for (int t = 0; t < nsteps; ++t) {
+        DBGB(0);
         const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
         float nxt_lse2 = 0.f, nxt_dl = 0.f;
         if constexpr (kDKV) {
@@ -318,7 +345,8 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         }
         mbar_wait(bar_mma, t & 1);                  // T_t ready; accumulations of step t-1 retired
         tc_fence_after();
-        if (tid == 0) {
+        DBGB(1);
+        if (warp == 0) {
             if (head_start && pl.rowbuf == 2 && cur.hd + 1 < pl.hpc) issue_row_load(cur.hd + 1);
             if (t >= 1 && t + 1 < nsteps) issue_block_load(t + 1, nxt);
         }
@@ -404,19 +432,23 @@ l3d_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         if constexpr (kDKV) {
             if (t + 1 < nsteps) store_colvec((t + 1) & 1, nxt_lse2, nxt_dl);
         }
+        DBGB(2);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        DBGB(3);
+        if (warp == 0) {
             tc_fence_after();
             issue_acc_mma(t, !head_start);
+            DBGB(4);
             if (t + 1 < nsteps) {
                 mbar_wait(&bar_b[(t + 1) & 1], ((t + 1) >> 1) & 1);
                 if (nxt.hd != cur.hd) mbar_wait(&bar_a[nxt.hd & 1], (nxt.hd >> 1) & 1);   // hpc > 1 implies two row buffers
                 tc_fence_after();
                 issue_t_mma(t + 1, nxt.hd);
             }
-            umma_commit(bar_mma);
+            if (leader) umma_commit(bar_mma);
+            DBGB(5);
         }
         cur = nxt;
         advance(nxt);
@@ -466,6 +498,12 @@ static int launch_bwd_d(const void* q, const void* k, const void* v, const void*
     if (int rc = launch_one<D, kBwdDQ>(q, dout, k, v, lse, delta, dq, nullptr, s, st)) return rc;
     return launch_one<D, kBwdDKV>(k, v, q, dout, lse, delta, dv, dk, s, st);
 }
+
+#if WM_EXPERIMENT == 7
+extern "C" __attribute__((visibility("default"))) int wm_debug_read_bwd(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, g_dbg_bwd, sizeof(long long) * 2 * 64 * 16);
+}
+#endif
 
 int launch_bwd_tc(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout,
                   void* dq, void* dk, void* dv, float* delta, const AttnShape& s, cudaStream_t st) {
