@@ -78,7 +78,7 @@ size_t smem_bytes_for(Mode mode, int d, int ncols_pad, int nstage, int rowbuf) {
     const size_t blk = (size_t)slabs_of(d) * ncols_pad * row_bytes_of(d);
     const size_t ptile = (size_t)round_up(ncols_pad, 64) / 64 * 128 * 128;
     switch (mode) {
-        case kFwd: return kFixedSmem + rowbuf * row_tile + nstage * 2 * blk + 2 * ptile;       // Q | (K,V) stages | 2xP
+        case kFwd: return kFixedSmem + rowbuf * row_tile + nstage * 2 * blk;                   // Q | (K,V) stages (P lives in TMEM)
         case kBwdDQ: return kFixedSmem + rowbuf * 2 * row_tile + nstage * 2 * blk + ptile;     // Q,dO | (K,V) stages | dS
         default: return kFixedSmem + rowbuf * 2 * row_tile + nstage * 2 * blk + 2 * ptile + 4 * ncols_pad * 4;   // K,V | (Q,dO) | P,dS | lse,delta
     }
@@ -86,7 +86,7 @@ size_t smem_bytes_for(Mode mode, int d, int ncols_pad, int nstage, int rowbuf) {
 
 int tmem_cols_for(Mode mode, int d, int ncols_pad) {
     switch (mode) {
-        case kFwd: return 2 * d + 2 * ncols_pad;         // O x2 (per head parity) | S x2 (double buffered)
+        case kFwd: return d + 3 * ncols_pad;             // O (x2 if it fits) | S x2 | P x2 (bf16, half the columns)
         case kBwdDQ: return d + 2 * ncols_pad;           // dQ | S | dP
         default: return 2 * d + 2 * ncols_pad;           // dV | dK | S^T | dP^T
     }
@@ -141,7 +141,8 @@ bool make_plan(const AttnShape& s, Mode mode, Plan& best) {
             if (cost < best_cost) {
                 best_cost = cost;
                 p.smem_bytes = (int)smem_bytes_for(mode, s.d, p.ncols_pad, p.nstage, p.rowbuf);
-                p.tmem_cols = next_pow2(tmem_cols_for(mode, s.d, p.ncols_pad));
+                p.obufs = (mode == kFwd && 2 * s.d + 3 * p.ncols_pad <= 512) ? 2 : 1;
+                p.tmem_cols = next_pow2(tmem_cols_for(mode, s.d, p.ncols_pad) + (p.obufs == 2 ? s.d : 0));
                 p.scale_log2 = s.scale * 1.4426950408889634f;
                 p.lgTW = 0; while ((1 << p.lgTW) < p.tW) ++p.lgTW;
                 p.lgPlane = 0; while ((1 << p.lgPlane) < p.tH * p.tW) ++p.lgPlane;
@@ -199,10 +200,9 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
     uint8_t* sQ = smem;                                          // [rowbuf][slabs][128 rows]
     uint8_t* sKV = sQ + pl.rowbuf * q_tile_bytes;                // [nstage][K|V][slabs][ncols_pad rows]
-    uint8_t* sP = sKV + nstage * 2 * kv_tile_bytes;              // [2][ceil(ncols_pad/64)][128 rows][128 B]
     constexpr int kDriverWarp = 4 * NPART;
     constexpr int kThreadsAll = 32 * (4 * NPART + 1);
-    uint32_t* sMask = reinterpret_cast<uint32_t*>(sP + 2 * p_tile_bytes);      // [9 words][128 rows] (+ spare copy)
+    uint32_t* sMask = reinterpret_cast<uint32_t*>(sKV + nstage * 2 * kv_tile_bytes);   // [9 words][128 rows] (+ spare copy)
     float* sX = reinterpret_cast<float*>(sMask + 2 * 9 * 128);                 // [3 uses][2 parities][NPART][128 rows]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 3 * 2 * 4 * 128);
     uint64_t* bar_q = bars;           // [2]  Q tile of a head landed
@@ -266,7 +266,11 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // TMEM columns: O of even heads [0, D), O of odd heads [D, 2D), S buffers at 2D and 2D + ncols_pad
+    // TMEM columns: O (one buffer per head parity when it fits) | S x2 | P x2 (bf16 pairs, ncols_pad/2 columns each)
+    const uint32_t tmem_s0 = tmem_base + pl.obufs * D;
+    const uint32_t tmem_p0 = tmem_s0 + 2 * ncols_pad;
+    const int p_cols = ncols_pad >> 1;
+    (void)p_tile_bytes;
 
     // a step = (head, plane, h-chunk); steps run head-major, then chunk, then plane
     struct Cursor { int hd, ks, chunk; };
@@ -312,11 +316,10 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const uint64_t dq0 = make_smem_desc(smem_u32(sQ), 16, G::kAtomBytes, G::kSwizzleCode);
         const uint64_t dk0 = make_smem_desc(smem_u32(sKV), 16, G::kAtomBytes, G::kSwizzleCode);
         const uint64_t dv0 = make_smem_desc(smem_u32(sKV + kv_tile_bytes), (uint32_t)kv_slab_bytes, G::kAtomBytes, G::kSwizzleCode);
-        const uint64_t dp0 = make_smem_desc(smem_u32(sP), 16, 1024, 2u);
         const uint32_t q_buf_step = (pl.rowbuf == 2) ? (uint32_t)(q_tile_bytes >> 4) : 0u;
         const uint32_t stage_step = (uint32_t)((2 * kv_tile_bytes) >> 4);
         auto issue_s_mma = [&](int t, int stage, int hd) {     // S[t&1] = Q_hd K_t^T
-            const uint32_t tmem_s = tmem_base + 2 * D + (t & 1) * ncols_pad;
+            const uint32_t tmem_s = tmem_s0 + (t & 1) * ncols_pad;
             const uint64_t da0 = dq0 + (hd & 1) * q_buf_step, db0 = dk0 + stage * stage_step;
 #pragma unroll
             for (int kk = 0; kk < D / 16; ++kk) {
@@ -330,12 +333,12 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         };
         const int nk_o = ncols_pad / 16;
         auto issue_o_mma = [&](int t, int stage, int hd, bool accumulate) {   // O[hd&1] += P[t&1] V_t
-            const uint32_t tmem_o = tmem_base + (hd & 1) * D;
-            uint64_t da = dp0 + (t & 1) * (uint32_t)(p_tile_bytes >> 4);
+            const uint32_t tmem_o = tmem_base + (pl.obufs == 2 ? (hd & 1) : 0) * D;
+            uint32_t ta = tmem_p0 + (t & 1) * p_cols;                                // A = P from tensor memory
             uint64_t db = dv0 + stage * stage_step;
             for (int kk = 0; kk < nk_o; ++kk) {
-                if (leader) umma_bf16_ss(tmem_o, da, db, idesc_o, (accumulate || kk > 0) ? 1u : 0u);
-                da += ((kk & 3) == 3) ? (uint32_t)((128 * 128 - 96) >> 4) : 2u;     // next 16 columns of P
+                if (leader) umma_bf16_ts(tmem_o, ta, db, idesc_o, (accumulate || kk > 0) ? 1u : 0u);
+                ta += 8;                                                             // next 16 keys: 8 bf16-pair columns of P
                 db += (uint32_t)((16 * G::kRowBytes) >> 4);                          // next 16 keys of V
             }
             if (leader) umma_commit(&bar_o[t & 1]);
@@ -438,7 +441,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         auto xslot = [&](int use, int parity) { return sX + ((use * 2 + (parity & 1)) * 4) * 128; };
         // O / l -> bf16 and the LSE of head `hd`; called once that head's last P V has retired
         auto finish_head = [&](int hd) {
-            const uint32_t tmem_o = tmem_base + (hd & 1) * D;
+            const uint32_t tmem_o = tmem_base + (pl.obufs == 2 ? (hd & 1) : 0) * D;
             float* x = xslot(2, hd);
             x[part * 128 + row] = l_part;
             quad_sync();
@@ -471,19 +474,17 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         bool chunk_live = false, row_has_cols = false;
         const int nwords = (ncols_pad + 31) / 32;
         const int ngroups = ncols_pad >> 3;
-        const uint4 zero4 = make_uint4(0, 0, 0, 0);
 
         const bool dbg_on = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0 && tid == 0);
         (void)dbg_on;
         for (int t = 0; t < nsteps; ++t) {
             DBG(8);
             const int buf = t & 1;
-            const uint32_t tmem_s = tmem_base + 2 * D + buf * ncols_pad;
-            const uint32_t tmem_o = tmem_base + (cur.hd & 1) * D;
-            uint8_t* pbuf = sP + buf * p_tile_bytes;
-            auto p_addr = [&](int g) {     // 8 bf16 (one 16-byte chunk) of this row in the swizzled P tile
-                return reinterpret_cast<uint4*>(pbuf + (g >> 3) * (128 * 128) + sw128_offset(row, g & 7));
-            };
+            const uint32_t tmem_s = tmem_s0 + buf * ncols_pad;
+            const uint32_t tmem_o = tmem_base + (pl.obufs == 2 ? (cur.hd & 1) : 0) * D;
+            const uint32_t tmem_p = tmem_p0 + buf * p_cols + lane_sel;
+            // 8 bf16 of this row (one 8-column group) -> 4 bf16-pair columns of the P operand in tensor memory
+            auto p_store = [&](int g, uint32_t a, uint32_t b2, uint32_t c, uint32_t d2) { tmem_st4(tmem_p + g * 4, a, b2, c, d2); };
             auto mask_bits = [&](int g) -> uint32_t {     // live bits of columns [8g, 8g+16)
                 const uint32_t w0m = sMask[(g >> 2) * 128 + row], w1m = sMask[((g >> 2) + 1) * 128 + row];
                 return (uint32_t)(((((uint64_t)w1m) << 32) | w0m) >> ((g & 3) * 8));
@@ -492,6 +493,11 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             float prev_m = 0.f, prev_l = 0.f;
             if (head_start && t > 0) {               // the previous head is finished AFTER this step (its O buffer is not reused yet)
                 prev_m = m_used; prev_l = l_part;
+                if (pl.obufs == 1) {                 // single O accumulator: drain it before this head's first P V can be issued
+                    mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);
+                    tc_fence_after();
+                    finish_head(cur.hd - 1);
+                }
                 m_used = 0.f; l_part = 0.f;
                 head_has_blocks = false;
                 row_seen = false;
@@ -564,8 +570,8 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                         if (pm[0] == 123.456f)
 #endif
                         {
-                        *p_addr(g) = make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
-                        *p_addr(g + 1) = make_uint4(pack_bf16(p[8], p[9]), pack_bf16(p[10], p[11]), pack_bf16(p[12], p[13]), pack_bf16(p[14], p[15]));
+                        p_store(g, pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+                        p_store(g + 1, pack_bf16(p[8], p[9]), pack_bf16(p[10], p[11]), pack_bf16(p[12], p[13]), pack_bf16(p[14], p[15]));
                         }
                     }
                     if (g < gb) {
@@ -581,7 +587,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                             ls[i & 3] += p[i];
                             pm[i & 3] = fmaxf(pm[i & 3], p[i]);
                         }
-                        *p_addr(g) = make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+                        p_store(g, pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
                     }
                     const float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
                     float pmax = fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3]));
@@ -651,26 +657,26 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                             p[i] = (mword & (1u << i)) ? e : 0.f;
                             lsum += p[i];
                         }
-                        *p_addr(g) = make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+                        p_store(g, pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
                     }
                     l_part += lsum;
                 }
                 // columns outside the quadrant's live range: zero, shared round-robin between the parts
-                for (int g = part; g < g_lo; g += NPART) *p_addr(g) = zero4;
-                for (int g = g_hi + part; g < ngroups; g += NPART) *p_addr(g) = zero4;
+                for (int g = part; g < g_lo; g += NPART) p_store(g, 0u, 0u, 0u, 0u);
+                for (int g = g_hi + part; g < ngroups; g += NPART) p_store(g, 0u, 0u, 0u, 0u);
                 p_zero[buf] = false;
                 head_has_blocks = true;
                 row_seen = row_seen || row_has_cols;
             } else if (!p_zero[buf]) {
-                for (int g = part; g < ngroups; g += NPART) *p_addr(g) = zero4;
+                for (int g = part; g < ngroups; g += NPART) p_store(g, 0u, 0u, 0u, 0u);
                 p_zero[buf] = true;
             }
             DBG(11);
-            fence_proxy_async();          // P (generic proxy) -> visible to tcgen05.mma (async proxy)
-            tc_fence_before();            // our tcgen05.ld of S_t are complete before the driver reuses the buffer
+            tmem_wait_st();               // P is in tensor memory
+            tc_fence_before();            // ... and our tcgen05.ld of S_t are complete before the driver reuses the buffers
             mbar_arrive(&bar_p[buf]);
             DBG(12);
-            if (head_start && t > 0) {               // epilogue of the previous head, off the critical path
+            if (head_start && t > 0 && pl.obufs == 2) {   // epilogue of the previous head, off the critical path
                 mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);     // its last P V has retired
                 tc_fence_after();
                 const float keep_m = m_used, keep_l = l_part;
