@@ -50,8 +50,8 @@ extern "C" {
 #define WM_DTYPE_FP32 1              /* exact path, fp32 throughout                   */
 
 /* flags */
-#define WM_FLAG_SIMT 1               /* bf16 only: force the SIMT kernels (cross-check
-                                        of the tcgen05 kernels on the device)         */
+#define WM_FLAG_SIMT 1               /* force the SIMT kernels (bf16 attention, VQ): the
+                                        on-device cross-check of the tcgen05 kernels   */
 
 /* error codes */
 #define WM_OK            0
@@ -89,7 +89,9 @@ WM_API int wm_l3d_attn_bwd(const void* q, const void* k, const void* v, const vo
  *                                     x + (e_idx - x) in fp32 (vq.py:70)
  *   sq_err    [N, L]    fp32 or NULL  sum_d (e_idx - x)^2 (vq.py:35)
  * The winner is decided on distances accumulated in fp64 from the fp32 inputs, so the
- * index equals the exact-arithmetic argmin. */
+ * index equals the exact-arithmetic argmin.  For D in {32,64,96,128} and K <= 512 (multiple
+ * of 32) a tf32 tcgen05 distance GEMM selects the candidates that are re-checked exactly;
+ * other shapes (or WM_FLAG_SIMT) use the fp32 SIMT filter.  Same indices either way. */
 WM_API int wm_vq_nearest(const void* x, const void* codebook, int64_t* idx, void* quantized, float* sq_err,
                   long N, int L, int K, int D, int dtype, int flags, void* stream);
 

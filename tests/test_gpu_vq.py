@@ -124,3 +124,23 @@ def test_full_size_properties():
     idx2, ste2, err2 = ops.vq_nearest(codes.contiguous(), cb)
     assert torch.equal(idx2, idx) and err2.abs().max().item() == 0.0
     assert torch.equal(ste2, codes)
+
+
+@pytest.mark.parametrize('N,L,K,D', [(1000, 1, 512, 64), (257, 2, 96, 32), (4096, 1, 256, 128), (130, 3, 32, 96)])
+def test_tensor_core_filter_matches_exact_simt_kernel(N, L, K, D):
+    """tf32 tcgen05 candidate filter + fp64 re-check vs the fp32 SIMT kernel + fp64 re-scan: same indices
+    (both are the exact-arithmetic argmin), also with duplicated / nearly duplicated codes."""
+    g = torch.Generator().manual_seed(N + K + D)
+    cb = torch.randn(L, K, D, generator=g)
+    cb[:, 5] = cb[:, 3]
+    cb[:, K - 1] = cb[:, 3]
+    cb[:, 9] = cb[:, 8] + 1e-4
+    x = torch.randn(N, L, D, generator=g)
+    x[:7] = cb[:, 3].unsqueeze(0) + 1e-3 * torch.randn(7, L, D, generator=g)
+    x[7:14] = cb[:, 8].unsqueeze(0)
+    a = ops.vq_nearest(x.to(DEV), cb.to(DEV))
+    b = ops.vq_nearest(x.to(DEV), cb.to(DEV), flags=ops.FLAG_SIMT)
+    assert torch.equal(a[0], b[0])
+    assert torch.equal(a[1], b[1])
+    torch.testing.assert_close(a[2], b[2], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(a[0].cpu().numpy(), OV.encode(x.numpy(), cb.numpy()))

@@ -68,6 +68,22 @@ int make_tensor_map_5d(CUtensorMap* out, const void* base, int B, int S, int H, 
     return WM_OK;
 }
 
+// 2-D fp32 tensor map: [rows, cols] with an arbitrary row stride; box = (32 floats = 128 B, box_rows), 128B swizzle
+int make_tensor_map_2d_f32(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
+                           uint32_t box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (fn == nullptr) return fail(WM_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)row_stride_bytes};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(WM_ECUDA, "cuTensorMapEncodeTiled (2-D fp32) failed (%d)", (int)r);
+    return WM_OK;
+}
+
 // ------------------------------------------------------------------------------- plan
 static int row_bytes_of(int d) { return d == 32 ? 64 : 128; }
 static int slabs_of(int d) { return d == 128 ? 2 : 1; }

@@ -221,7 +221,6 @@ using namespace wm;
 
 extern "C" int wm_vq_nearest(const void* x, const void* codebook, int64_t* idx, void* quantized, float* sq_err,
                              long N, int L, int K, int D, int dtype, int flags, void* stream) {
-    (void)flags;
     if (dtype != WM_DTYPE_FP32) return fail(WM_EUNSUPPORTED, "wm_vq_nearest: only fp32 latents are supported");
     if (N < 0 || L <= 0 || K <= 0 || D <= 0) return fail(WM_EINVAL, "wm_vq_nearest: bad sizes N=%ld L=%d K=%d D=%d", N, L, K, D);
     if (N == 0) return WM_OK;
@@ -229,6 +228,8 @@ extern "C" int wm_vq_nearest(const void* x, const void* codebook, int64_t* idx, 
     if (D % 4 != 0 || D > 1024) return fail(WM_EUNSUPPORTED, "wm_vq_nearest: D=%d must be a multiple of 4, at most 1024", D);
     if (!aligned16(x) || !aligned16(codebook)) return fail(WM_EINVAL, "wm_vq_nearest: x / codebook must be 16-byte aligned");
     if (L > 65535) return fail(WM_EUNSUPPORTED, "wm_vq_nearest: L=%d too large", L);
+    if (!(flags & WM_FLAG_SIMT) && vq_tc_supported(N, L, K, D))          // tensor-core filter + exact re-check
+        return vq_nearest_tc(x, codebook, idx, quantized, sq_err, N, L, K, D, (cudaStream_t)stream);
     const size_t smem = (size_t)(kTileN + kTileK) * (D + kPad) * sizeof(float);
     if (smem > 200 * 1024) return fail(WM_EUNSUPPORTED, "wm_vq_nearest: D=%d needs %zu bytes of shared memory", D, smem);
     WM_CUDA_CHECK(cudaFuncSetAttribute(vq_nearest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -52,4 +52,8 @@ int attn_bwd_tc(const void* q, const void* k, const void* v, const void* o, cons
                 const void* dout, void* dq, void* dk, void* dv, float* delta,
                 const AttnShape& s, cudaStream_t st);
 
+bool vq_tc_supported(long N, int L, int K, int D);
+int vq_nearest_tc(const void* x, const void* cb, int64_t* idx, void* quantized, float* sq_err, long N, int L, int K,
+                  int D, cudaStream_t st);
+
 }  // namespace wm

@@ -11,7 +11,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import DTYPE_BF16, DTYPE_FP32, FLAG_SIMT, check
+from ._lib import DTYPE_BF16, DTYPE_FP32, FLAG_SIMT, check  # noqa: F401
 
 _launches = 0        # kernels launched by this library (claimed in bench.py's gpu_launches)
 
@@ -108,7 +108,7 @@ def local3d_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: 
 
 # ------------------------------------------------------------------------------------ VQ
 def vq_nearest(x: torch.Tensor, codebook: torch.Tensor, want_quantized: bool = True,
-               want_err: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
+               want_err: bool = True, flags: int = 0) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
     """``x [N,L,D]`` fp32, ``codebook [L,K,D]`` fp32 -> ``(idx int64 [N,L], ste [N,L,D], sq_err [N,L])``."""
     _require_cuda(x, codebook)
     if x.dtype != torch.float32 or codebook.dtype != torch.float32:
@@ -123,7 +123,7 @@ def vq_nearest(x: torch.Tensor, codebook: torch.Tensor, want_quantized: bool = T
     check(_lib.lib().wm_vq_nearest(x.data_ptr(), codebook.data_ptr(), idx.data_ptr(),
                                    ste.data_ptr() if ste is not None else None,
                                    err.data_ptr() if err is not None else None,
-                                   N, L, K, D, DTYPE_FP32, 0, _stream()), 'wm_vq_nearest')
+                                   N, L, K, D, DTYPE_FP32, flags, _stream()), 'wm_vq_nearest')
     _count(1)
     return idx, ste, err
 
