@@ -96,6 +96,8 @@ size_t smem_bytes_for(Mode mode, int d, int ncols_pad, int nstage, int rowbuf) {
     switch (mode) {
         case kFwd: return kFixedSmem + rowbuf * row_tile + nstage * 2 * blk;                   // Q | (K,V) stages (P lives in TMEM)
         case kBwdDQ: return kFixedSmem + rowbuf * 2 * row_tile + nstage * 2 * blk + ptile;     // Q,dO | (K,V) stages | dS
+        case kBwdDQws: return kFixedSmem + rowbuf * 2 * row_tile + nstage * 2 * blk;           // Q,dO | (K,V) stages (dS lives in TMEM)
+        case kBwdDKVws: return kFixedSmem + rowbuf * 2 * row_tile + nstage * 2 * blk + 2 * ptile + 4 * ncols_pad * 4;   // K,V | (Q,dO) | dS^T x2 | lse,delta (P^T in TMEM)
         default: return kFixedSmem + rowbuf * 2 * row_tile + nstage * 2 * blk + 2 * ptile + 4 * ncols_pad * 4;   // K,V | (Q,dO) | P,dS | lse,delta
     }
 }
@@ -104,6 +106,8 @@ int tmem_cols_for(Mode mode, int d, int ncols_pad) {
     switch (mode) {
         case kFwd: return d + 3 * ncols_pad;             // O (x2 if it fits) | S x2 | P x2 (bf16, half the columns)
         case kBwdDQ: return d + 2 * ncols_pad;           // dQ | S | dP
+        case kBwdDQws: return d + 3 * ncols_pad;         // dQ | S | dP | dS x2 (bf16 pairs)
+        case kBwdDKVws: return 2 * d + 3 * ncols_pad;    // dV | dK | S^T | dP^T | P^T x2 (bf16 pairs)
         default: return 2 * d + 2 * ncols_pad;           // dV | dK | S^T | dP^T
     }
 }
@@ -111,6 +115,8 @@ int tmem_cols_for(Mode mode, int d, int ncols_pad) {
 // Choose the brick and block shape: minimise the dense MMA columns executed per clip.
 bool make_plan(const AttnShape& s, Mode mode, Plan& best) {
     if (s.d != 32 && s.d != 64 && s.d != 128) return false;
+    const bool ws_bwd = (mode == kBwdDQws || mode == kBwdDKVws);
+    if (ws_bwd && s.d > 64) return false;
     static const int bricks[][3] = {{2, 8, 8}, {4, 4, 8}, {4, 8, 4}, {1, 8, 16}, {1, 16, 8}, {2, 4, 16}, {2, 16, 4}};
     double best_cost = 1e300;
     bool found = false;
@@ -143,8 +149,8 @@ bool make_plan(const AttnShape& s, Mode mode, Plan& best) {
             bool fits = false;
             const int opts[5][3] = {{3, 2, hpc}, {2, 2, hpc}, {3, 1, 1}, {2, 1, hpc}, {2, 1, 1}};    // {nstage, rowbuf, hpc}
             for (const auto& o : opts) {
-                if (mode != kFwd && o[0] != 2) continue;                               // bwd kernels: 2 block stages
-                if (mode != kFwd && o[1] == 1 && o[2] != 1) continue;                  // ... and a head loop only with 2 row buffers
+                if ((mode == kBwdDQ || mode == kBwdDKV) && o[0] != 2) continue;        // non-specialised bwd kernels: 2 block stages
+                if (mode != kFwd && o[1] == 1 && o[2] != 1) continue;                  // bwd: a head loop only with 2 row buffers
                 if (o[1] == 2 && hpc == 1) continue;
                 if (smem_bytes_for(mode, s.d, p.ncols_pad, o[0], o[1]) <= (size_t)kSmemLimit) {
                     p.nstage = o[0]; p.rowbuf = o[1]; p.hpc = o[2];

@@ -7,7 +7,7 @@
 namespace wm {
 namespace tc {
 
-enum Mode { kFwd = 0, kBwdDQ = 1, kBwdDKV = 2 };
+enum Mode { kFwd = 0, kBwdDQ = 1, kBwdDKV = 2, kBwdDQws = 3, kBwdDKVws = 4 };   // ws: warp-specialised backward (dim_head <= 64)
 
 struct Plan {
     int tS, tH, tW;            // row brick (queries; keys in the dK/dV kernel), tS*tH*tW == 128
@@ -53,6 +53,8 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk16) {
     return (uint32_t)row * 128u + (uint32_t)((chunk16 ^ (row & 7)) << 4);
 }
 
+int launch_bwd_ws(int mode, const void* a1, const void* a2, const void* b1, const void* b2, const float* lse,
+                  const float* delta, void* out1, void* out2, const AttnShape& s, cudaStream_t st);
 int launch_bwd_tc(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout,
                   void* dq, void* dk, void* dv, float* delta, const AttnShape& s, cudaStream_t st);
 

@@ -495,8 +495,13 @@ static int launch_bwd_d(const void* q, const void* k, const void* v, const void*
                                                                       static_cast<const __nv_bfloat16*>(dout), delta,
                                                                       items, s.d);
     WM_CUDA_CHECK(cudaGetLastError());
-    if (int rc = launch_one<D, kBwdDQ>(q, dout, k, v, lse, delta, dq, nullptr, s, st)) return rc;
-    return launch_one<D, kBwdDKV>(k, v, q, dout, lse, delta, dv, dk, s, st);
+    // warp-specialised kernels where the shape has a tiling for them (dim_head <= 64), else the two-role kernels
+    int rc = launch_bwd_ws(kBwdDQws, q, dout, k, v, lse, delta, dq, nullptr, s, st);
+    if (rc == WM_EUNSUPPORTED) rc = launch_one<D, kBwdDQ>(q, dout, k, v, lse, delta, dq, nullptr, s, st);
+    if (rc) return rc;
+    rc = launch_bwd_ws(kBwdDKVws, k, v, q, dout, lse, delta, dv, dk, s, st);
+    if (rc == WM_EUNSUPPORTED) rc = launch_one<D, kBwdDKV>(k, v, q, dout, lse, delta, dv, dk, s, st);
+    return rc;
 }
 
 #if WM_EXPERIMENT == 7

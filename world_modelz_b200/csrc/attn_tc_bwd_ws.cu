@@ -1,0 +1,493 @@
+// Warp-specialised backward kernels of the local windowed 3D attention (dim_head <= 64).
+//
+// Same math, brick / halo-block tiling, masks and determinism as attn_tc_bwd.cu; what changes is
+// who does what and where the probability tiles live:
+//   warps 0-7  compute (two threads per brick row), warp 8 = driver (TMA + every tcgen05.mma)
+//   T = (S, dP) accumulators: one TMEM buffer, handed to the compute warps per step (bar_t)
+//   dQ kernel : dS (bf16) goes back to TENSOR MEMORY (two buffers) and is the A operand of
+//               dQ += dS K (TS-mode MMA): no shared-memory round trip
+//   dK/dV     : P^T in tensor memory (two buffers, A of dV += P^T dO), dS^T in shared memory
+//               (two buffers, A of dK += dS^T Q)
+// so the accumulating MMAs of step t run while the compute warps are already in step t+1, and
+// the (S, dP) MMAs of step t+1 are issued before them, right when the buffers are drained.
+#include "attn_tc.cuh"
+
+#include <math.h>
+#include <stdlib.h>
+
+namespace wm {
+namespace tc {
+
+struct BwdWsParams {
+    AttnShape sh;
+    Plan pl;
+    const float* lse;
+    const float* delta;
+    __nv_bfloat16* out1;     // dQ kernel: dq.   dK/dV kernel: dv
+    __nv_bfloat16* out2;     //                  dK/dV kernel: dk
+};
+
+constexpr int kWsThreads = 288;
+
+template <int D, int MODE>
+__global__ void __launch_bounds__(kWsThreads, 1)
+l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
+                  const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
+                  const BwdWsParams prm) {
+    using G = Geo<D>;
+    constexpr bool kDKV = (MODE == kBwdDKVws);
+    const AttnShape& sh = prm.sh;
+    const Plan& pl = prm.pl;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ncols = pl.ncols, ncols_pad = pl.ncols_pad;
+    const int nstage = pl.nstage;
+    const int row_slab_bytes = 128 * G::kRowBytes;
+    const int row_tile_bytes = G::kSlabs * row_slab_bytes;
+    const int blk_slab_bytes = ncols_pad * G::kRowBytes;
+    const int blk_tile_bytes = G::kSlabs * blk_slab_bytes;
+    const int p_slabs = (ncols_pad + 63) / 64;
+    const int p_tile_bytes = p_slabs * 128 * 128;
+
+    uint8_t* sA = smem;                                    // [rowbuf][A1 | A2][slabs][128 rows]  (Q,dO | K,V)
+    uint8_t* sB = sA + pl.rowbuf * 2 * row_tile_bytes;     // [stage][B1 | B2][slab][ncols_pad rows]  (K,V | Q,dO)
+    uint8_t* sDS = sB + nstage * 2 * blk_tile_bytes;       // dK/dV kernel: dS^T x2, bf16, K-major 128B swizzle
+    uint32_t* sMask = reinterpret_cast<uint32_t*>(sDS + (kDKV ? 2 * p_tile_bytes : 0));   // [2 halves][9 words][128]
+    float* sCol = reinterpret_cast<float*>(sMask + 2 * 9 * 128);                          // [2 bufs][lse2|delta][ncols_pad]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + (kDKV ? 4 * ncols_pad : 0));
+    uint64_t* bar_a = bars;           // [2] row tiles of a head landed
+    uint64_t* bar_b = bars + 2;       // [3] halo block landed
+    uint64_t* bar_t = bars + 5;       //     (S, dP) of a step computed                  (tcgen05.commit)
+    uint64_t* bar_p = bars + 6;       // [2] dS / P written, (S, dP) drained             (256 compute threads)
+    uint64_t* bar_acc = bars + 8;     // [2] accumulating MMAs of a step retired          (tcgen05.commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+    const int tw_i = blockIdx.x % pl.tilesW, th_i = blockIdx.x / pl.tilesW;
+    const int ts_i = blockIdx.y;
+    const int hgroups = sh.heads / pl.hpc;
+    const int hg = blockIdx.z % hgroups, b = blockIdx.z / hgroups;
+    const int head0 = hg * pl.hpc;
+    const int s0 = ts_i * pl.tS, h0 = th_i * pl.tH, w0 = tw_i * pl.tW;
+
+    const int ks_first = max(0, sh.eS - s0), ks_last = min(pl.hS - 1, sh.S - 1 - s0 + sh.eS);
+    const int khg_lo = max(0, sh.eH - h0), khg_hi = min(pl.hH - 1, sh.H - 1 - h0 + sh.eH);
+    int chunk_first = 0, chunk_last = 0;
+    for (int c = 0; c < pl.nchunk; ++c) {
+        if (khg_lo >= (c + 1) * pl.ch) chunk_first = c + 1;
+        if (khg_hi >= c * pl.ch) chunk_last = c;
+    }
+    const int nplanes = ks_last - ks_first + 1;
+    const int nblocks = nplanes * (chunk_last - chunk_first + 1);
+    const int nsteps = nblocks * pl.hpc;
+
+    if (tid == 0) {
+        tma_prefetch_desc(&map_a1); tma_prefetch_desc(&map_a2); tma_prefetch_desc(&map_b1); tma_prefetch_desc(&map_b2);
+        mbar_init(&bar_a[0], 1);
+        mbar_init(&bar_a[1], 1);
+        for (int i = 0; i < 3; ++i) mbar_init(&bar_b[i], 1);
+        mbar_init(bar_t, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_p[i], 256);
+            mbar_init(&bar_acc[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc<512>(tmem_slot);
+    if (ncols_pad > ncols) {      // rows TMA never writes must stay finite (they meet zero dS / P columns)
+        const int pad_bytes = (ncols_pad - ncols) * G::kRowBytes;
+        for (int t = 0; t < nstage * 2 * G::kSlabs; ++t) {
+            uint8_t* base = sB + t * blk_slab_bytes + ncols * G::kRowBytes;
+            for (int i = tid * 16; i < pad_bytes; i += kWsThreads * 16) *reinterpret_cast<uint4*>(base + i) = make_uint4(0, 0, 0, 0);
+        }
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM columns: accumulators | T1 (S) | T2 (dP) | two buffers of bf16-pair columns (dS, resp. P^T)
+    const uint32_t tmem_acc1 = tmem_base;                                   // dQ | dV
+    const uint32_t tmem_acc2 = tmem_base + D;                               //      dK
+    const uint32_t tmem_t1 = tmem_base + (kDKV ? 2 * D : D);
+    const uint32_t tmem_t2 = tmem_t1 + ncols_pad;
+    const uint32_t tmem_pa = tmem_t2 + ncols_pad;                           // A operand buffers: [2][ncols_pad / 2]
+    const int pa_cols = ncols_pad >> 1;
+
+    struct Cursor { int hd, ks, chunk; };
+    auto advance = [&](Cursor& c) {
+        if (++c.ks > ks_last) {
+            c.ks = ks_first;
+            if (++c.chunk > chunk_last) { c.chunk = chunk_first; ++c.hd; }
+        }
+    };
+
+    if (warp == 8) {
+        // =============================== driver (warp-uniform; instructions on one lane) ==============
+        const bool leader = (lane == 0);
+        auto a_buf = [&](int hd) { return sA + (pl.rowbuf == 2 ? (hd & 1) : 0) * 2 * row_tile_bytes; };
+        auto issue_row_load = [&](int hd) {
+            if (leader) {
+                uint64_t* bar = &bar_a[hd & 1];
+                const int cb = (head0 + hd) * D;
+                mbar_expect_tx(bar, 2u * (uint32_t)row_tile_bytes);
+#pragma unroll
+                for (int sl = 0; sl < G::kSlabs; ++sl) {
+                    tma_load_5d(a_buf(hd) + sl * row_slab_bytes, &map_a1, bar, cb + sl * G::kSlabCh, w0, h0, s0, b);
+                    tma_load_5d(a_buf(hd) + row_tile_bytes + sl * row_slab_bytes, &map_a2, bar, cb + sl * G::kSlabCh, w0, h0, s0, b);
+                }
+            }
+        };
+        auto issue_block_load = [&](int stage, const Cursor& c) {
+            if (leader) {
+                const int cb = (head0 + c.hd) * D;
+                uint8_t* dst = sB + stage * 2 * blk_tile_bytes;
+                mbar_expect_tx(&bar_b[stage], 2u * G::kSlabs * (uint32_t)ncols * G::kRowBytes);
+#pragma unroll
+                for (int sl = 0; sl < G::kSlabs; ++sl) {
+                    tma_load_5d(dst + sl * blk_slab_bytes, &map_b1, &bar_b[stage], cb + sl * G::kSlabCh, w0 - sh.eW,
+                                h0 - sh.eH + c.chunk * pl.ch, s0 - sh.eS + c.ks, b);
+                    tma_load_5d(dst + blk_tile_bytes + sl * blk_slab_bytes, &map_b2, &bar_b[stage], cb + sl * G::kSlabCh,
+                                w0 - sh.eW, h0 - sh.eH + c.chunk * pl.ch, s0 - sh.eS + c.ks, b);
+                }
+            }
+        };
+        const uint32_t idesc_t = make_idesc_bf16(ncols_pad, false, false);
+        const uint32_t idesc_acc = make_idesc_bf16(D, false, true);
+        const uint64_t da0 = make_smem_desc(smem_u32(sA), 16, G::kAtomBytes, G::kSwizzleCode);
+        const uint64_t dbk0 = make_smem_desc(smem_u32(sB), 16, G::kAtomBytes, G::kSwizzleCode);                         // block, K-major
+        const uint64_t dbm0 = make_smem_desc(smem_u32(sB), (uint32_t)blk_slab_bytes, G::kAtomBytes, G::kSwizzleCode);   // block, MN-major
+        const uint64_t dds0 = make_smem_desc(smem_u32(sDS), 16, 1024, 2u);
+        const uint32_t a_buf_step = (pl.rowbuf == 2) ? (uint32_t)((2 * row_tile_bytes) >> 4) : 0u;
+        const uint32_t stage_step = (uint32_t)((2 * blk_tile_bytes) >> 4);
+        auto issue_t_mma = [&](int stage, int hd) {            // T1 = A1 B1^T, T2 = A2 B2^T
+            const uint64_t da_h = da0 + (hd & 1) * a_buf_step, db_s = dbk0 + stage * stage_step;
+#pragma unroll
+            for (int op = 0; op < 2; ++op) {
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk) {
+                    const uint32_t sl = (uint32_t)((kk * 16) / G::kSlabCh);
+                    const uint32_t koff = (uint32_t)((((kk * 16) % G::kSlabCh) * 2) >> 4);
+                    const uint64_t da = da_h + op * (uint32_t)(row_tile_bytes >> 4) + sl * (uint32_t)(row_slab_bytes >> 4) + koff;
+                    const uint64_t db = db_s + op * (uint32_t)(blk_tile_bytes >> 4) + sl * (uint32_t)(blk_slab_bytes >> 4) + koff;
+                    if (leader) umma_bf16_ss(op ? tmem_t2 : tmem_t1, da, db, idesc_t, kk > 0);
+                }
+            }
+            if (leader) umma_commit(bar_t);
+        };
+        const int nk_acc = ncols_pad / 16;
+        auto issue_acc_mma = [&](int t, int stage, bool accumulate) {
+            uint32_t ta = tmem_pa + (t & 1) * pa_cols;                              // dS (dQ kernel) or P^T (dK/dV kernel), from TMEM
+            uint64_t d_ds = dds0 + (t & 1) * (uint32_t)(p_tile_bytes >> 4);         // dS^T (dK/dV kernel), from shared memory
+            uint64_t d_b1 = dbm0 + stage * stage_step;
+            uint64_t d_b2 = d_b1 + (uint32_t)(blk_tile_bytes >> 4);
+            for (int kk = 0; kk < nk_acc; ++kk) {
+                const uint32_t acc = (accumulate || kk > 0) ? 1u : 0u;
+                if constexpr (kDKV) {
+                    if (leader) {
+                        umma_bf16_ts(tmem_acc1, ta, d_b2, idesc_acc, acc);          // dV += P^T dO_t
+                        umma_bf16_ss(tmem_acc2, d_ds, d_b1, idesc_acc, acc);        // dK += dS^T Q_t
+                    }
+                } else {
+                    if (leader) umma_bf16_ts(tmem_acc1, ta, d_b1, idesc_acc, acc);  // dQ += dS K_t
+                }
+                ta += 8;
+                d_ds += ((kk & 3) == 3) ? (uint32_t)((128 * 128 - 96) >> 4) : 2u;
+                d_b1 += (uint32_t)((16 * G::kRowBytes) >> 4);
+                d_b2 += (uint32_t)((16 * G::kRowBytes) >> 4);
+            }
+            if (leader) umma_commit(&bar_acc[t & 1]);
+        };
+
+        Cursor ld = {0, ks_first, chunk_first};
+        int ld_t = 0, ld_stage = 0;
+        issue_row_load(0);
+        for (; ld_t < nstage && ld_t < nsteps; ++ld_t) {
+            issue_block_load(ld_stage, ld);
+            advance(ld);
+            if (++ld_stage == nstage) ld_stage = 0;
+        }
+        Cursor cur = {0, ks_first, chunk_first}, nxt = cur;
+        advance(nxt);
+        mbar_wait(&bar_a[0], 0);
+        mbar_wait(&bar_b[0], 0);
+        tc_fence_after();
+        issue_t_mma(0, 0);
+        int st_cur = 0, st_nxt = (nstage > 1) ? 1 : 0;
+        uint32_t b_par = 1u;                         // bit s = parity of stage s's next completion (stage 0 consumed once)
+        for (int t = 0; t < nsteps; ++t) {
+            const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
+            if (head_start && pl.rowbuf == 2 && cur.hd + 1 < pl.hpc) issue_row_load(cur.hd + 1);   // buffer of head hd-1
+            // the compute warps have drained (S, dP) of step t and written its dS / P
+            mbar_wait(&bar_p[t & 1], (t >> 1) & 1);
+            tc_fence_after();
+            auto refill = [&]() {        // refill the stage freed by step t-1 once its accumulating MMAs have retired
+                if (t >= 1 && ld_t < nsteps) {
+                    mbar_wait(&bar_acc[(t - 1) & 1], ((t - 1) >> 1) & 1);
+                    issue_block_load(ld_stage, ld);
+                    advance(ld);
+                    ++ld_t;
+                    if (++ld_stage == nstage) ld_stage = 0;
+                }
+            };
+            if (nstage < 3) refill();    // two stages: the block of step t+1 is the one being refilled
+            if (t + 1 < nsteps) {                                        // (S, dP) of step t+1 first: it is what they wait for
+                mbar_wait(&bar_b[st_nxt], (b_par >> st_nxt) & 1u);
+                b_par ^= 1u << st_nxt;
+                if (nxt.hd != cur.hd) mbar_wait(&bar_a[nxt.hd & 1], (nxt.hd >> 1) & 1);
+                tc_fence_after();
+                issue_t_mma(st_nxt, nxt.hd);
+            }
+            issue_acc_mma(t, st_cur, !head_start);
+            if (nstage >= 3) refill();
+            cur = nxt;
+            advance(nxt);
+            st_cur = st_nxt;
+            if (++st_nxt == nstage) st_nxt = 0;
+        }
+    } else {
+        // =============================== compute warps ==================================================
+        const int quad = warp & 3, half = warp >> 2;
+        const int row = quad * 32 + lane;
+        const int ctid = tid;                                            // 0..255
+        const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
+        uint32_t* myMask = sMask + half * 9 * 128;
+        const int plane_mask = (1 << pl.lgPlane) - 1;
+        const int rs = row >> pl.lgPlane, rh = (row & plane_mask) >> pl.lgTW, rw = row & (pl.tW - 1);
+        const bool row_valid = (s0 + rs < sh.S) && (h0 + rh < sh.H) && (w0 + rw < sh.W);
+        const int kh_lo = max(rh, sh.eH - h0), kh_hi = min(rh + 2 * sh.eH, sh.H - 1 - h0 + sh.eH);
+        const int kw_lo = max(rw, sh.eW - w0), kw_hi = min(rw + 2 * sh.eW, sh.W - 1 - w0 + sh.eW);
+        const uint32_t wbits = (row_valid && kw_hi >= kw_lo) ? ((kw_hi - kw_lo == 31) ? 0xffffffffu : ((1u << (kw_hi - kw_lo + 1)) - 1u)) << kw_lo : 0u;
+        const int w_rs = (quad * 32) >> pl.lgPlane;
+        const int w_rh_lo = ((quad * 32) & plane_mask) >> pl.lgTW, w_rh_hi = ((quad * 32 + 31) & plane_mask) >> pl.lgTW;
+        const long row_tok = (((long)b * sh.S + (s0 + rs)) * sh.H + (h0 + rh)) * sh.W + (w0 + rw);
+        constexpr float kLog2e = 1.4426950408889634f;
+
+        auto load_colvec = [&](const Cursor& c, float& lse2, float& dl) {     // dK/dV kernel: one halo column per thread
+            const int gs = s0 - sh.eS + c.ks;
+            const int col = ctid;
+            lse2 = 0.f;
+            dl = 0.f;
+            if (col < ncols) {
+                const int khl = col / pl.hW, kw = col - khl * pl.hW;
+                const int gh = h0 - sh.eH + c.chunk * pl.ch + khl, gw = w0 - sh.eW + kw;
+                if (gs >= 0 && gs < sh.S && gh >= 0 && gh < sh.H && gw >= 0 && gw < sh.W) {
+                    const long idx = ((((long)b * sh.S + gs) * sh.H + gh) * sh.W + gw) * sh.heads + head0 + c.hd;
+                    lse2 = __ldg(prm.lse + idx) * kLog2e;
+                    dl = __ldg(prm.delta + idx);
+                }
+            }
+        };
+        auto store_colvec = [&](int buf, float lse2, float dl) {
+            if (ctid < ncols_pad) {
+                sCol[(buf * 2 + 0) * ncols_pad + ctid] = lse2;
+                sCol[(buf * 2 + 1) * ncols_pad + ctid] = dl;
+            }
+        };
+        auto finish_head = [&](int hd) {            // accumulators of head `hd` -> bf16 -> global
+            const long row_off = row_tok * (long)sh.inner() + (head0 + hd) * D + half * (D / 2);
+#pragma unroll
+            for (int which = 0; which < (kDKV ? 2 : 1); ++which) {
+                __nv_bfloat16* dst = (which == 0 ? prm.out1 : prm.out2) + row_off;
+                const uint32_t src = (which == 0 ? tmem_acc1 : tmem_acc2) + lane_sel + half * (D / 2);
+#pragma unroll
+                for (int c = 0; c < D / 2; c += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(src + c, r);
+                    tmem_wait_ld();
+                    if (row_valid) {
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+                        *reinterpret_cast<uint4*>(dst + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(dst + c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
+                }
+            }
+        };
+
+        Cursor cur{0, ks_first, chunk_first};
+        Cursor nxt = cur;
+        advance(nxt);
+        float row_lse2 = 0.f, row_delta = 0.f;
+        if constexpr (kDKV) {
+            float a, c;
+            load_colvec(cur, a, c);
+            store_colvec(0, a, c);
+            asm volatile("bar.sync 5, 256;" ::: "memory");               // the 256 compute threads only
+        }
+        bool p_zero[2] = {false, false};
+        int mask_chunk = -1;
+        int g_lo = 0, g_hi = 0;
+        bool chunk_live = false;
+        const int nwords = (ncols_pad + 31) / 32;
+        const int ngroups = ncols_pad >> 4;
+        const uint32_t zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+        for (int t = 0; t < nsteps; ++t) {
+            const int buf = t & 1;
+            const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
+            float nxt_lse2 = 0.f, nxt_dl = 0.f;
+            if constexpr (kDKV) {
+                if (t + 1 < nsteps) load_colvec(nxt, nxt_lse2, nxt_dl);      // global loads in flight during the waits
+            } else {
+                if (head_start && row_valid) {
+                    row_lse2 = __ldg(prm.lse + row_tok * sh.heads + head0 + cur.hd) * kLog2e;
+                    row_delta = __ldg(prm.delta + row_tok * sh.heads + head0 + cur.hd);
+                }
+            }
+            if (head_start && t > 0) {               // one accumulator set: drain the previous head before this head's first MMA
+                mbar_wait(&bar_acc[(t - 1) & 1], ((t - 1) >> 1) & 1);
+                tc_fence_after();
+                finish_head(cur.hd - 1);
+            }
+            const int kh0 = cur.chunk * pl.ch;
+            if (cur.chunk != mask_chunk) {
+                mask_chunk = cur.chunk;
+                for (int w = 0; w <= nwords; ++w) myMask[w * 128 + row] = 0u;
+                if (wbits != 0u) {
+                    const int ra = max(kh_lo, kh0), rb = min(kh_hi, kh0 + pl.ch - 1);
+                    for (int kh = ra; kh <= rb; ++kh) {
+                        const int pos = (kh - kh0) * pl.hW;
+                        const int w = pos >> 5, sft = pos & 31;
+                        myMask[w * 128 + row] |= wbits << sft;
+                        if (sft != 0 && (wbits >> (32 - sft)) != 0u) myMask[(w + 1) * 128 + row] |= wbits >> (32 - sft);
+                    }
+                }
+                const int ua = max(w_rh_lo, kh0), ub = min(w_rh_hi + 2 * sh.eH, kh0 + pl.ch - 1);
+                chunk_live = ub >= ua;
+                g_lo = ((ua - kh0) * pl.hW) >> 4;
+                g_hi = min(((ub - kh0 + 1) * pl.hW + 15) >> 4, ngroups);
+            }
+            // the dS / P buffers of parity `buf` are free once the accumulating MMAs of step t-2 have retired
+            if (t >= 2) mbar_wait(&bar_acc[buf], ((t - 2) >> 1) & 1);
+            mbar_wait(bar_t, t & 1);                  // (S, dP) of this step
+            tc_fence_after();
+
+            const uint32_t tmem_a = tmem_pa + buf * pa_cols + lane_sel;       // this row's bf16-pair columns
+            uint8_t* ds_tile = sDS + buf * p_tile_bytes;
+            auto store_ds_smem = [&](int g, const uint32_t (&pk)[8]) {        // dK/dV kernel: 16 bf16 -> swizzled smem tile
+                const uint32_t slab_off = (g >> 2) * (128 * 128);
+                const int c16 = (g & 3) * 2;
+                *reinterpret_cast<uint4*>(ds_tile + slab_off + sw128_offset(row, c16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(ds_tile + slab_off + sw128_offset(row, c16 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            };
+            auto store_tmem = [&](int g, const uint32_t (&pk)[8]) {           // 16 bf16 -> 8 pair columns of the TMEM A operand
+                tmem_st8(tmem_a + g * 8, pk);
+            };
+            const bool live = chunk_live && (cur.ks >= w_rs) && (cur.ks <= w_rs + 2 * sh.eS);
+            if (live) {
+                const int g_mid = (g_lo + g_hi + 1) >> 1;
+                const int ga = half ? g_mid : g_lo, gb = half ? g_hi : g_mid;
+                const int za = half ? g_hi : 0, zb = half ? ngroups : g_lo;
+                const float* col_lse2 = sCol + (buf * 2 + 0) * ncols_pad;
+                const float* col_dl = sCol + (buf * 2 + 1) * ncols_pad;
+                for (int g = ga; g < gb; ++g) {
+                    const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
+                    uint32_t s[16], dp[16];
+                    tmem_ld16(tmem_t1 + lane_sel + g * 16, s);
+                    tmem_ld16(tmem_t2 + lane_sel + g * 16, dp);
+                    float l2[16], dl[16];
+                    if constexpr (kDKV) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 a = *reinterpret_cast<const float4*>(col_lse2 + g * 16 + 4 * i);
+                            const float4 c = *reinterpret_cast<const float4*>(col_dl + g * 16 + 4 * i);
+                            l2[4 * i] = a.x; l2[4 * i + 1] = a.y; l2[4 * i + 2] = a.z; l2[4 * i + 3] = a.w;
+                            dl[4 * i] = c.x; dl[4 * i + 1] = c.y; dl[4 * i + 2] = c.z; dl[4 * i + 3] = c.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { l2[i] = row_lse2; dl[i] = row_delta; }
+                    }
+                    tmem_wait_ld();
+                    float pv[16], dsv[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const bool on = (mword >> i) & 1u;
+                        const float p = ex2(fmaf(__uint_as_float(s[i]), pl.scale_log2, -l2[i]));
+                        const float ds = p * (__uint_as_float(dp[i]) - dl[i]) * sh.scale;
+                        pv[i] = on ? p : 0.f;
+                        dsv[i] = on ? ds : 0.f;
+                    }
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(dsv[2 * i], dsv[2 * i + 1]);
+                    if constexpr (kDKV) {
+                        store_ds_smem(g, pk);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
+                        store_tmem(g, pk);
+                    } else {
+                        store_tmem(g, pk);
+                    }
+                }
+                for (int g = za; g < zb; ++g) {
+                    store_tmem(g, zero8);
+                    if constexpr (kDKV) store_ds_smem(g, zero8);
+                }
+                p_zero[buf] = false;
+            } else if (!p_zero[buf]) {
+                const int za = half ? (ngroups >> 1) : 0, zb = half ? ngroups : (ngroups >> 1);
+                for (int g = za; g < zb; ++g) {
+                    store_tmem(g, zero8);
+                    if constexpr (kDKV) store_ds_smem(g, zero8);
+                }
+                p_zero[buf] = true;
+            }
+            if constexpr (kDKV) {
+                if (t + 1 < nsteps) store_colvec((t + 1) & 1, nxt_lse2, nxt_dl);
+                fence_proxy_async();              // dS^T (generic proxy) -> visible to tcgen05.mma
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            if constexpr (kDKV) asm volatile("bar.sync 5, 256;" ::: "memory");   // next step's lse / delta columns are in place
+            mbar_arrive(&bar_p[buf]);
+            cur = nxt;
+            advance(nxt);
+        }
+        mbar_wait(&bar_acc[(nsteps - 1) & 1], ((nsteps - 1) >> 1) & 1);
+        tc_fence_after();
+        finish_head(pl.hpc - 1);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc<512>(tmem_base);
+}
+
+template <int D, int MODE>
+static int launch_ws(const void* a1, const void* a2, const void* b1, const void* b2, const float* lse,
+                     const float* delta, void* out1, void* out2, const AttnShape& s, const Plan& pl, cudaStream_t st) {
+    using G = Geo<D>;
+    CUtensorMap ma1, ma2, mb1, mb2;
+    const int C = s.inner();
+    if (int rc = make_tensor_map_5d(&ma1, a1, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.tW, pl.tH, pl.tS, G::kSwizzleBytes)) return rc;
+    if (int rc = make_tensor_map_5d(&ma2, a2, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.tW, pl.tH, pl.tS, G::kSwizzleBytes)) return rc;
+    if (int rc = make_tensor_map_5d(&mb1, b1, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
+    if (int rc = make_tensor_map_5d(&mb2, b2, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
+    BwdWsParams prm{s, pl, lse, delta, static_cast<__nv_bfloat16*>(out1), static_cast<__nv_bfloat16*>(out2)};
+    WM_CUDA_CHECK(cudaFuncSetAttribute(l3d_bwd_ws_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
+    const dim3 grid((unsigned)(pl.tilesW * pl.tilesH), (unsigned)pl.tilesS, (unsigned)(s.B * (s.heads / pl.hpc)));
+    if (grid.y > 65535u || grid.z > 65535u) return fail(WM_EUNSUPPORTED, "grid too large for the tensor-core kernel");
+    l3d_bwd_ws_kernel<D, MODE><<<grid, kWsThreads, pl.smem_bytes, st>>>(ma1, ma2, mb1, mb2, prm);
+    WM_CUDA_CHECK(cudaGetLastError());
+    return WM_OK;
+}
+
+// returns WM_OK when it launched, WM_EUNSUPPORTED when the shape has no warp-specialised tiling
+int launch_bwd_ws(int mode, const void* a1, const void* a2, const void* b1, const void* b2, const float* lse,
+                  const float* delta, void* out1, void* out2, const AttnShape& s, cudaStream_t st) {
+    Plan pl;
+    if (getenv("WM_TC_NO_WS") != nullptr || !make_plan(s, (Mode)mode, pl)) return WM_EUNSUPPORTED;
+    if (mode == kBwdDQws) {
+        if (s.d == 32) return launch_ws<32, kBwdDQws>(a1, a2, b1, b2, lse, delta, out1, out2, s, pl, st);
+        return launch_ws<64, kBwdDQws>(a1, a2, b1, b2, lse, delta, out1, out2, s, pl, st);
+    }
+    if (s.d == 32) return launch_ws<32, kBwdDKVws>(a1, a2, b1, b2, lse, delta, out1, out2, s, pl, st);
+    return launch_ws<64, kBwdDKVws>(a1, a2, b1, b2, lse, delta, out1, out2, s, pl, st);
+}
+
+}  // namespace tc
+}  // namespace wm
