@@ -190,14 +190,47 @@ def micro_benchmarks(dev, clips, hbm_gbs, tf_peak):
                        'peak': hbm_gbs, 'unit': 'GB/s', 'frac': ach / hbm_gbs, 'traffic': None,
                        'algorithmic_bytes_per_launch_set': bytes_fb,
                        'note': 'algorithmic bytes = 12*inner*2 B + 12*heads B per token (q,k,v,o,dO read; o,dq,dk,dv written)'}
+    # config 4 widths: 32x32x32 tokens, 4 heads x 128, window 5x7x7 (2 clips)
+    S4, heads4, d4, ext4 = 32, 4, 128, (2, 3, 3)
+    q4, k4, v4, do4 = (torch.randn(2, S4, S4, S4, heads4 * d4, device=dev, generator=g).bfloat16() for _ in range(4))
+    o4, lse4 = ops.attn_forward(q4, k4, v4, heads4, ext4, d4 ** -0.5)
+    t4f = time_kernel(lambda: ops.attn_forward(q4, k4, v4, heads4, ext4, d4 ** -0.5), 10)
+    t4b = time_kernel(lambda: ops.attn_backward(q4, k4, v4, o4, lse4, do4, heads4, ext4, d4 ** -0.5), 5)
+    tok4 = 2 * S4 ** 3
+    out['attn_config4'] = {'shape': '2x32x32x32x(4x128) window 245', 'fwd_ms': t4f, 'bwd_ms': t4b,
+                           'fwd_bwd_tokens_per_s': tok4 / ((t4f + t4b) * 1e-3),
+                           'fwd_bwd_algorithmic_tflops': 3.5 * 4.0 * 245 * 512 * tok4 / ((t4f + t4b) * 1e-3) / 1e12,
+                           'fwd_bwd_algorithmic_gbs': tok4 * (12 * 512 * 2 + 12 * 4) / ((t4f + t4b) * 1e-3) / 1e9}
+    del q4, k4, v4, do4, o4, lse4
     # VQ nearest: 4096 frames of 16x16 latents (D=64) against 512 codes
     n = 1 << 20
     x = torch.randn(n, 1, 64, device=dev, generator=g)
     cb = torch.randn(1, 512, 64, device=dev, generator=g)
     t_v = time_kernel(lambda: ops.vq_nearest(x, cb), 5)
     out['vq'] = {'shape': f'{n} latents x 64 vs 512 codes (fp32, bit-exact indices)', 'ms': t_v,
-                 'latents_per_s': n / (t_v * 1e-3), 'algorithmic_gbs': n * 520 / (t_v * 1e-3) / 1e9}
+                 'latents_per_s': n / (t_v * 1e-3), 'algorithmic_gbs': n * 524 / (t_v * 1e-3) / 1e9,
+                 'kernel': 'tf32 tcgen05 filter + exact re-check'}
     return out
+
+
+def sampling_benchmark(dev, model, clips):
+    """Config 5 per GPU: mask/replace sampling of the next frame (30 denoiser forwards) for `clips` clips."""
+    import world_modelz_b200 as wm
+    K = C3['num_classes']
+    tokens = torch.randint(0, K, (clips, *C3['data_shape']), device=dev)
+    tokens[:, -1] = K
+    model.eval()
+    wm.sample_next_frame(model, tokens, iterations=2)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    frame = wm.sample_next_frame(model, tokens, iterations=30)
+    e1.record()
+    torch.cuda.synchronize()
+    model.train()
+    ms = e0.elapsed_time(e1)
+    return {'clips': clips, 'iterations': 30, 'ms_per_frame': ms, 'clips_per_s': clips / (ms * 1e-3),
+            'tokens_ok': bool((frame >= 0).all().item() and (frame < K).all().item())}
 
 
 # ---------------------------------------------------------------------------------- main
@@ -313,7 +346,14 @@ def run_b200(args):
     if not args.no_micro:
         micro = micro_benchmarks(dev, B, hbm_gbs, tf_peak)
         line['roofline'] = micro.pop('roofline')
+        traffic_file = os.path.join(ROOT, 'profiles', 'ncu_traffic_r1.json')
+        if os.path.exists(traffic_file):      # dram__bytes_read+write of the three attention kernels, ncu --set full, same shape
+            tr = json.load(open(traffic_file))
+            if tr.get('clips') == B:
+                line['roofline']['traffic'] = tr['fwd_bwd_dram_bytes']
+                line['roofline']['traffic_source'] = tr['source']
         line.update(micro)
+        line['sampling_config5'] = sampling_benchmark(dev, model, 8)
     else:
         line['roofline'] = None
     if world == 1 and not args.no_cpu_baseline:

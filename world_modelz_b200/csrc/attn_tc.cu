@@ -147,9 +147,10 @@ bool make_plan(const AttnShape& s, Mode mode, Plan& best) {
             if (p.ncols_pad > max_cols || tmem_cols_for(mode, s.d, p.ncols_pad) > 512) continue;
             // shared-memory variants, best first
             bool fits = false;
-            const int opts[5][3] = {{3, 2, hpc}, {2, 2, hpc}, {3, 1, 1}, {2, 1, hpc}, {2, 1, 1}};    // {nstage, rowbuf, hpc}
+            const int opts[7][3] = {{4, 2, hpc}, {3, 2, hpc}, {2, 2, hpc}, {4, 1, 1}, {3, 1, 1}, {2, 1, hpc}, {2, 1, 1}};    // {nstage, rowbuf, hpc}
             for (const auto& o : opts) {
                 if ((mode == kBwdDQ || mode == kBwdDKV) && o[0] != 2) continue;        // non-specialised bwd kernels: 2 block stages
+                if (mode != kFwd && o[0] > 3) continue;                                // 4 stages: forward kernel only
                 if (mode != kFwd && o[1] == 1 && o[2] != 1) continue;                  // bwd: a head loop only with 2 row buffers
                 if (o[1] == 2 && hpc == 1) continue;
                 if (smem_bytes_for(mode, s.d, p.ncols_pad, o[0], o[1]) <= (size_t)kSmemLimit) {
@@ -228,11 +229,11 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     float* sX = reinterpret_cast<float*>(sMask + 2 * 9 * 128);                 // [3 uses][2 parities][NPART][128 rows]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 3 * 2 * 4 * 128);
     uint64_t* bar_q = bars;           // [2]  Q tile of a head landed
-    uint64_t* bar_kv = bars + 2;      // [3]  K/V block landed
-    uint64_t* bar_s = bars + 5;       // [2]  S buffer computed            (tcgen05.commit)
-    uint64_t* bar_p = bars + 7;       // [2]  P buffer written, S buffer drained (256 compute threads)
-    uint64_t* bar_o = bars + 9;       // [2]  O += P V of a step retired   (tcgen05.commit)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+    uint64_t* bar_kv = bars + 2;      // [4]  K/V block landed
+    uint64_t* bar_s = bars + 6;       // [2]  S buffer computed            (tcgen05.commit)
+    uint64_t* bar_p = bars + 8;       // [2]  P buffer written, S buffer drained (256 compute threads)
+    uint64_t* bar_o = bars + 10;      // [2]  O += P V of a step retired   (tcgen05.commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     // ---- which brick / head group ----------------------------------------------------------
     const int tw_i = blockIdx.x % pl.tilesW, th_i = blockIdx.x / pl.tilesW;
@@ -261,7 +262,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         tma_prefetch_desc(&map_kv_v);
         mbar_init(&bar_q[0], 1);
         mbar_init(&bar_q[1], 1);
-        for (int i = 0; i < 3; ++i) mbar_init(&bar_kv[i], 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&bar_kv[i], 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bar_s[i], 1);
             mbar_init(&bar_p[i], 128 * NPART);
@@ -385,6 +386,49 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         uint32_t kv_par = 1u;                        // bit s = parity of stage s's next completion (stage 0 was consumed once)
         const bool dbg_on = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0) && leader;
         (void)dbg_on;
+        // With >= 4 K/V stages S runs TWO steps ahead: S_{t+2} is queued right behind O += P_t V_t the moment the
+        // compute warps release step t, so they never wait for a score tile and the tensor pipe never idles on us.
+        const bool ahead2 = (nstage >= 4) && (nblocks >= 2) && (pl.rowbuf == 2 || pl.hpc == 1) && (nsteps >= 2);
+        if (ahead2) {
+            Cursor nn = nxt;                         // step t + 2
+            advance(nn);
+            int st_nn = 2;                           // its stage (nstage >= 4)
+            mbar_wait(&bar_kv[1], 0);
+            kv_par ^= 1u << 1;
+            tc_fence_after();
+            issue_s_mma(1, 1, nxt.hd);
+            for (int t = 0; t < nsteps; ++t) {
+                DBG(0);
+                const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
+                if (head_start && pl.rowbuf == 2 && cur.hd + 1 < pl.hpc) issue_q_load(cur.hd + 1);
+                mbar_wait(&bar_p[t & 1], (t >> 1) & 1);      // step t released: P_t written, S buffer t&1 drained
+                tc_fence_after();
+                DBG(4);
+                issue_o_mma(t, st_cur, cur.hd, !head_start);
+                DBG(5);
+                if (t + 2 < nsteps) {
+                    mbar_wait(&bar_kv[st_nn], (kv_par >> st_nn) & 1u);
+                    kv_par ^= 1u << st_nn;
+                    if (nn.hd != nxt.hd) mbar_wait(&bar_q[nn.hd & 1], (nn.hd >> 1) & 1);
+                    tc_fence_after();
+                    DBG(1);
+                    issue_s_mma(t + 2, st_nn, nn.hd);
+                    DBG(2);
+                }
+                if (t >= 1 && ld_t < nsteps) {               // refill the stage freed by step t-1
+                    mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);
+                    issue_kv_load(ld_stage, ld);
+                    advance(ld);
+                    ++ld_t;
+                    if (++ld_stage == nstage) ld_stage = 0;
+                }
+                DBG(3);
+                cur = nxt; nxt = nn;
+                advance(nn);
+                st_cur = st_nxt; st_nxt = st_nn;
+                if (++st_nn == nstage) st_nn = 0;
+            }
+        } else
         for (int t = 0; t < nsteps; ++t) {
             DBG(0);
             const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
