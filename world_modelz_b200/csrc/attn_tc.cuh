@@ -21,7 +21,8 @@ struct Plan {
     int hpc;                   // heads walked by one CTA (divides heads)
     int nstage;                // halo-block stages in shared memory (2 or 3)
     int rowbuf;                // row-brick buffers (2 when the CTA walks several heads)
-    int obufs;                 // forward: O accumulators in TMEM (2 = one per head parity)
+    int obufs;                 // forward: O accumulator sets in TMEM (2 = one per head parity)
+    int osplit;                // forward: independent accumulation chains of O += P V (summed in the epilogue)
     int smem_bytes;
     int tmem_cols;             // power of two
     float scale_log2;
