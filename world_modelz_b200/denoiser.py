@@ -210,8 +210,10 @@ class DenoiserTrainer:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(3):                 # warm-up on a side stream (allocator, cuBLAS handles, autograd)
+                before = ops.launch_count()
                 self._forward_backward(st_tokens, st_r)
                 self._update()
+                self._launches_per_step = ops.launch_count() - before
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph_a = torch.cuda.CUDAGraph()
@@ -228,9 +230,9 @@ class DenoiserTrainer:
         self._graph, self._static = (graph_a, graph_b), (st_tokens, st_r, st_loss, st_ps)
 
     def launches_per_step(self) -> int:
-        """Kernels of libwm_b200 per step: depth x (attention fwd 1 + bwd 2) + AdamW."""
-        depth = len(self.model.transformer.layers)
-        return depth * 3 + 1
+        """Launches of libwm_b200 kernels per step (attention fwd/bwd, add+LayerNorm fwd/bwd, bias column sums,
+        AdamW), counted by ``ops`` during the last eager warm-up step; the graphs replay exactly those."""
+        return getattr(self, '_launches_per_step', 0)
 
 
 @torch.no_grad()

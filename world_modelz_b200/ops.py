@@ -73,7 +73,7 @@ def attn_backward(q, k, v, out, lse, dout, heads: int, extents: Sequence[int], s
                                      dout.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), delta.data_ptr(),
                                      B, S, H, W, heads, C // heads, *[int(e) for e in extents], float(scale),
                                      _dtype_code(q), flags, _stream()), 'wm_l3d_attn_bwd')
-    _count(2)
+    _count(3)
     return dq, dk, dv
 
 
