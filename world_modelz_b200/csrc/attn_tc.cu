@@ -116,7 +116,6 @@ int tmem_cols_for(Mode mode, int d, int ncols_pad) {
 bool make_plan(const AttnShape& s, Mode mode, Plan& best) {
     if (s.d != 32 && s.d != 64 && s.d != 128) return false;
     const bool ws_bwd = (mode == kBwdDQws || mode == kBwdDKVws);
-    if (ws_bwd && s.d > 64) return false;
     static const int bricks[][3] = {{2, 8, 8}, {4, 4, 8}, {4, 8, 4}, {1, 8, 16}, {1, 16, 8}, {2, 4, 16}, {2, 16, 4}};
     double best_cost = 1e300;
     bool found = false;

@@ -483,10 +483,12 @@ int launch_bwd_ws(int mode, const void* a1, const void* a2, const void* b1, cons
     if (getenv("WM_TC_NO_WS") != nullptr || !make_plan(s, (Mode)mode, pl)) return WM_EUNSUPPORTED;
     if (mode == kBwdDQws) {
         if (s.d == 32) return launch_ws<32, kBwdDQws>(a1, a2, b1, b2, lse, delta, out1, out2, s, pl, st);
-        return launch_ws<64, kBwdDQws>(a1, a2, b1, b2, lse, delta, out1, out2, s, pl, st);
+        if (s.d == 64) return launch_ws<64, kBwdDQws>(a1, a2, b1, b2, lse, delta, out1, out2, s, pl, st);
+        return launch_ws<128, kBwdDQws>(a1, a2, b1, b2, lse, delta, out1, out2, s, pl, st);
     }
     if (s.d == 32) return launch_ws<32, kBwdDKVws>(a1, a2, b1, b2, lse, delta, out1, out2, s, pl, st);
-    return launch_ws<64, kBwdDKVws>(a1, a2, b1, b2, lse, delta, out1, out2, s, pl, st);
+    if (s.d == 64) return launch_ws<64, kBwdDKVws>(a1, a2, b1, b2, lse, delta, out1, out2, s, pl, st);
+    return launch_ws<128, kBwdDKVws>(a1, a2, b1, b2, lse, delta, out1, out2, s, pl, st);
 }
 
 }  // namespace tc
