@@ -124,23 +124,31 @@ add_layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dres, c
     const float inv_dim = 1.f / dim;
     for (long row = (long)blockIdx.x * 8 + warp; row < rows; row += (long)gridDim.x * 8) {
         const float mu = mean[row], rs = rstd[row];
-        float xh[CHUNKS][8], gy[CHUNKS][8];
+        float xh[CHUNKS][8], gy[CHUNKS][8], rr[CHUNKS][8];
         float c1 = 0.f, c2 = 0.f;
+        // issue every load of the row up front (dy, x and the residual-path gradient): one memory round trip per row
 #pragma unroll
         for (int c = 0; c < CHUNKS; ++c) {
             const int col = c * 256 + lane * 8;
             if (col < dim) {
-                float d[8], xv[8];
-                load8(dy + row * dim + col, d);
-                load8(x + row * dim + col, xv);
+                load8(dy + row * dim + col, gy[c]);
+                load8(x + row * dim + col, xh[c]);
+                if (dres != nullptr) load8(dres + row * dim + col, rr[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+            const int col = c * 256 + lane * 8;
+            if (col < dim) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    xh[c][i] = (xv[i] - mu) * rs;
-                    gy[c][i] = d[i] * g[c][i];
+                    const float d = gy[c][i];
+                    xh[c][i] = (xh[c][i] - mu) * rs;
+                    gy[c][i] = d * g[c][i];
                     c1 = fmaf(gy[c][i], xh[c][i], c1);
                     c2 += gy[c][i];
-                    dg[c][i] = fmaf(d[i], xh[c][i], dg[c][i]);
-                    db[c][i] += d[i];
+                    dg[c][i] = fmaf(d, xh[c][i], dg[c][i]);
+                    db[c][i] += d;
                 }
             }
         }
@@ -152,12 +160,9 @@ add_layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dres, c
             if (col < dim) {
                 float o[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = rs * (gy[c][i] - c2 - xh[c][i] * c1);
-                if (dres != nullptr) {
-                    float r[8];
-                    load8(dres + row * dim + col, r);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o[i] += r[i];
+                for (int i = 0; i < 8; ++i) {
+                    o[i] = rs * (gy[c][i] - c2 - xh[c][i] * c1);
+                    if (dres != nullptr) o[i] += rr[c][i];
                 }
                 store8(dx + row * dim + col, o);
             }

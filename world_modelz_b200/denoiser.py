@@ -113,8 +113,8 @@ class DenoiserTrainer:
     """One training step of the denoiser, batch-sharded over ``world_size`` GPUs.
 
     Parameters live in three flat buffers: fp32 master weights, a compute-dtype shadow the
-    modules read (``param.data`` are views into it) and a flat gradient buffer the autograd
-    engine accumulates into (``param.grad`` are views).  A step is: zero grads, corruption,
+    modules read (``param.data`` are views into it) and a flat gradient buffer that one
+    multi-tensor copy fills from the per-parameter gradients after backward.  A step is: zero grads, corruption,
     forward, mean CE, backward, ONE all-reduce(SUM) of the flat gradients over NCCL, ONE
     fused AdamW launch (``wm_adamw_step``) that also refreshes the shadow copy.
     """
@@ -138,6 +138,8 @@ class DenoiserTrainer:
         self.exp_avg = torch.zeros_like(self.master)
         self.exp_avg_sq = torch.zeros_like(self.master)
         self.master.zero_()
+        self._params = params
+        self._grad_views = []
         off = 0
         for p in params:
             k = p.numel()
@@ -145,7 +147,7 @@ class DenoiserTrainer:
             store = self.shadow if self.shadow is not None else self.master
             store[off:off + k].copy_(p.detach().reshape(-1))
             p.data = store[off:off + k].view_as(p)
-            p.grad = self.grad[off:off + k].view_as(p)
+            self._grad_views.append(self.grad[off:off + k].view_as(p))
             off += k
         if self.world > 1:   # identical replicas: rank 0's weights win
             dist.broadcast(self.master, src=dist.get_global_rank(self.pg, 0) if self.pg else 0, group=self.pg)
@@ -159,13 +161,16 @@ class DenoiserTrainer:
 
     # -- the step, in three pieces: graph A | one NCCL all-reduce | graph B ------------------------
     def _forward_backward(self, tokens, r):
-        self.grad.zero_()
+        for p in self._params:                # autograd then ASSIGNS fresh gradients instead of launching one add per parameter
+            p.grad = None
         corrupted, target = corrupt_last_frame(tokens, r, self.K)
         logits = self.model(corrupted)
         ce = F.cross_entropy(logits.reshape(-1, self.K).float(), target.reshape(-1), reduction='none')
         per_sample = ce.view(tokens.shape[0], -1).mean(dim=1)
         loss = ce.mean()
         loss.backward()
+        # one multi-tensor copy gathers every parameter gradient into the flat buffer (the all-reduce / AdamW operand)
+        torch._foreach_copy_(self._grad_views, [p.grad for p in self._params])
         return loss.detach(), per_sample.detach()
 
     def _exchange(self):
