@@ -214,23 +214,30 @@ def micro_benchmarks(dev, clips, hbm_gbs, tf_peak):
 
 
 def sampling_benchmark(dev, model, clips):
-    """Config 5 per GPU: mask/replace sampling of the next frame (30 denoiser forwards) for `clips` clips."""
+    """Config 5 per GPU: mask/replace sampling of the next frame (30 denoiser forwards) for `clips` clips,
+    then VQ decode of the sampled latents (codebook gather, 512 x 64)."""
     import world_modelz_b200 as wm
     K = C3['num_classes']
+    vq = wm.VectorQuantizerEMA(64, K).to(dev)
     tokens = torch.randint(0, K, (clips, *C3['data_shape']), device=dev)
     tokens[:, -1] = K
     model.eval()
-    wm.sample_next_frame(model, tokens, iterations=2)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    frame = wm.sample_next_frame(model, tokens, iterations=30)
-    e1.record()
-    torch.cuda.synchronize()
+    out = {}
+    for graph in (False, True):
+        wm.sample_next_frame(model, tokens, iterations=2, use_cuda_graph=graph)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        frame = wm.sample_next_frame(model, tokens, iterations=30, use_cuda_graph=graph)
+        latents = vq.decode(frame)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        out['cuda_graph' if graph else 'eager'] = {'ms_per_frame': ms, 'clips_per_s': clips / (ms * 1e-3)}
     model.train()
-    ms = e0.elapsed_time(e1)
-    return {'clips': clips, 'iterations': 30, 'ms_per_frame': ms, 'clips_per_s': clips / (ms * 1e-3),
-            'tokens_ok': bool((frame >= 0).all().item() and (frame < K).all().item())}
+    out.update({'clips': clips, 'iterations': 30, 'decoded_latents_shape': list(latents.shape),
+                'tokens_ok': bool((frame >= 0).all().item() and (frame < K).all().item())})
+    return out
 
 
 # ---------------------------------------------------------------------------------- main

@@ -240,29 +240,55 @@ class DenoiserTrainer:
         return getattr(self, '_launches_per_step', 0)
 
 
+def _sample_iteration(model, work, logits, alpha, K):
+    """One mask/replace iteration (``main.py:79-111``): draw every position, re-mask a ``1 - alpha`` fraction,
+    run the denoiser.  ``alpha`` is a 0-d device tensor so that the captured graph can be replayed."""
+    B, _, H, W = work.shape
+    probs = torch.softmax(logits.float(), dim=-1)
+    sample = torch.multinomial(probs, 1, replacement=True).view(B, H, W)
+    remask = torch.rand(B, H, W, device=work.device) > alpha
+    work[:, -1] = torch.where(remask, torch.full_like(sample, K), sample)
+    return sample, model(work).reshape(B * H * W, K)
+
+
 @torch.no_grad()
 def sample_next_frame(model: VqVideoDiffusionModel, tokens: torch.Tensor, iterations: int = 30,
-                      sample_topk: int = -1) -> torch.Tensor:
+                      sample_topk: int = -1, use_cuda_graph: bool = False) -> torch.Tensor:
     """Iteratively denoise the last frame (reference ``main.py:71-111``).
 
     ``tokens [B,S,H,W]`` with the last frame set to the mask token.  Each iteration draws
     every position from the current logits, re-masks a ``1 - (i+1)/iterations`` fraction
     and runs one denoiser forward.  Returns the final draw ``[B,H,W]`` (what the reference
-    hands to ``decoder_model.decode``).
+    hands to ``decoder_model.decode``).  With ``use_cuda_graph`` one iteration is captured
+    and replayed (the loop is launch-bound at the reference's 8-clip evaluation batch).
     """
     B, _, H, W = tokens.shape
     K = model.num_classes
     work = tokens.clone()
     logits = torch.zeros(B * H * W, K, device=tokens.device)
     sample = None
+    if use_cuda_graph and sample_topk <= 0:
+        alpha = torch.zeros((), device=tokens.device)
+        side = torch.cuda.Stream(device=tokens.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                 # warm-up outside the capture
+            _sample_iteration(model, work.clone(), logits, alpha, K)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            g_sample, g_logits = _sample_iteration(model, work, logits, alpha, K)
+        work.copy_(tokens)
+        logits.zero_()
+        for i in range(iterations):
+            alpha.fill_(min(max((i + 1) / iterations, 0.0), 1.0))
+            graph.replay()
+            logits.copy_(g_logits)
+        return g_sample.clone()
     for i in range(iterations):
         if sample_topk > 0:
             kth = torch.topk(logits, sample_topk, dim=-1).values[:, -1:]
             logits = logits.masked_fill(logits < kth, float('-inf'))
-        probs = torch.softmax(logits.float(), dim=-1)
-        sample = torch.multinomial(probs, 1, replacement=True).view(B, H, W)
-        alpha = min(max((i + 1) / iterations, 0.0), 1.0)
-        remask = torch.rand(B, H, W, device=tokens.device) > alpha
-        work[:, -1] = torch.where(remask, torch.full_like(sample, K), sample)
-        logits = model(work).reshape(B * H * W, K)
+        alpha = torch.tensor(min(max((i + 1) / iterations, 0.0), 1.0), device=tokens.device)
+        sample, logits = _sample_iteration(model, work, logits, alpha, K)
     return sample
