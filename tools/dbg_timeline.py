@@ -38,3 +38,19 @@ for m, name in ((0, 'dQ'), (1, 'dK/dV')):
         ev = [(a[t, s] - a[t, 0], nb[s]) for s in nb if a[t, s] != 0]
         print(f'step {t} (+{a[t,0]-t0}): ' + '  '.join(f'{n}@{c}' for c, n in ev))
     print('period:', np.diff(a[2:26, 0]).tolist())
+
+
+# ---- warp-specialised backward kernels
+if hasattr(_lib.lib(), 'wm_debug_read_ws'):
+    buf3 = (ctypes.c_longlong * (2 * 64 * 16))()
+    _lib.lib().wm_debug_read_ws(buf3)
+    b3 = np.array(buf3[:], dtype=np.int64).reshape(2, 64, 16)
+    nw = {0: 'drv:top', 1: 'drv:p ok', 2: 'drv:T issued', 3: 'drv:acc issued', 4: 'drv:refilled', 8: 'cmp:top', 9: 'cmp:bufs free',
+          10: 'cmp:T ready', 11: 'cmp:done', 12: 'cmp:arrived'}
+    for m, name in ((0, 'dQ ws'), (1, 'dK/dV ws')):
+        a = b3[m]; t0 = a[0, 0]
+        print('====', name)
+        for t in range(2, 11):
+            ev = sorted((a[t, s] - t0, nw[s]) for s in nw if a[t, s] != 0)
+            print(f'step {t}: ' + '  '.join(f'{n}@{c}' for c, n in ev))
+        print('driver period:', np.diff(a[2:26, 0]).tolist())

@@ -12,6 +12,16 @@
 // the (S, dP) MMAs of step t+1 are issued before them, right when the buffers are drained.
 #include "attn_tc.cuh"
 
+#ifndef WM_EXPERIMENT
+#define WM_EXPERIMENT 0
+#endif
+#if WM_EXPERIMENT == 7
+namespace wm { namespace tc { __device__ long long g_dbg_ws[2 * 64 * 16]; } }
+#define DBGW(slot) do { if (dbg_on && t < 64) g_dbg_ws[(MODE - 3) * 1024 + t * 16 + (slot)] = clock64(); } while (0)
+#else
+#define DBGW(slot) do { } while (0)
+#endif
+
 #include <math.h>
 #include <stdlib.h>
 
@@ -216,12 +226,16 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         issue_t_mma(0, 0);
         int st_cur = 0, st_nxt = (nstage > 1) ? 1 : 0;
         uint32_t b_par = 1u;                         // bit s = parity of stage s's next completion (stage 0 consumed once)
+        const bool dbg_on = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0) && leader;
+        (void)dbg_on;
         for (int t = 0; t < nsteps; ++t) {
+            DBGW(0);
             const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
             if (head_start && pl.rowbuf == 2 && cur.hd + 1 < pl.hpc) issue_row_load(cur.hd + 1);   // buffer of head hd-1
             // the compute warps have drained (S, dP) of step t and written its dS / P
             mbar_wait(&bar_p[t & 1], (t >> 1) & 1);
             tc_fence_after();
+            DBGW(1);
             auto refill = [&]() {        // refill the stage freed by step t-1 once its accumulating MMAs have retired
                 if (t >= 1 && ld_t < nsteps) {
                     mbar_wait(&bar_acc[(t - 1) & 1], ((t - 1) >> 1) & 1);
@@ -239,8 +253,11 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                 tc_fence_after();
                 issue_t_mma(st_nxt, nxt.hd);
             }
+            DBGW(2);
             issue_acc_mma(t, st_cur, !head_start);
+            DBGW(3);
             if (nstage >= 3) refill();
+            DBGW(4);
             cur = nxt;
             advance(nxt);
             st_cur = st_nxt;
@@ -325,7 +342,10 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         const int ngroups = ncols_pad >> 4;
         const uint32_t zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
+        const bool dbg_on = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0 && tid == 0);
+        (void)dbg_on;
         for (int t = 0; t < nsteps; ++t) {
+            DBGW(8);
             const int buf = t & 1;
             const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
             float nxt_lse2 = 0.f, nxt_dl = 0.f;
@@ -336,11 +356,6 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                     row_lse2 = __ldg(prm.lse + row_tok * sh.heads + head0 + cur.hd) * kLog2e;
                     row_delta = __ldg(prm.delta + row_tok * sh.heads + head0 + cur.hd);
                 }
-            }
-            if (head_start && t > 0) {               // one accumulator set: drain the previous head before this head's first MMA
-                mbar_wait(&bar_acc[(t - 1) & 1], ((t - 1) >> 1) & 1);
-                tc_fence_after();
-                finish_head(cur.hd - 1);
             }
             const int kh0 = cur.chunk * pl.ch;
             if (cur.chunk != mask_chunk) {
@@ -362,8 +377,10 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             }
             // the dS / P buffers of parity `buf` are free once the accumulating MMAs of step t-2 have retired
             if (t >= 2) mbar_wait(&bar_acc[buf], ((t - 2) >> 1) & 1);
+            DBGW(9);
             mbar_wait(bar_t, t & 1);                  // (S, dP) of this step
             tc_fence_after();
+            DBGW(10);
 
             const uint32_t tmem_a = tmem_pa + buf * pa_cols + lane_sel;       // this row's bf16-pair columns
             uint8_t* ds_tile = sDS + buf * p_tile_bytes;
@@ -440,10 +457,20 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                 if (t + 1 < nsteps) store_colvec((t + 1) & 1, nxt_lse2, nxt_dl);
                 fence_proxy_async();              // dS^T (generic proxy) -> visible to tcgen05.mma
             }
+            DBGW(11);
+            if (head_start && t > 0) {
+                // One accumulator set: the previous head must be drained before this head's first accumulating MMA, which
+                // the driver issues only after every compute thread has arrived below.  Doing it here, after this step's
+                // math, lets the wait for the previous head's last MMAs overlap that math.
+                mbar_wait(&bar_acc[(t - 1) & 1], ((t - 1) >> 1) & 1);
+                tc_fence_after();
+                finish_head(cur.hd - 1);
+            }
             tmem_wait_st();
             tc_fence_before();
             if constexpr (kDKV) asm volatile("bar.sync 5, 256;" ::: "memory");   // next step's lse / delta columns are in place
             mbar_arrive(&bar_p[buf]);
+            DBGW(12);
             cur = nxt;
             advance(nxt);
         }
@@ -475,6 +502,12 @@ static int launch_ws(const void* a1, const void* a2, const void* b1, const void*
     WM_CUDA_CHECK(cudaGetLastError());
     return WM_OK;
 }
+
+#if WM_EXPERIMENT == 7
+extern "C" __attribute__((visibility("default"))) int wm_debug_read_ws(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, g_dbg_ws, sizeof(long long) * 2 * 64 * 16);
+}
+#endif
 
 // returns WM_OK when it launched, WM_EUNSUPPORTED when the shape has no warp-specialised tiling
 int launch_bwd_ws(int mode, const void* a1, const void* a2, const void* b1, const void* b2, const float* lse,
