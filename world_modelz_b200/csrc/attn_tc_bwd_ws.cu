@@ -292,7 +292,7 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                 if (gs >= 0 && gs < sh.S && gh >= 0 && gh < sh.H && gw >= 0 && gw < sh.W) {
                     const long idx = ((((long)b * sh.S + gs) * sh.H + gh) * sh.W + gw) * sh.heads + head0 + c.hd;
                     lse2 = __ldg(prm.lse + idx) * kLog2e;
-                    dl = __ldg(prm.delta + idx);
+                    dl = __ldg(prm.delta + idx) * sh.scale;
                 }
             }
         };
@@ -354,7 +354,7 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             } else {
                 if (head_start && row_valid) {
                     row_lse2 = __ldg(prm.lse + row_tok * sh.heads + head0 + cur.hd) * kLog2e;
-                    row_delta = __ldg(prm.delta + row_tok * sh.heads + head0 + cur.hd);
+                    row_delta = __ldg(prm.delta + row_tok * sh.heads + head0 + cur.hd) * sh.scale;
                 }
             }
             const int kh0 = cur.chunk * pl.ch;
@@ -422,11 +422,10 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                     float pv[16], dsv[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const bool on = (mword >> i) & 1u;
+                        // dl[] holds delta * scale: dS = P * (dP * scale - delta * scale); masking P masks dS with it
                         const float p = ex2(fmaf(__uint_as_float(s[i]), pl.scale_log2, -l2[i]));
-                        const float ds = p * (__uint_as_float(dp[i]) - dl[i]) * sh.scale;
-                        pv[i] = on ? p : 0.f;
-                        dsv[i] = on ? ds : 0.f;
+                        pv[i] = ((mword >> i) & 1u) ? p : 0.f;
+                        dsv[i] = pv[i] * fmaf(__uint_as_float(dp[i]), sh.scale, -dl[i]);
                     }
                     uint32_t pk[8];
 #pragma unroll
