@@ -1,0 +1,8 @@
+#!/bin/bash
+# Builds the stand-alone micro-benchmarks (not part of libwm_b200).
+set -e
+cd "$(dirname "$0")"
+mkdir -p _bin
+for f in *.cu; do
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -o _bin/${f%.cu} $f -lcuda
+done

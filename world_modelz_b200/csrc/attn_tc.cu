@@ -311,7 +311,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         // =============================== driver ===============================================
         // The whole warp runs this code so that addresses and descriptors stay warp-uniform (uniform
         // datapath); only the TMA / tcgen05 instructions themselves are predicated on one lane.
-        const bool leader = (lane == 0);
+        const bool leader = elect_one();      // whole driver warp is converged here
         auto q_buf = [&](int hd) { return sQ + (pl.rowbuf == 2 ? (hd & 1) : 0) * q_tile_bytes; };
         auto issue_q_load = [&](int hd) {
             if (leader) {

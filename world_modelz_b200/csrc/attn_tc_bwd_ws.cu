@@ -135,7 +135,7 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
 
     if (warp == 8) {
         // =============================== driver (warp-uniform; instructions on one lane) ==============
-        const bool leader = (lane == 0);
+        const bool leader = elect_one();      // whole driver warp is converged here
         auto a_buf = [&](int hd) { return sA + (pl.rowbuf == 2 ? (hd & 1) : 0) * 2 * row_tile_bytes; };
         auto issue_row_load = [&](int hd) {
             if (leader) {

@@ -67,6 +67,14 @@ template <int kCols>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {     // same warp that allocated
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols));
 }
+// One lane of a converged warp.  Issuing tcgen05.mma / TMA under this predicate (instead of `lane == 0`) lets ptxas emit
+// back-to-back UTCHMMA; with `lane == 0` it wraps every MMA in an ELECT / R2UR.BROADCAST / branch loop, which costs
+// ~80 cycles per MMA against ~19-35 (measured, tools/micro/mma_issue_clean.cu).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
