@@ -1,6 +1,6 @@
 #!/bin/bash
 # Builds the stand-alone micro-benchmarks (not part of libwm_b200).
-set -e
+set -eo pipefail
 cd "$(dirname "$0")"
 mkdir -p _bin
 for f in *.cu; do

@@ -291,15 +291,15 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                 const int gh = h0 - sh.eH + c.chunk * pl.ch + khl, gw = w0 - sh.eW + kw;
                 if (gs >= 0 && gs < sh.S && gh >= 0 && gh < sh.H && gw >= 0 && gw < sh.W) {
                     const long idx = ((((long)b * sh.S + gs) * sh.H + gh) * sh.W + gw) * sh.heads + head0 + c.hd;
-                    lse2 = __ldg(prm.lse + idx) * kLog2e;
-                    dl = __ldg(prm.delta + idx) * sh.scale;
+                    lse2 = __ldg(prm.lse + idx);          // raw: scaled in store_colvec, a whole step later, so that
+                    dl = __ldg(prm.delta + idx);          // the load latency is never waited for at the top of a step
                 }
             }
         };
-        auto store_colvec = [&](int buf, float lse2, float dl) {
+        auto store_colvec = [&](int buf, float lse_raw, float dl_raw) {
             if (ctid < ncols_pad) {
-                sCol[(buf * 2 + 0) * ncols_pad + ctid] = lse2;
-                sCol[(buf * 2 + 1) * ncols_pad + ctid] = dl;
+                sCol[(buf * 2 + 0) * ncols_pad + ctid] = lse_raw * kLog2e;
+                sCol[(buf * 2 + 1) * ncols_pad + ctid] = dl_raw * sh.scale;
             }
         };
         auto finish_head = [&](int hd) {            // accumulators of head `hd` -> bf16 -> global
@@ -328,6 +328,13 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         Cursor nxt = cur;
         advance(nxt);
         float row_lse2 = 0.f, row_delta = 0.f;
+        float ahead_lse = 0.f, ahead_delta = 0.f;                        // dQ kernel: raw values of the next head, in flight
+        if constexpr (!kDKV) {
+            if (row_valid) {
+                ahead_lse = __ldg(prm.lse + row_tok * sh.heads + head0);
+                ahead_delta = __ldg(prm.delta + row_tok * sh.heads + head0);
+            }
+        }
         if constexpr (kDKV) {
             float a, c;
             load_colvec(cur, a, c);
@@ -352,9 +359,14 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             if constexpr (kDKV) {
                 if (t + 1 < nsteps) load_colvec(nxt, nxt_lse2, nxt_dl);      // global loads in flight during the waits
             } else {
-                if (head_start && row_valid) {
-                    row_lse2 = __ldg(prm.lse + row_tok * sh.heads + head0 + cur.hd) * kLog2e;
-                    row_delta = __ldg(prm.delta + row_tok * sh.heads + head0 + cur.hd) * sh.scale;
+                if (head_start) {
+                    asm volatile("" : "+f"(ahead_lse), "+f"(ahead_delta));   // first use of the loads issued one head ago
+                    row_lse2 = ahead_lse * kLog2e;
+                    row_delta = ahead_delta * sh.scale;
+                    if (row_valid && cur.hd + 1 < pl.hpc) {
+                        ahead_lse = __ldg(prm.lse + row_tok * sh.heads + head0 + cur.hd + 1);
+                        ahead_delta = __ldg(prm.delta + row_tok * sh.heads + head0 + cur.hd + 1);
+                    }
                 }
             }
             const int kh0 = cur.chunk * pl.ch;
@@ -453,6 +465,8 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                 p_zero[buf] = true;
             }
             if constexpr (kDKV) {
+                // ptxas otherwise hoists the scaling multiplies up to the loads (top of the step) and stalls there for DRAM
+                asm volatile("" : "+f"(nxt_lse2), "+f"(nxt_dl));
                 if (t + 1 < nsteps) store_colvec((t + 1) & 1, nxt_lse2, nxt_dl);
                 fence_proxy_async();              // dS^T (generic proxy) -> visible to tcgen05.mma
             }
