@@ -115,18 +115,21 @@ WM_API int wm_adamw_step(float* master, void* shadow, const void* grad, float* e
  * (local_3d_attention.py:11-17,159-161) and the bias gradients of its nn.Linear layers.
  * Rows are tokens, `dim` channels contiguous (multiple of 8, <= 2048); dtype bf16 or fp32.
  *
- * wm_add_layernorm_fwd: sum = res (+ delta, when delta != NULL; written to sum_out when that
- *   is != NULL); y = LayerNorm(sum) * gamma + beta; mean / rstd [rows] fp32 kept for backward.
+ * wm_add_layernorm_fwd: sum = res (+ delta (+ delta_bias[dim]), when != NULL; written to sum_out
+ *   when that is != NULL); y = LayerNorm(sum) * gamma + beta; mean / rstd [rows] fp32 kept for
+ *   backward.  delta_bias is the bias of the nn.Linear that produced delta (to_out.0 / net.3,
+ *   local_3d_attention.py:24-27,52), applied here so that its gradient falls out of the backward.
  * wm_add_layernorm_bwd: dx = (dres, when != NULL, +) dLayerNorm(dy; x, mean, rstd, gamma);
- *   dgamma / dbeta [dim].  workspace: wm_reduce_blocks(rows) * 2 * dim floats.
+ *   dgamma / dbeta [dim]; dsum [dim] (when != NULL) = column sums of dx = gradient of delta_bias.
+ *   workspace: wm_reduce_blocks(rows) * 3 * dim floats.
  * wm_colsum: out[c] = sum_r a[r, c] (bias gradient).  workspace: wm_reduce_blocks(rows) * cols floats. */
 WM_API int wm_reduce_blocks(long rows);
-WM_API int wm_add_layernorm_fwd(const void* res, const void* delta, const void* gamma, const void* beta,
-                                void* sum_out, void* y, float* mean, float* rstd, long rows, int dim, float eps,
-                                int dtype, void* stream);
+WM_API int wm_add_layernorm_fwd(const void* res, const void* delta, const void* delta_bias, const void* gamma,
+                                const void* beta, void* sum_out, void* y, float* mean, float* rstd, long rows,
+                                int dim, float eps, int dtype, void* stream);
 WM_API int wm_add_layernorm_bwd(const void* dy, const void* dres, const void* x, const float* mean,
                                 const float* rstd, const void* gamma, void* dx, void* dgamma, void* dbeta,
-                                float* workspace, long rows, int dim, int dtype, void* stream);
+                                void* dsum, float* workspace, long rows, int dim, int dtype, void* stream);
 WM_API int wm_colsum(const void* a, void* out, float* workspace, long rows, int cols, int dtype, void* stream);
 
 #ifdef __cplusplus

@@ -58,3 +58,62 @@ def test_linear_bias_gradient(dtype, rtol, atol, rows, cin, cout):
     torch.testing.assert_close(out.float().cpu(), F.linear(*ref).detach(), rtol=rtol, atol=atol)
     for a, r in zip(got, ref):
         torch.testing.assert_close(a.grad.float().cpu(), r.grad, rtol=rtol, atol=atol * max(1.0, rows ** 0.5 / 8))
+
+
+@pytest.mark.parametrize('dtype,rtol,atol', [(torch.float32, 1e-5, 1e-5), (torch.bfloat16, 2e-2, 2e-2)])
+@pytest.mark.parametrize('rows,dim', [(4096, 256), (999, 48), (130, 1024)])
+def test_add_layernorm_deferred_bias(dtype, rtol, atol, rows, dim):
+    """sum = res + delta + delta_bias; the backward also returns the bias gradient (column sums of d sum)."""
+    g = torch.Generator().manual_seed(rows * 7 + dim)
+    res, delta = torch.randn(rows, dim, generator=g), torch.randn(rows, dim, generator=g)
+    bias = torch.randn(dim, generator=g)
+    gamma, beta = torch.rand(dim, generator=g) + 0.5, torch.randn(dim, generator=g)
+    w_sum, w_y = torch.randn(rows, dim, generator=g), torch.randn(rows, dim, generator=g)
+    cast = lambda t: t.detach().to(dtype).float().clone().requires_grad_(True)
+    r_res, r_delta, r_bias, r_gamma, r_beta = (cast(t) for t in (res, delta, bias, gamma, beta))
+    exact = r_res + r_delta + r_bias
+    total = exact + (exact.to(dtype).float() - exact).detach()
+    y = F.layer_norm(total, (dim,), r_gamma, r_beta, 1e-5)
+    (total * w_sum).sum().add((y * w_y).sum()).backward()
+    dev = lambda t: t.detach().to(DEV, dtype).requires_grad_(True)
+    d_res, d_delta, d_bias, d_gamma, d_beta = (dev(t) for t in (res, delta, bias, gamma, beta))
+    o_total, o_y = ops.add_layernorm(d_res, d_delta, d_gamma, d_beta, 1e-5, d_bias)
+    ((o_total.float() * w_sum.to(DEV)).sum() + (o_y.float() * w_y.to(DEV)).sum()).backward()
+    torch.testing.assert_close(o_total.float().cpu(), total.detach(), rtol=rtol, atol=atol)
+    torch.testing.assert_close(o_y.float().cpu(), y.detach(), rtol=rtol, atol=atol)
+    torch.testing.assert_close(d_res.grad.float().cpu(), r_res.grad, rtol=rtol, atol=atol * 4)
+    torch.testing.assert_close(d_delta.grad.float().cpu(), r_delta.grad, rtol=rtol, atol=atol * 4)
+    scale = max(1.0, rows ** 0.5)
+    torch.testing.assert_close(d_bias.grad.float().cpu(), r_bias.grad, rtol=rtol, atol=atol * scale)
+    torch.testing.assert_close(d_gamma.grad.float().cpu(), r_gamma.grad, rtol=rtol, atol=atol * scale)
+
+
+@pytest.mark.parametrize('dtype,rtol,atol', [(torch.float32, 1e-4, 1e-4), (torch.bfloat16, 2e-2, 3e-2)])
+def test_attention_module_deferred_bias_matches_forward(dtype, rtol, atol):
+    """Local3dAttention.forward_deferred_bias(x, q) = (y, b) with y + b == forward(x, q), values and gradients
+    (to_v's bias folded through the softmax into the output bias); same for FeedForward."""
+    from world_modelz_b200.local_3d_attention import Local3dAttention, FeedForward
+    torch.manual_seed(5)
+    attn = Local3dAttention((1, 1, 1), 64, heads=4, dim_head=16).to(DEV, dtype)
+    ff = FeedForward(64, 128).to(DEV, dtype)
+    with torch.no_grad():
+        attn.to_v.bias.normal_()
+        attn.to_out[0].bias.normal_()
+        ff.net[3].bias.normal_()
+    x = torch.randn(2, 4, 6, 8, 64, device=DEV, dtype=dtype)
+    q = torch.randn_like(x)
+    w = torch.randn_like(x)
+    for mod, args in ((attn, (x, q)), (ff, (x,))):
+        names = [n for n, _ in mod.named_parameters()]
+        mod.zero_grad()
+        ref = mod(*args)
+        (ref.float() * w.float()).sum().backward()
+        ref_grads = [p.grad.float().clone() for p in mod.parameters()]
+        mod.zero_grad()
+        y, b = mod.forward_deferred_bias(*args)
+        assert b is not None
+        got = y.float() + b.float()
+        (got * w.float()).sum().backward()
+        torch.testing.assert_close(got, ref.float(), rtol=rtol, atol=atol)
+        for n, p, r in zip(names, mod.parameters(), ref_grads):
+            torch.testing.assert_close(p.grad.float(), r, rtol=rtol, atol=atol * 8, msg=lambda m, n=n: f'{n}: {m}')

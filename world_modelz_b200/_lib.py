@@ -50,9 +50,9 @@ def lib() -> ctypes.CDLL:
     L.wm_reduce_blocks.restype = c_int
     L.wm_reduce_blocks.argtypes = [c_long]
     L.wm_add_layernorm_fwd.restype = c_int
-    L.wm_add_layernorm_fwd.argtypes = [c_void_p] * 8 + [c_long, c_int, c_float, c_int, c_void_p]
+    L.wm_add_layernorm_fwd.argtypes = [c_void_p] * 9 + [c_long, c_int, c_float, c_int, c_void_p]
     L.wm_add_layernorm_bwd.restype = c_int
-    L.wm_add_layernorm_bwd.argtypes = [c_void_p] * 10 + [c_long, c_int, c_int, c_void_p]
+    L.wm_add_layernorm_bwd.argtypes = [c_void_p] * 11 + [c_long, c_int, c_int, c_void_p]
     L.wm_colsum.restype = c_int
     L.wm_colsum.argtypes = [c_void_p] * 3 + [c_long, c_int, c_int, c_void_p]
     _lib = L

@@ -256,6 +256,10 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             DBGW(2);
             issue_acc_mma(t, st_cur, !head_start);
             DBGW(3);
+#if WM_EXPERIMENT == 7 && defined(WM_DBG_ACC_DONE)
+            // diagnostic only: the instrumented CTA's driver waits for its own accumulating MMAs and records when they retire
+            if (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0) { mbar_wait(&bar_acc[t & 1], (t >> 1) & 1); DBGW(5); }
+#endif
             if (nstage >= 3) refill();
             DBGW(4);
             cur = nxt;

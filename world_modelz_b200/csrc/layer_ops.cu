@@ -46,14 +46,39 @@ __device__ __forceinline__ void store8(float* p, const float (&f)[8]) {
     *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
     *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
 }
+// 8 consecutive elements as loaded (no conversion): lets a prefetch sit in few registers
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> {
+    uint4 v;
+    __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ void unpack(float (&f)[8]) const {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 t = __bfloat1622float2(h[i]);
+            f[2 * i] = t.x;
+            f[2 * i + 1] = t.y;
+        }
+    }
+};
+template <> struct Raw8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float* p) {
+        a = *reinterpret_cast<const float4*>(p);
+        b = *reinterpret_cast<const float4*>(p + 4);
+    }
+    __device__ __forceinline__ void unpack(float (&f)[8]) const {
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+};
 __device__ __forceinline__ float round_to(float v, const __nv_bfloat16*) { return __bfloat162float(__float2bfloat16_rn(v)); }
 __device__ __forceinline__ float round_to(float v, const float*) { return v; }
 
 // sum = res (+ delta); y = LayerNorm(sum) * gamma + beta; mean / rstd kept for backward
 template <typename T, int CHUNKS>
 __global__ void __launch_bounds__(256)
-add_layernorm_fwd_kernel(const T* __restrict__ res, const T* __restrict__ delta, const T* __restrict__ gamma,
-                         const T* __restrict__ beta, T* __restrict__ sum_out, T* __restrict__ y,
+add_layernorm_fwd_kernel(const T* __restrict__ res, const T* __restrict__ delta, const T* __restrict__ delta_bias,
+                         const T* __restrict__ gamma, const T* __restrict__ beta, T* __restrict__ sum_out, T* __restrict__ y,
                          float* __restrict__ mean_out, float* __restrict__ rstd_out, long rows, int dim, float eps) {
     const int lane = threadIdx.x & 31;
     const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -68,6 +93,12 @@ add_layernorm_fwd_kernel(const T* __restrict__ res, const T* __restrict__ delta,
             if (delta != nullptr) {
                 float d[8];
                 load8(delta + row * dim + col, d);
+                if (delta_bias != nullptr) {             // bias of the linear layer that produced delta, applied here
+                    float bb[8];
+                    load8(delta_bias + col, bb);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) d[i] += bb[i];
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[c][i] = round_to(x[c][i] + d[i], res);   // the sum as the next layer reads it
                 if (sum_out != nullptr) store8(sum_out + row * dim + col, x[c]);
@@ -107,64 +138,99 @@ add_layernorm_fwd_kernel(const T* __restrict__ res, const T* __restrict__ delta,
 
 // dx = (dres +) LayerNorm backward(dy); per-block partial sums of dgamma / dbeta
 template <typename T, int CHUNKS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, CHUNKS == 1 ? 2 : 1)
 add_layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dres, const T* __restrict__ x,
                          const float* __restrict__ mean, const float* __restrict__ rstd, const T* __restrict__ gamma,
-                         T* __restrict__ dx, float* __restrict__ part, long rows, int dim) {
-    extern __shared__ float red[];          // [8 warps][2][dim]
+                         T* __restrict__ dx, float* __restrict__ part, long rows, int dim, int nwhich) {
+    extern __shared__ float red[];          // [8 warps][nwhich][dim]; nwhich = 3 adds the column sums of dx
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float g[CHUNKS][8], dg[CHUNKS][8], db[CHUNKS][8];
+    float g[CHUNKS][8], dg[CHUNKS][8], db[CHUNKS][8], ds[CHUNKS][8];
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
         const int col = c * 256 + lane * 8;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { dg[c][i] = 0.f; db[c][i] = 0.f; g[c][i] = 0.f; }
+        for (int i = 0; i < 8; ++i) { dg[c][i] = 0.f; db[c][i] = 0.f; ds[c][i] = 0.f; g[c][i] = 0.f; }
         if (col < dim) load8(gamma + col, g[c]);
     }
     const float inv_dim = 1.f / dim;
-    for (long row = (long)blockIdx.x * 8 + warp; row < rows; row += (long)gridDim.x * 8) {
-        const float mu = mean[row], rs = rstd[row];
-        float xh[CHUNKS][8], gy[CHUNKS][8], rr[CHUNKS][8];
-        float c1 = 0.f, c2 = 0.f;
-        // issue every load of the row up front (dy, x and the residual-path gradient): one memory round trip per row
+    // The kernel is a pure stream, so what matters is the number of bytes each warp keeps in flight: two rows per
+    // iteration, and the (raw, unconverted) loads of the NEXT two rows are issued before the current two are reduced.
+    constexpr int R = CHUNKS == 1 ? 2 : 1;      // wider rows already carry enough bytes per warp
+    const long stride = (long)gridDim.x * 8;
+    Raw8<T> n_dy[R][CHUNKS], n_x[R][CHUNKS], n_r[R][CHUNKS];
+    float n_mu[R], n_rs[R];
+    auto prefetch = [&](long row0) {
 #pragma unroll
-        for (int c = 0; c < CHUNKS; ++c) {
-            const int col = c * 256 + lane * 8;
-            if (col < dim) {
-                load8(dy + row * dim + col, gy[c]);
-                load8(x + row * dim + col, xh[c]);
-                if (dres != nullptr) load8(dres + row * dim + col, rr[c]);
-            }
-        }
+        for (int r = 0; r < R; ++r) {
+            const long row = row0 + r * stride;
+            if (row < rows) {
+                n_mu[r] = mean[row];
+                n_rs[r] = rstd[row];
 #pragma unroll
-        for (int c = 0; c < CHUNKS; ++c) {
-            const int col = c * 256 + lane * 8;
-            if (col < dim) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float d = gy[c][i];
-                    xh[c][i] = (xh[c][i] - mu) * rs;
-                    gy[c][i] = d * g[c][i];
-                    c1 = fmaf(gy[c][i], xh[c][i], c1);
-                    c2 += gy[c][i];
-                    dg[c][i] = fmaf(d, xh[c][i], dg[c][i]);
-                    db[c][i] += d;
+                for (int c = 0; c < CHUNKS; ++c) {
+                    const int col = c * 256 + lane * 8;
+                    if (col < dim) {
+                        n_dy[r][c].load(dy + row * dim + col);
+                        n_x[r][c].load(x + row * dim + col);
+                        if (dres != nullptr) n_r[r][c].load(dres + row * dim + col);
+                    }
                 }
             }
         }
-        c1 = warp_sum(c1) * inv_dim;
-        c2 = warp_sum(c2) * inv_dim;
+    };
+    long row0 = (long)blockIdx.x * 8 + warp;
+    prefetch(row0);
+    for (; row0 < rows; row0 += R * stride) {
+        float xh[R][CHUNKS][8], gy[R][CHUNKS][8], rr[R][CHUNKS][8];
+        float mu[R], rs[R];
 #pragma unroll
-        for (int c = 0; c < CHUNKS; ++c) {
-            const int col = c * 256 + lane * 8;
-            if (col < dim) {
-                float o[8];
+        for (int r = 0; r < R; ++r) {
+            mu[r] = n_mu[r];
+            rs[r] = n_rs[r];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    o[i] = rs * (gy[c][i] - c2 - xh[c][i] * c1);
-                    if (dres != nullptr) o[i] += rr[c][i];
+            for (int c = 0; c < CHUNKS; ++c) {
+                n_dy[r][c].unpack(gy[r][c]);
+                n_x[r][c].unpack(xh[r][c]);
+                if (dres != nullptr) n_r[r][c].unpack(rr[r][c]);
+            }
+        }
+        prefetch(row0 + R * stride);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const long row = row0 + r * stride;
+            if (row >= rows) break;
+            float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c) {
+                const int col = c * 256 + lane * 8;
+                if (col < dim) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float d = gy[r][c][i];
+                        xh[r][c][i] = (xh[r][c][i] - mu[r]) * rs[r];
+                        gy[r][c][i] = d * g[c][i];
+                        c1 = fmaf(gy[r][c][i], xh[r][c][i], c1);
+                        c2 += gy[r][c][i];
+                        dg[c][i] = fmaf(d, xh[r][c][i], dg[c][i]);
+                        db[c][i] += d;
+                    }
                 }
-                store8(dx + row * dim + col, o);
+            }
+            c1 = warp_sum(c1) * inv_dim;
+            c2 = warp_sum(c2) * inv_dim;
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c) {
+                const int col = c * 256 + lane * 8;
+                if (col < dim) {
+                    float o[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        o[i] = rs[r] * (gy[r][c][i] - c2 - xh[r][c][i] * c1);
+                        if (dres != nullptr) o[i] += rr[r][c][i];
+                        ds[c][i] += round_to(o[i], dx);      // what a column sum over the stored dx would add
+                    }
+                    store8(dx + row * dim + col, o);
+                }
             }
         }
     }
@@ -175,42 +241,53 @@ add_layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dres, c
         if (col < dim)
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                red[(warp * 2 + 0) * dim + col + i] = dg[c][i];
-                red[(warp * 2 + 1) * dim + col + i] = db[c][i];
+                red[(warp * nwhich + 0) * dim + col + i] = dg[c][i];
+                red[(warp * nwhich + 1) * dim + col + i] = db[c][i];
+                if (nwhich == 3) red[(warp * nwhich + 2) * dim + col + i] = ds[c][i];
             }
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < 2 * dim; e += blockDim.x) {
+    for (int e = threadIdx.x; e < nwhich * dim; e += blockDim.x) {
         const int which = e / dim, col = e - which * dim;
         float a = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) a += red[(w * 2 + which) * dim + col];
-        part[((long)blockIdx.x * 2 + which) * dim + col] = a;
+        for (int w = 0; w < 8; ++w) a += red[(w * nwhich + which) * dim + col];
+        part[((long)blockIdx.x * nwhich + which) * dim + col] = a;
     }
 }
 
 // out[which][col] = sum_b part[b][which][col]   (final stage of the parameter-gradient reduction)
-// block = 32 columns x 8 partial-lanes; the partial index runs across lanes, then shared memory
+// block = 32 columns x 32 partial-lanes; the partial index runs across warps (four independent loads in flight per
+// thread), then shared memory.  Fixed summation order: the result is deterministic.
 template <typename T>
-__global__ void __launch_bounds__(256)
-reduce_partials_kernel(const float* __restrict__ part, T* __restrict__ out0, T* __restrict__ out1, int nblocks,
-                       int dim, int nwhich) {
-    __shared__ float red[8][33];
+__global__ void __launch_bounds__(1024)
+reduce_partials_kernel(const float* __restrict__ part, T* __restrict__ out0, T* __restrict__ out1, T* __restrict__ out2,
+                       int nblocks, int dim, int nwhich) {
+    __shared__ float red[32][33];
     const int c = threadIdx.x & 31, l = threadIdx.x >> 5;
     const int e = blockIdx.x * 32 + c;                  // flattened (which, col)
-    float a = 0.f;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     if (e < nwhich * dim) {
         const int which = e / dim, col = e - which * dim;
-        for (int b = l; b < nblocks; b += 8) a += part[((long)b * nwhich + which) * dim + col];
+        const float* src = part + (long)which * dim + col;
+        const long bs = (long)nwhich * dim;
+        int b = l;
+        for (; b + 96 < nblocks; b += 128) {
+            a0 += src[(long)b * bs];
+            a1 += src[(long)(b + 32) * bs];
+            a2 += src[(long)(b + 64) * bs];
+            a3 += src[(long)(b + 96) * bs];
+        }
+        for (; b < nblocks; b += 32) a0 += src[(long)b * bs];
     }
-    red[l][c] = a;
+    red[l][c] = (a0 + a1) + (a2 + a3);
     __syncthreads();
     if (l == 0 && e < nwhich * dim) {
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s += red[i][c];
+        for (int i = 0; i < 32; ++i) s += red[i][c];
         const int which = e / dim, col = e - which * dim;
-        T* out = which == 0 ? out0 : out1;
+        T* out = which == 0 ? out0 : (which == 1 ? out1 : out2);
         if constexpr (sizeof(T) == 2) out[col] = __float2bfloat16_rn(s);
         else out[col] = s;
     }
@@ -228,7 +305,16 @@ colsum_partial_kernel(const T* __restrict__ a, float* __restrict__ part, long ro
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     if (rl < lanes) {
-        for (long row = (long)blockIdx.x * lanes + rl; row < rows; row += (long)gridDim.x * lanes) {
+        const long stride = (long)gridDim.x * lanes;
+        long row = (long)blockIdx.x * lanes + rl;
+        for (; row + 3 * stride < rows; row += 4 * stride) {        // four independent 16-byte loads in flight per thread
+            float v[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) load8(a + (row + u * stride) * C + grp * 8, v[u]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += (v[0][i] + v[1][i]) + (v[2][i] + v[3][i]);
+        }
+        for (; row < rows; row += stride) {
             float v[8];
             load8(a + row * C + grp * 8, v);
 #pragma unroll
@@ -246,12 +332,13 @@ colsum_partial_kernel(const T* __restrict__ a, float* __restrict__ part, long ro
 }
 
 template <typename T>
-int launch_ln_fwd(const void* res, const void* delta, const void* gamma, const void* beta, void* sum_out, void* y,
+int launch_ln_fwd(const void* res, const void* delta, const void* delta_bias, const void* gamma, const void* beta, void* sum_out, void* y,
                   float* mean, float* rstd, long rows, int dim, float eps, cudaStream_t st) {
     const int chunks = (dim + 255) / 256;
     const unsigned grid = (unsigned)((rows + 7) / 8);
 #define WM_LN_FWD(CH)                                                                                           \
     add_layernorm_fwd_kernel<T, CH><<<grid, 256, 0, st>>>(static_cast<const T*>(res), static_cast<const T*>(delta), \
+                                                         static_cast<const T*>(delta_bias),                        \
                                                          static_cast<const T*>(gamma), static_cast<const T*>(beta), \
                                                          static_cast<T*>(sum_out), static_cast<T*>(y), mean, rstd, \
                                                          rows, dim, eps)
@@ -268,16 +355,17 @@ int launch_ln_fwd(const void* res, const void* delta, const void* gamma, const v
 
 template <typename T>
 int launch_ln_bwd(const void* dy, const void* dres, const void* x, const float* mean, const float* rstd,
-                  const void* gamma, void* dx, void* dgamma, void* dbeta, float* part, int nblocks, long rows, int dim,
-                  cudaStream_t st) {
+                  const void* gamma, void* dx, void* dgamma, void* dbeta, void* dsum, float* part, int nblocks, long rows,
+                  int dim, cudaStream_t st) {
     const int chunks = (dim + 255) / 256;
-    const size_t smem = (size_t)8 * 2 * dim * sizeof(float);
+    const int nwhich = dsum != nullptr ? 3 : 2;
+    const size_t smem = (size_t)8 * nwhich * dim * sizeof(float);
 #define WM_LN_BWD(CH)                                                                                              \
     do {                                                                                                           \
         WM_CUDA_CHECK(cudaFuncSetAttribute(add_layernorm_bwd_kernel<T, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         add_layernorm_bwd_kernel<T, CH><<<nblocks, 256, smem, st>>>(static_cast<const T*>(dy), static_cast<const T*>(dres), \
                                                                   static_cast<const T*>(x), mean, rstd,              \
-                                                                  static_cast<const T*>(gamma), static_cast<T*>(dx), part, rows, dim); \
+                                                                  static_cast<const T*>(gamma), static_cast<T*>(dx), part, rows, dim, nwhich); \
     } while (0)
     switch (chunks) {
         case 1: WM_LN_BWD(1); break;
@@ -287,8 +375,8 @@ int launch_ln_bwd(const void* dy, const void* dres, const void* x, const float* 
     }
 #undef WM_LN_BWD
     WM_CUDA_CHECK(cudaGetLastError());
-    reduce_partials_kernel<T><<<(2 * dim + 31) / 32, 256, 0, st>>>(part, static_cast<T*>(dgamma), static_cast<T*>(dbeta),
-                                                                   nblocks, dim, 2);
+    reduce_partials_kernel<T><<<(nwhich * dim + 31) / 32, 1024, 0, st>>>(part, static_cast<T*>(dgamma), static_cast<T*>(dbeta),
+                                                                        static_cast<T*>(dsum), nblocks, dim, nwhich);
     WM_CUDA_CHECK(cudaGetLastError());
     return WM_OK;
 }
@@ -299,7 +387,7 @@ int launch_colsum(const void* a, void* out, float* part, int nblocks, long rows,
     WM_CUDA_CHECK(cudaFuncSetAttribute(colsum_partial_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     colsum_partial_kernel<T><<<nblocks, 256, smem, st>>>(static_cast<const T*>(a), part, rows, C);
     WM_CUDA_CHECK(cudaGetLastError());
-    reduce_partials_kernel<T><<<(C + 31) / 32, 256, 0, st>>>(part, static_cast<T*>(out), static_cast<T*>(out), nblocks, C, 1);
+    reduce_partials_kernel<T><<<(C + 31) / 32, 1024, 0, st>>>(part, static_cast<T*>(out), static_cast<T*>(out), static_cast<T*>(out), nblocks, C, 1);
     WM_CUDA_CHECK(cudaGetLastError());
     return WM_OK;
 }
@@ -323,24 +411,25 @@ extern "C" int wm_reduce_blocks(long rows) {
     return (int)b;
 }
 
-extern "C" int wm_add_layernorm_fwd(const void* res, const void* delta, const void* gamma, const void* beta,
-                                    void* sum_out, void* y, float* mean, float* rstd, long rows, int dim, float eps,
-                                    int dtype, void* stream) {
+extern "C" int wm_add_layernorm_fwd(const void* res, const void* delta, const void* delta_bias, const void* gamma,
+                                    const void* beta, void* sum_out, void* y, float* mean, float* rstd, long rows, int dim,
+                                    float eps, int dtype, void* stream) {
     if (int rc = check_rows("wm_add_layernorm_fwd", rows, dim, dtype)) return rc;
     if (rows == 0) return WM_OK;
     if (!res || !gamma || !beta || !y || !mean || !rstd) return fail(WM_EINVAL, "wm_add_layernorm_fwd: null pointer");
     if (!aligned16(res) || !aligned16(y) || (delta && !aligned16(delta)) || (sum_out && !aligned16(sum_out)) ||
-        !aligned16(gamma) || !aligned16(beta))
+        !aligned16(gamma) || !aligned16(beta) || (delta_bias && !aligned16(delta_bias)))
         return fail(WM_EINVAL, "wm_add_layernorm_fwd: pointers must be 16-byte aligned");
+    if (delta_bias && !delta) return fail(WM_EINVAL, "wm_add_layernorm_fwd: delta_bias needs delta");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return dtype == WM_DTYPE_BF16
-               ? launch_ln_fwd<__nv_bfloat16>(res, delta, gamma, beta, sum_out, y, mean, rstd, rows, dim, eps, st)
-               : launch_ln_fwd<float>(res, delta, gamma, beta, sum_out, y, mean, rstd, rows, dim, eps, st);
+               ? launch_ln_fwd<__nv_bfloat16>(res, delta, delta_bias, gamma, beta, sum_out, y, mean, rstd, rows, dim, eps, st)
+               : launch_ln_fwd<float>(res, delta, delta_bias, gamma, beta, sum_out, y, mean, rstd, rows, dim, eps, st);
 }
 
 extern "C" int wm_add_layernorm_bwd(const void* dy, const void* dres, const void* x, const float* mean,
                                     const float* rstd, const void* gamma, void* dx, void* dgamma, void* dbeta,
-                                    float* workspace, long rows, int dim, int dtype, void* stream) {
+                                    void* dsum, float* workspace, long rows, int dim, int dtype, void* stream) {
     if (int rc = check_rows("wm_add_layernorm_bwd", rows, dim, dtype)) return rc;
     if (rows == 0) return WM_OK;
     if (!dy || !x || !mean || !rstd || !gamma || !dx || !dgamma || !dbeta || !workspace)
@@ -350,8 +439,8 @@ extern "C" int wm_add_layernorm_bwd(const void* dy, const void* dres, const void
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int nb = wm_reduce_blocks(rows);
     return dtype == WM_DTYPE_BF16
-               ? launch_ln_bwd<__nv_bfloat16>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, workspace, nb, rows, dim, st)
-               : launch_ln_bwd<float>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, workspace, nb, rows, dim, st);
+               ? launch_ln_bwd<__nv_bfloat16>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, dsum, workspace, nb, rows, dim, st)
+               : launch_ln_bwd<float>(dy, dres, x, mean, rstd, gamma, dx, dgamma, dbeta, dsum, workspace, nb, rows, dim, st);
 }
 
 extern "C" int wm_colsum(const void* a, void* out, float* workspace, long rows, int cols, int dtype, void* stream) {

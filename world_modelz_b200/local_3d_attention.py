@@ -37,11 +37,23 @@ class FeedForward(nn.Module):
                   nn.Linear(hidden_dim, dim), nn.Dropout(dropout)]
         self.net = nn.Sequential(*stages)
 
+    def _no_dropout(self):
+        return not self.training or (self.net[2].p == 0.0 and self.net[4].p == 0.0)
+
     def forward(self, x):
-        if x.is_cuda and (not self.training or (self.net[2].p == 0.0 and self.net[4].p == 0.0)):
+        if x.is_cuda and self._no_dropout():
             h = torch.nn.functional.gelu(ops.linear(x, self.net[0].weight, self.net[0].bias))
             return ops.linear(h, self.net[3].weight, self.net[3].bias)
         return self.net(x)
+
+    def forward_deferred_bias(self, x):
+        """``(y, bias)`` with ``forward(x) == y + bias``: the caller adds ``net.3``'s bias inside its fused
+        residual-add + LayerNorm kernel, whose backward then also reduces the bias gradient.  ``bias`` is None when the
+        bias could not be deferred (dropout active, CPU tensors)."""
+        if x.is_cuda and self._no_dropout():
+            h = torch.nn.functional.gelu(ops.linear(x, self.net[0].weight, self.net[0].bias))
+            return torch.nn.functional.linear(h, self.net[3].weight), self.net[3].bias
+        return self.forward(x), None
 
 
 class Local3dAttention(nn.Module):
@@ -78,6 +90,25 @@ class Local3dAttention(nn.Module):
         """Reference-shaped core: ``[B,S,H,W,heads*d]`` in, ``[(B S H W), heads, 1, d]`` out."""
         out = ops.local3d_attention(q, k, v, self.heads, self.extents, self.scale, self.kernel_flags)
         return out.reshape(-1, self.heads, 1, out.shape[-1] // self.heads)
+
+    def forward_deferred_bias(self, x, q):
+        """``(y, bias)`` with ``forward(x, q) == y + bias``.  Softmax rows sum to one, so ``to_v``'s bias passes through
+        the attention core unchanged: ``attn(q, k, v + b_v) = attn(q, k, v) + b_v``, and with the output projection
+        the whole module equals ``attn(q, k, x W_v^T) W_o^T + (W_o b_v + b_o)``.  The caller adds that [dim] vector in
+        its fused residual-add + LayerNorm kernel; autograd routes its gradient (reduced by that kernel's backward) to
+        ``to_v.bias``, ``to_out.0.bias`` and ``to_out.0.weight``.  ``bias`` is None when this does not apply
+        (no output projection, dropout active, CPU tensors)."""
+        deferrable = (x.is_cuda and isinstance(self.to_out, nn.Sequential)
+                      and (not self.training or self.to_out[1].p == 0.0))
+        if not deferrable:
+            return self.forward(x, q), None
+        if x.dim() != 5 or q.shape[:-1] != x.shape[:-1]:
+            raise ValueError(f'expected x, q of shape [B,S,H,W,dim], got {tuple(x.shape)} and {tuple(q.shape)}')
+        w_o = self.to_out[0].weight
+        core = ops.local3d_attention(self.to_q(q), self.to_k(x), torch.nn.functional.linear(x, self.to_v.weight),
+                                     self.heads, self.extents, self.scale, self.kernel_flags)
+        bias = torch.addmv(self.to_out[0].bias, w_o, self.to_v.bias)      # W_o b_v + b_o, one GEMV
+        return torch.nn.functional.linear(core, w_o).reshape(q.shape), bias
 
     def forward(self, x, q):
         if x.dim() != 5 or q.shape[:-1] != x.shape[:-1]:
@@ -118,10 +149,12 @@ class Local3dAttentionTransformer(nn.Module):
         """``x = attn(LN(x), q=x) + x; x = ff(LN(x)) + x`` per layer (reference ``:159-161``), scheduled so
         that every residual add is fused with the LayerNorm that follows it (``wm_add_layernorm_*``)."""
         x = self.embedding(img_z) + self.get_pos_embedding(img_z.shape)
-        pending = None                               # branch output not yet added to the residual stream
+        pending = pending_bias = None                # branch output (and its deferred bias) not yet added to the stream
         for attn, ff in self.layers:
-            x, xn = ops.add_layernorm(x, pending, attn.norm.weight, attn.norm.bias, attn.norm.eps)
-            a = attn.forward_prenormed(xn, q=x)
-            x, xn = ops.add_layernorm(x, a, ff.norm.weight, ff.norm.bias, ff.norm.eps)
-            pending = ff.forward_prenormed(xn)
-        return x + pending if pending is not None else x
+            x, xn = ops.add_layernorm(x, pending, attn.norm.weight, attn.norm.bias, attn.norm.eps, pending_bias)
+            a, a_bias = attn.fn.forward_deferred_bias(xn, q=x)
+            x, xn = ops.add_layernorm(x, a, ff.norm.weight, ff.norm.bias, ff.norm.eps, a_bias)
+            pending, pending_bias = ff.fn.forward_deferred_bias(xn)
+        if pending is None:
+            return x
+        return x + pending if pending_bias is None else x + (pending + pending_bias.to(pending.dtype))

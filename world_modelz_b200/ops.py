@@ -157,10 +157,11 @@ def _rows(t: torch.Tensor) -> int:
 
 
 class _AddLayerNormFn(torch.autograd.Function):
-    """(res, delta) -> (sum = res + delta, LayerNorm(sum)); ``delta`` may be None (then sum is res)."""
+    """(res, delta, delta_bias) -> (sum = res + delta + delta_bias, LayerNorm(sum)); ``delta`` may be None (then sum is
+    res) and so may ``delta_bias`` (the [dim] bias of the linear layer that produced ``delta``)."""
 
     @staticmethod
-    def forward(ctx, res, delta, gamma, beta, eps):
+    def forward(ctx, res, delta, delta_bias, gamma, beta, eps):
         _require_cuda(res)
         res = res.contiguous()
         dim = res.shape[-1]
@@ -171,9 +172,14 @@ class _AddLayerNormFn(torch.autograd.Function):
         if delta is not None:
             delta = delta.contiguous()
             total = torch.empty_like(res)
+            if delta_bias is not None:
+                delta_bias = delta_bias.to(res.dtype).contiguous()
         else:
+            if delta_bias is not None:
+                raise ValueError('delta_bias without delta')
             total = res
         check(_lib.lib().wm_add_layernorm_fwd(res.data_ptr(), delta.data_ptr() if delta is not None else None,
+                                              delta_bias.data_ptr() if delta_bias is not None else None,
                                               gamma.data_ptr(), beta.data_ptr(),
                                               total.data_ptr() if delta is not None else None, y.data_ptr(),
                                               mean.data_ptr(), rstd.data_ptr(), rows, dim, float(eps), _dtype_code(res),
@@ -181,6 +187,7 @@ class _AddLayerNormFn(torch.autograd.Function):
         _count(1)
         ctx.save_for_backward(total, mean, rstd, gamma)
         ctx.has_delta = delta is not None
+        ctx.has_bias = delta_bias is not None
         return total, y
 
     @staticmethod
@@ -193,27 +200,31 @@ class _AddLayerNormFn(torch.autograd.Function):
         dx = torch.empty_like(total)
         dgamma = torch.empty_like(gamma)
         dbeta = torch.empty_like(gamma)
-        ws = torch.empty(_lib.lib().wm_reduce_blocks(rows) * 2 * dim, device=total.device, dtype=torch.float32)
+        dbias = torch.empty_like(gamma) if ctx.has_bias else None
+        ws = torch.empty(_lib.lib().wm_reduce_blocks(rows) * 3 * dim, device=total.device, dtype=torch.float32)
         check(_lib.lib().wm_add_layernorm_bwd(dy.data_ptr(), dres.data_ptr() if dres is not None else None,
                                               total.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
-                                              dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), rows,
+                                              dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                                              dbias.data_ptr() if dbias is not None else None, ws.data_ptr(), rows,
                                               dim, _dtype_code(total), _stream()), 'wm_add_layernorm_bwd')
         _count(2)
-        return dx, (dx if ctx.has_delta else None), dgamma, dbeta, None
+        return dx, (dx if ctx.has_delta else None), dbias, dgamma, dbeta, None
 
 
 def add_layernorm(res: torch.Tensor, delta: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor,
-                  eps: float = 1e-5) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Fused ``s = res + delta; y = LayerNorm(s)``; returns ``(s, y)`` (``s is res`` when delta is None).
+                  eps: float = 1e-5, delta_bias: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fused ``s = res + delta (+ delta_bias); y = LayerNorm(s)``; returns ``(s, y)`` (``s is res`` when delta is None).
 
-    One kernel forward, one backward (which also folds the gradient arriving at ``s`` from the
-    residual path into ``dx``).  Reference: PreNorm + residual adds, local_3d_attention.py:11-17,159-161.
+    One kernel forward, one backward (which also folds the gradient arriving at ``s`` from the residual path into
+    ``dx`` and, when ``delta_bias`` is given, reduces the bias gradient in the same pass).  ``delta_bias`` is the
+    bias of the linear layer that produced ``delta`` (``to_out.0`` / ``net.3``), deferred to here.
+    Reference: PreNorm + residual adds, local_3d_attention.py:11-17,159-161.
     """
     dim = res.shape[-1]
     if dim % 8 != 0 or dim > 2048:      # widths the kernel does not tile: stock CUDA ops (still on the device)
-        total = res if delta is None else res + delta
+        total = res if delta is None else (res + delta if delta_bias is None else res + (delta + delta_bias))
         return total, torch.nn.functional.layer_norm(total, (dim,), gamma, beta, eps)
-    return _AddLayerNormFn.apply(res, delta, gamma, beta, eps)
+    return _AddLayerNormFn.apply(res, delta, delta_bias, gamma, beta, eps)
 
 
 class _LinearFn(torch.autograd.Function):
