@@ -97,7 +97,7 @@ size_t smem_bytes_for(Mode mode, int d, int ncols_pad, int nstage, int rowbuf) {
         case kFwd: return kFixedSmem + rowbuf * row_tile + nstage * 2 * blk;                   // Q | (K,V) stages (P lives in TMEM)
         case kBwdDQ: return kFixedSmem + rowbuf * 2 * row_tile + nstage * 2 * blk + ptile;     // Q,dO | (K,V) stages | dS
         case kBwdDQws: return kFixedSmem + rowbuf * 2 * row_tile + nstage * 2 * blk;           // Q,dO | (K,V) stages (dS lives in TMEM)
-        case kBwdDKVws: return kFixedSmem + rowbuf * 2 * row_tile + nstage * 2 * blk + 2 * ptile + 4 * ncols_pad * 4;   // K,V | (Q,dO) | dS^T x2 | lse,delta (P^T in TMEM)
+        case kBwdDKVws: return kFixedSmem + rowbuf * 2 * row_tile + nstage * 2 * blk + 2 * ptile + 6 * ncols_pad * 4;   // K,V | (Q,dO) | dS^T x2 | lse,delta x3 (P^T in TMEM)
         default: return kFixedSmem + rowbuf * 2 * row_tile + nstage * 2 * blk + 2 * ptile + 4 * ncols_pad * 4;   // K,V | (Q,dO) | P,dS | lse,delta
     }
 }
@@ -268,7 +268,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int i = 0; i < 4; ++i) mbar_init(&bar_kv[i], 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bar_s[i], 1);
-            mbar_init(&bar_p[i], 128 * NPART);
+            mbar_init(&bar_p[i], 4 * NPART);       // one arrival per compute warp (hundreds of arrivals on one word serialise)
             mbar_init(&bar_o[i], 1);
         }
         fence_barrier_init();
@@ -753,7 +753,8 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             DBG(11);
             tmem_wait_st();               // P is in tensor memory
             tc_fence_before();            // ... and our tcgen05.ld of S_t are complete before the driver reuses the buffers
-            mbar_arrive(&bar_p[buf]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_p[buf]);
             DBG(12);
             if (head_start && t > 0 && pl.obufs == 2) {   // epilogue of the previous head, off the critical path
                 mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);     // its last P V has retired

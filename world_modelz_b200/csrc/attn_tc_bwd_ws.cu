@@ -1,19 +1,27 @@
-// Warp-specialised backward kernels of the local windowed 3D attention (dim_head <= 64).
+// Warp-specialised backward kernels of the local windowed 3D attention.
 //
 // Same math, brick / halo-block tiling, masks and determinism as attn_tc_bwd.cu; what changes is
 // who does what and where the probability tiles live:
-//   warps 0-7  compute (two threads per brick row), warp 8 = driver (TMA + every tcgen05.mma)
-//   T = (S, dP) accumulators: one TMEM buffer, handed to the compute warps per step (bar_t)
+//   warps 0-7  compute (two threads per brick row)
+//   warp 8     issues the (S, dP) MMAs of the NEXT step, in two column halves (A, then B)
+//   warp 9     issues the accumulating MMAs of the current step
+//   warp 10    TMA loader (row tiles of the next head, halo blocks nstage steps ahead)
+//   T = (S, dP) accumulators: one TMEM buffer.  Half A of step t+1 is produced as soon as every
+//       compute thread is done with half A of step t, i.e. while they work on half B (and vice versa),
+//       so the compute warps never wait for the tensor pipe.
 //   dQ kernel : dS (bf16) goes back to TENSOR MEMORY (two buffers) and is the A operand of
 //               dQ += dS K (TS-mode MMA): no shared-memory round trip
 //   dK/dV     : P^T in tensor memory (two buffers, A of dV += P^T dO), dS^T in shared memory
 //               (two buffers, A of dK += dS^T Q)
-// so the accumulating MMAs of step t run while the compute warps are already in step t+1, and
-// the (S, dP) MMAs of step t+1 are issued before them, right when the buffers are drained.
+// One issuing thread costs ~20-60 cycles per tcgen05.mma (tools/micro/mma_issue_clean.cu); three
+// single-purpose warps keep each of the per-step chains short.
 #include "attn_tc.cuh"
 
 #ifndef WM_EXPERIMENT
 #define WM_EXPERIMENT 0
+#endif
+#ifndef WM_WS_PROBE
+#define WM_WS_PROBE 1
 #endif
 #if WM_EXPERIMENT == 7
 namespace wm { namespace tc { __device__ long long g_dbg_ws[2 * 64 * 16]; } }
@@ -37,7 +45,7 @@ struct BwdWsParams {
     __nv_bfloat16* out2;     //                  dK/dV kernel: dk
 };
 
-constexpr int kWsThreads = 288;
+constexpr int kWsThreads = 352;        // 8 compute warps + (S,dP) issuer + accumulate issuer + TMA loader
 
 template <int D, int MODE>
 __global__ void __launch_bounds__(kWsThreads, 1)
@@ -65,14 +73,20 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     uint8_t* sB = sA + pl.rowbuf * 2 * row_tile_bytes;     // [stage][B1 | B2][slab][ncols_pad rows]  (K,V | Q,dO)
     uint8_t* sDS = sB + nstage * 2 * blk_tile_bytes;       // dK/dV kernel: dS^T x2, bf16, K-major 128B swizzle
     uint32_t* sMask = reinterpret_cast<uint32_t*>(sDS + (kDKV ? 2 * p_tile_bytes : 0));   // [2 halves][9 words][128]
-    float* sCol = reinterpret_cast<float*>(sMask + 2 * 9 * 128);                          // [2 bufs][lse2|delta][ncols_pad]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + (kDKV ? 4 * ncols_pad : 0));
+    float* sCol = reinterpret_cast<float*>(sMask + 2 * 9 * 128);                          // [3 bufs][lse2|delta][ncols_pad]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + (kDKV ? 6 * ncols_pad : 0));
     uint64_t* bar_a = bars;           // [2] row tiles of a head landed
     uint64_t* bar_b = bars + 2;       // [3] halo block landed
-    uint64_t* bar_t = bars + 5;       //     (S, dP) of a step computed                  (tcgen05.commit)
-    uint64_t* bar_p = bars + 6;       // [2] dS / P written, (S, dP) drained             (256 compute threads)
+    // (S, dP) of a step are produced and drained in two column halves, A = [0, nA) and B = [nA, ncols_pad): half A of
+    // step t+1 is issued as soon as every compute thread is done with half A of step t, i.e. while they work on half B.
+    uint64_t* bar_tA = bars + 5;      //     columns A of (S, dP) of a step computed     (tcgen05.commit)
+    uint64_t* bar_p = bars + 6;       // [2] all of dS / P written, columns B drained     (8 compute warps)
     uint64_t* bar_acc = bars + 8;     // [2] accumulating MMAs of a step retired          (tcgen05.commit)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* bar_tB = bars + 10;     //     columns B of (S, dP) of a step computed     (tcgen05.commit)
+    uint64_t* bar_pA = bars + 11;     // [2] columns A drained                            (8 compute warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    const int gA = (ncols_pad >> 4) >= 2 ? (ncols_pad >> 5) : 0;   // 16-column groups in half A (0: a single half)
+    const int nA = gA * 16;
 
     const int tw_i = blockIdx.x % pl.tilesW, th_i = blockIdx.x / pl.tilesW;
     const int ts_i = blockIdx.y;
@@ -97,9 +111,11 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         mbar_init(&bar_a[0], 1);
         mbar_init(&bar_a[1], 1);
         for (int i = 0; i < 3; ++i) mbar_init(&bar_b[i], 1);
-        mbar_init(bar_t, 1);
+        mbar_init(bar_tA, 1);
+        mbar_init(bar_tB, 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&bar_p[i], 256);
+            mbar_init(&bar_p[i], 8);           // one arrival per compute warp (256 arrivals on one word serialise)
+            mbar_init(&bar_pA[i], 8);
             mbar_init(&bar_acc[i], 1);
         }
         fence_barrier_init();
@@ -133,9 +149,9 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         }
     };
 
-    if (warp == 8) {
-        // =============================== driver (warp-uniform; instructions on one lane) ==============
-        const bool leader = elect_one();      // whole driver warp is converged here
+    if (warp >= 8) {
+        // =============================== issuing warps (warp-uniform code; instructions on one elected lane) =========
+        const bool leader = elect_one();      // each of these warps is converged here
         auto a_buf = [&](int hd) { return sA + (pl.rowbuf == 2 ? (hd & 1) : 0) * 2 * row_tile_bytes; };
         auto issue_row_load = [&](int hd) {
             if (leader) {
@@ -163,7 +179,7 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                 }
             }
         };
-        const uint32_t idesc_t = make_idesc_bf16(ncols_pad, false, false);
+        const uint32_t idesc_tA = make_idesc_bf16(nA > 0 ? nA : 16, false, false), idesc_tB = make_idesc_bf16(ncols_pad - nA, false, false);
         const uint32_t idesc_acc = make_idesc_bf16(D, false, true);
         const uint64_t da0 = make_smem_desc(smem_u32(sA), 16, G::kAtomBytes, G::kSwizzleCode);
         const uint64_t dbk0 = make_smem_desc(smem_u32(sB), 16, G::kAtomBytes, G::kSwizzleCode);                         // block, K-major
@@ -171,8 +187,11 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         const uint64_t dds0 = make_smem_desc(smem_u32(sDS), 16, 1024, 2u);
         const uint32_t a_buf_step = (pl.rowbuf == 2) ? (uint32_t)((2 * row_tile_bytes) >> 4) : 0u;
         const uint32_t stage_step = (uint32_t)((2 * blk_tile_bytes) >> 4);
-        auto issue_t_mma = [&](int stage, int hd) {            // T1 = A1 B1^T, T2 = A2 B2^T
-            const uint64_t da_h = da0 + (hd & 1) * a_buf_step, db_s = dbk0 + stage * stage_step;
+        auto issue_t_mma = [&](int stage, int hd, int part) {  // T1 = A1 B1^T, T2 = A2 B2^T; columns A (part 0) or B (part 1)
+            const uint32_t col0 = part ? (uint32_t)nA : 0u;        // columns = rows of the K-major block
+            const uint32_t idesc_t = part ? idesc_tB : idesc_tA;
+            const uint64_t da_h = da0 + (hd & 1) * a_buf_step;
+            const uint64_t db_s = dbk0 + stage * stage_step + ((col0 * (uint32_t)G::kRowBytes) >> 4);
 #pragma unroll
             for (int op = 0; op < 2; ++op) {
 #pragma unroll
@@ -181,10 +200,10 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                     const uint32_t koff = (uint32_t)((((kk * 16) % G::kSlabCh) * 2) >> 4);
                     const uint64_t da = da_h + op * (uint32_t)(row_tile_bytes >> 4) + sl * (uint32_t)(row_slab_bytes >> 4) + koff;
                     const uint64_t db = db_s + op * (uint32_t)(blk_tile_bytes >> 4) + sl * (uint32_t)(blk_slab_bytes >> 4) + koff;
-                    if (leader) umma_bf16_ss(op ? tmem_t2 : tmem_t1, da, db, idesc_t, kk > 0);
+                    if (leader) umma_bf16_ss((op ? tmem_t2 : tmem_t1) + col0, da, db, idesc_t, kk > 0);
                 }
             }
-            if (leader) umma_commit(bar_t);
+            if (leader) umma_commit(part ? bar_tB : bar_tA);
         };
         const int nk_acc = ncols_pad / 16;
         auto issue_acc_mma = [&](int t, int stage, bool accumulate) {
@@ -209,63 +228,78 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             }
             if (leader) umma_commit(&bar_acc[t & 1]);
         };
-
-        Cursor ld = {0, ks_first, chunk_first};
-        int ld_t = 0, ld_stage = 0;
-        issue_row_load(0);
-        for (; ld_t < nstage && ld_t < nsteps; ++ld_t) {
-            issue_block_load(ld_stage, ld);
-            advance(ld);
-            if (++ld_stage == nstage) ld_stage = 0;
-        }
-        Cursor cur = {0, ks_first, chunk_first}, nxt = cur;
-        advance(nxt);
-        mbar_wait(&bar_a[0], 0);
-        mbar_wait(&bar_b[0], 0);
-        tc_fence_after();
-        issue_t_mma(0, 0);
-        int st_cur = 0, st_nxt = (nstage > 1) ? 1 : 0;
-        uint32_t b_par = 1u;                         // bit s = parity of stage s's next completion (stage 0 consumed once)
         const bool dbg_on = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0) && leader;
         (void)dbg_on;
-        for (int t = 0; t < nsteps; ++t) {
-            DBGW(0);
-            const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
-            if (head_start && pl.rowbuf == 2 && cur.hd + 1 < pl.hpc) issue_row_load(cur.hd + 1);   // buffer of head hd-1
-            // the compute warps have drained (S, dP) of step t and written its dS / P
-            mbar_wait(&bar_p[t & 1], (t >> 1) & 1);
-            tc_fence_after();
-            DBGW(1);
-            auto refill = [&]() {        // refill the stage freed by step t-1 once its accumulating MMAs have retired
-                if (t >= 1 && ld_t < nsteps) {
+        Cursor cur = {0, ks_first, chunk_first};
+
+        if (warp == 10) {
+            // ---- TMA loader: row tiles one head ahead, halo blocks nstage steps ahead -------------------------------
+            Cursor ld = cur;
+            int ld_t = 0, ld_stage = 0;
+            issue_row_load(0);
+            for (; ld_t < nstage && ld_t < nsteps; ++ld_t) {
+                issue_block_load(ld_stage, ld);
+                advance(ld);
+                if (++ld_stage == nstage) ld_stage = 0;
+            }
+            for (int t = 0; t < nsteps; ++t) {
+                const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
+                if (head_start && pl.rowbuf == 2 && cur.hd + 1 < pl.hpc) {
+                    // the buffer of head hd-1: its last (S, dP) was drained when every thread arrived for step t-1
+                    if (t > 0) mbar_wait(&bar_p[(t - 1) & 1], ((t - 1) >> 1) & 1);
+                    issue_row_load(cur.hd + 1);
+                }
+                if (t >= 1 && ld_t < nsteps) {   // the stage of step t-1 is free once its accumulating MMAs have retired
                     mbar_wait(&bar_acc[(t - 1) & 1], ((t - 1) >> 1) & 1);
                     issue_block_load(ld_stage, ld);
                     advance(ld);
                     ++ld_t;
                     if (++ld_stage == nstage) ld_stage = 0;
                 }
-            };
-            if (nstage < 3) refill();    // two stages: the block of step t+1 is the one being refilled
-            if (t + 1 < nsteps) {                                        // (S, dP) of step t+1 first: it is what they wait for
+                advance(cur);
+            }
+        } else if (warp == 8) {
+            // ---- (S, dP) of step t+1, half A after the threads leave half A of step t, half B likewise ----------------
+            Cursor nxt = cur;
+            advance(nxt);
+            mbar_wait(&bar_a[0], 0);
+            mbar_wait(&bar_b[0], 0);
+            tc_fence_after();
+            if (gA > 0) issue_t_mma(0, 0, 0);
+            issue_t_mma(0, 0, 1);
+            int st_nxt = (nstage > 1) ? 1 : 0;
+            uint32_t b_par = 1u;                         // bit s = parity of stage s's next completion (stage 0 consumed once)
+            for (int t = 0; t + 1 < nsteps; ++t) {
+                DBGW(0);
+                if (gA > 0) {
+                    mbar_wait(&bar_pA[t & 1], (t >> 1) & 1);
+                    DBGW(1);
+                }
                 mbar_wait(&bar_b[st_nxt], (b_par >> st_nxt) & 1u);
                 b_par ^= 1u << st_nxt;
                 if (nxt.hd != cur.hd) mbar_wait(&bar_a[nxt.hd & 1], (nxt.hd >> 1) & 1);
                 tc_fence_after();
-                issue_t_mma(st_nxt, nxt.hd);
+                if (gA > 0) issue_t_mma(st_nxt, nxt.hd, 0);
+                DBGW(2);
+                mbar_wait(&bar_p[t & 1], (t >> 1) & 1);
+                tc_fence_after();
+                issue_t_mma(st_nxt, nxt.hd, 1);
+                DBGW(3);
+                cur = nxt;
+                advance(nxt);
+                if (++st_nxt == nstage) st_nxt = 0;
             }
-            DBGW(2);
-            issue_acc_mma(t, st_cur, !head_start);
-            DBGW(3);
-#if WM_EXPERIMENT == 7 && defined(WM_DBG_ACC_DONE)
-            // diagnostic only: the instrumented CTA's driver waits for its own accumulating MMAs and records when they retire
-            if (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0) { mbar_wait(&bar_acc[t & 1], (t >> 1) & 1); DBGW(5); }
-#endif
-            if (nstage >= 3) refill();
-            DBGW(4);
-            cur = nxt;
-            advance(nxt);
-            st_cur = st_nxt;
-            if (++st_nxt == nstage) st_nxt = 0;
+        } else {
+            // ---- accumulating MMAs of step t, once all of its dS / P is written -------------------------------------
+            int st_cur = 0;
+            for (int t = 0; t < nsteps; ++t) {
+                const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
+                mbar_wait(&bar_p[t & 1], (t >> 1) & 1);
+                tc_fence_after();
+                issue_acc_mma(t, st_cur, !head_start);
+                advance(cur);
+                if (++st_cur == nstage) st_cur = 0;
+            }
         }
     } else {
         // =============================== compute warps ==================================================
@@ -348,6 +382,8 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         bool p_zero[2] = {false, false};
         int mask_chunk = -1;
         int g_lo = 0, g_hi = 0;
+        int cbuf = 0;                      // dK/dV kernel: lse / delta column buffer of the current step (t mod 3)
+        bool tA_seen = false;              // columns A of this step were already seen complete by last step's probe
         bool chunk_live = false;
         const int nwords = (ncols_pad + 31) / 32;
         const int ngroups = ncols_pad >> 4;
@@ -391,12 +427,10 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                 g_lo = ((ua - kh0) * pl.hW) >> 4;
                 g_hi = min(((ub - kh0 + 1) * pl.hW + 15) >> 4, ngroups);
             }
-            // the dS / P buffers of parity `buf` are free once the accumulating MMAs of step t-2 have retired
+            const bool live = chunk_live && (cur.ks >= w_rs) && (cur.ks <= w_rs + 2 * sh.eS);
+            // The dS / P buffers of parity `buf` are free once the accumulating MMAs of step t-2 have retired.
             if (t >= 2) mbar_wait(&bar_acc[buf], ((t - 2) >> 1) & 1);
             DBGW(9);
-            mbar_wait(bar_t, t & 1);                  // (S, dP) of this step
-            tc_fence_after();
-            DBGW(10);
 
             const uint32_t tmem_a = tmem_pa + buf * pa_cols + lane_sel;       // this row's bf16-pair columns
             uint8_t* ds_tile = sDS + buf * p_tile_bytes;
@@ -409,69 +443,108 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             auto store_tmem = [&](int g, const uint32_t (&pk)[8]) {           // 16 bf16 -> 8 pair columns of the TMEM A operand
                 tmem_st8(tmem_a + g * 8, pk);
             };
-            const bool live = chunk_live && (cur.ks >= w_rs) && (cur.ks <= w_rs + 2 * sh.eS);
-            if (live) {
-                const int g_mid = (g_lo + g_hi + 1) >> 1;
-                const int ga = half ? g_mid : g_lo, gb = half ? g_hi : g_mid;
-                const int za = half ? g_hi : 0, zb = half ? ngroups : g_lo;
-                const float* col_lse2 = sCol + (buf * 2 + 0) * ncols_pad;
-                const float* col_dl = sCol + (buf * 2 + 1) * ncols_pad;
-                for (int g = ga; g < gb; ++g) {
-                    const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
-                    uint32_t s[16], dp[16];
-                    tmem_ld16(tmem_t1 + lane_sel + g * 16, s);
-                    tmem_ld16(tmem_t2 + lane_sel + g * 16, dp);
-                    float l2[16], dl[16];
-                    if constexpr (kDKV) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float4 a = *reinterpret_cast<const float4*>(col_lse2 + g * 16 + 4 * i);
-                            const float4 c = *reinterpret_cast<const float4*>(col_dl + g * 16 + 4 * i);
-                            l2[4 * i] = a.x; l2[4 * i + 1] = a.y; l2[4 * i + 2] = a.z; l2[4 * i + 3] = a.w;
-                            dl[4 * i] = c.x; dl[4 * i + 1] = c.y; dl[4 * i + 2] = c.z; dl[4 * i + 3] = c.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) { l2[i] = row_lse2; dl[i] = row_delta; }
-                    }
-                    tmem_wait_ld();
-                    float pv[16], dsv[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        // dl[] holds delta * scale: dS = P * (dP * scale - delta * scale); masking P masks dS with it
-                        const float p = ex2(fmaf(__uint_as_float(s[i]), pl.scale_log2, -l2[i]));
-                        pv[i] = ((mword >> i) & 1u) ? p : 0.f;
-                        dsv[i] = pv[i] * fmaf(__uint_as_float(dp[i]), sh.scale, -dl[i]);
-                    }
-                    uint32_t pk[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(dsv[2 * i], dsv[2 * i + 1]);
-                    if constexpr (kDKV) {
-                        store_ds_smem(g, pk);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
-                        store_tmem(g, pk);
-                    } else {
-                        store_tmem(g, pk);
-                    }
-                }
+            auto zero_groups = [&](int za, int zb) {
                 for (int g = za; g < zb; ++g) {
                     store_tmem(g, zero8);
                     if constexpr (kDKV) store_ds_smem(g, zero8);
                 }
+            };
+            const float* col_lse2 = sCol + (cbuf * 2 + 0) * ncols_pad;
+            const float* col_dl = sCol + (cbuf * 2 + 1) * ncols_pad;
+            auto math_group = [&](int g) {
+                const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
+                uint32_t s[16], dp[16];
+                tmem_ld16(tmem_t1 + lane_sel + g * 16, s);
+                tmem_ld16(tmem_t2 + lane_sel + g * 16, dp);
+                float l2[16], dl[16];
+                if constexpr (kDKV) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 a = *reinterpret_cast<const float4*>(col_lse2 + g * 16 + 4 * i);
+                        const float4 c = *reinterpret_cast<const float4*>(col_dl + g * 16 + 4 * i);
+                        l2[4 * i] = a.x; l2[4 * i + 1] = a.y; l2[4 * i + 2] = a.z; l2[4 * i + 3] = a.w;
+                        dl[4 * i] = c.x; dl[4 * i + 1] = c.y; dl[4 * i + 2] = c.z; dl[4 * i + 3] = c.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { l2[i] = row_lse2; dl[i] = row_delta; }
+                }
+                tmem_wait_ld();
+                float pv[16], dsv[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    // dl[] holds delta * scale: dS = P * (dP * scale - delta * scale); masking P masks dS with it
+                    const float p = ex2(fmaf(__uint_as_float(s[i]), pl.scale_log2, -l2[i]));
+                    pv[i] = ((mword >> i) & 1u) ? p : 0.f;
+                    dsv[i] = pv[i] * fmaf(__uint_as_float(dp[i]), sh.scale, -dl[i]);
+                }
+                uint32_t pk[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(dsv[2 * i], dsv[2 * i + 1]);
+                if constexpr (kDKV) {
+                    store_ds_smem(g, pk);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
+                    store_tmem(g, pk);
+                } else {
+                    store_tmem(g, pk);
+                }
+            };
+            // this warp's live groups inside [x0, x1), split between the two threads of a row; dead groups are zeroed.
+            // The barrier needed next is probed before the last group, so that the probe's latency hides under its math.
+            auto run_half = [&](int x0, int x1, int odd_to, uint64_t* probe_bar, uint32_t probe_parity) -> bool {
+                const int l0 = min(max(g_lo, x0), x1), l1 = max(min(g_hi, x1), l0);
+                const int mid = (l0 + l1 + (odd_to == 0 ? 1 : 0)) >> 1;
+                const int ga = half ? mid : l0, gb = half ? l1 : mid;
+                bool probed = false;
+                for (int g = ga; g < gb - 1; ++g) math_group(g);
+                if (WM_WS_PROBE) probed = mbar_test(probe_bar, probe_parity);
+                if (gb > ga) math_group(gb - 1);
+                zero_groups(half ? l1 : x0, half ? x1 : l0);
+                return __all_sync(0xffffffffu, probed);
+            };
+            auto zero_half = [&](int x0, int x1) {
+                const int mid = (x0 + x1) >> 1;
+                zero_groups(half ? mid : x0, half ? x1 : mid);
+            };
+            bool tB_seen = false;
+            if (gA > 0) {
+                if (live) {
+                    if (!tA_seen) mbar_wait(bar_tA, t & 1);   // columns A of (S, dP) of this step
+                    tc_fence_after();
+                    DBGW(10);
+                    tB_seen = run_half(0, gA, 0, bar_tB, t & 1);
+                } else if (!p_zero[buf]) {
+                    zero_half(0, gA);
+                }
+                if constexpr (kDKV) {
+                    // Next step's lse / delta columns, written BEFORE the arrival below: columns A of step t+1 are issued
+                    // after it, so whoever sees them also sees these stores.  Three buffers: the one written here was
+                    // last read in step t-2, which bar_acc(t-2) has put behind every thread.
+                    // (ptxas otherwise hoists the scaling multiplies up to the loads at the top of the step.)
+                    asm volatile("" : "+f"(nxt_lse2), "+f"(nxt_dl));
+                    if (t + 1 < nsteps) store_colvec(cbuf == 2 ? 0 : cbuf + 1, nxt_lse2, nxt_dl);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_pA[buf]);
+            }
+            tA_seen = false;
+            if (live) {
+                if (!tB_seen) mbar_wait(bar_tB, t & 1);   // columns B
+                tc_fence_after();
+                if (gA == 0) DBGW(10);
+                tA_seen = run_half(gA, ngroups, 1, bar_tA, (t + 1) & 1) && gA > 0 && t + 1 < nsteps;
                 p_zero[buf] = false;
             } else if (!p_zero[buf]) {
-                const int za = half ? (ngroups >> 1) : 0, zb = half ? ngroups : (ngroups >> 1);
-                for (int g = za; g < zb; ++g) {
-                    store_tmem(g, zero8);
-                    if constexpr (kDKV) store_ds_smem(g, zero8);
-                }
+                zero_half(gA, ngroups);
                 p_zero[buf] = true;
             }
             if constexpr (kDKV) {
-                // ptxas otherwise hoists the scaling multiplies up to the loads (top of the step) and stalls there for DRAM
-                asm volatile("" : "+f"(nxt_lse2), "+f"(nxt_dl));
-                if (t + 1 < nsteps) store_colvec((t + 1) & 1, nxt_lse2, nxt_dl);
+                if (gA == 0) {
+                    asm volatile("" : "+f"(nxt_lse2), "+f"(nxt_dl));
+                    if (t + 1 < nsteps) store_colvec(cbuf == 2 ? 0 : cbuf + 1, nxt_lse2, nxt_dl);
+                }
                 fence_proxy_async();              // dS^T (generic proxy) -> visible to tcgen05.mma
             }
             DBGW(11);
@@ -485,11 +558,12 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             }
             tmem_wait_st();
             tc_fence_before();
-            if constexpr (kDKV) asm volatile("bar.sync 5, 256;" ::: "memory");   // next step's lse / delta columns are in place
-            mbar_arrive(&bar_p[buf]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_p[buf]);
             DBGW(12);
             cur = nxt;
             advance(nxt);
+            cbuf = (cbuf == 2) ? 0 : cbuf + 1;
         }
         mbar_wait(&bar_acc[(nsteps - 1) & 1], ((nsteps - 1) >> 1) & 1);
         tc_fence_after();
