@@ -16,6 +16,14 @@ for _ in range(iters):
     o, lse = ops.attn_forward(q, k, v, heads, ext, scale)
     ops.attn_backward(q, k, v, o, lse, do, heads, ext, scale)
 torch.cuda.synchronize()
+# CHECK: the tensor-core kernels against the exact SIMT kernels on this very shape (a timing of wrong results is worthless)
+o_s, lse_s = ops.attn_forward(q, k, v, heads, ext, scale, ops.FLAG_SIMT)
+g_s = ops.attn_backward(q, k, v, o_s, lse_s, do, heads, ext, scale, ops.FLAG_SIMT)
+g_t = ops.attn_backward(q, k, v, o, lse, do, heads, ext, scale)
+for nm, a, b_ in zip(('out', 'dq', 'dk', 'dv'), (o,) + tuple(g_t), (o_s,) + tuple(g_s)):
+    d_ = (a.float() - b_.float()).abs()
+    bad = int((d_ > 1e-2 * b_.float().abs().max() + 2e-2 * b_.float().abs()).sum())
+    print(f'  check {nm}: max|diff|={d_.max().item():.3e} bad={bad}/{d_.numel()}' + ('  <-- MISMATCH' if bad else ''))
 e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
 e0.record()
 for _ in range(10):

@@ -508,9 +508,12 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                 zero_groups(half ? mid : x0, half ? x1 : mid);
             };
             bool tB_seen = false;
+            // Every warp waits for both halves of (S, dP), also when the block is dead for it: the parity waits below are
+            // only unambiguous for a thread that has seen every phase of the barrier, and nothing else orders a dead warp
+            // behind the (S, dP) MMAs now that they and the accumulating MMAs are issued by different warps.
             if (gA > 0) {
+                if (!tA_seen) mbar_wait(bar_tA, t & 1);       // columns A of (S, dP) of this step
                 if (live) {
-                    if (!tA_seen) mbar_wait(bar_tA, t & 1);   // columns A of (S, dP) of this step
                     tc_fence_after();
                     DBGW(10);
                     tB_seen = run_half(0, gA, 0, bar_tB, t & 1);
@@ -530,8 +533,8 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                 if (lane == 0) mbar_arrive(&bar_pA[buf]);
             }
             tA_seen = false;
+            if (!tB_seen) mbar_wait(bar_tB, t & 1);       // columns B
             if (live) {
-                if (!tB_seen) mbar_wait(bar_tB, t & 1);   // columns B
                 tc_fence_after();
                 if (gA == 0) DBGW(10);
                 tA_seen = run_half(gA, ngroups, 1, bar_tA, (t + 1) & 1) && gA > 0 && t + 1 < nsteps;
