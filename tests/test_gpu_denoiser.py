@@ -87,3 +87,22 @@ def test_sampler_produces_valid_tokens_and_is_batch_independent():
         a = m(tokens)
         b = torch.cat([m(tokens[:2]), m(tokens[2:])])
     torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+
+
+def test_graphed_sampler_reuses_one_capture():
+    """The captured sampling iteration is cached on the model and replayed for later frames (fresh inputs are copied
+    into the captured buffers); draws are valid tokens.  With iterations=1 there is no re-masking and the draw comes
+    from the zero-initialised logits, i.e. uniform: graph and eager sampling then differ only by the RNG stream."""
+    torch.manual_seed(2)
+    m = wm.VqVideoDiffusionModel(data_shape=(3, 8, 8), dim=32, num_classes=16, extents=(1, 1, 1), depth=1, heads=2,
+                                 dim_head=16, mlp_dim=32).to(DEV).eval()
+    tokens = torch.randint(0, 16, (4, 3, 8, 8), device=DEV)
+    tokens[:, -1] = 16
+    for it in (4, 30):
+        out = wm.sample_next_frame(m, tokens, iterations=it, use_cuda_graph=True)
+        assert out.shape == (4, 8, 8) and out.min().item() >= 0 and out.max().item() < 16
+    out2 = wm.sample_next_frame(m, tokens.flip(0), iterations=4, use_cuda_graph=True)
+    assert out2.shape == (4, 8, 8) and out2.min().item() >= 0 and out2.max().item() < 16
+    assert len(m.__dict__['_wm_sample_graphs']) == 1
+    # the frames before the last one are inputs only: the sampler must not have modified the caller's tensor
+    assert (tokens[:, -1] == 16).all()

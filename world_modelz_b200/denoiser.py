@@ -268,22 +268,29 @@ def sample_next_frame(model: VqVideoDiffusionModel, tokens: torch.Tensor, iterat
     logits = torch.zeros(B * H * W, K, device=tokens.device)
     sample = None
     if use_cuda_graph and sample_topk <= 0:
-        alpha = torch.zeros((), device=tokens.device)
-        side = torch.cuda.Stream(device=tokens.device)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):                 # warm-up outside the capture
-            _sample_iteration(model, work.clone(), logits, alpha, K)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            g_sample, g_logits = _sample_iteration(model, work, logits, alpha, K)
-        work.copy_(tokens)
-        logits.zero_()
+        # one captured iteration per (model, shape), kept on the model and replayed for every later frame
+        cache = model.__dict__.setdefault('_wm_sample_graphs', {})
+        key = (tuple(tokens.shape), str(tokens.device), model.training)
+        if key not in cache:
+            g_work, g_logits_in = tokens.clone(), torch.zeros(B * H * W, K, device=tokens.device)
+            alpha = torch.zeros((), device=tokens.device)
+            side = torch.cuda.Stream(device=tokens.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                 # warm-up outside the capture
+                _sample_iteration(model, g_work.clone(), g_logits_in, alpha, K)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g_sample, g_logits = _sample_iteration(model, g_work, g_logits_in, alpha, K)
+            cache[key] = (graph, g_work, g_logits_in, alpha, g_sample, g_logits)
+        graph, g_work, g_logits_in, alpha, g_sample, g_logits = cache[key]
+        g_work.copy_(tokens)
+        g_logits_in.zero_()
         for i in range(iterations):
             alpha.fill_(min(max((i + 1) / iterations, 0.0), 1.0))
             graph.replay()
-            logits.copy_(g_logits)
+            g_logits_in.copy_(g_logits)
         return g_sample.clone()
     for i in range(iterations):
         if sample_topk > 0:
