@@ -137,7 +137,7 @@ add_layernorm_fwd_kernel(const T* __restrict__ res, const T* __restrict__ delta,
 }
 
 // dx = (dres +) LayerNorm backward(dy); per-block partial sums of dgamma / dbeta
-template <typename T, int CHUNKS>
+template <typename T, int CHUNKS, bool DSUM>
 __global__ void __launch_bounds__(256, CHUNKS == 1 ? 2 : 1)
 add_layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dres, const T* __restrict__ x,
                          const float* __restrict__ mean, const float* __restrict__ rstd, const T* __restrict__ gamma,
@@ -227,7 +227,7 @@ add_layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dres, c
                     for (int i = 0; i < 8; ++i) {
                         o[i] = rs[r] * (gy[r][c][i] - c2 - xh[r][c][i] * c1);
                         if (dres != nullptr) o[i] += rr[r][c][i];
-                        ds[c][i] += round_to(o[i], dx);      // what a column sum over the stored dx would add
+                        if constexpr (DSUM) ds[c][i] += o[i];
                     }
                     store8(dx + row * dim + col, o);
                 }
@@ -243,7 +243,7 @@ add_layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dres, c
             for (int i = 0; i < 8; ++i) {
                 red[(warp * nwhich + 0) * dim + col + i] = dg[c][i];
                 red[(warp * nwhich + 1) * dim + col + i] = db[c][i];
-                if (nwhich == 3) red[(warp * nwhich + 2) * dim + col + i] = ds[c][i];
+                if constexpr (DSUM) red[(warp * nwhich + 2) * dim + col + i] = ds[c][i];
             }
     }
     __syncthreads();
@@ -360,19 +360,21 @@ int launch_ln_bwd(const void* dy, const void* dres, const void* x, const float* 
     const int chunks = (dim + 255) / 256;
     const int nwhich = dsum != nullptr ? 3 : 2;
     const size_t smem = (size_t)8 * nwhich * dim * sizeof(float);
-#define WM_LN_BWD(CH)                                                                                              \
+#define WM_LN_BWD_(CH, DS)                                                                                         \
     do {                                                                                                           \
-        WM_CUDA_CHECK(cudaFuncSetAttribute(add_layernorm_bwd_kernel<T, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        add_layernorm_bwd_kernel<T, CH><<<nblocks, 256, smem, st>>>(static_cast<const T*>(dy), static_cast<const T*>(dres), \
-                                                                  static_cast<const T*>(x), mean, rstd,              \
-                                                                  static_cast<const T*>(gamma), static_cast<T*>(dx), part, rows, dim, nwhich); \
+        WM_CUDA_CHECK(cudaFuncSetAttribute(add_layernorm_bwd_kernel<T, CH, DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        add_layernorm_bwd_kernel<T, CH, DS><<<nblocks, 256, smem, st>>>(static_cast<const T*>(dy), static_cast<const T*>(dres), \
+                                                                      static_cast<const T*>(x), mean, rstd,          \
+                                                                      static_cast<const T*>(gamma), static_cast<T*>(dx), part, rows, dim, nwhich); \
     } while (0)
+#define WM_LN_BWD(CH) do { if (dsum != nullptr) WM_LN_BWD_(CH, true); else WM_LN_BWD_(CH, false); } while (0)
     switch (chunks) {
         case 1: WM_LN_BWD(1); break;
         case 2: WM_LN_BWD(2); break;
         case 3: case 4: WM_LN_BWD(4); break;
         default: WM_LN_BWD(8); break;
     }
+#undef WM_LN_BWD_
 #undef WM_LN_BWD
     WM_CUDA_CHECK(cudaGetLastError());
     reduce_partials_kernel<T><<<(nwhich * dim + 31) / 32, 1024, 0, st>>>(part, static_cast<T*>(dgamma), static_cast<T*>(dbeta),
