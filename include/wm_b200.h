@@ -132,6 +132,15 @@ WM_API int wm_add_layernorm_bwd(const void* dy, const void* dres, const void* x,
                                 void* dsum, float* workspace, long rows, int dim, int dtype, void* stream);
 WM_API int wm_colsum(const void* a, void* out, float* workspace, long rows, int cols, int dtype, void* stream);
 
+/* Bias + exact (erf) GELU around the first MLP GEMM (FeedForward net.0 / net.1, local_3d_attention.py:24-27).
+ * h = x W1^T WITHOUT bias, [rows, cols]; cols a multiple of 8, <= 2048.
+ * wm_bias_gelu_fwd: y = gelu(h + bias).
+ * wm_bias_gelu_bwd: dh = dy * gelu'(h + bias); dbias [cols] = column sums of dh (the gradient of net.0.bias),
+ *   reduced in the same pass.  workspace: wm_reduce_blocks(rows) * cols floats. */
+WM_API int wm_bias_gelu_fwd(const void* h, const void* bias, void* y, long rows, int cols, int dtype, void* stream);
+WM_API int wm_bias_gelu_bwd(const void* dy, const void* h, const void* bias, void* dh, void* dbias, float* workspace,
+                            long rows, int cols, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

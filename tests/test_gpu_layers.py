@@ -117,3 +117,20 @@ def test_attention_module_deferred_bias_matches_forward(dtype, rtol, atol):
         torch.testing.assert_close(got, ref.float(), rtol=rtol, atol=atol)
         for n, p, r in zip(names, mod.parameters(), ref_grads):
             torch.testing.assert_close(p.grad.float(), r, rtol=rtol, atol=atol * 8, msg=lambda m, n=n: f'{n}: {m}')
+
+
+@pytest.mark.parametrize('dtype,rtol,atol', [(torch.float32, 1e-5, 1e-5), (torch.bfloat16, 2e-2, 2e-2)])
+@pytest.mark.parametrize('rows,cols', [(4096, 256), (1000, 48), (77, 2048), (5, 8)])
+def test_bias_gelu_forward_backward(dtype, rtol, atol, rows, cols):
+    """gelu(h + b) (exact erf form, FeedForward net.0/net.1) and its backward incl. the fused bias gradient."""
+    g = torch.Generator().manual_seed(rows + cols)
+    h, b, dy = torch.randn(rows, cols, generator=g) * 2, torch.randn(cols, generator=g), torch.randn(rows, cols, generator=g)
+    r_h, r_b = (t.to(dtype).float().clone().requires_grad_(True) for t in (h, b))
+    ref = F.gelu(r_h + r_b)
+    ref.backward(dy.to(dtype).float())
+    d_h, d_b = (t.to(DEV, dtype).requires_grad_(True) for t in (h, b))
+    out = ops.bias_gelu(d_h, d_b)
+    out.backward(dy.to(DEV, dtype))
+    torch.testing.assert_close(out.float().cpu(), ref.detach(), rtol=rtol, atol=atol)
+    torch.testing.assert_close(d_h.grad.float().cpu(), r_h.grad, rtol=rtol, atol=atol)
+    torch.testing.assert_close(d_b.grad.float().cpu(), r_b.grad, rtol=rtol, atol=atol * max(1.0, rows ** 0.5))

@@ -55,6 +55,10 @@ def lib() -> ctypes.CDLL:
     L.wm_add_layernorm_bwd.argtypes = [c_void_p] * 11 + [c_long, c_int, c_int, c_void_p]
     L.wm_colsum.restype = c_int
     L.wm_colsum.argtypes = [c_void_p] * 3 + [c_long, c_int, c_int, c_void_p]
+    L.wm_bias_gelu_fwd.restype = c_int
+    L.wm_bias_gelu_fwd.argtypes = [c_void_p] * 3 + [c_long, c_int, c_int, c_void_p]
+    L.wm_bias_gelu_bwd.restype = c_int
+    L.wm_bias_gelu_bwd.argtypes = [c_void_p] * 6 + [c_long, c_int, c_int, c_void_p]
     _lib = L
     return L
 
@@ -66,4 +70,4 @@ def check(rc: int, what: str) -> None:
 
 EXPORTS = ('wm_version', 'wm_last_error', 'wm_l3d_attn_uses_tensor_cores', 'wm_l3d_attn_fwd', 'wm_l3d_attn_bwd',
            'wm_vq_nearest', 'wm_vq_distance', 'wm_adamw_step', 'wm_reduce_blocks', 'wm_add_layernorm_fwd',
-           'wm_add_layernorm_bwd', 'wm_colsum')
+           'wm_add_layernorm_bwd', 'wm_colsum', 'wm_bias_gelu_fwd', 'wm_bias_gelu_bwd')

@@ -331,6 +331,120 @@ colsum_partial_kernel(const T* __restrict__ a, float* __restrict__ part, long ro
     }
 }
 
+// ---- bias + exact (erf) GELU around the first MLP GEMM (FeedForward, local_3d_attention.py:24-27) ------------------
+// forward:  y = gelu(h + b)            h = x W1^T without bias, [rows, C]
+// backward: dh = dy * gelu'(h + b), and per-block column sums of dh (= gradient of b) in the same pass
+// erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7): one exponential, one reciprocal, five FMAs.  The exponential
+// exp(-v^2/2) is also the Gaussian of gelu', so the backward needs no second one.  (erff + __expf made these kernels
+// instruction-bound: ~45 instructions per element against 6 bytes of traffic.)
+struct GeluTerms { float cdf, pdf_v; };        // Phi(v) and v * phi(v)
+__device__ __forceinline__ GeluTerms gelu_terms(float v) {
+    const float x = fabsf(v) * 0.70710678118654752f;
+    const float t = __fdividef(1.f, fmaf(0.3275911f, x, 1.f));
+    const float e = __expf(-x * x);
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float erf_abs = fmaf(-p * t, e, 1.f);
+    GeluTerms r;
+    r.cdf = 0.5f * (1.f + copysignf(erf_abs, v));
+    r.pdf_v = v * 0.3989422804014327f * e;
+    return r;
+}
+__device__ __forceinline__ float gelu_f(float v) { return v * gelu_terms(v).cdf; }
+__device__ __forceinline__ float gelu_grad_f(float v) {
+    const GeluTerms g = gelu_terms(v);
+    return g.cdf + g.pdf_v;
+}
+
+// thread = (column group of 8, row lane); four rows in flight per thread
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_gelu_fwd_kernel(const T* __restrict__ h, const T* __restrict__ bias, T* __restrict__ y, long rows, int C) {
+    const int groups = C / 8;
+    const int lanes = blockDim.x / groups;
+    const int grp = threadIdx.x % groups, rl = threadIdx.x / groups;
+    if (rl >= lanes) return;
+    float b[8];
+    load8(bias + grp * 8, b);
+    const long stride = (long)gridDim.x * lanes;
+    long row = (long)blockIdx.x * lanes + rl;
+    for (; row + 3 * stride < rows; row += 4 * stride) {
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) load8(h + (row + u * stride) * C + grp * 8, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[u][i] = gelu_f(v[u][i] + b[i]);
+            store8(y + (row + u * stride) * C + grp * 8, v[u]);
+        }
+    }
+    for (; row < rows; row += stride) {
+        float v[8];
+        load8(h + row * C + grp * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = gelu_f(v[i] + b[i]);
+        store8(y + row * C + grp * 8, v);
+    }
+}
+
+// same thread layout as colsum_partial_kernel; per-block column sums of dh go to `part`
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_gelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ h, const T* __restrict__ bias, T* __restrict__ dh,
+                     float* __restrict__ part, long rows, int C) {
+    extern __shared__ float red[];          // [row lanes][C]
+    const int groups = C / 8;
+    const int lanes = blockDim.x / groups;
+    const int grp = threadIdx.x % groups, rl = threadIdx.x / groups;
+    float acc[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    if (rl < lanes) {
+        load8(bias + grp * 8, b);
+        const long stride = (long)gridDim.x * lanes;
+        long row = (long)blockIdx.x * lanes + rl;
+        for (; row + 3 * stride < rows; row += 4 * stride) {
+            float g[4][8], v[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                load8(dy + (row + u * stride) * C + grp * 8, g[u]);
+                load8(h + (row + u * stride) * C + grp * 8, v[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    g[u][i] = round_to(g[u][i] * gelu_grad_f(v[u][i] + b[i]), dh);   // the value the GEMMs and the column sum both see
+                    acc[i] += g[u][i];
+                }
+                store8(dh + (row + u * stride) * C + grp * 8, g[u]);
+            }
+        }
+        for (; row < rows; row += stride) {
+            float g[8], v[8];
+            load8(dy + row * C + grp * 8, g);
+            load8(h + row * C + grp * 8, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                g[i] = round_to(g[i] * gelu_grad_f(v[i] + b[i]), dh);
+                acc[i] += g[i];
+            }
+            store8(dh + row * C + grp * 8, g);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[rl * C + grp * 8 + i] = acc[i];
+    }
+    __syncthreads();
+    for (int col = threadIdx.x; col < C; col += blockDim.x) {
+        float sacc = 0.f;
+        for (int l = 0; l < lanes; ++l) sacc += red[l * C + col];
+        part[(long)blockIdx.x * C + col] = sacc;
+    }
+}
+
 template <typename T>
 int launch_ln_fwd(const void* res, const void* delta, const void* delta_bias, const void* gamma, const void* beta, void* sum_out, void* y,
                   float* mean, float* rstd, long rows, int dim, float eps, cudaStream_t st) {
@@ -454,4 +568,55 @@ extern "C" int wm_colsum(const void* a, void* out, float* workspace, long rows, 
     const int nb = wm_reduce_blocks(rows);
     return dtype == WM_DTYPE_BF16 ? launch_colsum<__nv_bfloat16>(a, out, workspace, nb, rows, cols, st)
                                   : launch_colsum<float>(a, out, workspace, nb, rows, cols, st);
+}
+
+namespace wm {
+namespace {
+template <typename T>
+int launch_bias_gelu_fwd(const void* h, const void* bias, void* y, long rows, int C, cudaStream_t st) {
+    const int lanes = 256 / (C / 8) > 0 ? 256 / (C / 8) : 1;
+    long blocks = (rows + 4L * lanes - 1) / (4L * lanes);          // four rows per thread
+    if (blocks > 148L * 8) blocks = 148L * 8;
+    if (blocks < 1) blocks = 1;
+    bias_gelu_fwd_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const T*>(h), static_cast<const T*>(bias),
+                                                              static_cast<T*>(y), rows, C);
+    WM_CUDA_CHECK(cudaGetLastError());
+    return WM_OK;
+}
+template <typename T>
+int launch_bias_gelu_bwd(const void* dy, const void* h, const void* bias, void* dh, void* dbias, float* part, int nblocks,
+                         long rows, int C, cudaStream_t st) {
+    const size_t smem = (size_t)(256 / (C / 8) > 0 ? 256 / (C / 8) : 1) * C * sizeof(float);
+    WM_CUDA_CHECK(cudaFuncSetAttribute(bias_gelu_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bias_gelu_bwd_kernel<T><<<nblocks, 256, smem, st>>>(static_cast<const T*>(dy), static_cast<const T*>(h),
+                                                        static_cast<const T*>(bias), static_cast<T*>(dh), part, rows, C);
+    WM_CUDA_CHECK(cudaGetLastError());
+    reduce_partials_kernel<T><<<(C + 31) / 32, 1024, 0, st>>>(part, static_cast<T*>(dbias), static_cast<T*>(dbias),
+                                                              static_cast<T*>(dbias), nblocks, C, 1);
+    WM_CUDA_CHECK(cudaGetLastError());
+    return WM_OK;
+}
+}  // namespace
+}  // namespace wm
+
+extern "C" int wm_bias_gelu_fwd(const void* h, const void* bias, void* y, long rows, int cols, int dtype, void* stream) {
+    if (int rc = check_rows("wm_bias_gelu_fwd", rows, cols, dtype)) return rc;
+    if (rows == 0) return WM_OK;
+    if (!h || !bias || !y) return fail(WM_EINVAL, "wm_bias_gelu_fwd: null pointer");
+    if (!aligned16(h) || !aligned16(bias) || !aligned16(y)) return fail(WM_EINVAL, "wm_bias_gelu_fwd: pointers must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return dtype == WM_DTYPE_BF16 ? launch_bias_gelu_fwd<__nv_bfloat16>(h, bias, y, rows, cols, st)
+                                  : launch_bias_gelu_fwd<float>(h, bias, y, rows, cols, st);
+}
+
+extern "C" int wm_bias_gelu_bwd(const void* dy, const void* h, const void* bias, void* dh, void* dbias, float* workspace,
+                                long rows, int cols, int dtype, void* stream) {
+    if (int rc = check_rows("wm_bias_gelu_bwd", rows, cols, dtype)) return rc;
+    if (!dy || !h || !bias || !dh || !dbias || !workspace) return fail(WM_EINVAL, "wm_bias_gelu_bwd: null pointer");
+    if (!aligned16(dy) || !aligned16(h) || !aligned16(bias) || !aligned16(dh))
+        return fail(WM_EINVAL, "wm_bias_gelu_bwd: pointers must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nb = wm_reduce_blocks(rows);
+    return dtype == WM_DTYPE_BF16 ? launch_bias_gelu_bwd<__nv_bfloat16>(dy, h, bias, dh, dbias, workspace, nb, rows, cols, st)
+                                  : launch_bias_gelu_bwd<float>(dy, h, bias, dh, dbias, workspace, nb, rows, cols, st);
 }

@@ -42,7 +42,7 @@ class FeedForward(nn.Module):
 
     def forward(self, x):
         if x.is_cuda and self._no_dropout():
-            h = torch.nn.functional.gelu(ops.linear(x, self.net[0].weight, self.net[0].bias))
+            h = ops.bias_gelu(torch.nn.functional.linear(x, self.net[0].weight), self.net[0].bias)
             return ops.linear(h, self.net[3].weight, self.net[3].bias)
         return self.net(x)
 
@@ -51,7 +51,7 @@ class FeedForward(nn.Module):
         residual-add + LayerNorm kernel, whose backward then also reduces the bias gradient.  ``bias`` is None when the
         bias could not be deferred (dropout active, CPU tensors)."""
         if x.is_cuda and self._no_dropout():
-            h = torch.nn.functional.gelu(ops.linear(x, self.net[0].weight, self.net[0].bias))
+            h = ops.bias_gelu(torch.nn.functional.linear(x, self.net[0].weight), self.net[0].bias)
             return torch.nn.functional.linear(h, self.net[3].weight), self.net[3].bias
         return self.forward(x), None
 

@@ -256,6 +256,44 @@ class _LinearFn(torch.autograd.Function):
         return dx, dw, db
 
 
+class _BiasGeluFn(torch.autograd.Function):
+    """``gelu(h + bias)`` (exact erf form) in one kernel; the backward writes ``dh`` and reduces ``dbias`` in one pass."""
+
+    @staticmethod
+    def forward(ctx, h, bias):
+        _require_cuda(h)
+        h = h.contiguous()
+        bias = bias.to(h.dtype).contiguous()
+        y = torch.empty_like(h)
+        check(_lib.lib().wm_bias_gelu_fwd(h.data_ptr(), bias.data_ptr(), y.data_ptr(), _rows(h), h.shape[-1],
+                                          _dtype_code(h), _stream()), 'wm_bias_gelu_fwd')
+        _count(1)
+        ctx.save_for_backward(h, bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        h, bias = ctx.saved_tensors
+        dy = dy.contiguous()
+        rows, cols = _rows(h), h.shape[-1]
+        dh = torch.empty_like(h)
+        dbias = torch.empty_like(bias)
+        ws = torch.empty(_lib.lib().wm_reduce_blocks(rows) * cols, device=h.device, dtype=torch.float32)
+        check(_lib.lib().wm_bias_gelu_bwd(dy.data_ptr(), h.data_ptr(), bias.data_ptr(), dh.data_ptr(), dbias.data_ptr(),
+                                          ws.data_ptr(), rows, cols, _dtype_code(h), _stream()), 'wm_bias_gelu_bwd')
+        _count(2)
+        return dh, dbias
+
+
+def bias_gelu(h: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """``gelu(h + bias)`` with ``h = x @ W1^T`` computed WITHOUT bias (FeedForward ``net.0`` / ``net.1``,
+    local_3d_attention.py:24-27).  Widths the kernel does not tile fall back to stock CUDA ops."""
+    cols = h.shape[-1]
+    if not h.is_cuda or cols % 8 != 0 or cols > 2048 or h.dtype not in (torch.bfloat16, torch.float32):
+        return torch.nn.functional.gelu(h + bias)
+    return _BiasGeluFn.apply(h, bias)
+
+
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """nn.Linear forward on cuBLAS with the bias gradient reduced by ``wm_colsum``."""
     if bias is None or not x.is_cuda or bias.shape[0] % 8 != 0 or bias.shape[0] > 2048:
