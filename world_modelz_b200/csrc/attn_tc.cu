@@ -20,6 +20,7 @@
 // Replaces Local3dAttention.local_attention (local_3d_attention.py:78-99).
 #include "attn_tc.cuh"
 
+// -DWM_EXPERIMENT=7 compiles the clock64 timeline instrumentation in (tools/build_timeline_lib.sh, tools/dbg_timeline.py)
 #ifndef WM_EXPERIMENT
 #define WM_EXPERIMENT 0
 #endif
@@ -624,32 +625,18 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     for (; g + 2 <= gb; g += 2) {        // two 8-column groups per TMEM load
                         const uint32_t mword = mask_bits(g);
                         uint32_t r[16];
-#if WM_EXPERIMENT == 3
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(neg_m + i + g);
-#else
                         tmem_ld16(tmem_s + lane_sel + g * 8, r);
                         tmem_wait_ld();
-#endif
                         float p[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-#if WM_EXPERIMENT == 1
-                            const float e = fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m);
-#else
                             const float e = ex2(fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m));
-#endif
                             p[i] = (mword & (1u << i)) ? e : 0.f;
                             ls[i & 3] += p[i];
                             pm[i & 3] = fmaxf(pm[i & 3], p[i]);
                         }
-#if WM_EXPERIMENT == 2
-                        if (pm[0] == 123.456f)
-#endif
-                        {
                         p_store(g, pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
                         p_store(g + 1, pack_bf16(p[8], p[9]), pack_bf16(p[10], p[11]), pack_bf16(p[12], p[13]), pack_bf16(p[14], p[15]));
-                        }
                     }
                     if (g < gb) {
                         const uint32_t mword = mask_bits(g);

@@ -19,6 +19,7 @@
 // (local_3d_attention.py:78-99; recomputed under checkpoint at :110-111).
 #include "attn_tc.cuh"
 
+// -DWM_EXPERIMENT=7 compiles the clock64 timeline instrumentation in (tools/build_timeline_lib.sh, tools/dbg_timeline.py)
 #ifndef WM_EXPERIMENT
 #define WM_EXPERIMENT 0
 #endif

@@ -17,6 +17,7 @@
 // single-purpose warps keep each of the per-step chains short.
 #include "attn_tc.cuh"
 
+// -DWM_EXPERIMENT=7 compiles the clock64 timeline instrumentation in (tools/build_timeline_lib.sh, tools/dbg_timeline.py)
 #ifndef WM_EXPERIMENT
 #define WM_EXPERIMENT 0
 #endif
