@@ -45,8 +45,10 @@ if hasattr(_lib.lib(), 'wm_debug_read_ws'):
     buf3 = (ctypes.c_longlong * (2 * 64 * 16))()
     _lib.lib().wm_debug_read_ws(buf3)
     b3 = np.array(buf3[:], dtype=np.int64).reshape(2, 64, 16)
-    nw = {0: 'drv:top', 1: 'drv:p ok', 2: 'drv:T issued', 3: 'drv:acc issued', 4: 'drv:refilled', 5: 'drv:ACC RETIRED', 8: 'cmp:top', 9: 'cmp:bufs free',
-          10: 'cmp:T ready', 11: 'cmp:done', 12: 'cmp:arrived'}
+    # issuing side = warp 8 (the (S,dP) issuer): iteration top, columns A drained, (S,dP) half A of the next step issued,
+    # half B issued; compute side = thread 0
+    nw = {0: 'iss:top', 1: 'iss:pA ok', 2: 'iss:T_A(t+1) issued', 3: 'iss:T_B(t+1) issued', 8: 'cmp:top', 9: 'cmp:bufs free',
+          10: 'cmp:T_A ready', 11: 'cmp:done', 12: 'cmp:arrived'}
     for m, name in ((0, 'dQ ws'), (1, 'dK/dV ws')):
         a = b3[m]; t0 = a[0, 0]
         print('====', name)
