@@ -133,3 +133,26 @@ def test_data_parallel_gradient_exchange_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert out.get() < 1e-5
+
+
+def test_deferred_bias_host_paths_on_cpu():
+    """Host logic of the deferred-bias schedule that needs no GPU: widths the fused kernel does not tile go through
+    stock ops with the same math, and modules hand back ``bias=None`` when they cannot defer (CPU tensors)."""
+    import torch
+    import torch.nn.functional as F
+    from world_modelz_b200 import ops
+    from world_modelz_b200.local_3d_attention import FeedForward
+    torch.manual_seed(0)
+    res, delta = torch.randn(7, 12), torch.randn(7, 12)            # dim 12: not a multiple of 8 -> stock-op path
+    bias, gamma, beta = torch.randn(12), torch.rand(12) + 0.5, torch.randn(12)
+    total, y = ops.add_layernorm(res, delta, gamma, beta, 1e-5, bias)
+    torch.testing.assert_close(total, res + delta + bias)
+    torch.testing.assert_close(y, F.layer_norm(res + delta + bias, (12,), gamma, beta, 1e-5))
+    total2, _ = ops.add_layernorm(res, None, gamma, beta, 1e-5)
+    assert total2 is res
+    ff = FeedForward(12, 24)
+    x = torch.randn(3, 12)
+    out, b = ff.forward_deferred_bias(x)
+    assert b is None
+    torch.testing.assert_close(out, ff(x))
+    torch.testing.assert_close(ops.bias_gelu(x, torch.zeros(12)), F.gelu(x))     # CPU tensors: stock ops
