@@ -1,6 +1,6 @@
 """Device-side diagnostics: tcgen05 kernels vs the exact SIMT kernels and the CPU oracle.
 Prints error summaries for every case instead of stopping at the first failure."""
-import sys, os, time
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from world_modelz_b200 import ops

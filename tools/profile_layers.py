@@ -3,7 +3,7 @@ between launches, and report achieved HBM GB/s on their algorithmic bytes."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from world_modelz_b200 import ops, _lib
+from world_modelz_b200 import _lib
 from world_modelz_b200.ops import check, _stream
 
 rows, dim = 32 * 16 * 16 * 16, 256
