@@ -156,3 +156,44 @@ def test_deferred_bias_host_paths_on_cpu():
     assert b is None
     torch.testing.assert_close(out, ff(x))
     torch.testing.assert_close(ops.bias_gelu(x, torch.zeros(12)), F.gelu(x))     # CPU tensors: stock ops
+
+
+def test_reference_checkpoint_format_round_trip():
+    """``checkpoint.py``: flat AdamW moments <-> ``torch.optim.AdamW.state_dict()`` (the reference's
+    ``optimizer_state_dict``, main.py:300-307), checked against a real AdamW on the CPU."""
+    import torch
+    from world_modelz_b200 import checkpoint as ck
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3))
+    opt = torch.optim.AdamW(net.parameters(), lr=3e-4, weight_decay=1e-7)
+    for _ in range(3):
+        opt.zero_grad()
+        net(torch.randn(4, 6)).square().mean().backward()
+        opt.step()
+    ref_state = opt.state_dict()
+    params = list(net.parameters())
+    shapes = ck.param_shapes(params)
+    n = sum(p.numel() for p in params)
+    m, v = torch.full((n,), 7.0), torch.full((n,), 7.0)
+    steps = ck.adamw_state_to_flat(ref_state, shapes, m, v)
+    assert steps == 3
+    off = 0
+    for i, p in enumerate(params):
+        torch.testing.assert_close(m[off:off + p.numel()].view_as(p), ref_state['state'][i]['exp_avg'])
+        torch.testing.assert_close(v[off:off + p.numel()].view_as(p), ref_state['state'][i]['exp_avg_sq'])
+        off += p.numel()
+    back = ck.flat_to_adamw_state(shapes, m, v, steps, lr=3e-4, weight_decay=1e-7)
+    opt2 = torch.optim.AdamW(net.parameters(), lr=1.0)
+    opt2.load_state_dict(back)                                   # a stock AdamW accepts what we write
+    for i in range(len(params)):
+        torch.testing.assert_close(opt2.state_dict()['state'][i]['exp_avg'], ref_state['state'][i]['exp_avg'])
+        assert float(opt2.state_dict()['state'][i]['step']) == 3.0
+    assert opt2.state_dict()['param_groups'][0]['lr'] == 3e-4
+    data = ck.make_checkpoint(net.state_dict(), back, step=3, lr=3e-4, opt={'dim': 6})
+    assert set(data) == {'step', 'lr', 'model_state_dict', 'ema_model_state_dict', 'optimizer_state_dict', 'opt'}
+    # an optimizer that has not stepped yet: empty state, zeroed moments
+    fresh = torch.optim.AdamW(net.parameters()).state_dict()
+    assert ck.adamw_state_to_flat(fresh, shapes, m, v) == 0 and float(m.abs().sum()) == 0.0
+    import pytest
+    with pytest.raises(ValueError):
+        ck.adamw_state_to_flat(ref_state, shapes[:-1], m, v)

@@ -233,6 +233,53 @@ class DenoiserTrainer:
             self.shadow.copy_(saved[4])
         self._graph, self._static = (graph_a, graph_b), (st_tokens, st_r, st_loss, st_ps)
 
+    # -- checkpoints in the reference's format (main.py:297-309, 370-410) ------------------------------
+    def checkpoint(self, step: int, opt=None) -> dict:
+        """The dict the reference's training loop saves: fp32 ``model_state_dict`` from the master weights and an
+        ``optimizer_state_dict`` laid out like ``torch.optim.AdamW.state_dict()``."""
+        from . import checkpoint as ck
+        self._sync_params_from_master()
+        taken = int(round(float(self.dyn[0].item()))) - 1
+        shapes = ck.param_shapes(self._params)
+        opt_state = ck.flat_to_adamw_state(shapes, self.exp_avg, self.exp_avg_sq, taken, lr=float(self.dyn[1].item()),
+                                           betas=self.betas, eps=self.eps, weight_decay=self.weight_decay)
+        state = self.model.state_dict()
+        named = dict(self.model.named_parameters())
+        off = 0
+        for p in self._params:                       # parameters: full-precision master copy, not the bf16 shadow
+            k = p.numel()
+            for name, q in named.items():
+                if q is p:
+                    state[name] = self.master[off:off + k].view_as(p).clone()
+            off += k
+        return ck.make_checkpoint(state, opt_state, step, float(self.dyn[1].item()), opt)
+
+    def load_checkpoint(self, data: dict) -> int:
+        """Resume from a dict written by the reference (or by :meth:`checkpoint`); returns the stored step."""
+        from . import checkpoint as ck
+        self.model.load_state_dict(data['model_state_dict'], strict=True)      # copies into the shadow views
+        named = dict(self.model.named_parameters())
+        sd = data['model_state_dict']
+        off = 0
+        for p in self._params:
+            k = p.numel()
+            for name, q in named.items():
+                if q is p:
+                    self.master[off:off + k].copy_(sd[name].reshape(-1).float())
+            off += k
+        if data.get('optimizer_state_dict') is not None:
+            taken = ck.adamw_state_to_flat(data['optimizer_state_dict'], ck.param_shapes(self._params), self.exp_avg,
+                                           self.exp_avg_sq)
+            self.dyn[0:1].fill_(float(taken + 1))
+        lr = data.get('lr')
+        if lr:
+            self.set_lr(float(lr[0] if isinstance(lr, (list, tuple)) else lr))
+        return int(data.get('step', 0))
+
+    def _sync_params_from_master(self) -> None:
+        if self.shadow is not None:
+            self.shadow.copy_(self.master)
+
     def launches_per_step(self) -> int:
         """Launches of libwm_b200 kernels per step (attention fwd/bwd, add+LayerNorm fwd/bwd, bias column sums,
         AdamW), counted by ``ops`` during the last eager warm-up step; the graphs replay exactly those."""
