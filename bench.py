@@ -240,6 +240,23 @@ def sampling_benchmark(dev, model, clips):
     return out
 
 
+class StdoutGuard:
+    """Keeps stdout to the ONE JSON line: while active, file descriptor 1 points at stderr, so banners that native
+    libraries write straight to fd 1 (NCCL prints its version there) cannot end up next to the result."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def release(self):
+        if self._saved is not None:
+            sys.stdout.flush()
+            os.dup2(self._saved, 1)
+            os.close(self._saved)
+            self._saved = None
+
+
 # ---------------------------------------------------------------------------------- main
 def dbg(msg):
     if os.environ.get('WM_BENCH_DEBUG'):
@@ -252,6 +269,7 @@ def run_b200(args):
     from world_modelz_b200 import ops, parallel
     from world_modelz_b200.denoiser import LossAwareSamplerEma
 
+    guard = StdoutGuard()
     rank, local_rank, world = parallel.init_from_env('nccl')
     dbg(f'process group up: world={world}')
     if not torch.cuda.is_available():
@@ -388,6 +406,7 @@ def run_b200(args):
                                 'sample': f'{n} steps x 1 clip of config 3, fp32, oracle port on {cores} host threads'}
     else:
         line['cpu_baseline'] = None
+    guard.release()
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

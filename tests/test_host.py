@@ -197,3 +197,25 @@ def test_reference_checkpoint_format_round_trip():
     import pytest
     with pytest.raises(ValueError):
         ck.adamw_state_to_flat(ref_state, shapes[:-1], m, v)
+
+
+def test_bench_stdout_guard_keeps_native_banners_off_stdout(tmp_path):
+    """bench.py prints ONE JSON line on stdout; anything a native library writes to fd 1 before that goes to stderr."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / 'guard.py'
+    script.write_text(
+        'import os, sys, json, importlib.util\n'
+        f'spec = importlib.util.spec_from_file_location("bench", r"{root}/bench.py")\n'
+        'b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)\n'
+        'g = b.StdoutGuard()\n'
+        'os.write(1, b"NCCL version banner\\n")\n'
+        'print("guarded python print")\n'
+        'g.release()\n'
+        'print(json.dumps({"ok": 1}), flush=True)\n')
+    res = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    assert res.stdout.strip() == '{"ok": 1}'
+    assert 'NCCL version banner' in res.stderr and 'guarded python print' in res.stderr
