@@ -15,6 +15,12 @@
  *       replace the distance + argmin + gather + per-latent error of
  *       VectorQuantizerEMA.forward / .encode / .codebook_distance
  *       (vq-video-diffusion/vq.py:30-36, 77-87).
+ *   wm_add_layernorm_fwd / _bwd, wm_bias_gelu_fwd / _bwd, wm_colsum
+ *       replace PreNorm, the residual adds and the bias / GELU element-wise chains of the
+ *       transformer block around the attention core, with the bias gradients of its
+ *       nn.Linear layers (vq-video-diffusion/local_3d_attention.py:11-31, 159-161).
+ *   wm_adamw_step
+ *       replaces optim.AdamW.step() of the training loop (vq-video-diffusion/main.py:283, 433).
  *
  * Conventions
  *   - All pointers are device pointers owned by the caller (PyTorch's caching
