@@ -88,51 +88,46 @@ int make_tensor_map_2d_f32(CUtensorMap* out, const void* base, uint64_t cols, ui
 // ------------------------------------------------------------------------------- plan
 static int row_bytes_of(int d) { return d == 32 ? 64 : 128; }
 static int slabs_of(int d) { return d == 128 ? 2 : 1; }
-static const size_t kFixedSmem = 1024 /*alignment slack*/ + 2 * 9 * 128 * 4 /*masks*/ + 3 * 2 * 4 * 128 * 4 /*exchange*/ + 256 /*barriers*/;
+static const size_t kFixedSmem = 1024 /*alignment slack*/ + 3 * 2 * 4 * 128 * 4 /*exchange*/ + 256 /*barriers*/;
 
-size_t smem_bytes_for(Mode mode, int d, int ncols_pad, int nstage, int rowbuf) {
+static size_t mask_tile_bytes(int ncols_pad, int km, int nchunk) {      // row tile [128 x km] + nchunk column tiles, bf16
+    return (size_t)128 * km * 2 + (size_t)nchunk * ncols_pad * km * 2;
+}
+
+size_t smem_bytes_for(Mode mode, int d, int ncols_pad, int nstage, int rowbuf, int km, int nchunk) {
     const size_t row_tile = (size_t)slabs_of(d) * 128 * row_bytes_of(d);
     const size_t blk = (size_t)slabs_of(d) * ncols_pad * row_bytes_of(d);
     const size_t ptile = (size_t)round_up(ncols_pad, 64) / 64 * 128 * 128;
+    const size_t fixed = kFixedSmem + mask_tile_bytes(ncols_pad, km, nchunk);
     switch (mode) {
-        case kFwd: return kFixedSmem + rowbuf * row_tile + nstage * 2 * blk;                   // Q | (K,V) stages (P lives in TMEM)
-        case kBwdDQ: return kFixedSmem + rowbuf * 2 * row_tile + nstage * 2 * blk + ptile;     // Q,dO | (K,V) stages | dS
-        case kBwdDQws: return kFixedSmem + rowbuf * 2 * row_tile + nstage * 2 * blk;           // Q,dO | (K,V) stages (dS lives in TMEM)
-        case kBwdDKVws: return kFixedSmem + rowbuf * 2 * row_tile + nstage * 2 * blk + 2 * ptile + 6 * ncols_pad * 4;   // K,V | (Q,dO) | dS^T x2 | lse,delta x3 (P^T in TMEM)
-        default: return kFixedSmem + rowbuf * 2 * row_tile + nstage * 2 * blk + 2 * ptile + 4 * ncols_pad * 4;   // K,V | (Q,dO) | P,dS | lse,delta
+        case kFwd: return fixed + rowbuf * row_tile + nstage * 2 * blk;                   // Q | (K,V) stages (P lives in TMEM)
+        case kBwdDQws: return fixed + rowbuf * 2 * row_tile + nstage * 2 * blk;           // Q,dO | (K,V) stages (dS lives in TMEM)
+        default: return fixed + rowbuf * 2 * row_tile + nstage * 2 * blk + 2 * ptile + 6 * ncols_pad * 4;   // K,V | (Q,dO) | dS^T x2 | lse,delta x3 (P^T in TMEM)
     }
 }
 
 int tmem_cols_for(Mode mode, int d, int ncols_pad) {
     switch (mode) {
         case kFwd: return d + 3 * ncols_pad;             // O (x2 if it fits) | S x2 | P x2 (bf16, half the columns)
-        case kBwdDQ: return d + 2 * ncols_pad;           // dQ | S | dP
         case kBwdDQws: return d + 3 * ncols_pad;         // dQ | S | dP | dS x2 (bf16 pairs)
-        case kBwdDKVws: return 2 * d + 3 * ncols_pad;    // dV | dK | S^T | dP^T | P^T x2 (bf16 pairs)
-        default: return 2 * d + 2 * ncols_pad;           // dV | dK | S^T | dP^T
+        default: return 2 * d + 3 * ncols_pad;           // dV | dK | S^T | dP^T | P^T x2 (bf16 pairs)
     }
 }
 
 // Choose the brick and block shape: minimise the dense MMA columns executed per clip.
 bool make_plan(const AttnShape& s, Mode mode, Plan& best) {
     if (s.d != 32 && s.d != 64 && s.d != 128) return false;
-    const bool ws_bwd = (mode == kBwdDQws || mode == kBwdDKVws);
     static const int bricks[][3] = {{2, 8, 8}, {4, 4, 8}, {4, 8, 4}, {1, 8, 16}, {1, 16, 8}, {2, 4, 16}, {2, 16, 4}};
     double best_cost = 1e300;
     bool found = false;
-    // tuning knob (experiments only): cap the block width, e.g. WM_TC_MAXCOLS="144,80,80" (fwd,dq,dkv)
-    int max_cols = 256;
-    if (const char* env = getenv("WM_TC_MAXCOLS")) {
-        int v[3] = {256, 256, 256};
-        sscanf(env, "%d,%d,%d", &v[0], &v[1], &v[2]);
-        max_cols = v[(int)mode];
-    }
+    const int max_cols = 256;
     for (const auto& b : bricks) {
         Plan p{};
         p.tS = b[0]; p.tH = b[1]; p.tW = b[2];
         if (p.tS * p.tH * p.tW != 128 || (p.tH * p.tW) % 32 != 0) continue;
         p.hS = p.tS + 2 * s.eS; p.hH = p.tH + 2 * s.eH; p.hW = p.tW + 2 * s.eW;
         if (p.hW > 32 || p.hH > 256) continue;
+        p.km = round_up(p.tH + p.tW, 16);
         p.tilesS = (s.S + p.tS - 1) / p.tS; p.tilesH = (s.H + p.tH - 1) / p.tH; p.tilesW = (s.W + p.tW - 1) / p.tW;
         const double tiles = (double)p.tilesS * p.tilesH * p.tilesW;
         // heads per CTA (forward kernel): walk as many heads as possible while keeping the grid >= 4 CTAs per SM
@@ -149,11 +144,10 @@ bool make_plan(const AttnShape& s, Mode mode, Plan& best) {
             bool fits = false;
             const int opts[7][3] = {{4, 2, hpc}, {3, 2, hpc}, {2, 2, hpc}, {4, 1, 1}, {3, 1, 1}, {2, 1, hpc}, {2, 1, 1}};    // {nstage, rowbuf, hpc}
             for (const auto& o : opts) {
-                if ((mode == kBwdDQ || mode == kBwdDKV) && o[0] != 2) continue;        // non-specialised bwd kernels: 2 block stages
                 if (mode != kFwd && o[0] > 3) continue;                                // 4 stages: forward kernel only
                 if (mode != kFwd && o[1] == 1 && o[2] != 1) continue;                  // bwd: a head loop only with 2 row buffers
                 if (o[1] == 2 && hpc == 1) continue;
-                if (smem_bytes_for(mode, s.d, p.ncols_pad, o[0], o[1]) <= (size_t)kSmemLimit) {
+                if (smem_bytes_for(mode, s.d, p.ncols_pad, o[0], o[1], p.km, p.nchunk) <= (size_t)kSmemLimit) {
                     p.nstage = o[0]; p.rowbuf = o[1]; p.hpc = o[2];
                     fits = true;
                     break;
@@ -163,11 +157,9 @@ bool make_plan(const AttnShape& s, Mode mode, Plan& best) {
             const double cost = tiles * p.hS * p.nchunk * (p.ncols_pad + 24.0 /*per-block overhead*/);
             if (cost < best_cost) {
                 best_cost = cost;
-                p.smem_bytes = (int)smem_bytes_for(mode, s.d, p.ncols_pad, p.nstage, p.rowbuf);
+                p.smem_bytes = (int)smem_bytes_for(mode, s.d, p.ncols_pad, p.nstage, p.rowbuf, p.km, p.nchunk);
                 // forward: one O accumulator per head parity when TMEM has room (the previous head is drained off the
-                // critical path).  Measured at the config-3 shape: 0.279 ms vs 0.335 ms for the alternative use of the
-                // same columns, two independent accumulation chains (osplit = 2) with a single head parity.
-                p.osplit = 1;
+                // critical path)
                 p.obufs = (mode == kFwd && 2 * s.d + 3 * p.ncols_pad <= 512) ? 2 : 1;
                 p.tmem_cols = next_pow2(tmem_cols_for(mode, s.d, p.ncols_pad) + (p.obufs == 2 ? s.d : 0));
                 p.scale_log2 = s.scale * 1.4426950408889634f;
@@ -197,19 +189,25 @@ struct FwdParams {
     float* lse;
 };
 
+#ifndef WM_FWD_POLY
+#define WM_FWD_POLY 3      // of every 8 column pairs, this many take the FMA-pipe exp2 (the rest go to the MUFU)
+#endif
+
 // Warp-specialised forward kernel.
 //   warps 0-7  compute: warps w and w+4 share TMEM lane quadrant w&3 (32 query rows) and split
-//              the row's key columns ("half" 0 / 1): softmax, P -> smem, epilogue.
-//   warp  8    driver (one lane): TMA loads of Q / K / V blocks and every tcgen05.mma.
-// S lives in two TMEM buffers and P in two smem buffers, so S_{t+1} = Q K_{t+1}^T is
-// computed while the compute warps are still in the softmax of step t, and O += P_t V_t
-// runs while they are already in step t+1.  All hand-offs are mbarriers; there is no
-// CTA-wide barrier inside the loop.  A CTA walks `hpc` heads of its brick back to back.
-template <int D, int NPART>
-__global__ void __launch_bounds__(32 * (4 * NPART + 1), 1)
+//              the quadrant's live key columns ("part" 0 / 1): exponentials, P -> TMEM, epilogue.
+//   warp  8    driver (one elected lane): TMA loads of Q / K / V blocks and every tcgen05.mma.
+// S lives in two TMEM buffers and P in two more, so S_{t+1} (and S_{t+2} with four K/V stages) is
+// computed while the compute warps are still in step t, and O += P_t V_t runs while they are already in
+// step t+1.  All hand-offs are mbarriers; there is no CTA-wide barrier inside the loop.  A CTA walks
+// `hpc` heads of its brick back to back.  The window / border mask is part of the score MMA
+// (build_mask_tiles in attn_tc.cuh), so the element loop is: scale, 2^x, sum, pack.
+template <int D>
+__global__ void __launch_bounds__(kFwdThreads, 1)
 l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv_k,
                   const __grid_constant__ CUtensorMap map_kv_v, const FwdParams prm) {
     using G = Geo<D>;
+    constexpr int NPART = 2;
     const AttnShape& sh = prm.sh;
     const Plan& pl = prm.pl;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -222,20 +220,19 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const int q_tile_bytes = G::kSlabs * q_slab_bytes;
     const int kv_slab_bytes = ncols_pad * G::kRowBytes;
     const int kv_tile_bytes = G::kSlabs * kv_slab_bytes;
-    const int p_slabs = (ncols_pad + 63) / 64;
-    const int p_tile_bytes = p_slabs * 128 * 128;
+    const int cm_tile_bytes = ncols_pad * pl.km * 2;
 
     uint8_t* sQ = smem;                                          // [rowbuf][slabs][128 rows]
     uint8_t* sKV = sQ + pl.rowbuf * q_tile_bytes;                // [nstage][K|V][slabs][ncols_pad rows]
     constexpr int kDriverWarp = 4 * NPART;
-    constexpr int kThreadsAll = 32 * (4 * NPART + 1);
-    uint32_t* sMask = reinterpret_cast<uint32_t*>(sKV + nstage * 2 * kv_tile_bytes);   // [9 words][128 rows] (+ spare copy)
-    float* sX = reinterpret_cast<float*>(sMask + 2 * 9 * 128);                 // [3 uses][2 parities][NPART][128 rows]
+    uint8_t* sRm = sKV + nstage * 2 * kv_tile_bytes;             // mask operand of the rows:    [128 x km] bf16
+    uint8_t* sCm = sRm + 128 * pl.km * 2;                        // mask operand of the columns: [nchunk][ncols_pad x km] bf16
+    float* sX = reinterpret_cast<float*>(sCm + pl.nchunk * cm_tile_bytes);     // [3 uses][2 parities][4][128 rows]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 3 * 2 * 4 * 128);
     uint64_t* bar_q = bars;           // [2]  Q tile of a head landed
     uint64_t* bar_kv = bars + 2;      // [4]  K/V block landed
     uint64_t* bar_s = bars + 6;       // [2]  S buffer computed            (tcgen05.commit)
-    uint64_t* bar_p = bars + 8;       // [2]  P buffer written, S buffer drained (256 compute threads)
+    uint64_t* bar_p = bars + 8;       // [2]  P buffer written, S buffer drained (8 compute warps)
     uint64_t* bar_o = bars + 10;      // [2]  O += P V of a step retired   (tcgen05.commit)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
@@ -285,19 +282,19 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const int pad_bytes = (ncols_pad - ncols) * G::kRowBytes;
         for (int t = 0; t < nstage * 2 * G::kSlabs; ++t) {
             uint8_t* base = sKV + t * kv_slab_bytes + ncols * G::kRowBytes;
-            for (int i = tid * 16; i < pad_bytes; i += kThreadsAll * 16) *reinterpret_cast<uint4*>(base + i) = make_uint4(0, 0, 0, 0);
+            for (int i = tid * 16; i < pad_bytes; i += kFwdThreads * 16) *reinterpret_cast<uint4*>(base + i) = make_uint4(0, 0, 0, 0);
         }
-        fence_proxy_async();
     }
+    build_mask_tiles(sRm, sCm, pl, sh, h0, w0, tid, kFwdThreads);
+    fence_proxy_async();                 // generic-proxy writes above -> visible to tcgen05.mma
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // TMEM columns: O (one buffer per head parity when it fits) | S x2 | P x2 (bf16 pairs, ncols_pad/2 columns each)
-    const uint32_t tmem_s0 = tmem_base + pl.obufs * pl.osplit * D;
+    const uint32_t tmem_s0 = tmem_base + pl.obufs * D;
     const uint32_t tmem_p0 = tmem_s0 + 2 * ncols_pad;
     const int p_cols = ncols_pad >> 1;
-    (void)p_tile_bytes;
 
     // a step = (head, plane, h-chunk); steps run head-major, then chunk, then plane
     struct Cursor { int hd, ks, chunk; };
@@ -343,11 +340,14 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const uint64_t dq0 = make_smem_desc(smem_u32(sQ), 16, G::kAtomBytes, G::kSwizzleCode);
         const uint64_t dk0 = make_smem_desc(smem_u32(sKV), 16, G::kAtomBytes, G::kSwizzleCode);
         const uint64_t dv0 = make_smem_desc(smem_u32(sKV + kv_tile_bytes), (uint32_t)kv_slab_bytes, G::kAtomBytes, G::kSwizzleCode);
+        const uint64_t drm0 = make_smem_desc(smem_u32(sRm), 2048u, 128u, 0u);                       // mask operands: no swizzle
+        const uint64_t dcm0 = make_smem_desc(smem_u32(sCm), (uint32_t)ncols_pad * 16u, 128u, 0u);
         const uint32_t q_buf_step = (pl.rowbuf == 2) ? (uint32_t)(q_tile_bytes >> 4) : 0u;
         const uint32_t stage_step = (uint32_t)((2 * kv_tile_bytes) >> 4);
-        auto issue_s_mma = [&](int t, int stage, int hd) {     // S[t&1] = Q_hd K_t^T
+        const int nk_m = pl.km >> 4;
+        auto issue_s_mma = [&](int t, int stage, const Cursor& c) {     // S[t&1] = Q_hd K_t^T + R C_chunk^T
             const uint32_t tmem_s = tmem_s0 + (t & 1) * ncols_pad;
-            const uint64_t da0 = dq0 + (hd & 1) * q_buf_step, db0 = dk0 + stage * stage_step;
+            const uint64_t da0 = dq0 + (c.hd & 1) * q_buf_step, db0 = dk0 + stage * stage_step;
 #pragma unroll
             for (int kk = 0; kk < D / 16; ++kk) {
                 const uint32_t off = (uint32_t)(((kk * 16) / G::kSlabCh) * 1 /*slab*/);
@@ -356,16 +356,21 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     umma_bf16_ss(tmem_s, da0 + off * (uint32_t)(q_slab_bytes >> 4) + koff,
                                  db0 + off * (uint32_t)(kv_slab_bytes >> 4) + koff, idesc_s, kk > 0);
             }
+            const uint64_t dcm = dcm0 + (uint32_t)c.chunk * (uint32_t)(cm_tile_bytes >> 4);
+            for (int kk = 0; kk < nk_m; ++kk)       // 16 mask channels = two 8-channel core-matrix columns per MMA
+                if (leader)
+                    umma_bf16_ss(tmem_s, drm0 + (uint32_t)kk * (uint32_t)((2 * 2048) >> 4),
+                                 dcm + (uint32_t)kk * (uint32_t)((2 * ncols_pad * 16) >> 4), idesc_s, 1u);
             if (leader) umma_commit(&bar_s[t & 1]);
         };
         const int nk_o = ncols_pad / 16;
         auto issue_o_mma = [&](int t, int stage, int hd, bool accumulate) {   // O[hd&1] += P[t&1] V_t
-            const uint32_t tmem_o = tmem_base + (pl.obufs == 2 ? (hd & 1) : 0) * pl.osplit * D;
+            const uint32_t tmem_o = tmem_base + (pl.obufs == 2 ? (hd & 1) : 0) * D;
             uint32_t ta = tmem_p0 + (t & 1) * p_cols;                                // A = P from tensor memory
             uint64_t db = dv0 + stage * stage_step;
+#pragma unroll 3
             for (int kk = 0; kk < nk_o; ++kk) {
-                const uint32_t chain = (pl.osplit == 2) ? (uint32_t)(kk & 1) : 0u;   // alternate accumulators
-                if (leader) umma_bf16_ts(tmem_o + chain * D, ta, db, idesc_o, (accumulate || kk >= pl.osplit) ? 1u : 0u);
+                if (leader) umma_bf16_ts(tmem_o, ta, db, idesc_o, (accumulate || kk > 0) ? 1u : 0u);
                 ta += 8;                                                             // next 16 keys: 8 bf16-pair columns of P
                 db += (uint32_t)((16 * G::kRowBytes) >> 4);                          // next 16 keys of V
             }
@@ -385,7 +390,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         mbar_wait(&bar_q[0], 0);
         mbar_wait(&bar_kv[0], 0);
         tc_fence_after();
-        issue_s_mma(0, 0, 0);
+        issue_s_mma(0, 0, cur);
         int st_cur = 0;                              // stage of step t
         int st_nxt = (nstage > 1) ? 1 : 0;           // stage of step t+1 ...
         uint32_t kv_par = 1u;                        // bit s = parity of stage s's next completion (stage 0 was consumed once)
@@ -401,7 +406,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             mbar_wait(&bar_kv[1], 0);
             kv_par ^= 1u << 1;
             tc_fence_after();
-            issue_s_mma(1, 1, nxt.hd);
+            issue_s_mma(1, 1, nxt);
             for (int t = 0; t < nsteps; ++t) {
                 DBG(0);
                 const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
@@ -417,7 +422,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     if (nn.hd != nxt.hd) mbar_wait(&bar_q[nn.hd & 1], (nn.hd >> 1) & 1);
                     tc_fence_after();
                     DBG(1);
-                    issue_s_mma(t + 2, st_nn, nn.hd);
+                    issue_s_mma(t + 2, st_nn, nn);
                     DBG(2);
                 }
                 if (t >= 1 && ld_t < nsteps) {               // refill the stage freed by step t-1
@@ -462,7 +467,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 if (nxt.hd != cur.hd) mbar_wait(&bar_q[nxt.hd & 1], (nxt.hd >> 1) & 1);
                 tc_fence_after();
                 DBG(1);
-                issue_s_mma(t + 1, st_nxt, nxt.hd);
+                issue_s_mma(t + 1, st_nxt, nxt);
                 DBG(2);
             }
             if (nstage >= 3) refill();
@@ -480,9 +485,8 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         }
     } else {
         // =============================== compute warps ==========================================
-        // NPART threads per query row: warps w, w+4, ... share TMEM lane quadrant w&3 and split the
-        // row's live key columns (in groups of 8) between them.
-        constexpr int LOGP = (NPART == 4) ? 2 : 1;
+        // Two threads per query row: warps w and w+4 share TMEM lane quadrant w&3 and split the
+        // quadrant's live key columns (in groups of 8) between them.
         constexpr int CP = D / NPART;                  // O columns per thread in rescale / epilogue
         const int quad = warp & 3, part = warp >> 2;
         const int row = quad * 32 + lane;              // query row of the brick == TMEM lane
@@ -494,14 +498,14 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         // live key range of this row in halo coordinates (window AND grid), per axis
         const int kh_lo = max(qh, sh.eH - h0), kh_hi = min(qh + 2 * sh.eH, sh.H - 1 - h0 + sh.eH);
         const int kw_lo = max(qw, sh.eW - w0), kw_hi = min(qw + 2 * sh.eW, sh.W - 1 - w0 + sh.eW);
-        const uint32_t wbits = (q_valid && kw_hi >= kw_lo) ? ((kw_hi - kw_lo == 31) ? 0xffffffffu : ((1u << (kw_hi - kw_lo + 1)) - 1u)) << kw_lo : 0u;
+        const bool row_can = q_valid && kw_hi >= kw_lo;
         // warp-uniform ranges (identical for all warps of a quadrant)
         const int w_qs = (quad * 32) >> pl.lgPlane;
         const int w_qh_lo = ((quad * 32) & plane_mask) >> pl.lgTW, w_qh_hi = ((quad * 32 + 31) & plane_mask) >> pl.lgTW;
         const long tok = (((long)b * sh.S + (s0 + qs)) * sh.H + (h0 + qh)) * sh.W + (w0 + qw);
 
         // Reference exponent (log2 domain, scaled) this row's P values are relative to.  It starts at 0 and is
-        // only moved when a block's row maximum leaves [2^-64, 2^64] relative to it: bf16 P and the fp32 sums
+        // only moved when a block's row sum leaves [2^-64, 2^64] relative to it: bf16 P and the fp32 sums
         // keep full precision over that range, so no per-block max pass and (in practice) no O rescale is needed.
         float m_used = 0.f;
         float l_part = 0.f;            // this thread's share of the running sum of P
@@ -512,7 +516,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         auto xslot = [&](int use, int parity) { return sX + ((use * 2 + (parity & 1)) * 4) * 128; };
         // O / l -> bf16 and the LSE of head `hd`; called once that head's last P V has retired
         auto finish_head = [&](int hd) {
-            const uint32_t tmem_o = tmem_base + (pl.obufs == 2 ? (hd & 1) : 0) * pl.osplit * D;
+            const uint32_t tmem_o = tmem_base + (pl.obufs == 2 ? (hd & 1) : 0) * D;
             float* x = xslot(2, hd);
             x[part * 128 + row] = l_part;
             quad_sync();
@@ -523,23 +527,17 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             const int cb = (head0 + hd) * D;
             __nv_bfloat16* orow = prm.o + tok * (long)sh.inner() + cb + part * CP;
 #pragma unroll
-            for (int c = 0; c < CP; c += 8) {
-                uint32_t r[8];
-                tmem_ld8(tmem_o + lane_sel + part * CP + c, r);       // warp-collective: every lane takes part
-                if (pl.osplit == 2) {                                 // second accumulation chain
-                    uint32_t r2[8];
-                    tmem_ld8(tmem_o + D + lane_sel + part * CP + c, r2);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
-                }
+            for (int c = 0; c < CP; c += 16) {
+                uint32_t r[16];
+                tmem_ld16(tmem_o + lane_sel + part * CP + c, r);      // warp-collective: every lane takes part
                 tmem_wait_ld();
                 if (q_valid) {
-                    uint32_t pk[4];
+                    uint32_t pk[8];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < 8; ++i)
                         pk[i] = pack_bf16(__uint_as_float(r[2 * i]) * inv_l, __uint_as_float(r[2 * i + 1]) * inv_l);
                     *reinterpret_cast<uint4*>(orow + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4*>(orow + c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                 }
             }
             if (q_valid && part == 0) prm.lse[tok * sh.heads + head0 + hd] = (m_used + lg2(l_run)) * 0.6931471805599453f;
@@ -550,7 +548,6 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         int mask_chunk = -1;
         int g_lo = 0, g_hi = 0;            // live 8-column groups of this quadrant in the current h-chunk
         bool chunk_live = false, row_has_cols = false;
-        const int nwords = (ncols_pad + 31) / 32;
         const int ngroups = ncols_pad >> 3;
 
         const bool dbg_on = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0 && tid == 0);
@@ -558,15 +555,9 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int t = 0; t < nsteps; ++t) {
             DBG(8);
             const int buf = t & 1;
-            const uint32_t tmem_s = tmem_s0 + buf * ncols_pad;
-            const uint32_t tmem_o = tmem_base + (pl.obufs == 2 ? (cur.hd & 1) : 0) * pl.osplit * D;
+            const uint32_t tmem_s = tmem_s0 + buf * ncols_pad + lane_sel;
+            const uint32_t tmem_o = tmem_base + (pl.obufs == 2 ? (cur.hd & 1) : 0) * D;
             const uint32_t tmem_p = tmem_p0 + buf * p_cols + lane_sel;
-            // 8 bf16 of this row (one 8-column group) -> 4 bf16-pair columns of the P operand in tensor memory
-            auto p_store = [&](int g, uint32_t a, uint32_t b2, uint32_t c, uint32_t d2) { tmem_st4(tmem_p + g * 4, a, b2, c, d2); };
-            auto mask_bits = [&](int g) -> uint32_t {     // live bits of columns [8g, 8g+16)
-                const uint32_t w0m = sMask[(g >> 2) * 128 + row], w1m = sMask[((g >> 2) + 1) * 128 + row];
-                return (uint32_t)(((((uint64_t)w1m) << 32) | w0m) >> ((g & 3) * 8));
-            };
             const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
             float prev_m = 0.f, prev_l = 0.f;
             if (head_start && t > 0) {               // the previous head is finished AFTER this step (its O buffer is not reused yet)
@@ -581,108 +572,118 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 row_seen = false;
             }
             const int kh0 = cur.chunk * pl.ch;
-            if (cur.chunk != mask_chunk) {               // live-column bitmask of this row for this h-chunk
+            if (cur.chunk != mask_chunk) {               // live column range of this row / quadrant for this h-chunk
                 mask_chunk = cur.chunk;
                 const int ra = max(kh_lo, kh0), rb = min(kh_hi, kh0 + pl.ch - 1);
-                row_has_cols = (wbits != 0u) && (rb >= ra);
-                quad_sync();                             // every reader of the old mask is done
-                if (part == 0) {
-                    for (int w = 0; w <= nwords; ++w) sMask[w * 128 + row] = 0u;
-                    if (row_has_cols) {
-                        for (int kh = ra; kh <= rb; ++kh) {
-                            const int pos = (kh - kh0) * pl.hW;
-                            const int w = pos >> 5, sft = pos & 31;
-                            sMask[w * 128 + row] |= wbits << sft;
-                            if (sft != 0 && (wbits >> (32 - sft)) != 0u) sMask[(w + 1) * 128 + row] |= wbits >> (32 - sft);
-                        }
-                    }
-                }
-                quad_sync();
-                const int ua = max(w_qh_lo, kh0), ub = min(w_qh_hi + 2 * sh.eH, kh0 + pl.ch - 1);
+                row_has_cols = row_can && (rb >= ra);
+                // the quadrant's rows see halo rows [w_qh_lo, w_qh_hi + 2 eH]; rows outside the grid are never live
+                const int ua = max(max(w_qh_lo, kh0), khg_lo), ub = min(min(w_qh_hi + 2 * sh.eH, kh0 + pl.ch - 1), khg_hi);
                 chunk_live = ub >= ua;
                 g_lo = ((ua - kh0) * pl.hW) >> 3;
                 g_hi = min(((ub - kh0 + 1) * pl.hW + 7) >> 3, ngroups);
             }
-            // P buffer `buf` is free once the P V of step t-2 has retired
-            if (t >= 2) mbar_wait(&bar_o[buf], ((t - 2) >> 1) & 1);
-            DBG(9);
-
             // warp-uniform: can any of this quadrant's queries see this block?
             const bool live = chunk_live && (cur.ks >= w_qs) && (cur.ks <= w_qs + 2 * sh.eS);
             if (live) {
-                mbar_wait(&bar_s[buf], (t >> 1) & 1);    // S_t computed
+                // S_t computed.  The driver issued it behind O += P_{t-2} V_{t-2} (tcgen05 operations of one thread retire
+                // in order), so this also says that P buffer `buf` is free and that every warp has left step t-2.
+                mbar_wait(&bar_s[buf], (t >> 1) & 1);
                 tc_fence_after();
                 DBG(10);
                 const int n8 = g_hi - g_lo;
-                const int ga = g_lo + ((n8 * part) >> LOGP), gb = g_lo + ((n8 * (part + 1)) >> LOGP);
-                // Single pass against the stale reference max when every row that has live columns
-                // here already owns one; P may then exceed 1, which is fine up to 2^8.
+                const int ga = g_lo + ((n8 * part) >> 1), gb = g_lo + ((n8 * (part + 1)) >> 1);
+                // Single pass against the stale reference exponent; P may then exceed 1, which is fine up to 2^64.
                 bool two_pass = false;
                 {
-                    const float neg_m = -m_used;
-                    float ls[4] = {0.f, 0.f, 0.f, 0.f}, pm[4] = {0.f, 0.f, 0.f, 0.f};   // independent chains
-                    int g = ga;
-                    for (; g + 2 <= gb; g += 2) {        // two 8-column groups per TMEM load
-                        const uint32_t mword = mask_bits(g);
-                        uint32_t r[16];
-                        tmem_ld16(tmem_s + lane_sel + g * 8, r);
-                        tmem_wait_ld();
-                        float p[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float e = ex2(fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m));
-                            p[i] = (mword & (1u << i)) ? e : 0.f;
-                            ls[i & 3] += p[i];
-                            pm[i & 3] = fmaxf(pm[i & 3], p[i]);
-                        }
-                        p_store(g, pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
-                        p_store(g + 1, pack_bf16(p[8], p[9]), pack_bf16(p[10], p[11]), pack_bf16(p[12], p[13]), pack_bf16(p[14], p[15]));
-                    }
-                    if (g < gb) {
-                        const uint32_t mword = mask_bits(g);
-                        uint32_t r[8];
-                        tmem_ld8(tmem_s + lane_sel + g * 8, r);
-                        tmem_wait_ld();
-                        float p[8];
+                    const uint64_t cc = pk2(pl.scale_log2, pl.scale_log2), mm = pk2(-m_used, -m_used);
+                    uint64_t acc0 = pk2(0.f, 0.f), acc1 = acc0;
+                    // 16 scores of this row -> 16 probabilities (bf16) in the P operand; pairs [0, WM_FWD_POLY) take the
+                    // polynomial exp2 on the FMA pipe, the others the MUFU: the two pipes run side by side
+                    auto cols16 = [&](const uint32_t (&r)[16], int g) {
+                        uint32_t pk[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const float e = ex2(fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m));
-                            p[i] = (mword & (1u << i)) ? e : 0.f;
-                            ls[i & 3] += p[i];
-                            pm[i & 3] = fmaxf(pm[i & 3], p[i]);
+                            const uint64_t x = ffma2(pk2u(r[2 * i], r[2 * i + 1]), cc, mm);
+                            uint64_t e;
+                            if (i < WM_FWD_POLY) {
+                                e = exp2_poly2(x);
+                            } else {
+                                float x0, x1;
+                                upk2(x, x0, x1);
+                                e = pk2(ex2(x0), ex2(x1));
+                            }
+                            if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
+                            pk[i] = pack_bf16_2(e);
                         }
-                        p_store(g, pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
-                    }
-                    const float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
-                    float pmax = fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3]));
-                    float* x = xslot(0, t);
-                    x[part * 128 + row] = pmax;
-                    quad_sync();
+                        tmem_st8(tmem_p + g * 4, pk);
+                    };
+                    auto cols8 = [&](const uint32_t (&r)[8], int g) {
+                        uint32_t pk[4];
 #pragma unroll
-                    for (int pp = 0; pp < NPART; ++pp) pmax = fmaxf(pmax, x[pp * 128 + row]);
+                        for (int i = 0; i < 4; ++i) {
+                            const uint64_t x = ffma2(pk2u(r[2 * i], r[2 * i + 1]), cc, mm);
+                            float x0, x1;
+                            upk2(x, x0, x1);
+                            const uint64_t e = pk2(ex2(x0), ex2(x1));
+                            if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
+                            pk[i] = pack_bf16_2(e);
+                        }
+                        tmem_st4(tmem_p + g * 4, pk[0], pk[1], pk[2], pk[3]);
+                    };
+                    // two register sets: the TMEM load of the next 16 columns is in flight while these are processed
+                    uint32_t ra[16], rb[16];
+                    int g = ga;
+                    const int n16 = (gb - ga) >> 1;
+                    if (n16 > 0) tmem_ld16(tmem_s + g * 8, ra);
+                    for (int i = 0; i < n16; i += 2) {
+                        tmem_wait_ld();
+                        tmem_regs_ready(ra);
+                        if (i + 1 < n16) tmem_ld16(tmem_s + (g + 2) * 8, rb);
+                        cols16(ra, g);
+                        g += 2;
+                        if (i + 1 < n16) {
+                            tmem_wait_ld();
+                            tmem_regs_ready(rb);
+                            if (i + 2 < n16) tmem_ld16(tmem_s + (g + 2) * 8, ra);
+                            cols16(rb, g);
+                            g += 2;
+                        }
+                    }
+                    if (g < gb) {
+                        uint32_t r8[8];
+                        tmem_ld8(tmem_s + g * 8, r8);
+                        tmem_wait_ld();
+                        cols8(r8, g);
+                    }
+                    float a0, a1, a2, a3;
+                    upk2(acc0, a0, a1);
+                    upk2(acc1, a2, a3);
+                    const float lsum = (a0 + a1) + (a2 + a3);
+                    float* x = xslot(0, t);
+                    x[part * 128 + row] = lsum;
+                    quad_sync();
+                    const float ltot = x[row] + x[128 + row];
                     // rows with live columns must land in [2^-64, 2^64]; !(a && b) also catches inf / NaN
-                    const bool out_of_range = row_has_cols && !(pmax <= 1.8446744e19f && pmax >= 5.4210109e-20f);
+                    const bool out_of_range = row_has_cols && !(ltot <= 1.8446744e19f && ltot >= 5.4210109e-20f);
                     two_pass = __any_sync(0xffffffffu, out_of_range);
                     if (!two_pass) l_part += lsum;
                 }
                 if (two_pass) {
-                    // pass 1: row maximum over this thread's live columns
+                    // pass 1: row maximum over this thread's columns (masked scores are <= -2^60)
                     float mx = -INFINITY;
                     for (int g = ga; g < gb; ++g) {
-                        const uint32_t mword = mask_bits(g);
                         uint32_t r[8];
-                        tmem_ld8(tmem_s + lane_sel + g * 8, r);
+                        tmem_ld8(tmem_s + g * 8, r);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            if (mword & (1u << i)) mx = fmaxf(mx, __uint_as_float(r[i]));
+                        for (int i = 0; i < 8; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
                     }
                     float* x = xslot(1, t);
                     x[part * 128 + row] = mx;
                     quad_sync();
 #pragma unroll
                     for (int pp = 0; pp < NPART; ++pp) mx = fmaxf(mx, x[pp * 128 + row]);
-                    const float m_blk = mx * pl.scale_log2;          // scale > 0; -inf for rows without live columns
+                    const float m_blk = row_has_cols ? mx * pl.scale_log2 : -INFINITY;    // scale > 0
                     float alpha = 1.f;
                     // re-centre the reference on this block's maximum: upwards always (alpha < 2^-32), downwards
                     // only while the row has nothing accumulated yet (alpha would overflow otherwise)
@@ -695,47 +696,47 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     if (head_has_blocks && __any_sync(0xffffffffu, move)) {   // rescale this thread's share of the O row
                         mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);     // every earlier P V has retired
                         tc_fence_after();
-                        for (int ch = 0; ch < pl.osplit; ++ch) {
 #pragma unroll
-                            for (int c = 0; c < CP; c += 8) {
-                                uint32_t r[8];
-                                tmem_ld8(tmem_o + ch * D + lane_sel + part * CP + c, r);
-                                tmem_wait_ld();
+                        for (int c = 0; c < CP; c += 8) {
+                            uint32_t r[8];
+                            tmem_ld8(tmem_o + lane_sel + part * CP + c, r);
+                            tmem_wait_ld();
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-                                tmem_st8(tmem_o + ch * D + lane_sel + part * CP + c, r);
-                            }
+                            for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                            tmem_st8(tmem_o + lane_sel + part * CP + c, r);
                         }
                         tmem_wait_st();
                     }
-                    // pass 2: P = 2^(s*scale*log2e - m) on live columns -> bf16 -> smem (K-major, 128B swizzle)
+                    // pass 2: P = 2^(s*scale*log2e - m) -> bf16 -> TMEM
                     const float neg_m = -m_used;
                     float lsum = 0.f;
                     for (int g = ga; g < gb; ++g) {
-                        const uint32_t mword = mask_bits(g);
                         uint32_t r[8];
-                        tmem_ld8(tmem_s + lane_sel + g * 8, r);
+                        tmem_ld8(tmem_s + g * 8, r);
                         tmem_wait_ld();
                         float p[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const float e = ex2(fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m));
-                            p[i] = (mword & (1u << i)) ? e : 0.f;
+                            p[i] = ex2(fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m));
                             lsum += p[i];
                         }
-                        p_store(g, pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+                        tmem_st4(tmem_p + g * 4, pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
                     }
                     l_part += lsum;
                 }
                 // columns outside the quadrant's live range: zero, shared round-robin between the parts
-                for (int g = part; g < g_lo; g += NPART) p_store(g, 0u, 0u, 0u, 0u);
-                for (int g = g_hi + part; g < ngroups; g += NPART) p_store(g, 0u, 0u, 0u, 0u);
+                for (int g = part; g < g_lo; g += NPART) tmem_st4(tmem_p + g * 4, 0u, 0u, 0u, 0u);
+                for (int g = g_hi + part; g < ngroups; g += NPART) tmem_st4(tmem_p + g * 4, 0u, 0u, 0u, 0u);
                 p_zero[buf] = false;
                 head_has_blocks = true;
                 row_seen = row_seen || row_has_cols;
-            } else if (!p_zero[buf]) {
-                for (int g = part; g < ngroups; g += NPART) p_store(g, 0u, 0u, 0u, 0u);
-                p_zero[buf] = true;
+            } else {
+                // P buffer `buf` is free (and every warp has left step t-2) once the P V of step t-2 has retired
+                if (t >= 2) mbar_wait(&bar_o[buf], ((t - 2) >> 1) & 1);
+                if (!p_zero[buf]) {
+                    for (int g = part; g < ngroups; g += NPART) tmem_st4(tmem_p + g * 4, 0u, 0u, 0u, 0u);
+                    p_zero[buf] = true;
+                }
             }
             DBG(11);
             tmem_wait_st();               // P is in tensor memory
@@ -777,11 +778,10 @@ static int launch_fwd(const void* q, const void* k, const void* v, void* o, floa
     if (int rc = make_tensor_map_5d(&mk, k, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
     if (int rc = make_tensor_map_5d(&mv, v, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
     FwdParams prm{s, pl, static_cast<__nv_bfloat16*>(o), lse};
-    constexpr int NPART = 2;
-    WM_CUDA_CHECK(cudaFuncSetAttribute(l3d_fwd_tc_kernel<D, NPART>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
+    WM_CUDA_CHECK(cudaFuncSetAttribute(l3d_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
     const dim3 grid((unsigned)(pl.tilesW * pl.tilesH), (unsigned)pl.tilesS, (unsigned)(s.B * (s.heads / pl.hpc)));
     if (grid.y > 65535u || grid.z > 65535u) return fail(WM_EUNSUPPORTED, "grid too large for the tensor-core kernel");
-    l3d_fwd_tc_kernel<D, NPART><<<grid, 32 * (4 * NPART + 1), pl.smem_bytes, st>>>(mq, mk, mv, prm);
+    l3d_fwd_tc_kernel<D><<<grid, kFwdThreads, pl.smem_bytes, st>>>(mq, mk, mv, prm);
     WM_CUDA_CHECK(cudaGetLastError());
     return WM_OK;
 }
@@ -796,7 +796,7 @@ extern "C" __attribute__((visibility("default"))) int wm_debug_read(long long* o
 
 bool attn_tc_supported(const AttnShape& s) {
     tc::Plan pl;
-    return tc::make_plan(s, tc::kFwd, pl) && tc::make_plan(s, tc::kBwdDQ, pl) && tc::make_plan(s, tc::kBwdDKV, pl);
+    return tc::make_plan(s, tc::kFwd, pl) && tc::make_plan(s, tc::kBwdDQws, pl) && tc::make_plan(s, tc::kBwdDKVws, pl);
 }
 
 int attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse, const AttnShape& s, cudaStream_t st) {

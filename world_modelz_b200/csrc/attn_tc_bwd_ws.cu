@@ -15,6 +15,9 @@
 //               (two buffers, A of dK += dS^T Q)
 // One issuing thread costs ~20-60 cycles per tcgen05.mma (tools/micro/mma_issue_clean.cu); three
 // single-purpose warps keep each of the per-step chains short.
+//
+// The window / border mask is part of the S (resp. S^T) MMA (build_mask_tiles in attn_tc.cuh); the element loops
+// run on packed fp32x2 arithmetic with part of the exponentials on the FMA pipe (exp2_poly2).
 #include "attn_tc.cuh"
 
 // -DWM_EXPERIMENT=7 compiles the clock64 timeline instrumentation in (tools/build_timeline_lib.sh, tools/dbg_timeline.py)
@@ -36,6 +39,33 @@ namespace wm { namespace tc { __device__ long long g_dbg_ws[2 * 64 * 16]; } }
 
 namespace wm {
 namespace tc {
+
+#ifndef WM_BWD_POLY
+#define WM_BWD_POLY 2      // of every 8 column pairs, this many take the FMA-pipe exp2 (the rest go to the MUFU)
+#endif
+
+// ---------------------------------------------------------------------------- delta = rowsum(dO * O)
+__global__ void __launch_bounds__(256)
+l3d_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                 float* __restrict__ delta, long items, int d) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;       // (token, head)
+    if (i >= items) return;
+    const uint4* po = reinterpret_cast<const uint4*>(o + i * d);
+    const uint4* pg = reinterpret_cast<const uint4*>(dout + i * d);
+    float acc = 0.f;
+    for (int c = 0; c < d / 8; ++c) {
+        const uint4 a = __ldg(po + c), g = __ldg(pg + c);
+        const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+        const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 fa = __bfloat1622float2(ha[j]), fg = __bfloat1622float2(hg[j]);
+            acc = fmaf(fa.x, fg.x, acc);
+            acc = fmaf(fa.y, fg.y, acc);
+        }
+    }
+    delta[i] = acc;
+}
 
 struct BwdWsParams {
     AttnShape sh;
@@ -73,8 +103,10 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     uint8_t* sA = smem;                                    // [rowbuf][A1 | A2][slabs][128 rows]  (Q,dO | K,V)
     uint8_t* sB = sA + pl.rowbuf * 2 * row_tile_bytes;     // [stage][B1 | B2][slab][ncols_pad rows]  (K,V | Q,dO)
     uint8_t* sDS = sB + nstage * 2 * blk_tile_bytes;       // dK/dV kernel: dS^T x2, bf16, K-major 128B swizzle
-    uint32_t* sMask = reinterpret_cast<uint32_t*>(sDS + (kDKV ? 2 * p_tile_bytes : 0));   // [2 halves][9 words][128]
-    float* sCol = reinterpret_cast<float*>(sMask + 2 * 9 * 128);                          // [3 bufs][lse2|delta][ncols_pad]
+    const int cm_tile_bytes = ncols_pad * pl.km * 2;
+    uint8_t* sRm = sDS + (kDKV ? 2 * p_tile_bytes : 0);    // mask operand of the rows:    [128 x km] bf16
+    uint8_t* sCm = sRm + 128 * pl.km * 2;                  // mask operand of the columns: [nchunk][ncols_pad x km] bf16
+    float* sCol = reinterpret_cast<float*>(sCm + pl.nchunk * cm_tile_bytes);              // [3 bufs][-lse2|-delta][ncols_pad]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + (kDKV ? 6 * ncols_pad : 0));
     uint64_t* bar_a = bars;           // [2] row tiles of a head landed
     uint64_t* bar_b = bars + 2;       // [3] halo block landed
@@ -128,8 +160,9 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             uint8_t* base = sB + t * blk_slab_bytes + ncols * G::kRowBytes;
             for (int i = tid * 16; i < pad_bytes; i += kWsThreads * 16) *reinterpret_cast<uint4*>(base + i) = make_uint4(0, 0, 0, 0);
         }
-        fence_proxy_async();
     }
+    build_mask_tiles(sRm, sCm, pl, sh, h0, w0, tid, kWsThreads);
+    fence_proxy_async();                 // generic-proxy writes above -> visible to tcgen05.mma
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -188,7 +221,10 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         const uint64_t dds0 = make_smem_desc(smem_u32(sDS), 16, 1024, 2u);
         const uint32_t a_buf_step = (pl.rowbuf == 2) ? (uint32_t)((2 * row_tile_bytes) >> 4) : 0u;
         const uint32_t stage_step = (uint32_t)((2 * blk_tile_bytes) >> 4);
-        auto issue_t_mma = [&](int stage, int hd, int part) {  // T1 = A1 B1^T, T2 = A2 B2^T; columns A (part 0) or B (part 1)
+        const uint64_t drm0 = make_smem_desc(smem_u32(sRm), 2048u, 128u, 0u);                       // mask operands: no swizzle
+        const uint64_t dcm0 = make_smem_desc(smem_u32(sCm), (uint32_t)ncols_pad * 16u, 128u, 0u);
+        const int nk_m = pl.km >> 4;
+        auto issue_t_mma = [&](int stage, int hd, int chunk, int part) {  // T1 = A1 B1^T + mask, T2 = A2 B2^T; columns A (part 0) or B (part 1)
             const uint32_t col0 = part ? (uint32_t)nA : 0u;        // columns = rows of the K-major block
             const uint32_t idesc_t = part ? idesc_tB : idesc_tA;
             const uint64_t da_h = da0 + (hd & 1) * a_buf_step;
@@ -202,6 +238,13 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                     const uint64_t da = da_h + op * (uint32_t)(row_tile_bytes >> 4) + sl * (uint32_t)(row_slab_bytes >> 4) + koff;
                     const uint64_t db = db_s + op * (uint32_t)(blk_tile_bytes >> 4) + sl * (uint32_t)(blk_slab_bytes >> 4) + koff;
                     if (leader) umma_bf16_ss((op ? tmem_t2 : tmem_t1) + col0, da, db, idesc_t, kk > 0);
+                }
+                if (op == 0) {      // S += R C^T: window / border mask (16 channels = two core-matrix columns per MMA)
+                    const uint64_t dcm = dcm0 + (uint32_t)chunk * (uint32_t)(cm_tile_bytes >> 4) + ((col0 * 16u) >> 4);
+                    for (int kk = 0; kk < nk_m; ++kk)
+                        if (leader)
+                            umma_bf16_ss(tmem_t1 + col0, drm0 + (uint32_t)kk * (uint32_t)((2 * 2048) >> 4),
+                                         dcm + (uint32_t)kk * (uint32_t)((2 * ncols_pad * 16) >> 4), idesc_t, 1u);
                 }
             }
             if (leader) umma_commit(part ? bar_tB : bar_tA);
@@ -266,8 +309,8 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             mbar_wait(&bar_a[0], 0);
             mbar_wait(&bar_b[0], 0);
             tc_fence_after();
-            if (gA > 0) issue_t_mma(0, 0, 0);
-            issue_t_mma(0, 0, 1);
+            if (gA > 0) issue_t_mma(0, 0, cur.chunk, 0);
+            issue_t_mma(0, 0, cur.chunk, 1);
             int st_nxt = (nstage > 1) ? 1 : 0;
             uint32_t b_par = 1u;                         // bit s = parity of stage s's next completion (stage 0 consumed once)
             for (int t = 0; t + 1 < nsteps; ++t) {
@@ -280,11 +323,11 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                 b_par ^= 1u << st_nxt;
                 if (nxt.hd != cur.hd) mbar_wait(&bar_a[nxt.hd & 1], (nxt.hd >> 1) & 1);
                 tc_fence_after();
-                if (gA > 0) issue_t_mma(st_nxt, nxt.hd, 0);
+                if (gA > 0) issue_t_mma(st_nxt, nxt.hd, nxt.chunk, 0);
                 DBGW(2);
                 mbar_wait(&bar_p[t & 1], (t >> 1) & 1);
                 tc_fence_after();
-                issue_t_mma(st_nxt, nxt.hd, 1);
+                issue_t_mma(st_nxt, nxt.hd, nxt.chunk, 1);
                 DBGW(3);
                 cur = nxt;
                 advance(nxt);
@@ -308,13 +351,9 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         const int row = quad * 32 + lane;
         const int ctid = tid;                                            // 0..255
         const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
-        uint32_t* myMask = sMask + half * 9 * 128;
         const int plane_mask = (1 << pl.lgPlane) - 1;
         const int rs = row >> pl.lgPlane, rh = (row & plane_mask) >> pl.lgTW, rw = row & (pl.tW - 1);
         const bool row_valid = (s0 + rs < sh.S) && (h0 + rh < sh.H) && (w0 + rw < sh.W);
-        const int kh_lo = max(rh, sh.eH - h0), kh_hi = min(rh + 2 * sh.eH, sh.H - 1 - h0 + sh.eH);
-        const int kw_lo = max(rw, sh.eW - w0), kw_hi = min(rw + 2 * sh.eW, sh.W - 1 - w0 + sh.eW);
-        const uint32_t wbits = (row_valid && kw_hi >= kw_lo) ? ((kw_hi - kw_lo == 31) ? 0xffffffffu : ((1u << (kw_hi - kw_lo + 1)) - 1u)) << kw_lo : 0u;
         const int w_rs = (quad * 32) >> pl.lgPlane;
         const int w_rh_lo = ((quad * 32) & plane_mask) >> pl.lgTW, w_rh_hi = ((quad * 32 + 31) & plane_mask) >> pl.lgTW;
         const long row_tok = (((long)b * sh.S + (s0 + rs)) * sh.H + (h0 + rh)) * sh.W + (w0 + rw);
@@ -337,8 +376,8 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         };
         auto store_colvec = [&](int buf, float lse_raw, float dl_raw) {
             if (ctid < ncols_pad) {
-                sCol[(buf * 2 + 0) * ncols_pad + ctid] = lse_raw * kLog2e;
-                sCol[(buf * 2 + 1) * ncols_pad + ctid] = dl_raw * sh.scale;
+                sCol[(buf * 2 + 0) * ncols_pad + ctid] = -lse_raw * kLog2e;
+                sCol[(buf * 2 + 1) * ncols_pad + ctid] = -dl_raw * sh.scale;
             }
         };
         auto finish_head = [&](int hd) {            // accumulators of head `hd` -> bf16 -> global
@@ -386,7 +425,6 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         int cbuf = 0;                      // dK/dV kernel: lse / delta column buffer of the current step (t mod 3)
         bool tA_seen = false;              // columns A of this step were already seen complete by last step's probe
         bool chunk_live = false;
-        const int nwords = (ncols_pad + 31) / 32;
         const int ngroups = ncols_pad >> 4;
         const uint32_t zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
@@ -402,8 +440,8 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             } else {
                 if (head_start) {
                     asm volatile("" : "+f"(ahead_lse), "+f"(ahead_delta));   // first use of the loads issued one head ago
-                    row_lse2 = ahead_lse * kLog2e;
-                    row_delta = ahead_delta * sh.scale;
+                    row_lse2 = -ahead_lse * kLog2e;          // kept negated: the addends of the two FFMA2 below
+                    row_delta = -ahead_delta * sh.scale;
                     if (row_valid && cur.hd + 1 < pl.hpc) {
                         ahead_lse = __ldg(prm.lse + row_tok * sh.heads + head0 + cur.hd + 1);
                         ahead_delta = __ldg(prm.delta + row_tok * sh.heads + head0 + cur.hd + 1);
@@ -411,19 +449,10 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                 }
             }
             const int kh0 = cur.chunk * pl.ch;
-            if (cur.chunk != mask_chunk) {
+            if (cur.chunk != mask_chunk) {               // live column range of this quadrant for this h-chunk
                 mask_chunk = cur.chunk;
-                for (int w = 0; w <= nwords; ++w) myMask[w * 128 + row] = 0u;
-                if (wbits != 0u) {
-                    const int ra = max(kh_lo, kh0), rb = min(kh_hi, kh0 + pl.ch - 1);
-                    for (int kh = ra; kh <= rb; ++kh) {
-                        const int pos = (kh - kh0) * pl.hW;
-                        const int w = pos >> 5, sft = pos & 31;
-                        myMask[w * 128 + row] |= wbits << sft;
-                        if (sft != 0 && (wbits >> (32 - sft)) != 0u) myMask[(w + 1) * 128 + row] |= wbits >> (32 - sft);
-                    }
-                }
-                const int ua = max(w_rh_lo, kh0), ub = min(w_rh_hi + 2 * sh.eH, kh0 + pl.ch - 1);
+                // its rows see halo rows [w_rh_lo, w_rh_hi + 2 eH]; halo rows outside the grid are never live
+                const int ua = max(max(w_rh_lo, kh0), khg_lo), ub = min(min(w_rh_hi + 2 * sh.eH, kh0 + pl.ch - 1), khg_hi);
                 chunk_live = ub >= ua;
                 g_lo = ((ua - kh0) * pl.hW) >> 4;
                 g_hi = min(((ub - kh0 + 1) * pl.hW + 15) >> 4, ngroups);
@@ -452,43 +481,49 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             };
             const float* col_lse2 = sCol + (cbuf * 2 + 0) * ncols_pad;
             const float* col_dl = sCol + (cbuf * 2 + 1) * ncols_pad;
+            const uint64_t cc2 = pk2(pl.scale_log2, pl.scale_log2), sc2 = pk2(sh.scale, sh.scale);
+            const uint64_t rl2 = pk2(row_lse2, row_lse2), rd2 = pk2(row_delta, row_delta);
+            // 16 columns of this row: P = 2^(S c - lse2), dS = P (dP scale - delta scale).  Masked scores are <= -2^60
+            // (mask operand of the S MMA), so their P and dS are exactly 0.  nl / nd: NEGATED lse2 and delta*scale.
             auto math_group = [&](int g) {
-                const uint32_t mword = myMask[(g >> 1) * 128 + row] >> ((g & 1) * 16);
                 uint32_t s[16], dp[16];
                 tmem_ld16(tmem_t1 + lane_sel + g * 16, s);
                 tmem_ld16(tmem_t2 + lane_sel + g * 16, dp);
-                float l2[16], dl[16];
+                uint64_t nl[8], nd[8];
                 if constexpr (kDKV) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const float4 a = *reinterpret_cast<const float4*>(col_lse2 + g * 16 + 4 * i);
-                        const float4 c = *reinterpret_cast<const float4*>(col_dl + g * 16 + 4 * i);
-                        l2[4 * i] = a.x; l2[4 * i + 1] = a.y; l2[4 * i + 2] = a.z; l2[4 * i + 3] = a.w;
-                        dl[4 * i] = c.x; dl[4 * i + 1] = c.y; dl[4 * i + 2] = c.z; dl[4 * i + 3] = c.w;
+                        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(col_lse2 + g * 16 + 4 * i);
+                        const ulonglong2 c = *reinterpret_cast<const ulonglong2*>(col_dl + g * 16 + 4 * i);
+                        nl[2 * i] = a.x; nl[2 * i + 1] = a.y;
+                        nd[2 * i] = c.x; nd[2 * i + 1] = c.y;
                     }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) { l2[i] = row_lse2; dl[i] = row_delta; }
+                    for (int i = 0; i < 8; ++i) { nl[i] = rl2; nd[i] = rd2; }
                 }
                 tmem_wait_ld();
-                float pv[16], dsv[16];
+                uint32_t pkp[8], pkd[8];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    // dl[] holds delta * scale: dS = P * (dP * scale - delta * scale); masking P masks dS with it
-                    const float p = ex2(fmaf(__uint_as_float(s[i]), pl.scale_log2, -l2[i]));
-                    pv[i] = ((mword >> i) & 1u) ? p : 0.f;
-                    dsv[i] = pv[i] * fmaf(__uint_as_float(dp[i]), sh.scale, -dl[i]);
+                for (int i = 0; i < 8; ++i) {
+                    const uint64_t x = ffma2(pk2u(s[2 * i], s[2 * i + 1]), cc2, nl[i]);
+                    uint64_t pr;
+                    if (i < WM_BWD_POLY) {
+                        pr = exp2_poly2(x);
+                    } else {
+                        float x0, x1;
+                        upk2(x, x0, x1);
+                        pr = pk2(ex2(x0), ex2(x1));
+                    }
+                    const uint64_t y = ffma2(pk2u(dp[2 * i], dp[2 * i + 1]), sc2, nd[i]);
+                    pkd[i] = pack_bf16_2(fmul2(pr, y));
+                    if constexpr (kDKV) pkp[i] = pack_bf16_2(pr);
                 }
-                uint32_t pk[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(dsv[2 * i], dsv[2 * i + 1]);
                 if constexpr (kDKV) {
-                    store_ds_smem(g, pk);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
-                    store_tmem(g, pk);
+                    store_ds_smem(g, pkd);
+                    store_tmem(g, pkp);
                 } else {
-                    store_tmem(g, pk);
+                    store_tmem(g, pkd);
                 }
             };
             // this warp's live groups inside [x0, x1), split between the two threads of a row; dead groups are zeroed.
@@ -604,19 +639,29 @@ extern "C" __attribute__((visibility("default"))) int wm_debug_read_ws(long long
 }
 #endif
 
-// returns WM_OK when it launched, WM_EUNSUPPORTED when the shape has no warp-specialised tiling
-int launch_bwd_ws(int mode, const void* a1, const void* a2, const void* b1, const void* b2, const float* lse,
-                  const float* delta, void* out1, void* out2, const AttnShape& s, cudaStream_t st) {
-    Plan pl;
-    if (getenv("WM_TC_NO_WS") != nullptr || !make_plan(s, (Mode)mode, pl)) return WM_EUNSUPPORTED;
-    if (mode == kBwdDQws) {
-        if (s.d == 32) return launch_ws<32, kBwdDQws>(a1, a2, b1, b2, lse, delta, out1, out2, s, pl, st);
-        if (s.d == 64) return launch_ws<64, kBwdDQws>(a1, a2, b1, b2, lse, delta, out1, out2, s, pl, st);
-        return launch_ws<128, kBwdDQws>(a1, a2, b1, b2, lse, delta, out1, out2, s, pl, st);
+template <int D>
+static int launch_bwd_d(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout,
+                        void* dq, void* dk, void* dv, float* delta, const AttnShape& s, cudaStream_t st) {
+    Plan pq, pkv;
+    if (!make_plan(s, kBwdDQws, pq) || !make_plan(s, kBwdDKVws, pkv))
+        return fail(WM_EUNSUPPORTED, "no tensor-core backward tiling for this shape");
+    const long items = s.tokens() * s.heads;
+    l3d_delta_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(o),
+                                                                      static_cast<const __nv_bfloat16*>(dout), delta,
+                                                                      items, s.d);
+    WM_CUDA_CHECK(cudaGetLastError());
+    if (int rc = launch_ws<D, kBwdDQws>(q, dout, k, v, lse, delta, dq, nullptr, s, pq, st)) return rc;     // rows: queries
+    return launch_ws<D, kBwdDKVws>(k, v, q, dout, lse, delta, dv, dk, s, pkv, st);                         // rows: keys
+}
+
+int launch_bwd_tc(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout,
+                  void* dq, void* dk, void* dv, float* delta, const AttnShape& s, cudaStream_t st) {
+    switch (s.d) {
+        case 32: return launch_bwd_d<32>(q, k, v, o, lse, dout, dq, dk, dv, delta, s, st);
+        case 64: return launch_bwd_d<64>(q, k, v, o, lse, dout, dq, dk, dv, delta, s, st);
+        case 128: return launch_bwd_d<128>(q, k, v, o, lse, dout, dq, dk, dv, delta, s, st);
+        default: return fail(WM_EUNSUPPORTED, "dim_head=%d has no tensor-core kernel", s.d);
     }
-    if (s.d == 32) return launch_ws<32, kBwdDKVws>(a1, a2, b1, b2, lse, delta, out1, out2, s, pl, st);
-    if (s.d == 64) return launch_ws<64, kBwdDKVws>(a1, a2, b1, b2, lse, delta, out1, out2, s, pl, st);
-    return launch_ws<128, kBwdDKVws>(a1, a2, b1, b2, lse, delta, out1, out2, s, pl, st);
 }
 
 }  // namespace tc

@@ -160,6 +160,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+// tcgen05.ld results are defined only after tcgen05.wait::ld.  When a load is issued ahead of its use (software
+// pipelining), this pins the uses of `r` behind the wait in program order: the compiler must assume r changes here.
+__device__ __forceinline__ void tmem_regs_ready(uint32_t (&r)[16]) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                      "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -202,6 +208,69 @@ __device__ __forceinline__ float lg2(float x) {
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---------------------------------------------------------------- packed fp32x2 math (FFMA2 / FADD2 / FMUL2)
+// sm_100 issues two fp32 operations per instruction on a 64-bit register pair; the softmax / dS element loops are bound
+// by issue slots and the MUFU pipe, so every add / mul / fma of those loops is written pairwise.
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// 2^x for a PAIR of fp32 values on the FMA / ALU pipes instead of the MUFU: round-to-nearest split x = j + f,
+// f in [-0.5, 0.5], degree-3 minimax polynomial for 2^f (relative error 7.6e-5, far below the bf16 rounding of the
+// probabilities it feeds), exponent added with an integer shift-add.  x is clamped to >= -125 so that the result stays
+// a normal number (a masked score of -2^60 becomes 2^-125, i.e. nothing).  x must be <= ~125.
+__device__ __forceinline__ uint64_t exp2_poly2(uint64_t x2) {
+    float x0, x1;
+    upk2(x2, x0, x1);
+    x0 = fmaxf(x0, -125.f);
+    x1 = fmaxf(x1, -125.f);
+    const uint64_t x = pk2(x0, x1);
+    const uint64_t magic = pk2(12582912.f, 12582912.f), nmagic = pk2(-12582912.f, -12582912.f);
+    const uint64_t t = fadd2(x, magic);                       // integer part in the low mantissa bits
+    const uint64_t r = fadd2(t, nmagic);
+    const uint64_t f = ffma2(r, pk2(-1.f, -1.f), x);          // x - r
+    uint64_t p = ffma2(f, pk2(0.05520550534129143f, 0.05520550534129143f), pk2(0.24261397123336792f, 0.24261397123336792f));
+    p = ffma2(p, f, pk2(0.6932547688484192f, 0.6932547688484192f));
+    p = ffma2(p, f, pk2(0.9999276995658875f, 0.9999276995658875f));
+    float p0, p1, t0, t1;
+    upk2(p, p0, p1);
+    upk2(t, t0, t1);
+    const uint32_t b0 = __float_as_uint(p0) + (__float_as_uint(t0) << 23);
+    const uint32_t b1 = __float_as_uint(p1) + (__float_as_uint(t1) << 23);
+    return pk2u(b0, b1);
+}
+__device__ __forceinline__ uint32_t pack_bf16_2(uint64_t v) {   // (lo, hi) fp32 pair -> bf16x2 word, lo in the low half
+    float lo, hi;
+    upk2(v, lo, hi);
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 
 // ------------------------------------------------------------------ host: tensor maps
