@@ -13,13 +13,17 @@ rc = _lib.lib().wm_debug_read(buf)
 import numpy as np
 a = np.array(buf[:], dtype=np.int64).reshape(64, 16)
 t0 = a[0, 0]
-names = {0: 'drv:iter top', 1: 'drv:S deps ok', 2: 'drv:S issued', 3: 'drv:refill done', 4: 'drv:p_full ok', 5: 'drv:PV issued',
-         8: 'cmp:step top', 9: 'cmp:P buf free', 10: 'cmp:S ready', 11: 'cmp:compute done', 12: 'cmp:arrived'}
+names = {0: 'pv:top', 1: 'pv:kv ok', 4: 'pv:p ok', 5: 'pv:issued', 2: 's:top', 3: 's:p ok', 6: 's:inputs ok', 7: 's:issued',
+         14: 'cmp:HEAD top', 15: 'cmp:geometry done', 8: 'cmp:top', 9: 'cmp:o ok', 10: 'cmp:s ok', 13: 'cmp:math done', 11: 'cmp:st waited', 12: 'cmp:arrived'}
 print('rc', rc)
-for t in range(0, 14):
+for t in range(0, 14 if len(sys.argv) < 2 else 0):
     ev = sorted((a[t, s] - t0, names[s]) for s in names if a[t, s] != 0)
     print(f'step {t}: ' + '  '.join(f'{n}@{c}' for c, n in ev))
-d0 = np.diff(a[2:30, 0]); print('driver iteration period (cycles):', d0.tolist())
+for t in range(4, 13):
+    ev = sorted((a[t, s] - a[4, 8], names[s]) for s in names if a[t, s] != 0)
+    print(f'step {t}: ' + '  '.join(f'{n}@{c}' for c, n in ev))
+d0 = np.diff(a[2:30, 8]); print('compute step period (cycles):', d0.tolist())
+sys.exit(0)
 
 # ---- backward kernels
 do = torch.randn(B, S, H, W, heads * d, device='cuda', generator=g).bfloat16()
@@ -27,19 +31,6 @@ o, lse = ops.attn_forward(q, k, v, heads, ext, d ** -0.5)
 for _ in range(2):
     ops.attn_backward(q, k, v, o, lse, do, heads, ext, d ** -0.5)
 torch.cuda.synchronize()
-buf2 = (ctypes.c_longlong * (2 * 64 * 16))()
-rc = _lib.lib().wm_debug_read_bwd(buf2)
-b2 = np.array(buf2[:], dtype=np.int64).reshape(2, 64, 16)
-nb = {0: 'top', 1: 'mma ok', 2: 'compute done', 3: 'synced', 4: 'acc issued', 5: 'T issued+commit'}
-for m, name in ((0, 'dQ'), (1, 'dK/dV')):
-    a = b2[m]; t0 = a[0, 0]
-    print('====', name)
-    for t in range(2, 10):
-        ev = [(a[t, s] - a[t, 0], nb[s]) for s in nb if a[t, s] != 0]
-        print(f'step {t} (+{a[t,0]-t0}): ' + '  '.join(f'{n}@{c}' for c, n in ev))
-    print('period:', np.diff(a[2:26, 0]).tolist())
-
-
 # ---- warp-specialised backward kernels
 if hasattr(_lib.lib(), 'wm_debug_read_ws'):
     buf3 = (ctypes.c_longlong * (2 * 64 * 16))()
@@ -47,7 +38,7 @@ if hasattr(_lib.lib(), 'wm_debug_read_ws'):
     b3 = np.array(buf3[:], dtype=np.int64).reshape(2, 64, 16)
     # issuing side = warp 8 (the (S,dP) issuer): iteration top, columns A drained, (S,dP) half A of the next step issued,
     # half B issued; compute side = thread 0
-    nw = {0: 'iss:top', 1: 'iss:pA ok', 2: 'iss:T_A(t+1) issued', 3: 'iss:T_B(t+1) issued', 8: 'cmp:top', 9: 'cmp:bufs free',
+    nw = {0: 'iss:top', 1: 'iss:pA ok', 2: 'iss:T_A(t+1) issued', 3: 'iss:T_B(t+1) issued', 14: 'cmp:HEAD top', 15: 'cmp:geometry done', 8: 'cmp:top', 9: 'cmp:bufs free',
           10: 'cmp:T_A ready', 11: 'cmp:done', 12: 'cmp:arrived'}
     for m, name in ((0, 'dQ ws'), (1, 'dK/dV ws')):
         a = b3[m]; t0 = a[0, 0]

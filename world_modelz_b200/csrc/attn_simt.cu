@@ -95,17 +95,12 @@ __device__ __forceinline__ long neighbour(const AttnShape& sh, const Item& it, i
 }
 
 // ------------------------------------------------------------------------------ forward
+// One (token, head) by one warp; qs / ps: this warp's d + Wn floats of shared memory.
 template <typename T>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-l3d_fwd_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
-                    T* __restrict__ o, float* __restrict__ lse, const AttnShape sh) {
-    extern __shared__ float smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__device__ __forceinline__ void fwd_item(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
+                                         T* __restrict__ o, float* __restrict__ lse, const AttnShape& sh, const Item& it,
+                                         float* qs, float* ps, int lane) {
     const int Wn = sh.window(), d = sh.d;
-    float* qs = smem + warp * (d + Wn);
-    float* ps = qs + d;
-    Item it;
-    if (!decode_item(sh, (long)blockIdx.x * kWarpsPerBlock + warp, it)) return;
     const long inner = sh.inner();
     const long hoff = (long)it.head * d;
     for (int c = lane; c < d; c += 32) qs[c] = to_f(q[it.tok * inner + hoff + c]);
@@ -151,6 +146,43 @@ l3d_fwd_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* _
         if (c < d) from_f(o + it.tok * inner + hoff + c, acc[i] * inv);
     }
     if (lane == 0) lse[it.tok * sh.heads + it.head] = mx + logf(sum);
+    __syncwarp();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+l3d_fwd_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
+                    T* __restrict__ o, float* __restrict__ lse, const AttnShape sh) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* qs = smem + warp * (sh.d + sh.window());
+    Item it;
+    if (!decode_item(sh, (long)blockIdx.x * kWarpsPerBlock + warp, it)) return;
+    fwd_item(q, k, v, o, lse, sh, it, qs, qs + sh.d, lane);
+}
+
+// Fix-up pass behind the tensor-core forward: every lane looks at one (token, head); the warp then recomputes, one
+// after the other, those whose LSE the tensor-core kernel marked NaN (row sum outside the range of its max-free
+// softmax).  Normally nothing is marked and the kernel is one coalesced read of the LSE tensor.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+l3d_fwd_fixup_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                     const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ o, float* __restrict__ lse,
+                     const AttnShape sh) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* qs = smem + warp * (sh.d + sh.window());
+    const long total = sh.tokens() * sh.heads;
+    const long base = ((long)blockIdx.x * kWarpsPerBlock + warp) * 32;
+    const long mine = base + lane;
+    const float l = mine < total ? lse[mine] : 0.f;
+    unsigned todo = __ballot_sync(0xffffffffu, l != l);
+    while (todo) {
+        const int j = __ffs(todo) - 1;
+        todo &= todo - 1;
+        Item it;
+        decode_item(sh, base + j, it);
+        fwd_item(q, k, v, o, lse, sh, it, qs, qs + sh.d, lane);
+    }
 }
 
 // --------------------------------------------------------------------------- backward dQ
@@ -333,6 +365,19 @@ int attn_fwd_simt(const void* q, const void* k, const void* v, void* o, float* l
     if (int rc = check_simt_shape(s, dtype)) return rc;
     return dtype == WM_DTYPE_FP32 ? launch_fwd<float>(q, k, v, o, lse, s, st)
                                   : launch_fwd<__nv_bfloat16>(q, k, v, o, lse, s, st);
+}
+
+int attn_fwd_fixup(const void* q, const void* k, const void* v, void* o, float* lse, const AttnShape& s, cudaStream_t st) {
+    if (int rc = check_simt_shape(s, WM_DTYPE_BF16)) return rc;
+    const long items = s.tokens() * s.heads;
+    const long blocks = (items + kWarpsPerBlock * 32 - 1) / (kWarpsPerBlock * 32);
+    const size_t smem = (size_t)kWarpsPerBlock * (s.d + s.window()) * sizeof(float);
+    WM_CUDA_CHECK(cudaFuncSetAttribute(l3d_fwd_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    l3d_fwd_fixup_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, st>>>(
+        static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k), static_cast<const __nv_bfloat16*>(v),
+        static_cast<__nv_bfloat16*>(o), lse, s);
+    WM_CUDA_CHECK(cudaGetLastError());
+    return WM_OK;
 }
 
 int attn_bwd_simt(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout,

@@ -28,6 +28,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <mutex>
+#include <type_traits>
 
 namespace wm {
 namespace tc {
@@ -142,10 +143,9 @@ bool make_plan(const AttnShape& s, Mode mode, Plan& best) {
             if (p.ncols_pad > max_cols || tmem_cols_for(mode, s.d, p.ncols_pad) > 512) continue;
             // shared-memory variants, best first
             bool fits = false;
-            const int opts[7][3] = {{4, 2, hpc}, {3, 2, hpc}, {2, 2, hpc}, {4, 1, 1}, {3, 1, 1}, {2, 1, hpc}, {2, 1, 1}};    // {nstage, rowbuf, hpc}
+            const int opts[6][3] = {{4, 2, hpc}, {3, 2, hpc}, {2, 2, hpc}, {4, 1, 1}, {3, 1, 1}, {2, 1, 1}};    // {nstage, rowbuf, hpc}: a head loop needs two row buffers
             for (const auto& o : opts) {
                 if (mode != kFwd && o[0] > 3) continue;                                // 4 stages: forward kernel only
-                if (mode != kFwd && o[1] == 1 && o[2] != 1) continue;                  // bwd: a head loop only with 2 row buffers
                 if (o[1] == 2 && hpc == 1) continue;
                 if (smem_bytes_for(mode, s.d, p.ncols_pad, o[0], o[1], p.km, p.nchunk) <= (size_t)kSmemLimit) {
                     p.nstage = o[0]; p.rowbuf = o[1]; p.hpc = o[2];
@@ -177,8 +177,10 @@ bool make_plan(const AttnShape& s, Mode mode, Plan& best) {
 #if WM_EXPERIMENT == 7
 __device__ long long g_dbg[64 * 16];
 #define DBG(slot) do { if (dbg_on && t < 64) g_dbg[t * 16 + (slot)] = clock64(); } while (0)
+#define DBGT(slot, tt) do { if (dbg_on && (tt) < 64) g_dbg[(tt) * 16 + (slot)] = clock64(); } while (0)
 #else
 #define DBG(slot) do { } while (0)
+#define DBGT(slot, tt) do { } while (0)
 #endif
 
 // ------------------------------------------------------------------------------ kernel
@@ -189,6 +191,10 @@ struct FwdParams {
     float* lse;
 };
 
+#ifndef WM_SKEL
+#define WM_SKEL 0             // timing experiments only: 1 no element math, 2 no P V MMAs, 4 no S MMAs, 8 no K/V reloads,
+                              // 16 no S loads, 32 no exp / sum, 64 no P stores, 128 no agreement barrier
+#endif
 #ifndef WM_FWD_POLY
 #define WM_FWD_POLY 3      // of every 8 column pairs, this many take the FMA-pipe exp2 (the rest go to the MUFU)
 #endif
@@ -305,11 +311,13 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         }
     };
 
-    if (warp == kDriverWarp) {
-        // =============================== driver ===============================================
-        // The whole warp runs this code so that addresses and descriptors stay warp-uniform (uniform
-        // datapath); only the TMA / tcgen05 instructions themselves are predicated on one lane.
-        const bool leader = elect_one();      // whole driver warp is converged here
+    if (warp >= kDriverWarp) {
+        // =============================== issuing warps ===========================================
+        // warp 8: S = Q K^T (+ mask) two steps ahead; warp 9: O += P V; warp 10: TMA loads.  Each runs warp-uniform
+        // code (addresses and descriptors stay in the uniform datapath); only the TMA / tcgen05 instructions
+        // themselves are predicated on one elected lane.  One thread pays 20-70 cycles per tcgen05.mma it issues, so
+        // the per-step chains (3 score MMAs, ncols/16 P V MMAs, 2 TMA boxes) are spread over three warps.
+        const bool leader = elect_one();      // each of these warps is converged here
         auto q_buf = [&](int hd) { return sQ + (pl.rowbuf == 2 ? (hd & 1) : 0) * q_tile_bytes; };
         auto issue_q_load = [&](int hd) {
             if (leader) {
@@ -345,143 +353,134 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const uint32_t q_buf_step = (pl.rowbuf == 2) ? (uint32_t)(q_tile_bytes >> 4) : 0u;
         const uint32_t stage_step = (uint32_t)((2 * kv_tile_bytes) >> 4);
         const int nk_m = pl.km >> 4;
+        // Issue discipline (tools/micro/mma_issue_clean.cu, sync_latency.cu): ONE branch on the elected lane around a
+        // whole chain of tcgen05.mma whose operand offsets are compile-time constants costs ~20-35 cycles per MMA; a
+        // predicate per MMA, or a run-time trip count, costs ~100 (VOTEU / R2UR.BROADCAST per instruction).  Hence the
+        // chains below are fully unrolled templates selected by a switch on the (per-launch constant) trip count.
         auto issue_s_mma = [&](int t, int stage, const Cursor& c) {     // S[t&1] = Q_hd K_t^T + R C_chunk^T
-            const uint32_t tmem_s = tmem_s0 + (t & 1) * ncols_pad;
-            const uint64_t da0 = dq0 + (c.hd & 1) * q_buf_step, db0 = dk0 + stage * stage_step;
+            if (leader) {
+                const uint32_t tmem_s = tmem_s0 + (t & 1) * ncols_pad;
+                const uint64_t da0 = dq0 + (c.hd & 1) * q_buf_step, db0 = dk0 + stage * stage_step;
 #pragma unroll
-            for (int kk = 0; kk < D / 16; ++kk) {
-                const uint32_t off = (uint32_t)(((kk * 16) / G::kSlabCh) * 1 /*slab*/);
-                const uint32_t koff = (uint32_t)((((kk * 16) % G::kSlabCh) * 2) >> 4);
-                if (leader)
+                for (int kk = 0; kk < ((WM_SKEL & 4) ? 0 : D / 16); ++kk) {
+                    const uint32_t off = (uint32_t)(((kk * 16) / G::kSlabCh) * 1 /*slab*/);
+                    const uint32_t koff = (uint32_t)((((kk * 16) % G::kSlabCh) * 2) >> 4);
                     umma_bf16_ss(tmem_s, da0 + off * (uint32_t)(q_slab_bytes >> 4) + koff,
                                  db0 + off * (uint32_t)(kv_slab_bytes >> 4) + koff, idesc_s, kk > 0);
+                }
+                const uint64_t dcm = dcm0 + (uint32_t)c.chunk * (uint32_t)(cm_tile_bytes >> 4);
+                // 16 mask channels = two 8-channel core-matrix columns per MMA (km is 16 or 32)
+                if (!(WM_SKEL & 4)) umma_bf16_ss(tmem_s, drm0, dcm, idesc_s, 1u);
+                if (nk_m > 1 && !(WM_SKEL & 4)) umma_bf16_ss(tmem_s, drm0 + (uint32_t)((2 * 2048) >> 4), dcm + (uint32_t)((2 * ncols_pad * 16) >> 4), idesc_s, 1u);
+                umma_commit(&bar_s[t & 1]);
             }
-            const uint64_t dcm = dcm0 + (uint32_t)c.chunk * (uint32_t)(cm_tile_bytes >> 4);
-            for (int kk = 0; kk < nk_m; ++kk)       // 16 mask channels = two 8-channel core-matrix columns per MMA
-                if (leader)
-                    umma_bf16_ss(tmem_s, drm0 + (uint32_t)kk * (uint32_t)((2 * 2048) >> 4),
-                                 dcm + (uint32_t)kk * (uint32_t)((2 * ncols_pad * 16) >> 4), idesc_s, 1u);
-            if (leader) umma_commit(&bar_s[t & 1]);
+            __syncwarp();
         };
         const int nk_o = ncols_pad / 16;
-        auto issue_o_mma = [&](int t, int stage, int hd, bool accumulate) {   // O[hd&1] += P[t&1] V_t
-            const uint32_t tmem_o = tmem_base + (pl.obufs == 2 ? (hd & 1) : 0) * D;
-            uint32_t ta = tmem_p0 + (t & 1) * p_cols;                                // A = P from tensor memory
-            uint64_t db = dv0 + stage * stage_step;
-#pragma unroll 3
-            for (int kk = 0; kk < nk_o; ++kk) {
-                if (leader) umma_bf16_ts(tmem_o, ta, db, idesc_o, (accumulate || kk > 0) ? 1u : 0u);
-                ta += 8;                                                             // next 16 keys: 8 bf16-pair columns of P
-                db += (uint32_t)((16 * G::kRowBytes) >> 4);                          // next 16 keys of V
-            }
-            if (leader) umma_commit(&bar_o[t & 1]);
+        auto issue_o_chain = [&](auto nk_tag, uint32_t tmem_o, uint32_t ta, uint64_t db, bool accumulate, uint64_t* bar) {
+            constexpr int NK = decltype(nk_tag)::value;
+#pragma unroll
+            for (int kk = 0; kk < ((WM_SKEL & 2) ? 0 : NK); ++kk)
+                umma_bf16_ts(tmem_o, ta + 8 * kk /*8 bf16-pair columns of P per 16 keys*/,
+                             db + (uint32_t)kk * (uint32_t)((16 * G::kRowBytes) >> 4), idesc_o, (accumulate || kk > 0) ? 1u : 0u);
+            umma_commit(bar);
         };
-
-        Cursor ld = {0, ks_first, chunk_first};      // next block to load, its step index and stage
-        int ld_t = 0, ld_stage = 0;
-        issue_q_load(0);
-        for (; ld_t < nstage && ld_t < nsteps; ++ld_t) {
-            issue_kv_load(ld_stage, ld);
-            advance(ld);
-            if (++ld_stage == nstage) ld_stage = 0;
-        }
-        Cursor cur = {0, ks_first, chunk_first}, nxt = cur;
-        advance(nxt);
-        mbar_wait(&bar_q[0], 0);
-        mbar_wait(&bar_kv[0], 0);
-        tc_fence_after();
-        issue_s_mma(0, 0, cur);
-        int st_cur = 0;                              // stage of step t
-        int st_nxt = (nstage > 1) ? 1 : 0;           // stage of step t+1 ...
-        uint32_t kv_par = 1u;                        // bit s = parity of stage s's next completion (stage 0 was consumed once)
-        const bool dbg_on = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0) && leader;
-        (void)dbg_on;
-        // With >= 4 K/V stages S runs TWO steps ahead: S_{t+2} is queued right behind O += P_t V_t the moment the
-        // compute warps release step t, so they never wait for a score tile and the tensor pipe never idles on us.
-        const bool ahead2 = (nstage >= 4) && (nblocks >= 2) && (pl.rowbuf == 2 || pl.hpc == 1) && (nsteps >= 2);
-        if (ahead2) {
-            Cursor nn = nxt;                         // step t + 2
-            advance(nn);
-            int st_nn = 2;                           // its stage (nstage >= 4)
-            mbar_wait(&bar_kv[1], 0);
-            kv_par ^= 1u << 1;
-            tc_fence_after();
-            issue_s_mma(1, 1, nxt);
-            for (int t = 0; t < nsteps; ++t) {
-                DBG(0);
-                const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
-                if (head_start && pl.rowbuf == 2 && cur.hd + 1 < pl.hpc) issue_q_load(cur.hd + 1);
-                mbar_wait(&bar_p[t & 1], (t >> 1) & 1);      // step t released: P_t written, S buffer t&1 drained
-                tc_fence_after();
-                DBG(4);
-                issue_o_mma(t, st_cur, cur.hd, !head_start);
-                DBG(5);
-                if (t + 2 < nsteps) {
-                    mbar_wait(&bar_kv[st_nn], (kv_par >> st_nn) & 1u);
-                    kv_par ^= 1u << st_nn;
-                    if (nn.hd != nxt.hd) mbar_wait(&bar_q[nn.hd & 1], (nn.hd >> 1) & 1);
-                    tc_fence_after();
-                    DBG(1);
-                    issue_s_mma(t + 2, st_nn, nn);
-                    DBG(2);
+        auto issue_o_mma = [&](int t, int stage, int hd, bool accumulate) {   // O[hd&1] += P[t&1] V_t
+            if (leader) {
+                const uint32_t tmem_o = tmem_base + (pl.obufs == 2 ? (hd & 1) : 0) * D;
+                const uint32_t ta = tmem_p0 + (t & 1) * p_cols;                          // A = P from tensor memory
+                const uint64_t db = dv0 + stage * stage_step;
+                uint64_t* bar = &bar_o[t & 1];
+#define WM_O_CASE(n) case n: issue_o_chain(std::integral_constant<int, n>{}, tmem_o, ta, db, accumulate, bar); break;
+                switch (nk_o) {
+                    WM_O_CASE(1) WM_O_CASE(2) WM_O_CASE(3) WM_O_CASE(4) WM_O_CASE(5) WM_O_CASE(6) WM_O_CASE(7) WM_O_CASE(8)
+                    WM_O_CASE(9) WM_O_CASE(10) WM_O_CASE(11) WM_O_CASE(12) WM_O_CASE(13) WM_O_CASE(14) WM_O_CASE(15)
+                    default: issue_o_chain(std::integral_constant<int, 16>{}, tmem_o, ta, db, accumulate, bar); break;
                 }
-                if (t >= 1 && ld_t < nsteps) {               // refill the stage freed by step t-1
-                    mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);
-                    issue_kv_load(ld_stage, ld);
-                    advance(ld);
-                    ++ld_t;
-                    if (++ld_stage == nstage) ld_stage = 0;
-                }
-                DBG(3);
-                cur = nxt; nxt = nn;
-                advance(nn);
-                st_cur = st_nxt; st_nxt = st_nn;
-                if (++st_nn == nstage) st_nn = 0;
+#undef WM_O_CASE
             }
-        } else
-        for (int t = 0; t < nsteps; ++t) {
-            DBG(0);
-            const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
-            // (a) Q of the next head: its buffer was last read by the S MMAs of head hd-1 (rowbuf 2)
-            if (head_start && pl.rowbuf == 2 && cur.hd + 1 < pl.hpc) issue_q_load(cur.hd + 1);
-            auto refill = [&]() {        // (b) refill the stage freed by step t-1 once its P V has retired
+            __syncwarp();
+        };
+        uint32_t dbg_flag = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0) && leader;
+        asm volatile("" : "+r"(dbg_flag));
+        const bool dbg_on = dbg_flag != 0;
+        (void)dbg_on;
+        Cursor cur = {0, ks_first, chunk_first};
+
+        if (warp == kDriverWarp + 2) {
+            // ---- TMA loader: K/V blocks nstage steps ahead, Q one head ahead ---------------------------------------
+            Cursor ld = cur;
+            int ld_t = 0, ld_stage = 0;
+            issue_q_load(0);
+            for (; ld_t < nstage && ld_t < nsteps; ++ld_t) {
+                issue_kv_load(ld_stage, ld);
+                advance(ld);
+                if (++ld_stage == nstage) ld_stage = 0;
+            }
+            for (int t = 0; t < nsteps; ++t) {
+                const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
+                // O += P V of step t-1 has retired: its K/V stage is free, and (the compute warps had to see S_{t-1} before
+                // they released that step) every S MMA of the head that ended with step t-1 has retired as well
+                if (t >= 1) mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);
+                if (head_start && cur.hd + 1 < pl.hpc) issue_q_load(cur.hd + 1);     // hpc > 1 implies two Q buffers
                 if (t >= 1 && ld_t < nsteps) {
-                    mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);
+                    if (WM_SKEL & 8) { if (leader) mbar_arrive(&bar_kv[ld_stage]); } else
                     issue_kv_load(ld_stage, ld);          // == stage of step t-1
                     advance(ld);
                     ++ld_t;
                     if (++ld_stage == nstage) ld_stage = 0;
                 }
-            };
-            if (nstage < 3) refill();    // two stages: the block of step t+1 is the one being refilled
-            // (c) S of step t+1 into the other TMEM buffer, as soon as its K block is in.  That buffer was
-            //     drained by step t-1, which iteration t-1 already waited for (bar_p) before issuing P V.
-            if (t + 1 < nsteps) {
-                if (nxt.hd != cur.hd && pl.rowbuf == 1) {
-                    // single Q buffer: every S MMA of this head has been issued (S_t was) and retired (bar_s of t)
-                    mbar_wait(&bar_s[t & 1], (t >> 1) & 1);
-                    issue_q_load(nxt.hd);
-                }
-                mbar_wait(&bar_kv[st_nxt], (kv_par >> st_nxt) & 1u);
-                kv_par ^= 1u << st_nxt;
-                if (nxt.hd != cur.hd) mbar_wait(&bar_q[nxt.hd & 1], (nxt.hd >> 1) & 1);
-                tc_fence_after();
-                DBG(1);
-                issue_s_mma(t + 1, st_nxt, nxt);
-                DBG(2);
+                advance(cur);
             }
-            if (nstage >= 3) refill();
-            DBG(3);
-            // (d) O += P_t V_t once the compute warps have written P_t
-            mbar_wait(&bar_p[t & 1], (t >> 1) & 1);
-            tc_fence_after();
-            DBG(4);
-            issue_o_mma(t, st_cur, cur.hd, !head_start);
-            DBG(5);
-            cur = nxt;
-            advance(nxt);
-            st_cur = st_nxt;
-            if (++st_nxt == nstage) st_nxt = 0;
+        } else if (warp == kDriverWarp) {
+            // ---- S of step t+2 as soon as the compute warps have drained S buffer t&1 and the K block is in ----------
+            uint32_t kv_par = 0u;                        // bit s = parity of stage s's next completion
+            int stage = 0;
+            auto wait_inputs = [&](const Cursor& c, bool new_head) {
+                mbar_wait(&bar_kv[stage], (kv_par >> stage) & 1u);
+                kv_par ^= 1u << stage;
+                if (new_head) mbar_wait(&bar_q[c.hd & 1], (c.hd >> 1) & 1);
+                tc_fence_after();
+            };
+            Cursor c2 = cur;
+            int prev_hd = -1;
+            for (int u = 0; u < 2 && u < nsteps; ++u) {                  // S_0, S_1
+                wait_inputs(c2, c2.hd != prev_hd);
+                issue_s_mma(u, stage, c2);
+                prev_hd = c2.hd;
+                advance(c2);
+                if (++stage == nstage) stage = 0;
+            }
+            for (int t = 0; t + 2 < nsteps; ++t) {
+                DBG(2);
+                mbar_wait(&bar_p[t & 1], (t >> 1) & 1);                  // S buffer t&1 drained
+                DBG(3);
+                wait_inputs(c2, c2.hd != prev_hd);
+                DBG(6);
+                issue_s_mma(t + 2, stage, c2);
+                DBG(7);
+                prev_hd = c2.hd;
+                advance(c2);
+                if (++stage == nstage) stage = 0;
+            }
+        } else {
+            // ---- O += P_t V_t once the compute warps have written P_t -------------------------------------------------
+            uint32_t kv_par = 0u;
+            int stage = 0;
+            for (int t = 0; t < nsteps; ++t) {
+                DBG(0);
+                const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
+                mbar_wait(&bar_kv[stage], (kv_par >> stage) & 1u);       // V block (long since there: S_t came from its K)
+                kv_par ^= 1u << stage;
+                DBG(1);
+                mbar_wait(&bar_p[t & 1], (t >> 1) & 1);
+                tc_fence_after();
+                DBG(4);
+                issue_o_mma(t, stage, cur.hd, !head_start);
+                DBG(5);
+                advance(cur);
+                if (++stage == nstage) stage = 0;
+            }
         }
     } else {
         // =============================== compute warps ==========================================
@@ -495,268 +494,199 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const int plane_mask = (1 << pl.lgPlane) - 1;
         const int qs = row >> pl.lgPlane, qh = (row & plane_mask) >> pl.lgTW, qw = row & (pl.tW - 1);
         const bool q_valid = (s0 + qs < sh.S) && (h0 + qh < sh.H) && (w0 + qw < sh.W);
-        // live key range of this row in halo coordinates (window AND grid), per axis
-        const int kh_lo = max(qh, sh.eH - h0), kh_hi = min(qh + 2 * sh.eH, sh.H - 1 - h0 + sh.eH);
-        const int kw_lo = max(qw, sh.eW - w0), kw_hi = min(qw + 2 * sh.eW, sh.W - 1 - w0 + sh.eW);
-        const bool row_can = q_valid && kw_hi >= kw_lo;
         // warp-uniform ranges (identical for all warps of a quadrant)
         const int w_qs = (quad * 32) >> pl.lgPlane;
         const int w_qh_lo = ((quad * 32) & plane_mask) >> pl.lgTW, w_qh_hi = ((quad * 32 + 31) & plane_mask) >> pl.lgTW;
         const long tok = (((long)b * sh.S + (s0 + qs)) * sh.H + (h0 + qh)) * sh.W + (w0 + qw);
 
-        // Reference exponent (log2 domain, scaled) this row's P values are relative to.  It starts at 0 and is
-        // only moved when a block's row sum leaves [2^-64, 2^64] relative to it: bf16 P and the fp32 sums
-        // keep full precision over that range, so no per-block max pass and (in practice) no O rescale is needed.
-        float m_used = 0.f;
+        // Softmax without a running maximum.  P = 2^(s*scale*log2e) is taken relative to the FIXED exponent 0: bf16 P, the
+        // fp32 row sums and the fp32 accumulation of P V keep full relative precision as long as the row sum stays
+        // inside [2^-100, 2^100], i.e. for logits within about +-69 nats -- no max pass, no O rescale, and the two
+        // threads of a row never have to agree on anything.  A row whose sum leaves that range (or is inf / NaN) gets
+        // LSE = NaN here and is recomputed exactly by l3d_fwd_fixup_kernel, launched right behind this kernel.
         float l_part = 0.f;            // this thread's share of the running sum of P
-        bool head_has_blocks = false;  // warp-uniform: this quadrant already accumulated a block of the current head
-        bool row_seen = false;         // this row had live columns in an earlier block of the current head
-        // exchange slot: [use][parity][part][row]; parity alternates so that a slot is rewritten only
+        // exchange slot: [parity][part][row]; parity alternates so that a slot is rewritten only
         // after a later quad_sync has proven every reader of its previous contents done
-        auto xslot = [&](int use, int parity) { return sX + ((use * 2 + (parity & 1)) * 4) * 128; };
+        auto xslot = [&](int parity) { return sX + ((parity & 1) * 4) * 128; };
         // O / l -> bf16 and the LSE of head `hd`; called once that head's last P V has retired
-        auto finish_head = [&](int hd) {
+        auto finish_head = [&](int hd, float l_mine) {
             const uint32_t tmem_o = tmem_base + (pl.obufs == 2 ? (hd & 1) : 0) * D;
-            float* x = xslot(2, hd);
-            x[part * 128 + row] = l_part;
-            quad_sync();
-            float l_run = 0.f;
+            float* x = xslot(hd);
+            x[part * 128 + row] = l_mine;
+            uint32_t r[CP];
 #pragma unroll
-            for (int pp = 0; pp < NPART; ++pp) l_run += x[pp * 128 + row];
+            for (int c = 0; c < CP; c += 16) tmem_ld16(tmem_o + lane_sel + part * CP + c, *reinterpret_cast<uint32_t(*)[16]>(&r[c]));
+            quad_sync();
+            const float l_run = x[row] + x[128 + row];
+            const bool ok = l_run >= 7.8886091e-31f && l_run <= 1.2676506e30f;       // [2^-100, 2^100]; false for NaN
             const float inv_l = 1.f / l_run;
             const int cb = (head0 + hd) * D;
             __nv_bfloat16* orow = prm.o + tok * (long)sh.inner() + cb + part * CP;
+            tmem_wait_ld();
+            if (q_valid) {
 #pragma unroll
-            for (int c = 0; c < CP; c += 16) {
-                uint32_t r[16];
-                tmem_ld16(tmem_o + lane_sel + part * CP + c, r);      // warp-collective: every lane takes part
-                tmem_wait_ld();
-                if (q_valid) {
-                    uint32_t pk[8];
+                for (int c = 0; c < CP; c += 8) {
+                    uint32_t pk[4];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        pk[i] = pack_bf16(__uint_as_float(r[2 * i]) * inv_l, __uint_as_float(r[2 * i + 1]) * inv_l);
+                    for (int i = 0; i < 4; ++i)
+                        pk[i] = pack_bf16(__uint_as_float(r[c + 2 * i]) * inv_l, __uint_as_float(r[c + 2 * i + 1]) * inv_l);
                     *reinterpret_cast<uint4*>(orow + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    *reinterpret_cast<uint4*>(orow + c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                 }
+                if (part == 0) prm.lse[tok * sh.heads + head0 + hd] = ok ? lg2(l_run) * 0.6931471805599453f : __int_as_float(0x7fc00000);
             }
-            if (q_valid && part == 0) prm.lse[tok * sh.heads + head0 + hd] = (m_used + lg2(l_run)) * 0.6931471805599453f;
         };
 
-        Cursor cur{0, ks_first, chunk_first};
-        bool p_zero[2] = {false, false};   // this thread's share of P buffer i is known to be all zero
-        int mask_chunk = -1;
-        int g_lo = 0, g_hi = 0;            // live 8-column groups of this quadrant in the current h-chunk
-        bool chunk_live = false, row_has_cols = false;
         const int ngroups = ncols_pad >> 3;
-
-        const bool dbg_on = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0 && tid == 0);
+        int dlo0 = 0, dhi0 = ngroups, dlo1 = 0, dhi1 = ngroups;   // 8-column groups of P buffer 0 / 1 that may be non-zero
+        bool seen_o = false, seen_s = false;   // next step's barriers already seen complete by this step's probes
+        uint32_t dbg_flag = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0 && tid == 0);
+        asm volatile("" : "+r"(dbg_flag));
+        const bool dbg_on = dbg_flag != 0;
         (void)dbg_on;
-        for (int t = 0; t < nsteps; ++t) {
-            DBG(8);
-            const int buf = t & 1;
-            const uint32_t tmem_s = tmem_s0 + buf * ncols_pad + lane_sel;
-            const uint32_t tmem_o = tmem_base + (pl.obufs == 2 ? (cur.hd & 1) : 0) * D;
-            const uint32_t tmem_p = tmem_p0 + buf * p_cols + lane_sel;
-            const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
-            float prev_m = 0.f, prev_l = 0.f;
-            if (head_start && t > 0) {               // the previous head is finished AFTER this step (its O buffer is not reused yet)
-                prev_m = m_used; prev_l = l_part;
-                if (pl.obufs == 1) {                 // single O accumulator: drain it before this head's first P V can be issued
-                    mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);
-                    tc_fence_after();
-                    finish_head(cur.hd - 1);
-                }
-                m_used = 0.f; l_part = 0.f;
-                head_has_blocks = false;
-                row_seen = false;
-            }
-            const int kh0 = cur.chunk * pl.ch;
-            if (cur.chunk != mask_chunk) {               // live column range of this row / quadrant for this h-chunk
-                mask_chunk = cur.chunk;
-                const int ra = max(kh_lo, kh0), rb = min(kh_hi, kh0 + pl.ch - 1);
-                row_has_cols = row_can && (rb >= ra);
-                // the quadrant's rows see halo rows [w_qh_lo, w_qh_hi + 2 eH]; rows outside the grid are never live
-                const int ua = max(max(w_qh_lo, kh0), khg_lo), ub = min(min(w_qh_hi + 2 * sh.eH, kh0 + pl.ch - 1), khg_hi);
-                chunk_live = ub >= ua;
-                g_lo = ((ua - kh0) * pl.hW) >> 3;
-                g_hi = min(((ub - kh0 + 1) * pl.hW + 7) >> 3, ngroups);
-            }
-            // warp-uniform: can any of this quadrant's queries see this block?
-            const bool live = chunk_live && (cur.ks >= w_qs) && (cur.ks <= w_qs + 2 * sh.eS);
-            if (live) {
-                // S_t computed.  The driver issued it behind O += P_{t-2} V_{t-2} (tcgen05 operations of one thread retire
-                // in order), so this also says that P buffer `buf` is free and that every warp has left step t-2.
-                mbar_wait(&bar_s[buf], (t >> 1) & 1);
+        const uint64_t cc = pk2(pl.scale_log2, pl.scale_log2), zz = pk2(0.f, 0.f);
+
+        int t = 0;
+        for (int hd = 0; hd < pl.hpc; ++hd) {
+            DBGT(14, t);
+            // ---- head start: the previous head is finished AFTER this head's first step (its O buffer is not reused yet) ----
+            const float prev_l = l_part;
+            bool drain_prev = hd > 0;
+            if (hd > 0 && pl.obufs == 1) {           // single O accumulator: drain it before this head's first P V can be issued
+                mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);
                 tc_fence_after();
-                DBG(10);
-                const int n8 = g_hi - g_lo;
-                const int ga = g_lo + ((n8 * part) >> 1), gb = g_lo + ((n8 * (part + 1)) >> 1);
-                // Single pass against the stale reference exponent; P may then exceed 1, which is fine up to 2^64.
-                bool two_pass = false;
-                {
-                    const uint64_t cc = pk2(pl.scale_log2, pl.scale_log2), mm = pk2(-m_used, -m_used);
-                    uint64_t acc0 = pk2(0.f, 0.f), acc1 = acc0;
-                    // 16 scores of this row -> 16 probabilities (bf16) in the P operand; pairs [0, WM_FWD_POLY) take the
-                    // polynomial exp2 on the FMA pipe, the others the MUFU: the two pipes run side by side
-                    auto cols16 = [&](const uint32_t (&r)[16], int g) {
-                        uint32_t pk[8];
+                finish_head(hd - 1, prev_l);
+                drain_prev = false;
+            }
+            l_part = 0.f;
+            for (int chunk = chunk_first; chunk <= chunk_last; ++chunk) {
+                // ---- live column range of this quadrant / thread in this h-chunk (warp-uniform) ----
+                // the quadrant's rows see halo rows [w_qh_lo, w_qh_hi + 2 eH]; rows outside the grid are never live
+                const int kh0 = chunk * pl.ch;
+                const int ua = max(max(w_qh_lo, kh0), khg_lo), ub = min(min(w_qh_hi + 2 * sh.eH, kh0 + pl.ch - 1), khg_hi);
+                const bool chunk_live = ub >= ua;
+                const int g_lo = chunk_live ? ((ua - kh0) * pl.hW) >> 3 : 0;
+                const int g_hi = chunk_live ? min(((ub - kh0 + 1) * pl.hW + 7) >> 3, ngroups) : 0;
+                // the two threads of a row split [g_lo, g_hi) at an even group (16-column loads)
+                const int gm = min(g_lo + ((((g_hi - g_lo) + 2) >> 2) << 1), g_hi);
+                const int ga = part ? gm : g_lo, gb = part ? g_hi : gm;
+                const int n16 = (gb - ga) >> 1;
+                DBGT(15, t);
+                for (int ks = ks_first; ks <= ks_last; ++ks, ++t) {
+                    DBG(8);
+                    const int buf = t & 1;
+                    const uint32_t tmem_s = tmem_s0 + buf * ncols_pad + lane_sel;
+                    const uint32_t tmem_p = tmem_p0 + buf * p_cols + lane_sel;
+                    // warp-uniform: can any of this quadrant's queries see this block?
+                    const bool live = chunk_live && (ks >= w_qs) && (ks <= w_qs + 2 * sh.eS);
+                    // Both barriers of this step were probed during the previous one (a satisfied try_wait still costs
+                    // ~100 cycles); every warp observes every phase, live step or not (parity waits are unambiguous then).
+                    if (t >= 2 && !seen_o) mbar_wait(&bar_o[buf], ((t - 2) >> 1) & 1);     // P buffer free: P V of step t-2 retired
+                    DBG(9);
+                    if (!seen_s) mbar_wait(&bar_s[buf], (t >> 1) & 1);                     // S_t computed
+                    seen_o = seen_s = false;
+                    const int dl = buf ? dlo1 : dlo0, dh = buf ? dhi1 : dhi0;
+                    int nl = 0, nh = 0;
+                    if (live) {
+                        tc_fence_after();
+                        DBG(10);
+#if !(WM_SKEL & 1)     // WM_SKEL bit 0: pipeline skeleton only (no element math) -- timing floor of TMA + MMA + barriers
+                        uint64_t acc0 = zz, acc1 = zz;
+                        // 16 scores of this row -> 16 probabilities (bf16) in the P operand; pairs [0, WM_FWD_POLY) take
+                        // the polynomial exp2 on the FMA pipe, the others the MUFU: the two pipes run side by side.
+                        // Masked scores are <= -2^60 (mask operand of the S MMA): their exponential is 0.
+                        auto cols16 = [&](const uint32_t (&r)[16], int g) {
+                            uint32_t pk[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const uint64_t x = ffma2(pk2u(r[2 * i], r[2 * i + 1]), cc, mm);
-                            uint64_t e;
-                            if (i < WM_FWD_POLY) {
-                                e = exp2_poly2(x);
-                            } else {
+                            for (int i = 0; i < 8; ++i) {
+                                const uint64_t x = fmul2(pk2u(r[2 * i], r[2 * i + 1]), cc);
+                                uint64_t e;
+                                if (i < WM_FWD_POLY) {
+                                    e = exp2_poly2(x);
+                                } else {
+                                    float x0, x1;
+                                    upk2(x, x0, x1);
+                                    e = pk2(ex2(x0), ex2(x1));
+                                }
+                                if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
+                                pk[i] = pack_bf16_2(e);
+                            }
+                            tmem_st8(tmem_p + g * 4, pk);
+                        };
+                        // two register sets: the TMEM load of the next 16 columns is in flight while these are processed
+                        uint32_t r0[16], r1[16];
+                        int g = ga;
+                        if (n16 > 0) tmem_ld16(tmem_s + g * 8, r0);
+                        // probe the two barriers of the next step: the answers arrive under the math
+                        bool pr_o = t < 1, pr_s = false;
+                        for (int i = 0; i < n16; i += 2) {
+                            tmem_wait_ld();
+                            tmem_regs_ready(r0);
+                            if (i + 1 < n16) tmem_ld16(tmem_s + (g + 2) * 8, r1);
+                            cols16(r0, g);
+                            g += 2;
+                            if (i + 1 < n16) {
+                                tmem_wait_ld();
+                                tmem_regs_ready(r1);
+                                if (i + 2 < n16) tmem_ld16(tmem_s + (g + 2) * 8, r0);
+                                if (t >= 1 && !pr_o) pr_o = mbar_test(&bar_o[buf ^ 1], ((t - 1) >> 1) & 1);
+                                if (t + 1 < nsteps && !pr_s) pr_s = mbar_test(&bar_s[buf ^ 1], ((t + 1) >> 1) & 1);
+                                cols16(r1, g);
+                                g += 2;
+                            }
+                        }
+                        if (g < gb) {                 // odd group count of the quadrant: 8 columns left for part 1
+                            uint32_t r8[8];
+                            tmem_ld8(tmem_s + g * 8, r8);
+                            tmem_wait_ld();
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const uint64_t x = fmul2(pk2u(r8[2 * i], r8[2 * i + 1]), cc);
                                 float x0, x1;
                                 upk2(x, x0, x1);
-                                e = pk2(ex2(x0), ex2(x1));
+                                const uint64_t e = pk2(ex2(x0), ex2(x1));
+                                if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
+                                pk[i] = pack_bf16_2(e);
                             }
-                            if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
-                            pk[i] = pack_bf16_2(e);
+                            tmem_st4(tmem_p + g * 4, pk[0], pk[1], pk[2], pk[3]);
                         }
-                        tmem_st8(tmem_p + g * 4, pk);
-                    };
-                    auto cols8 = [&](const uint32_t (&r)[8], int g) {
-                        uint32_t pk[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint64_t x = ffma2(pk2u(r[2 * i], r[2 * i + 1]), cc, mm);
-                            float x0, x1;
-                            upk2(x, x0, x1);
-                            const uint64_t e = pk2(ex2(x0), ex2(x1));
-                            if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
-                            pk[i] = pack_bf16_2(e);
-                        }
-                        tmem_st4(tmem_p + g * 4, pk[0], pk[1], pk[2], pk[3]);
-                    };
-                    // two register sets: the TMEM load of the next 16 columns is in flight while these are processed
-                    uint32_t ra[16], rb[16];
-                    int g = ga;
-                    const int n16 = (gb - ga) >> 1;
-                    if (n16 > 0) tmem_ld16(tmem_s + g * 8, ra);
-                    for (int i = 0; i < n16; i += 2) {
-                        tmem_wait_ld();
-                        tmem_regs_ready(ra);
-                        if (i + 1 < n16) tmem_ld16(tmem_s + (g + 2) * 8, rb);
-                        cols16(ra, g);
-                        g += 2;
-                        if (i + 1 < n16) {
-                            tmem_wait_ld();
-                            tmem_regs_ready(rb);
-                            if (i + 2 < n16) tmem_ld16(tmem_s + (g + 2) * 8, ra);
-                            cols16(rb, g);
-                            g += 2;
-                        }
+                        DBG(13);
+                        float a0, a1, a2, a3;
+                        upk2(acc0, a0, a1);
+                        upk2(acc1, a2, a3);
+                        l_part += (a0 + a1) + (a2 + a3);
+                        if (t >= 1 && !pr_o) pr_o = mbar_test(&bar_o[buf ^ 1], ((t - 1) >> 1) & 1);
+                        if (t + 1 < nsteps && !pr_s) pr_s = mbar_test(&bar_s[buf ^ 1], ((t + 1) >> 1) & 1);
+                        seen_o = __all_sync(0xffffffffu, pr_o) && t >= 1;
+                        seen_s = __all_sync(0xffffffffu, pr_s);
+#endif
+                        // Columns outside the quadrant's live range must be zero in the P operand.  They stay zero from step
+                        // to step: only what an earlier step left non-zero outside today's range is cleared (normally nothing).
+                        for (int gz = dl + part; gz < min(dh, g_lo); gz += NPART) tmem_st4(tmem_p + gz * 4, 0u, 0u, 0u, 0u);
+                        for (int gz = max(dl, g_hi) + part; gz < dh; gz += NPART) tmem_st4(tmem_p + gz * 4, 0u, 0u, 0u, 0u);
+                        nl = g_lo; nh = g_hi;
+                    } else {
+                        for (int gz = dl + part; gz < dh; gz += NPART) tmem_st4(tmem_p + gz * 4, 0u, 0u, 0u, 0u);
                     }
-                    if (g < gb) {
-                        uint32_t r8[8];
-                        tmem_ld8(tmem_s + g * 8, r8);
-                        tmem_wait_ld();
-                        cols8(r8, g);
-                    }
-                    float a0, a1, a2, a3;
-                    upk2(acc0, a0, a1);
-                    upk2(acc1, a2, a3);
-                    const float lsum = (a0 + a1) + (a2 + a3);
-                    float* x = xslot(0, t);
-                    x[part * 128 + row] = lsum;
-                    quad_sync();
-                    const float ltot = x[row] + x[128 + row];
-                    // rows with live columns must land in [2^-64, 2^64]; !(a && b) also catches inf / NaN
-                    const bool out_of_range = row_has_cols && !(ltot <= 1.8446744e19f && ltot >= 5.4210109e-20f);
-                    two_pass = __any_sync(0xffffffffu, out_of_range);
-                    if (!two_pass) l_part += lsum;
-                }
-                if (two_pass) {
-                    // pass 1: row maximum over this thread's columns (masked scores are <= -2^60)
-                    float mx = -INFINITY;
-                    for (int g = ga; g < gb; ++g) {
-                        uint32_t r[8];
-                        tmem_ld8(tmem_s + g * 8, r);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-                    }
-                    float* x = xslot(1, t);
-                    x[part * 128 + row] = mx;
-                    quad_sync();
-#pragma unroll
-                    for (int pp = 0; pp < NPART; ++pp) mx = fmaxf(mx, x[pp * 128 + row]);
-                    const float m_blk = row_has_cols ? mx * pl.scale_log2 : -INFINITY;    // scale > 0
-                    float alpha = 1.f;
-                    // re-centre the reference on this block's maximum: upwards always (alpha < 2^-32), downwards
-                    // only while the row has nothing accumulated yet (alpha would overflow otherwise)
-                    const bool move = (m_blk != -INFINITY) && (m_blk > m_used + 32.f || (!row_seen && m_blk < m_used - 32.f));
-                    if (move) {
-                        alpha = row_seen ? ex2(m_used - m_blk) : 0.f;
-                        m_used = m_blk;
-                    }
-                    l_part *= alpha;
-                    if (head_has_blocks && __any_sync(0xffffffffu, move)) {   // rescale this thread's share of the O row
-                        mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);     // every earlier P V has retired
+                    if (buf) { dlo1 = nl; dhi1 = nh; } else { dlo0 = nl; dhi0 = nh; }
+                    DBG(11);
+                    tmem_wait_st();               // P is in tensor memory
+                    tc_fence_before();            // ... and our tcgen05.ld of S_t are complete before the issuers reuse the buffers
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_p[buf]);
+                    DBG(12);
+                    if (drain_prev && pl.obufs == 2) {   // epilogue of the previous head, off the critical path
+                        mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);     // its last P V has retired
                         tc_fence_after();
-#pragma unroll
-                        for (int c = 0; c < CP; c += 8) {
-                            uint32_t r[8];
-                            tmem_ld8(tmem_o + lane_sel + part * CP + c, r);
-                            tmem_wait_ld();
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-                            tmem_st8(tmem_o + lane_sel + part * CP + c, r);
-                        }
-                        tmem_wait_st();
+                        finish_head(hd - 1, prev_l);
+                        drain_prev = false;
                     }
-                    // pass 2: P = 2^(s*scale*log2e - m) -> bf16 -> TMEM
-                    const float neg_m = -m_used;
-                    float lsum = 0.f;
-                    for (int g = ga; g < gb; ++g) {
-                        uint32_t r[8];
-                        tmem_ld8(tmem_s + g * 8, r);
-                        tmem_wait_ld();
-                        float p[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            p[i] = ex2(fmaf(__uint_as_float(r[i]), pl.scale_log2, neg_m));
-                            lsum += p[i];
-                        }
-                        tmem_st4(tmem_p + g * 4, pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
-                    }
-                    l_part += lsum;
-                }
-                // columns outside the quadrant's live range: zero, shared round-robin between the parts
-                for (int g = part; g < g_lo; g += NPART) tmem_st4(tmem_p + g * 4, 0u, 0u, 0u, 0u);
-                for (int g = g_hi + part; g < ngroups; g += NPART) tmem_st4(tmem_p + g * 4, 0u, 0u, 0u, 0u);
-                p_zero[buf] = false;
-                head_has_blocks = true;
-                row_seen = row_seen || row_has_cols;
-            } else {
-                // P buffer `buf` is free (and every warp has left step t-2) once the P V of step t-2 has retired
-                if (t >= 2) mbar_wait(&bar_o[buf], ((t - 2) >> 1) & 1);
-                if (!p_zero[buf]) {
-                    for (int g = part; g < ngroups; g += NPART) tmem_st4(tmem_p + g * 4, 0u, 0u, 0u, 0u);
-                    p_zero[buf] = true;
                 }
             }
-            DBG(11);
-            tmem_wait_st();               // P is in tensor memory
-            tc_fence_before();            // ... and our tcgen05.ld of S_t are complete before the driver reuses the buffers
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_p[buf]);
-            DBG(12);
-            if (head_start && t > 0 && pl.obufs == 2) {   // epilogue of the previous head, off the critical path
-                mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);     // its last P V has retired
-                tc_fence_after();
-                const float keep_m = m_used, keep_l = l_part;
-                m_used = prev_m; l_part = prev_l;
-                finish_head(cur.hd - 1);
-                m_used = keep_m; l_part = keep_l;
-            }
-            advance(cur);
         }
         mbar_wait(&bar_o[(nsteps - 1) & 1], ((nsteps - 1) >> 1) & 1);
         tc_fence_after();
-        finish_head(pl.hpc - 1);
+        finish_head(pl.hpc - 1, l_part);
     }
 
     tc_fence_before();
@@ -802,11 +732,15 @@ bool attn_tc_supported(const AttnShape& s) {
 int attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse, const AttnShape& s, cudaStream_t st) {
     tc::Plan pl;
     if (!tc::make_plan(s, tc::kFwd, pl)) return fail(WM_EUNSUPPORTED, "no tensor-core tiling for this shape");
+    int rc;
     switch (s.d) {
-        case 32: return tc::launch_fwd<32>(q, k, v, o, lse, s, pl, st);
-        case 64: return tc::launch_fwd<64>(q, k, v, o, lse, s, pl, st);
-        default: return tc::launch_fwd<128>(q, k, v, o, lse, s, pl, st);
+        case 32: rc = tc::launch_fwd<32>(q, k, v, o, lse, s, pl, st); break;
+        case 64: rc = tc::launch_fwd<64>(q, k, v, o, lse, s, pl, st); break;
+        default: rc = tc::launch_fwd<128>(q, k, v, o, lse, s, pl, st); break;
     }
+    if (rc) return rc;
+    // rows whose softmax left the range of the max-free formulation (LSE = NaN) are recomputed exactly
+    return attn_fwd_fixup(q, k, v, o, lse, s, st);
 }
 
 int attn_bwd_tc(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout,

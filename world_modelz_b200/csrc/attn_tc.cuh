@@ -28,7 +28,7 @@ struct Plan {
     float scale_log2;
 };
 
-constexpr int kFwdThreads = 288;     // fwd: 8 compute warps + 1 driver warp (TMA + MMA issue)
+constexpr int kFwdThreads = 352;     // fwd: 8 compute warps + S issuer + P V issuer + TMA loader
 constexpr int kSmemLimit = 227 * 1024;
 
 template <int D> struct Geo {

@@ -244,12 +244,12 @@ __device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
 // 2^x for a PAIR of fp32 values on the FMA / ALU pipes instead of the MUFU: round-to-nearest split x = j + f,
 // f in [-0.5, 0.5], degree-3 minimax polynomial for 2^f (relative error 7.6e-5, far below the bf16 rounding of the
 // probabilities it feeds), exponent added with an integer shift-add.  x is clamped to >= -125 so that the result stays
-// a normal number (a masked score of -2^60 becomes 2^-125, i.e. nothing).  x must be <= ~125.
+// a normal number (a masked score of -2^60 becomes 2^-125, i.e. nothing) and to <= 126 (overflow shows as a huge finite value).
 __device__ __forceinline__ uint64_t exp2_poly2(uint64_t x2) {
     float x0, x1;
     upk2(x2, x0, x1);
-    x0 = fmaxf(x0, -125.f);
-    x1 = fmaxf(x1, -125.f);
+    x0 = fminf(fmaxf(x0, -125.f), 126.f);
+    x1 = fminf(fmaxf(x1, -125.f), 126.f);
     const uint64_t x = pk2(x0, x1);
     const uint64_t magic = pk2(12582912.f, 12582912.f), nmagic = pk2(-12582912.f, -12582912.f);
     const uint64_t t = fadd2(x, magic);                       // integer part in the low mantissa bits

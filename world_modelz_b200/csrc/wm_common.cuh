@@ -45,6 +45,10 @@ int attn_bwd_simt(const void* q, const void* k, const void* v, const void* o, co
                   const void* dout, void* dq, void* dk, void* dv, float* delta,
                   const AttnShape& s, int dtype, cudaStream_t st);
 
+// bf16: recompute (exactly, like attn_fwd_simt) every (token, head) whose lse is NaN -- the tensor-core forward's
+// marker for rows outside the range of its max-free softmax
+int attn_fwd_fixup(const void* q, const void* k, const void* v, void* o, float* lse, const AttnShape& s, cudaStream_t st);
+
 bool attn_tc_supported(const AttnShape& s);
 int attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse,
                 const AttnShape& s, cudaStream_t st);
