@@ -36,6 +36,7 @@ namespace wm { namespace tc { __device__ long long g_dbg_ws[2 * 64 * 16]; } }
 
 #include <math.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace wm {
 namespace tc {
@@ -224,53 +225,70 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         const uint64_t drm0 = make_smem_desc(smem_u32(sRm), 2048u, 128u, 0u);                       // mask operands: no swizzle
         const uint64_t dcm0 = make_smem_desc(smem_u32(sCm), (uint32_t)ncols_pad * 16u, 128u, 0u);
         const int nk_m = pl.km >> 4;
+        // Issue discipline (tools/micro/mma_cost.cu, sync_latency.cu): ONE branch on the elected lane around a whole chain of
+        // tcgen05.mma with compile-time operand offsets costs ~20-35 cycles per MMA; a predicate per MMA or a run-time
+        // trip count costs ~100.  The accumulation chains are therefore unrolled templates picked by a switch.
         auto issue_t_mma = [&](int stage, int hd, int chunk, int part) {  // T1 = A1 B1^T + mask, T2 = A2 B2^T; columns A (part 0) or B (part 1)
-            const uint32_t col0 = part ? (uint32_t)nA : 0u;        // columns = rows of the K-major block
-            const uint32_t idesc_t = part ? idesc_tB : idesc_tA;
-            const uint64_t da_h = da0 + (hd & 1) * a_buf_step;
-            const uint64_t db_s = dbk0 + stage * stage_step + ((col0 * (uint32_t)G::kRowBytes) >> 4);
+            if (leader) {
+                const uint32_t col0 = part ? (uint32_t)nA : 0u;        // columns = rows of the K-major block
+                const uint32_t idesc_t = part ? idesc_tB : idesc_tA;
+                const uint64_t da_h = da0 + (hd & 1) * a_buf_step;
+                const uint64_t db_s = dbk0 + stage * stage_step + ((col0 * (uint32_t)G::kRowBytes) >> 4);
 #pragma unroll
-            for (int op = 0; op < 2; ++op) {
+                for (int op = 0; op < 2; ++op) {
 #pragma unroll
-                for (int kk = 0; kk < D / 16; ++kk) {
-                    const uint32_t sl = (uint32_t)((kk * 16) / G::kSlabCh);
-                    const uint32_t koff = (uint32_t)((((kk * 16) % G::kSlabCh) * 2) >> 4);
-                    const uint64_t da = da_h + op * (uint32_t)(row_tile_bytes >> 4) + sl * (uint32_t)(row_slab_bytes >> 4) + koff;
-                    const uint64_t db = db_s + op * (uint32_t)(blk_tile_bytes >> 4) + sl * (uint32_t)(blk_slab_bytes >> 4) + koff;
-                    if (leader) umma_bf16_ss((op ? tmem_t2 : tmem_t1) + col0, da, db, idesc_t, kk > 0);
+                    for (int kk = 0; kk < D / 16; ++kk) {
+                        const uint32_t sl = (uint32_t)((kk * 16) / G::kSlabCh);
+                        const uint32_t koff = (uint32_t)((((kk * 16) % G::kSlabCh) * 2) >> 4);
+                        const uint64_t da = da_h + op * (uint32_t)(row_tile_bytes >> 4) + sl * (uint32_t)(row_slab_bytes >> 4) + koff;
+                        const uint64_t db = db_s + op * (uint32_t)(blk_tile_bytes >> 4) + sl * (uint32_t)(blk_slab_bytes >> 4) + koff;
+                        umma_bf16_ss((op ? tmem_t2 : tmem_t1) + col0, da, db, idesc_t, kk > 0);
+                    }
+                    if (op == 0) {      // S += R C^T: window / border mask (16 channels = two core-matrix columns per MMA; km is 16 or 32)
+                        const uint64_t dcm = dcm0 + (uint32_t)chunk * (uint32_t)(cm_tile_bytes >> 4) + ((col0 * 16u) >> 4);
+                        umma_bf16_ss(tmem_t1 + col0, drm0, dcm, idesc_t, 1u);
+                        if (nk_m > 1)
+                            umma_bf16_ss(tmem_t1 + col0, drm0 + (uint32_t)((2 * 2048) >> 4), dcm + (uint32_t)((2 * ncols_pad * 16) >> 4), idesc_t, 1u);
+                    }
                 }
-                if (op == 0) {      // S += R C^T: window / border mask (16 channels = two core-matrix columns per MMA)
-                    const uint64_t dcm = dcm0 + (uint32_t)chunk * (uint32_t)(cm_tile_bytes >> 4) + ((col0 * 16u) >> 4);
-                    for (int kk = 0; kk < nk_m; ++kk)
-                        if (leader)
-                            umma_bf16_ss(tmem_t1 + col0, drm0 + (uint32_t)kk * (uint32_t)((2 * 2048) >> 4),
-                                         dcm + (uint32_t)kk * (uint32_t)((2 * ncols_pad * 16) >> 4), idesc_t, 1u);
-                }
+                umma_commit(part ? bar_tB : bar_tA);
             }
-            if (leader) umma_commit(part ? bar_tB : bar_tA);
+            __syncwarp();
         };
         const int nk_acc = ncols_pad / 16;
-        auto issue_acc_mma = [&](int t, int stage, bool accumulate) {
-            uint32_t ta = tmem_pa + (t & 1) * pa_cols;                              // dS (dQ kernel) or P^T (dK/dV kernel), from TMEM
-            uint64_t d_ds = dds0 + (t & 1) * (uint32_t)(p_tile_bytes >> 4);         // dS^T (dK/dV kernel), from shared memory
-            uint64_t d_b1 = dbm0 + stage * stage_step;
-            uint64_t d_b2 = d_b1 + (uint32_t)(blk_tile_bytes >> 4);
-            for (int kk = 0; kk < nk_acc; ++kk) {
+        auto issue_acc_chain = [&](auto nk_tag, uint32_t ta, uint64_t d_ds, uint64_t d_b1, uint64_t d_b2, bool accumulate, uint64_t* bar) {
+            constexpr int NK = decltype(nk_tag)::value;
+#pragma unroll
+            for (int kk = 0; kk < NK; ++kk) {
                 const uint32_t acc = (accumulate || kk > 0) ? 1u : 0u;
+                const uint32_t boff = (uint32_t)kk * (uint32_t)((16 * G::kRowBytes) >> 4);      // next 16 rows of the halo block
                 if constexpr (kDKV) {
-                    if (leader) {
-                        umma_bf16_ts(tmem_acc1, ta, d_b2, idesc_acc, acc);          // dV += P^T dO_t
-                        umma_bf16_ss(tmem_acc2, d_ds, d_b1, idesc_acc, acc);        // dK += dS^T Q_t
-                    }
+                    // dS^T tile: 64-column (128-byte) slabs of 128 rows; 16 columns = 2 sixteen-byte units inside a slab
+                    const uint32_t dsoff = (uint32_t)(kk >> 2) * (uint32_t)((128 * 128) >> 4) + (uint32_t)(kk & 3) * 2u;
+                    umma_bf16_ts(tmem_acc1, ta + 8 * kk, d_b2 + boff, idesc_acc, acc);          // dV += P^T dO_t
+                    umma_bf16_ss(tmem_acc2, d_ds + dsoff, d_b1 + boff, idesc_acc, acc);         // dK += dS^T Q_t
                 } else {
-                    if (leader) umma_bf16_ts(tmem_acc1, ta, d_b1, idesc_acc, acc);  // dQ += dS K_t
+                    umma_bf16_ts(tmem_acc1, ta + 8 * kk, d_b1 + boff, idesc_acc, acc);          // dQ += dS K_t
                 }
-                ta += 8;
-                d_ds += ((kk & 3) == 3) ? (uint32_t)((128 * 128 - 96) >> 4) : 2u;
-                d_b1 += (uint32_t)((16 * G::kRowBytes) >> 4);
-                d_b2 += (uint32_t)((16 * G::kRowBytes) >> 4);
             }
-            if (leader) umma_commit(&bar_acc[t & 1]);
+            umma_commit(bar);
+        };
+        auto issue_acc_mma = [&](int t, int stage, bool accumulate) {
+            if (leader) {
+                const uint32_t ta = tmem_pa + (t & 1) * pa_cols;                              // dS (dQ kernel) or P^T (dK/dV kernel), from TMEM
+                const uint64_t d_ds = dds0 + (t & 1) * (uint32_t)(p_tile_bytes >> 4);         // dS^T (dK/dV kernel), from shared memory
+                const uint64_t d_b1 = dbm0 + stage * stage_step;
+                const uint64_t d_b2 = d_b1 + (uint32_t)(blk_tile_bytes >> 4);
+                uint64_t* bar = &bar_acc[t & 1];
+#define WM_ACC_CASE(n) case n: issue_acc_chain(std::integral_constant<int, n>{}, ta, d_ds, d_b1, d_b2, accumulate, bar); break;
+                switch (nk_acc) {
+                    WM_ACC_CASE(1) WM_ACC_CASE(2) WM_ACC_CASE(3) WM_ACC_CASE(4) WM_ACC_CASE(5) WM_ACC_CASE(6) WM_ACC_CASE(7) WM_ACC_CASE(8)
+                    WM_ACC_CASE(9) WM_ACC_CASE(10) WM_ACC_CASE(11) WM_ACC_CASE(12) WM_ACC_CASE(13) WM_ACC_CASE(14) WM_ACC_CASE(15)
+                    default: issue_acc_chain(std::integral_constant<int, 16>{}, ta, d_ds, d_b1, d_b2, accumulate, bar); break;
+                }
+#undef WM_ACC_CASE
+            }
+            __syncwarp();
         };
         const bool dbg_on = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0) && leader;
         (void)dbg_on;
