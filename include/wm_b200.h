@@ -19,8 +19,17 @@
  *       replace PreNorm, the residual adds and the bias / GELU element-wise chains of the
  *       transformer block around the attention core, with the bias gradients of its
  *       nn.Linear layers (vq-video-diffusion/local_3d_attention.py:11-31, 159-161).
- *   wm_adamw_step
- *       replaces optim.AdamW.step() of the training loop (vq-video-diffusion/main.py:283, 433).
+ *   wm_adamw_step / wm_adamw_step_norm
+ *       replace optim.AdamW.step() of the training loop (vq-video-diffusion/main.py:283, 433) and, with
+ *       the squared gradient norm reduced in the same pass, grad_norm() (main.py:189-193).
+ *   wm_vq_stats / wm_vq_onehot
+ *       replace the one-hot based codebook statistics of VectorQuantizerEMA.forward in training mode
+ *       (vq.py:35-46: accumulated_error, embeding_onehot_sum, dw) and the dense float one-hot it returns (vq.py:39).
+ *   wm_sample_step
+ *       replaces one draw of the mask/replace sampler: top_k_logits + softmax + multinomial + re-masking
+ *       (vq-video-diffusion/main.py:39-43, 80-109).
+ *   wm_loss_hist_update
+ *       replaces LossAwareSamplerEma.update_with_losses (vq-video-diffusion/importance_sampling.py:35-41).
  *
  * Conventions
  *   - All pointers are device pointers owned by the caller (PyTorch's caching
@@ -49,7 +58,7 @@ extern "C" {
 #define WM_API
 #endif
 
-#define WM_B200_VERSION 100          /* major*100 + minor */
+#define WM_B200_VERSION 110          /* major*100 + minor */
 
 /* dtype of q/k/v/o and their gradients */
 #define WM_DTYPE_BF16 0              /* tensor-core path (tcgen05), fp32 accumulate   */
@@ -115,6 +124,41 @@ WM_API int wm_vq_distance(const void* x, const void* codebook, float* dist,
 WM_API int wm_adamw_step(float* master, void* shadow, const void* grad, float* exp_avg, float* exp_avg_sq,
                          long n, const float* dyn, float beta1, float beta2, float eps, float weight_decay,
                          float grad_scale, int grad_dtype, void* stream);
+
+/* As wm_adamw_step; additionally (grad_sq != NULL) the squared L2 norm of the scaled gradient is reduced in the same
+ * pass: grad_sq is a DEVICE array of two floats, both zero before the first step; step s adds its sum to
+ * grad_sq[s & 1] and clears the other slot, so after step s the value is grad_sq[s & 1] (main.py:189-193). */
+WM_API int wm_adamw_step_norm(float* master, void* shadow, const void* grad, float* exp_avg, float* exp_avg_sq,
+                              long n, const float* dyn, float beta1, float beta2, float eps, float weight_decay,
+                              float grad_scale, int grad_dtype, float* grad_sq, void* stream);
+
+/* Codebook statistics of one quantizer forward (vq.py:35-46) from the indices, without a one-hot:
+ *   counts  [L, K] += number of latents assigned to each code          (embeding_onehot_sum, activation_count)
+ *   dw      [L, K, D] += sum of the latents x assigned to each code     (may be NULL; then x may be NULL)
+ *   acc_err [L, K] += sum of sq_err over the latents of each code       (accumulated_error; NULL with sq_err NULL)
+ * x [N, L, D] fp32, idx [N, L] int64, sq_err [N, L] fp32.  Outputs are ACCUMULATED into (zero them for per-call
+ * statistics).  fp32 atomics: each sum is exact up to the order of its terms. */
+WM_API int wm_vq_stats(const void* x, const int64_t* idx, const float* sq_err, float* counts, float* dw,
+                       float* acc_err, long N, int L, int K, int D, void* stream);
+
+/* encodings [rows, K] fp32 = one_hot(idx[rows]) (vq.py:39), every element written once; K a multiple of 4. */
+WM_API int wm_vq_onehot(const int64_t* idx, float* encodings, long rows, int K, void* stream);
+
+/* One draw of the iterative sampler (main.py:80-109) for P = clips * per_clip positions:
+ *   logits [P, K] (dtype bf16 / fp32); topk > 0 keeps every logit >= the topk-th largest of its row (main.py:39-43);
+ *   sample [P] int64 ~ multinomial(softmax(filtered logits)) (drawn as a Gumbel-max, Philox-4x32-10 keyed by
+ *   (seed, call counter, position, code)); frame, when != NULL, receives the draw, or mask_token where an independent
+ *   uniform exceeds alpha, at frame[clip * frame_stride + pos] (the last frame of the token tensor).
+ *   dyn: DEVICE array {alpha, call counter} so that a captured CUDA graph can be replayed. */
+WM_API int wm_sample_step(const void* logits, int64_t* sample, int64_t* frame, long frame_stride, long per_clip,
+                          long P, int K, int topk, int mask_token, const float* dyn, uint64_t seed, int dtype,
+                          void* stream);
+
+/* Loss-aware diffusion-time histogram (importance_sampling.py:35-41): for i in order,
+ * b = clamp(int(ts[i] * buckets)); weights[b] = weights[b] * alpha + losses[i] * (1 - alpha); counts[b] += 1.
+ * All device arrays: ts, losses [B] fp32, weights [buckets] fp32, counts [buckets] int64. */
+WM_API int wm_loss_hist_update(const float* ts, const float* losses, float* weights, int64_t* counts, int B,
+                               int buckets, float alpha, void* stream);
 
 /* ---- layer-level kernels around the attention core -------------------------------------
  * Replace the ATen chains of PreNorm + the residual adds of the transformer block

@@ -135,6 +135,48 @@ def attention_core_backward(q, k, v, dout, heads: int, extents: Sequence[int],
     return dq.reshape(shp), dk.reshape(shp), dv.reshape(shp)
 
 
+@torch.no_grad()
+def attention_core_slab(q, k, v, dout, heads: int, extents: Sequence[int], query_ids: torch.Tensor,
+                        scale: Optional[float] = None, chunk: int = 512):
+    """Forward and closed-form gradients of :func:`attention_core` restricted to the queries ``query_ids`` (flat
+    token ids of the (S,H,W) grid).  Returns ``(out_q, dq_q, dk, dv)``: outputs and dQ for those queries
+    ``[B, len(ids), C]``, and dK / dV ``[B,S,H,W,C]`` holding ONLY those queries' contributions -- complete for
+    every key whose whole set of observers lies inside ``query_ids`` (e.g. the middle plane of a slab of
+    ``2*eS+1`` query planes).  This is how full-size config 4 (32x32x32 tokens, window 5x7x7) is checked in
+    seconds: same arithmetic as ``local_3d_attention.py:78-99``, a slab of queries at a time.
+    """
+    B, S, H, W, C = q.shape
+    d = C // heads
+    if scale is None:
+        scale = d ** -0.5
+    N = S * H * W
+    ids, valid = window_table(S, H, W, extents)
+    qf, kf, vf = (t.reshape(B, N, heads, d) for t in (q, k, v))
+    dof = dout.reshape(B, N, heads, d)
+    nq = query_ids.numel()
+    out = torch.zeros(B, nq, heads, d)
+    dq = torch.zeros(B, nq, heads, d)
+    dk = torch.zeros_like(kf)
+    dv = torch.zeros_like(vf)
+    for c0 in range(0, nq, chunk):
+        qi = query_ids[c0:c0 + chunk]
+        sel, ok = ids[qi], valid[qi]
+        n, Wn = sel.shape
+        kg, vg = kf[:, sel], vf[:, sel]
+        qc, doc = qf[:, qi], dof[:, qi]
+        dots = torch.einsum('bnhd,bnwhd->bnhw', qc, kg) * scale
+        dots = dots.masked_fill(~ok[None, :, None, :], MASK_FILL)
+        p = torch.softmax(dots, dim=-1)
+        out[:, c0:c0 + chunk] = torch.einsum('bnhw,bnwhd->bnhd', p, vg)
+        dp = torch.einsum('bnhd,bnwhd->bnhw', doc, vg)
+        ds = p * (dp - (p * dp).sum(-1, keepdim=True)) * scale
+        dq[:, c0:c0 + chunk] = torch.einsum('bnhw,bnwhd->bnhd', ds, kg)
+        flat = sel.reshape(-1)
+        dk.index_add_(1, flat, torch.einsum('bnhw,bnhd->bnwhd', ds, qc).reshape(B, n * Wn, heads, d))
+        dv.index_add_(1, flat, torch.einsum('bnhw,bnhd->bnwhd', p, doc).reshape(B, n * Wn, heads, d))
+    return out.reshape(B, nq, C), dq.reshape(B, nq, C), dk.reshape(B, S, H, W, C), dv.reshape(B, S, H, W, C)
+
+
 # ---------------------------------------------------------------------- module level
 @dataclass
 class DenoiserConfig:
@@ -300,27 +342,50 @@ def train_step(p: Dict[str, torch.Tensor], opt_state: Dict[str, Dict[str, torch.
     return float(loss.detach())
 
 
+def top_k_logits(logits: torch.Tensor, k: int) -> torch.Tensor:
+    """Keep the ``k`` largest logits of every row, ``-inf`` elsewhere (``main.py:39-43``; ties at the k-th value stay)."""
+    kth = torch.topk(logits, k, dim=-1).values[:, -1:]
+    return logits.masked_fill(logits < kth, float('-inf'))
+
+
 @torch.no_grad()
 def sample_next_frame(p: Dict[str, torch.Tensor], tokens: torch.Tensor, cfg: DenoiserConfig,
-                      iterations: int = 30, gen: Optional[torch.Generator] = None) -> torch.Tensor:
+                      iterations: int = 30, gen: Optional[torch.Generator] = None, sample_topk: int = -1) -> torch.Tensor:
     """Iterative mask/replace denoising of the last frame (``main.py:71-111``).
 
-    ``tokens [B,S,H,W]`` with the last frame already set to the mask token.  Every
-    iteration samples all positions from the current logits, re-masks a
-    ``1-(i+1)/iterations`` fraction and runs one denoiser forward.  Returns the
-    final sampled last frame ``[B,H,W]``.
+    ``tokens [B,S,H,W]``; the last frame's content is irrelevant (iteration 0 draws from flat logits and re-masks).
+    Every iteration samples all positions from the current (optionally top-k filtered, ``:83-84``) logits, re-masks a
+    ``1-(i+1)/iterations`` fraction and runs one denoiser forward.  ``tokens`` is updated IN PLACE like the
+    reference's ``batch_z`` (``:107-109``); returns the final sampled last frame ``[B,H,W]``.
     """
     B, _, H, W = tokens.shape
     K = cfg.num_classes
-    logits = torch.zeros(B, H * W, K)
-    work = tokens.clone()
+    logits = torch.zeros(B * H * W, K)
     sample = None
     for i in range(iterations):
-        probs = torch.softmax(logits.view(-1, K), dim=-1)
+        if sample_topk > 0:
+            logits = top_k_logits(logits, sample_topk)
+        probs = torch.softmax(logits, dim=-1)
         sample = torch.multinomial(probs, 1, replacement=True, generator=gen).view(B, H, W)
         alpha = min(max((i + 1) / iterations, 0.0), 1.0)
         remask = torch.rand(B, H * W, generator=gen) > alpha
-        frame = torch.where(remask.view(B, H, W), torch.full_like(sample, K), sample)
-        work[:, -1] = frame
-        logits = denoiser_forward(p, work, cfg).reshape(B, H * W, K)
+        tokens[:, -1] = torch.where(remask.view(B, H, W), torch.full_like(sample, K), sample)
+        logits = denoiser_forward(p, tokens, cfg).reshape(B * H * W, K)
     return sample
+
+
+@torch.no_grad()
+def sample_frames(p: Dict[str, torch.Tensor], tokens: torch.Tensor, cfg: DenoiserConfig, num_steps: int,
+                  iterations: int = 30, gen: Optional[torch.Generator] = None, sample_topk: int = -1) -> torch.Tensor:
+    """The outer loop of ``evaluate_model`` (``main.py:71-115``): ``num_steps`` new frames, each by
+    :func:`sample_next_frame`, with the context shifted by one frame in between (``:115``; the reference's
+    in-place overlapping assignment ``batch_z[:,:-1] = batch_z[:,1:]`` raises on current PyTorch, the intended
+    shift is restated with a copy).  Returns the sampled token frames ``[num_steps, B, H, W]``.
+    """
+    work = tokens.clone()
+    work[:, -1] = cfg.num_classes                       # main.py:62: destroy all information in the last frame
+    frames = []
+    for _ in range(num_steps):
+        frames.append(sample_next_frame(p, work, cfg, iterations, gen, sample_topk))
+        work[:, :-1] = work[:, 1:].clone()
+    return torch.stack(frames)

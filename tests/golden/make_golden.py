@@ -45,7 +45,7 @@ def main():
     sys.path.insert(0, REF)
     from local_3d_attention import Local3dAttention, Local3dAttentionTransformer  # noqa
     from vq import VectorQuantizerEMA  # noqa
-    from autoencoder import SimpleResidualEncoder  # noqa
+    from autoencoder import SimpleResidualEncoder, SimpleResidualDecoder  # noqa
     torch.set_num_threads(max(1, os.cpu_count() or 1))
 
     # ---- 1. small module: everything stored ---------------------------------------
@@ -190,6 +190,42 @@ def main():
     vq.embedding.copy_(seeded(23, 1, 512, 64) * lat.std() + lat.mean())
     np.savez_compressed(os.path.join(HERE, 'vq_c2_latents.npz'), latents=lat.numpy(), embedding=vq.embedding.numpy(),
                         encode=vq.encode(lat).view(2, 16, 16).numpy())
+    # ---- 6. VqAutoEncoder (train_vqae.py:22-55 cannot be imported: matplotlib): the reference encoder, quantizer and
+    #         decoder composed under the reference's attribute names; encode / decode / forward in eval and train mode ----
+    class RefVqAutoEncoder(torch.nn.Module):
+        def __init__(self, embedding_dim, num_embeddings, downscale_steps, hidden_planes, in_channels):
+            super().__init__()
+            self.encoder = SimpleResidualEncoder(in_channels, embedding_dim, downscale_steps, hidden_planes)
+            self.decoder = SimpleResidualDecoder([hidden_planes] * downscale_steps, in_channels=embedding_dim,
+                                                 out_channels=in_channels)
+            self.vq = VectorQuantizerEMA(embedding_dim, num_embeddings)
+
+    torch.manual_seed(8)
+    ae = RefVqAutoEncoder(16, 64, 2, 32, 1)
+    for m_ in ae.modules():                         # non-trivial BatchNorm statistics
+        if isinstance(m_, torch.nn.BatchNorm2d):
+            m_.running_mean.normal_(0, 0.1)
+            m_.running_var.uniform_(0.5, 1.5)
+            m_.weight.data.uniform_(0.5, 1.5)
+            m_.bias.data.normal_(0, 0.1)
+    frames = torch.rand(3, 1, 32, 32)
+    sd0 = {'sd/' + k: v.detach().clone().numpy() for k, v in ae.state_dict().items()}
+    ae.eval()
+    with torch.no_grad():
+        h = ae.encoder(frames).permute(0, 2, 3, 1)
+        ae.vq.embedding.copy_(torch.randn(1, 64, 16) * h.std() + h.mean())
+        sd0['sd/vq.embedding'] = ae.vq.embedding.clone().numpy()
+        z = ae.vq.encode(h).view(h.shape[:-1])                                      # train_vqae.py:45-49
+        dec = ae.decoder(ae.vq.decode(z).permute(0, 3, 1, 2))                       # :51-55
+        q, _, latent_loss, ppl = ae.vq.forward(h)                                   # :33-43
+        recon = ae.decoder(q.permute(0, 3, 1, 2).contiguous())
+    ae.train()                                      # main.py never calls .eval() on the tokenizer: batch statistics
+    with torch.no_grad():
+        z_train = ae.vq.encode(ae.encoder(frames).permute(0, 2, 3, 1)).view(3, 8, 8)
+    np.savez_compressed(os.path.join(HERE, 'vqae_small.npz'), frames=frames.numpy(), latents=h.numpy(), z=z.numpy(),
+                        decoded=dec.numpy(), recon=recon.numpy(), latent_loss=latent_loss.item(), ppl=ppl.item(),
+                        z_train=z_train.numpy(), cfg=np.array([16, 64, 2, 32, 1]), **sd0)
+
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')

@@ -34,7 +34,7 @@ def test_header_symbols_exported():
 def test_version_and_argument_errors():
     _lib = _ensure_built()
     L = _lib.lib()
-    assert L.wm_version() == 100
+    assert L.wm_version() == 110
     # null pointers / bad shapes are rejected before any CUDA call
     rc = L.wm_l3d_attn_fwd(None, None, None, None, None, 1, 4, 4, 4, 2, 16, 1, 1, 1, 0.25, _lib.DTYPE_FP32, 0, None)
     assert rc == -1 and b'null pointer' in L.wm_last_error()
@@ -62,3 +62,25 @@ def test_ops_refuse_cpu_tensors():
         ops.local3d_attention(x, x, x, 1, (1, 1, 1))
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         ops.vq_nearest(torch.zeros(4, 1, 8), torch.zeros(1, 3, 8))
+    # the layer-level wrappers refuse too (no silent stock-op path for CPU tensors)
+    g = torch.ones(8)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        ops.add_layernorm(torch.zeros(3, 8), torch.zeros(3, 8), g, g)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        ops.bias_gelu(torch.zeros(3, 8), g)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        ops.linear(torch.zeros(3, 8), torch.zeros(8, 8), g)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        ops.vq_onehot(torch.zeros(4, 1, dtype=torch.long), 8)
+
+
+def test_new_entry_points_reject_bad_arguments():
+    _lib = _ensure_built()
+    L = _lib.lib()
+    assert L.wm_vq_stats(None, None, None, None, None, None, 4, 1, 8, 8, None) == -1
+    assert L.wm_vq_stats(None, None, None, None, None, None, 0, 1, 8, 8, None) == 0          # empty input
+    assert L.wm_vq_onehot(16, 16, 4, 6, None) == -1 and b'multiple of 4' in L.wm_last_error()
+    assert L.wm_sample_step(None, None, None, 0, 1, 4, 8, 0, 8, None, 0, _lib.DTYPE_FP32, None) == -1
+    assert L.wm_sample_step(16, 16, None, 0, 1, 4, 8, 0, 8, 16, 0, 5, None) == -1 and b'dtype' in L.wm_last_error()
+    assert L.wm_loss_hist_update(None, None, None, None, 4, 10, 0.9, None) == -1
+    assert L.wm_adamw_step_norm(None, None, None, None, None, 8, None, 0.9, 0.999, 1e-8, 0.0, 1.0, _lib.DTYPE_FP32, None, None) == -1

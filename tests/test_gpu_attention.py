@@ -143,11 +143,41 @@ def test_config4_core_reduced_grid_fixture():
             _close(t.grad[0, ::2, ::3, ::3], torch.from_numpy(f[name]), rtol, 2 * af, f'{name} {dtype}')
 
 
+def test_full_size_config4_against_oracle_slabs():
+    """BASELINE config 4 at FULL size -- 32x32x32 tokens, dim 512 (4 heads x 128), window 5x7x7 -- forward and all
+    three gradients against the CPU oracle on query slabs (planes around s = 0, 15, 31: both grid borders and the
+    interior).  ``oracle.attention_core_slab`` evaluates only the slab's queries; dK / dV are compared on the slab's
+    middle plane, whose observers all lie inside the slab."""
+    shape, heads, ext = (1, 32, 32, 32, 512), 4, (2, 3, 3)
+    S, H, W = shape[1:4]
+    g = torch.Generator().manual_seed(3)
+    q = (torch.randn(shape, generator=g) * 0.3).bfloat16()
+    k = (torch.randn(shape, generator=g) * 0.3).bfloat16()
+    v = torch.randn(shape, generator=g).bfloat16()
+    do = torch.randn(shape, generator=g).bfloat16()
+    qd, kd, vd, dod = (t.to(DEV) for t in (q, k, v, do))
+    scale = 128 ** -0.5
+    o_tc, lse_tc = ops.attn_forward(qd, kd, vd, heads, ext, scale)
+    dq_tc, dk_tc, dv_tc = ops.attn_backward(qd, kd, vd, o_tc, lse_tc, dod, heads, ext, scale)
+    torch.cuda.synchronize()
+    plane = H * W
+    for centre in (0, 15, 31):
+        s_lo, s_hi = max(0, centre - ext[0]), min(S - 1, centre + ext[0])           # query planes of the slab
+        k_lo, k_hi = max(0, s_lo - ext[0]), min(S - 1, s_hi + ext[0])               # planes their windows touch
+        sub = [t[:, k_lo:k_hi + 1].float() for t in (q, k, v, do)]
+        ids = torch.arange((s_lo - k_lo) * plane, (s_hi - k_lo + 1) * plane)
+        out, dq, dk, dv = O.attention_core_slab(*sub, heads, ext, ids, scale=scale, chunk=256)
+        C = shape[-1]
+        _close(o_tc[0, s_lo:s_hi + 1].reshape(-1, C), out[0], 2e-2, 4e-3, f'out, planes {s_lo}..{s_hi}')
+        _close(dq_tc[0, s_lo:s_hi + 1].reshape(-1, C), dq[0], 2e-2, 1e-2, f'dq, planes {s_lo}..{s_hi}')
+        _close(dk_tc[0, centre], dk[0, centre - k_lo], 2e-2, 1e-2, f'dk, plane {centre}')
+        _close(dv_tc[0, centre], dv[0, centre - k_lo], 2e-2, 1e-2, f'dv, plane {centre}')
+
+
 def test_full_size_properties_config4():
-    """32x32x32 tokens, dim 512 (4 heads x 128), window 5x7x7: too big for the CPU oracle to
-    finish in seconds, so check size-independent properties: (i) tensor-core and SIMT
-    kernels agree, (ii) constant V rows give constant outputs (softmax weights sum to 1),
-    (iii) gradients of sum(out) w.r.t. q vanish and dv sums to the number of queries."""
+    """Size-independent properties at the full config-4 size (the oracle comparison is the test above): (i) the
+    tensor-core and SIMT kernels agree everywhere, (ii) constant V rows give constant outputs (softmax weights sum
+    to 1), (iii) gradients of sum(out) w.r.t. q vanish and dv sums to the number of queries."""
     shape, heads, ext = (1, 32, 32, 32, 512), 4, (2, 3, 3)
     g = torch.Generator().manual_seed(3)
     q = (torch.randn(shape, generator=g) * 0.3).to(DEV, torch.bfloat16)
@@ -170,6 +200,26 @@ def test_full_size_properties_config4():
     assert dq.float().abs().max().item() < 2e-2 * max(1.0, k.float().abs().max().item())
     n_queries = shape[1] * shape[2] * shape[3]
     assert abs(dv.float()[..., 0].sum().item() / n_queries - 1) < 1e-2
+
+
+def test_rows_outside_the_max_free_range_are_recomputed_exactly():
+    """The tensor-core forward computes 2^(s*scale*log2e) against a FIXED exponent; rows whose sum leaves
+    [2^-100, 2^100] are marked (LSE = NaN) and recomputed by the exact fix-up kernel.  Mix ordinary rows with rows of
+    +-150-nat logits in one launch: no NaN may survive and everything matches the exact SIMT kernels."""
+    shape, heads, ext = (1, 4, 16, 16, 64), 2, (1, 2, 2)
+    g = torch.Generator().manual_seed(9)
+    q, k, v = (torch.randn(shape, generator=g).bfloat16() for _ in range(3))
+    qf = q.float()
+    qf[0, 1, :8] *= 60.0                  # huge positive and negative logits
+    qf[0, 2, 8:, :4] *= -45.0
+    q = qf.bfloat16()
+    qd, kd, vd = (t.to(DEV) for t in (q, k, v))
+    o_si, l_si = ops.attn_forward(qd, kd, vd, heads, ext, 32 ** -0.5, ops.FLAG_SIMT)
+    o_tc, l_tc = ops.attn_forward(qd, kd, vd, heads, ext, 32 ** -0.5, 0)
+    assert not torch.isnan(l_tc).any() and not torch.isnan(o_tc.float()).any()
+    assert l_si.abs().max().item() > 100
+    _close(o_tc, o_si, 2e-2, 4e-3, 'out')
+    _close(l_tc, l_si, 1e-3, 1e-4, 'lse')
 
 
 def test_unsupported_dtype_and_shape_raise():

@@ -7,7 +7,7 @@ import torch
 import world_modelz_b200 as wm
 from world_modelz_b200 import ops
 from oracle import vq as OV
-from tests._golden import load, seeded, checksum
+from tests._golden import load, seeded, checksum, state_dict_of
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
@@ -144,3 +144,54 @@ def test_tensor_core_filter_matches_exact_simt_kernel(N, L, K, D):
     assert torch.equal(a[1], b[1])
     torch.testing.assert_close(a[2], b[2], rtol=1e-5, atol=1e-6)
     assert np.array_equal(a[0].cpu().numpy(), OV.encode(x.numpy(), cb.numpy()))
+
+
+def test_fused_statistics_and_onehot_kernels():
+    """wm_vq_stats / wm_vq_onehot against index_add / scatter on random assignments (multi-latent, K not a power of 2)."""
+    g = torch.Generator().manual_seed(3)
+    N, L, K, D = 3001, 3, 20, 24
+    x = torch.randn(N, L, D, generator=g).to(DEV)
+    idx = torch.randint(0, K, (N, L), generator=g).to(DEV)
+    idx[:, 0] = idx[:, 0] % 7                                   # codes 7.. of latent 0 stay empty
+    err = torch.rand(N, L, generator=g).to(DEV)
+    counts = torch.zeros(L, K, device=DEV)
+    dw = torch.zeros(L, K, D, device=DEV)
+    acc = torch.ones(L, K, device=DEV)                           # accumulates INTO the buffer
+    ops.vq_stats(x, idx, err, counts, dw, acc)
+    onehot = torch.zeros(N, L, K, device=DEV).scatter_(-1, idx.unsqueeze(-1), 1.0)
+    torch.testing.assert_close(counts, onehot.sum(0))
+    torch.testing.assert_close(dw, onehot.permute(1, 2, 0) @ x.transpose(0, 1), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(acc, 1 + (onehot * err.unsqueeze(-1)).sum(0), rtol=1e-4, atol=1e-4)
+    assert torch.equal(ops.vq_onehot(idx, K), onehot)
+    small = idx[:5].clamp(max=17)
+    assert torch.equal(ops.vq_onehot(small, 18), torch.zeros(5, L, 18, device=DEV).scatter_(-1, small.unsqueeze(-1), 1.0))
+
+
+def test_vqautoencoder_against_reference_fixture():
+    """frames -> tokens bit-exact, tokens -> frames and the training-mode forward within 1e-5 of the reference
+    VqAutoEncoder (train_vqae.py:22-55), in eval mode and with the batch statistics main.py actually runs with."""
+    f = load('vqae_small.npz')
+    emb, K, steps, hidden, cin = (int(v) for v in f['cfg'])
+    ae = wm.VqAutoEncoder(emb, K, downscale_steps=steps, hidden_planes=hidden, in_channels=cin)
+    ae.load_state_dict(state_dict_of(f))
+    ae = ae.to(DEV).eval()
+    frames = torch.from_numpy(f['frames']).to(DEV)
+    # the conv stacks are stock cuDNN: compare in true fp32 (PyTorch lets cuDNN use TF32 for convolutions by default)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        _vqae_checks(ae, frames, f)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+
+
+def _vqae_checks(ae, frames, f):
+    z = ae.encode(frames)
+    assert z.dtype == torch.int64 and np.array_equal(z.cpu().numpy(), f['z'])
+    np.testing.assert_allclose(ae.decode(z).cpu().numpy(), f['decoded'], rtol=1e-4, atol=1e-5)
+    recon, latent_loss, ppl = ae(frames)
+    np.testing.assert_allclose(recon.detach().cpu().numpy(), f['recon'], rtol=1e-4, atol=1e-5)
+    assert abs(latent_loss.item() - float(f['latent_loss'])) < 1e-5 * max(1.0, float(f['latent_loss']))
+    assert abs(ppl.item() - float(f['ppl'])) < 1e-4 * float(f['ppl'])
+    ae.train()
+    assert np.array_equal(ae.encode(frames).cpu().numpy(), f['z_train'])

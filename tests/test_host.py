@@ -135,27 +135,74 @@ def test_data_parallel_gradient_exchange_gloo():
     assert out.get() < 1e-5
 
 
-def test_deferred_bias_host_paths_on_cpu():
-    """Host logic of the deferred-bias schedule that needs no GPU: widths the fused kernel does not tile go through
-    stock ops with the same math, and modules hand back ``bias=None`` when they cannot defer (CPU tensors)."""
-    import torch
-    import torch.nn.functional as F
-    from world_modelz_b200 import ops
+def test_modules_refuse_cpu_tensors():
+    """north_star: no CPU fallback.  The drop-in modules raise on CPU tensors instead of quietly running stock ops."""
     from world_modelz_b200.local_3d_attention import FeedForward
-    torch.manual_seed(0)
-    res, delta = torch.randn(7, 12), torch.randn(7, 12)            # dim 12: not a multiple of 8 -> stock-op path
-    bias, gamma, beta = torch.randn(12), torch.rand(12) + 0.5, torch.randn(12)
-    total, y = ops.add_layernorm(res, delta, gamma, beta, 1e-5, bias)
-    torch.testing.assert_close(total, res + delta + bias)
-    torch.testing.assert_close(y, F.layer_norm(res + delta + bias, (12,), gamma, beta, 1e-5))
-    total2, _ = ops.add_layernorm(res, None, gamma, beta, 1e-5)
-    assert total2 is res
-    ff = FeedForward(12, 24)
-    x = torch.randn(3, 12)
-    out, b = ff.forward_deferred_bias(x)
-    assert b is None
-    torch.testing.assert_close(out, ff(x))
-    torch.testing.assert_close(ops.bias_gelu(x, torch.zeros(12)), F.gelu(x))     # CPU tensors: stock ops
+    ff = FeedForward(16, 24)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        ff(torch.randn(3, 16))
+    m = wm.VqVideoDiffusionModel(data_shape=(2, 4, 4), dim=16, num_classes=8, extents=(1, 1, 1), depth=1, heads=2,
+                                 dim_head=8, mlp_dim=16)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m(torch.zeros(1, 2, 4, 4, dtype=torch.long))
+    vq = wm.VectorQuantizerEMA(8, 16)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        vq(torch.randn(2, 4, 8))
+
+
+def test_vqautoencoder_surface_and_conv_stacks_match_reference_fixture():
+    """``VqAutoEncoder`` (train_vqae.py:22-55): state_dict keys / shapes equal the reference's, a strict load of its
+    checkpoint works, and the (stock-op) encoder / decoder stacks reproduce the reference's latents and decoded
+    frames on the CPU; the quantizer step in between needs the GPU (tests/test_gpu_vq.py)."""
+    f = load('vqae_small.npz')
+    emb, K, steps, hidden, cin = (int(v) for v in f['cfg'])
+    ae = wm.VqAutoEncoder(emb, K, downscale_steps=steps, hidden_planes=hidden, in_channels=cin)
+    ref = state_dict_of(f)
+    sd = ae.state_dict()
+    assert set(sd) == set(ref)
+    for k in ref:
+        assert tuple(sd[k].shape) == tuple(ref[k].shape), k
+    ae.load_state_dict(ref)
+    ae.eval()
+    with torch.no_grad():
+        h = ae.encoder(torch.from_numpy(f['frames'])).permute(0, 2, 3, 1)
+        np.testing.assert_allclose(h.numpy(), f['latents'], rtol=1e-5, atol=1e-6)
+        dec = ae.decoder(ae.vq.decode(torch.from_numpy(f['z'])).permute(0, 3, 1, 2))
+        np.testing.assert_allclose(dec.numpy(), f['decoded'], rtol=1e-5, atol=1e-6)
+
+
+def test_oracle_sampler_topk_and_frame_shift():
+    """Oracle side of the multi-frame sampler (main.py:39-43, 62-117): top-k keeps exactly the k largest logits
+    (ties at the k-th value stay), frames shift by one after each generated frame."""
+    lg = torch.tensor([[0.1, 3.0, 2.0, 2.0, -1.0]])
+    out = O.top_k_logits(lg, 2)
+    assert torch.isinf(out[0, [0, 4]]).all() and torch.equal(out[0, 1:4], lg[0, 1:4])
+    cfg = O.DenoiserConfig(data_shape=(3, 4, 4), dim=16, num_classes=8, extents=(1, 1, 1), depth=1, heads=2,
+                           dim_head=8, mlp_dim=16)
+    p = O.init_denoiser_params(cfg, seed=1)
+    tok = torch.randint(0, 8, (2, 3, 4, 4), generator=torch.Generator().manual_seed(0))
+    frames = O.sample_frames(p, tok, cfg, 2, iterations=3, gen=torch.Generator().manual_seed(0), sample_topk=3)
+    assert frames.shape == (2, 2, 4, 4) and frames.min() >= 0 and frames.max() < 8
+    assert torch.equal(tok, tok.clone())          # the caller's tensor is not touched
+
+
+def test_flat_buffer_offsets_are_aligned_in_checkpoint_mapping():
+    """Parameters whose sizes are not multiples of 8 must not misalign their successors in the trainer's flat buffers:
+    the checkpoint mapping takes explicit (aligned) offsets."""
+    from world_modelz_b200 import checkpoint as ck
+    from world_modelz_b200.denoiser import _align
+    shapes = [torch.Size([3, 5]), torch.Size([7]), torch.Size([4, 4])]
+    offs, off = [], 0
+    for shp in shapes:
+        offs.append(off)
+        off = _align(off + shp.numel())
+    assert offs == [0, 16, 24] and off == 40
+    m, v = torch.arange(40.), torch.arange(40.) * 2
+    st = ck.flat_to_adamw_state(shapes, m, v, 3, lr=1e-3, offsets=offs)
+    assert torch.equal(st['state'][1]['exp_avg'], torch.arange(16., 23.))
+    m2, v2 = torch.zeros(40), torch.zeros(40)
+    assert ck.adamw_state_to_flat(st, shapes, m2, v2, offsets=offs) == 3
+    assert torch.equal(m2[24:40], m[24:40]) and torch.equal(v2[16:23], v[16:23]) and m2[15] == 0
 
 
 def test_reference_checkpoint_format_round_trip():

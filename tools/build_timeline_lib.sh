@@ -6,7 +6,7 @@ HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 SRC="${HERE}/../world_modelz_b200/csrc"; OUT="${HERE}/../world_modelz_b200/_C"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr)
 OBJS=()
-for src in api attn_simt attn_tc attn_tc_bwd_ws vq_exact vq_tc optim layer_ops; do
+for src in api attn_simt attn_tc attn_tc_bwd_ws vq_exact vq_tc optim layer_ops train_ops; do
   case $src in
     attn_tc|attn_tc_bwd_ws) nvcc "${FLAGS[@]}" -DWM_EXPERIMENT=7 ${WM_EXTRA_DEFS:-} -c "${SRC}/${src}.cu" -o "${OUT}/${src}_exp7.o"; OBJS+=("${OUT}/${src}_exp7.o");;
     *) OBJS+=("${OUT}/${src}.o");;

@@ -23,7 +23,7 @@ for t in range(4, 13):
     ev = sorted((a[t, s] - a[4, 8], names[s]) for s in names if a[t, s] != 0)
     print(f'step {t}: ' + '  '.join(f'{n}@{c}' for c, n in ev))
 d0 = np.diff(a[2:30, 8]); print('compute step period (cycles):', d0.tolist())
-sys.exit(0)
+
 
 # ---- backward kernels
 do = torch.randn(B, S, H, W, heads * d, device='cuda', generator=g).bfloat16()
@@ -43,7 +43,7 @@ if hasattr(_lib.lib(), 'wm_debug_read_ws'):
     for m, name in ((0, 'dQ ws'), (1, 'dK/dV ws')):
         a = b3[m]; t0 = a[0, 0]
         print('====', name)
-        for t in range(2, 11):
-            ev = sorted((a[t, s] - t0, nw[s]) for s in nw if a[t, s] != 0)
+        for t in range(4, 13):
+            ev = sorted((a[t, s] - a[4, 8], nw[s]) for s in nw if a[t, s] != 0)
             print(f'step {t}: ' + '  '.join(f'{n}@{c}' for c, n in ev))
-        print('driver period:', np.diff(a[2:26, 0]).tolist())
+        print('compute period:', np.diff(a[2:30, 8]).tolist())

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_long, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_long, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('WM_B200_LIB') or os.path.join(_HERE, '_C', 'libwm_b200.so')   # env override: tuning experiments only
@@ -47,6 +47,16 @@ def lib() -> ctypes.CDLL:
     L.wm_vq_distance.argtypes = [c_void_p] * 3 + [c_long, c_int, c_int, c_int, c_int, c_void_p]
     L.wm_adamw_step.restype = c_int
     L.wm_adamw_step.argtypes = [c_void_p] * 5 + [c_long, c_void_p] + [c_float] * 5 + [c_int, c_void_p]
+    L.wm_adamw_step_norm.restype = c_int
+    L.wm_adamw_step_norm.argtypes = [c_void_p] * 5 + [c_long, c_void_p] + [c_float] * 5 + [c_int, c_void_p, c_void_p]
+    L.wm_vq_stats.restype = c_int
+    L.wm_vq_stats.argtypes = [c_void_p] * 6 + [c_long, c_int, c_int, c_int, c_void_p]
+    L.wm_vq_onehot.restype = c_int
+    L.wm_vq_onehot.argtypes = [c_void_p, c_void_p, c_long, c_int, c_void_p]
+    L.wm_sample_step.restype = c_int
+    L.wm_sample_step.argtypes = [c_void_p] * 3 + [c_long, c_long, c_long, c_int, c_int, c_int, c_void_p, c_uint64, c_int, c_void_p]
+    L.wm_loss_hist_update.restype = c_int
+    L.wm_loss_hist_update.argtypes = [c_void_p] * 4 + [c_int, c_int, c_float, c_void_p]
     L.wm_reduce_blocks.restype = c_int
     L.wm_reduce_blocks.argtypes = [c_long]
     L.wm_add_layernorm_fwd.restype = c_int
@@ -69,5 +79,6 @@ def check(rc: int, what: str) -> None:
 
 
 EXPORTS = ('wm_version', 'wm_last_error', 'wm_l3d_attn_uses_tensor_cores', 'wm_l3d_attn_fwd', 'wm_l3d_attn_bwd',
-           'wm_vq_nearest', 'wm_vq_distance', 'wm_adamw_step', 'wm_reduce_blocks', 'wm_add_layernorm_fwd',
+           'wm_vq_nearest', 'wm_vq_distance', 'wm_adamw_step', 'wm_adamw_step_norm', 'wm_vq_stats', 'wm_vq_onehot',
+           'wm_sample_step', 'wm_loss_hist_update', 'wm_reduce_blocks', 'wm_add_layernorm_fwd',
            'wm_add_layernorm_bwd', 'wm_colsum', 'wm_bias_gelu_fwd', 'wm_bias_gelu_bwd')

@@ -290,7 +290,9 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             }
             __syncwarp();
         };
-        const bool dbg_on = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0) && leader;
+        uint32_t dbg_flag = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0) && leader;
+        asm volatile("" : "+r"(dbg_flag));
+        const bool dbg_on = dbg_flag != 0;
         (void)dbg_on;
         Cursor cur = {0, ks_first, chunk_first};
 
@@ -358,7 +360,9 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                 const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
                 mbar_wait(&bar_p[t & 1], (t >> 1) & 1);
                 tc_fence_after();
+                DBGW(4);
                 issue_acc_mma(t, st_cur, !head_start);
+                DBGW(5);
                 advance(cur);
                 if (++st_cur == nstage) st_cur = 0;
             }
@@ -446,7 +450,9 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         const int ngroups = ncols_pad >> 4;
         const uint32_t zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
-        const bool dbg_on = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0 && tid == 0);
+        uint32_t dbg_flag = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0 && tid == 0);
+        asm volatile("" : "+r"(dbg_flag));
+        const bool dbg_on = dbg_flag != 0;
         (void)dbg_on;
         for (int t = 0; t < nsteps; ++t) {
             DBGW(8);
@@ -582,12 +588,14 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                     asm volatile("" : "+f"(nxt_lse2), "+f"(nxt_dl));
                     if (t + 1 < nsteps) store_colvec(cbuf == 2 ? 0 : cbuf + 1, nxt_lse2, nxt_dl);
                 }
+                DBGW(13);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_pA[buf]);
             }
             tA_seen = false;
             if (!tB_seen) mbar_wait(bar_tB, t & 1);       // columns B
+            DBGW(14);
             if (live) {
                 tc_fence_after();
                 if (gA == 0) DBGW(10);

@@ -1,0 +1,237 @@
+// Device-side pieces of the training / sampling loops around the denoiser, so that a step never leaves the GPU:
+//   wm_vq_stats          codebook statistics of VectorQuantizerEMA.forward in training mode (vq.py:35-46) without the
+//                        dense one-hot: counts, per-code sums of the latents (dw) and accumulated error in one pass
+//   wm_vq_onehot         the float one-hot `encodings` tensor the reference returns (vq.py:39), written directly
+//   wm_sample_step       one draw of the mask/replace sampler (main.py:80-109): optional top-k filter, softmax +
+//                        multinomial as a Gumbel-max, re-masking -- one warp per position, no [P,K] temporaries
+//   wm_loss_hist_update  LossAwareSamplerEma.update_with_losses (importance_sampling.py:35-41) on the device
+//   wm_colsq             (see optim.cu) squared gradient norm for main.py:189-193
+#include "wm_common.cuh"
+
+#include <math.h>
+
+namespace wm {
+namespace {
+
+// ------------------------------------------------------------------------------------------ VQ statistics
+// One CTA accumulates its slice of the latents into shared memory (counts, error, and the [K, D] sums when they
+// fit), then adds its non-zero partials to global memory.  fp32 atomics: sums are exact per code up to ordering.
+__global__ void __launch_bounds__(256)
+vq_stats_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, const float* __restrict__ err,
+                float* __restrict__ counts, float* __restrict__ dw, float* __restrict__ acc_err, long N, int L, int K,
+                int D, int dw_in_smem) {
+    extern __shared__ float sm[];
+    float* s_cnt = sm;                  // [K]
+    float* s_err = sm + K;              // [K]
+    float* s_dw = sm + 2 * K;           // [K * D] (if dw_in_smem)
+    const int l = blockIdx.y;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 2 * K + (dw_in_smem ? K * D : 0); i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const long per = (N + gridDim.x - 1) / gridDim.x;
+    const long n0 = (long)blockIdx.x * per, n1 = min(N, n0 + per);
+    // a warp walks latents; lanes run over channels
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    for (long n = n0 + warp; n < n1; n += nwarps) {
+        const int k = (int)idx[n * L + l];
+        if (lane == 0) {
+            atomicAdd(&s_cnt[k], 1.f);
+            if (err != nullptr) atomicAdd(&s_err[k], err[n * L + l]);
+        }
+        if (dw != nullptr) {
+            const float* xr = x + (n * L + l) * (long)D;
+            float* dst = dw_in_smem ? (s_dw + (long)k * D) : (dw + ((long)l * K + k) * D);
+            for (int c = lane; c < D; c += 32) atomicAdd(&dst[c], xr[c]);
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += blockDim.x) {
+        if (s_cnt[k] != 0.f) {
+            atomicAdd(&counts[(long)l * K + k], s_cnt[k]);
+            if (acc_err != nullptr) atomicAdd(&acc_err[(long)l * K + k], s_err[k]);
+        }
+    }
+    if (dw != nullptr && dw_in_smem)
+        for (int i = tid; i < K * D; i += blockDim.x)
+            if (s_cnt[i / D] != 0.f) atomicAdd(&dw[(long)l * K * D + i], s_dw[i]);
+}
+
+__global__ void __launch_bounds__(256)
+vq_onehot_kernel(const int64_t* __restrict__ idx, float* __restrict__ out, long rows, int K) {
+    // rows = N*L; each row K floats; 4 floats per thread-iteration
+    const long total4 = rows * (long)(K / 4);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / (K / 4);
+        const int c = (int)(i - r * (K / 4)) * 4;
+        const int k = (int)idx[r];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k >= c && k < c + 4) (&v.x)[k - c] = 1.f;
+        reinterpret_cast<float4*>(out)[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ sampler step
+// Philox-4x32-10 (Salmon et al., SC'11): counter-based, so that any (call, position, code) has its own stream.
+__device__ __forceinline__ uint4 philox(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t r) { return ((r >> 8) + 0.5f) * (1.f / 16777216.f); }   // (0, 1)
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// one warp per position: logits row [K] -> sample (Gumbel-max over the top-k-filtered row == multinomial(softmax)),
+// frame = mask token where a uniform draw exceeds alpha (main.py:86-109).  dyn = {alpha, call counter} on the device.
+template <typename T>
+__global__ void __launch_bounds__(128)
+sample_step_kernel(const T* __restrict__ logits, int64_t* __restrict__ sample, int64_t* __restrict__ frame, long frame_stride,
+                   long per_clip, long P, int K, int topk, int mask_token, const float* __restrict__ dyn, uint64_t seed) {
+    const int lane = threadIdx.x & 31;
+    const long p = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= P) return;
+    const float alpha = dyn[0];
+    const uint32_t call = (uint32_t)dyn[1];
+    const T* row = logits + p * (long)K;
+    float kth = -INFINITY;
+    if (topk > 0 && topk < K) {
+        // k-th largest value by bisection on the order-preserving integer image of the floats
+        auto key_of = [](float f) { const uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); };
+        uint32_t lo = 0u, hi = 0xffffffffu;              // invariant: count(key >= lo) >= topk, count(key > hi) < topk
+        while (lo < hi) {
+            const uint32_t mid = lo + (uint32_t)(((uint64_t)hi - lo + 1) >> 1);
+            int c = 0;
+            for (int j = lane; j < K; j += 32) c += key_of(ldf(row + j)) >= mid;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (c >= topk) lo = mid; else hi = mid - 1;
+        }
+        const uint32_t u = (lo & 0x80000000u) ? (lo & 0x7fffffffu) : ~lo;
+        kth = __uint_as_float(u);
+    }
+    float best = -INFINITY;
+    int best_j = 0x7fffffff;
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    for (int j0 = lane * 4; j0 < K; j0 += 128) {
+        const uint4 r = philox(make_uint4((uint32_t)p, (uint32_t)(p >> 32), call, (uint32_t)(j0 >> 2)), key);
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = j0 + e;
+            if (j < K) {
+                const float lg = ldf(row + j);
+                if (lg >= kth) {                                   // main.py:42: logits < kth -> -inf
+                    const float g = lg - __logf(-__logf(u01(rr[e])));
+                    if (g > best || (g == best && j < best_j)) { best = g; best_j = j; }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+        if (ob > best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
+    }
+    if (lane == 0) {
+        const uint4 r = philox(make_uint4((uint32_t)p, (uint32_t)(p >> 32), call, 0xffffffffu), key);
+        const bool remask = u01(r.x) > alpha;
+        sample[p] = best_j;
+        if (frame != nullptr) {
+            const long clip = p / per_clip, pos = p - clip * per_clip;
+            frame[clip * frame_stride + pos] = remask ? mask_token : best_j;
+        }
+    }
+}
+
+// weights[b] = weights[b] * alpha + loss * (1 - alpha), in sample order within a bucket (importance_sampling.py:40-41)
+__global__ void loss_hist_update_kernel(const float* __restrict__ ts, const float* __restrict__ losses, float* __restrict__ weights,
+                                        int64_t* __restrict__ counts, int B, int nb, float alpha) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    float w = weights[b];
+    long c = counts[b];
+    for (int i = 0; i < B; ++i) {
+        int bi = (int)(ts[i] * nb);
+        bi = bi < 0 ? 0 : (bi > nb - 1 ? nb - 1 : bi);
+        if (bi == b) { w = w * alpha + losses[i] * (1.f - alpha); ++c; }
+    }
+    weights[b] = w;
+    counts[b] = c;
+}
+
+}  // namespace
+}  // namespace wm
+
+using namespace wm;
+
+extern "C" int wm_vq_stats(const void* x, const int64_t* idx, const float* sq_err, float* counts, float* dw,
+                           float* acc_err, long N, int L, int K, int D, void* stream) {
+    if (N < 0 || L <= 0 || K <= 0 || D <= 0) return fail(WM_EINVAL, "wm_vq_stats: bad shape N=%ld L=%d K=%d D=%d", N, L, K, D);
+    if (N == 0) return WM_OK;
+    if (!idx || !counts || (dw && !x)) return fail(WM_EINVAL, "wm_vq_stats: null pointer");
+    if (L > 65535) return fail(WM_EUNSUPPORTED, "wm_vq_stats: L=%d", L);
+    int sms = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t small = (size_t)2 * K * sizeof(float), full = small + (size_t)K * D * sizeof(float);
+    const int dw_in_smem = (dw != nullptr && full <= 200 * 1024) ? 1 : 0;
+    const size_t smem = dw_in_smem ? full : small;
+    if (smem > 200 * 1024) return fail(WM_EUNSUPPORTED, "wm_vq_stats: K=%d too large", K);
+    WM_CUDA_CHECK(cudaFuncSetAttribute(vq_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long ctas = (N + 255) / 256;
+    const long cap = sms / L > 0 ? sms / L : 1;
+    if (ctas > cap) ctas = cap;
+    vq_stats_kernel<<<dim3((unsigned)ctas, (unsigned)L), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float*>(x), idx, sq_err, counts, dw, acc_err, N, L, K, D, dw_in_smem);
+    WM_CUDA_CHECK(cudaGetLastError());
+    return WM_OK;
+}
+
+extern "C" int wm_vq_onehot(const int64_t* idx, float* encodings, long rows, int K, void* stream) {
+    if (rows < 0 || K <= 0 || K % 4 != 0) return fail(WM_EINVAL, "wm_vq_onehot: rows=%ld K=%d (K must be a multiple of 4)", rows, K);
+    if (rows == 0) return WM_OK;
+    if (!idx || !encodings || !aligned16(encodings)) return fail(WM_EINVAL, "wm_vq_onehot: null or misaligned pointer");
+    long blocks = (rows * (K / 4) + 255) / 256;
+    if (blocks > 148L * 32) blocks = 148L * 32;
+    vq_onehot_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(idx, encodings, rows, K);
+    WM_CUDA_CHECK(cudaGetLastError());
+    return WM_OK;
+}
+
+extern "C" int wm_sample_step(const void* logits, int64_t* sample, int64_t* frame, long frame_stride, long per_clip,
+                              long P, int K, int topk, int mask_token, const float* dyn, uint64_t seed, int dtype,
+                              void* stream) {
+    if (P < 0 || K <= 0 || per_clip <= 0) return fail(WM_EINVAL, "wm_sample_step: P=%ld K=%d per_clip=%ld", P, K, per_clip);
+    if (P == 0) return WM_OK;
+    if (!logits || !sample || !dyn) return fail(WM_EINVAL, "wm_sample_step: null pointer");
+    if (dtype != WM_DTYPE_BF16 && dtype != WM_DTYPE_FP32) return fail(WM_EINVAL, "wm_sample_step: dtype %d", dtype);
+    const unsigned blocks = (unsigned)((P + 3) / 4);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == WM_DTYPE_FP32)
+        sample_step_kernel<float><<<blocks, 128, 0, st>>>(static_cast<const float*>(logits), sample, frame, frame_stride, per_clip,
+                                                         P, K, topk, mask_token, dyn, seed);
+    else
+        sample_step_kernel<__nv_bfloat16><<<blocks, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(logits), sample, frame,
+                                                                 frame_stride, per_clip, P, K, topk, mask_token, dyn, seed);
+    WM_CUDA_CHECK(cudaGetLastError());
+    return WM_OK;
+}
+
+extern "C" int wm_loss_hist_update(const float* ts, const float* losses, float* weights, int64_t* counts, int B, int buckets,
+                                   float alpha, void* stream) {
+    if (B < 0 || buckets <= 0) return fail(WM_EINVAL, "wm_loss_hist_update: B=%d buckets=%d", B, buckets);
+    if (!ts || !losses || !weights || !counts) return fail(WM_EINVAL, "wm_loss_hist_update: null pointer");
+    loss_hist_update_kernel<<<(buckets + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(ts, losses, weights, counts, B,
+                                                                                                 buckets, alpha);
+    WM_CUDA_CHECK(cudaGetLastError());
+    return WM_OK;
+}

@@ -41,15 +41,17 @@ class FeedForward(nn.Module):
         return not self.training or (self.net[2].p == 0.0 and self.net[4].p == 0.0)
 
     def forward(self, x):
-        if x.is_cuda and self._no_dropout():
+        if not x.is_cuda:
+            raise RuntimeError('world_modelz_b200 modules run on a CUDA device only (no CPU fallback)')
+        if self._no_dropout():
             h = ops.bias_gelu(torch.nn.functional.linear(x, self.net[0].weight), self.net[0].bias)
             return ops.linear(h, self.net[3].weight, self.net[3].bias)
-        return self.net(x)
+        return self.net(x)                # dropout active: stock modules, still on the device
 
     def forward_deferred_bias(self, x):
         """``(y, bias)`` with ``forward(x) == y + bias``: the caller adds ``net.3``'s bias inside its fused
         residual-add + LayerNorm kernel, whose backward then also reduces the bias gradient.  ``bias`` is None when the
-        bias could not be deferred (dropout active, CPU tensors)."""
+        bias could not be deferred (dropout active)."""
         if x.is_cuda and self._no_dropout():
             h = ops.bias_gelu(torch.nn.functional.linear(x, self.net[0].weight), self.net[0].bias)
             return torch.nn.functional.linear(h, self.net[3].weight), self.net[3].bias

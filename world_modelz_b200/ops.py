@@ -141,13 +141,61 @@ def vq_distance(x: torch.Tensor, codebook: torch.Tensor, normalize: bool) -> tor
     return dist
 
 
-def adamw_step(master, shadow, grad, exp_avg, exp_avg_sq, dyn, beta1, beta2, eps, weight_decay, grad_scale) -> None:
-    """One fused AdamW launch over flat buffers (see ``wm_adamw_step`` in the header)."""
+def adamw_step(master, shadow, grad, exp_avg, exp_avg_sq, dyn, beta1, beta2, eps, weight_decay, grad_scale,
+               grad_sq=None) -> None:
+    """One fused AdamW launch over flat buffers (see ``wm_adamw_step_norm`` in the header); ``grad_sq`` (two device
+    floats) also receives the squared gradient norm of the step."""
     _require_cuda(master, grad)
-    check(_lib.lib().wm_adamw_step(master.data_ptr(), shadow.data_ptr() if shadow is not None else None,
-                                   grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), master.numel(),
-                                   dyn.data_ptr(), beta1, beta2, eps, weight_decay, grad_scale,
-                                   _dtype_code(grad), _stream()), 'wm_adamw_step')
+    check(_lib.lib().wm_adamw_step_norm(master.data_ptr(), shadow.data_ptr() if shadow is not None else None,
+                                        grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), master.numel(),
+                                        dyn.data_ptr(), beta1, beta2, eps, weight_decay, grad_scale,
+                                        _dtype_code(grad), grad_sq.data_ptr() if grad_sq is not None else None,
+                                        _stream()), 'wm_adamw_step_norm')
+    _count(1)
+
+
+def vq_stats(x, idx, sq_err, counts, dw=None, acc_err=None) -> None:
+    """Accumulate the per-code statistics of one quantizer forward (``vq.py:35-46``) into ``counts [L,K]``,
+    ``dw [L,K,D]`` and ``acc_err [L,K]`` -- one kernel, no one-hot."""
+    _require_cuda(idx, counts)
+    N, L = idx.shape
+    K = counts.shape[-1]
+    D = x.shape[-1] if x is not None else 1
+    check(_lib.lib().wm_vq_stats(x.data_ptr() if x is not None else None, idx.data_ptr(),
+                                 sq_err.data_ptr() if sq_err is not None else None, counts.data_ptr(),
+                                 dw.data_ptr() if dw is not None else None,
+                                 acc_err.data_ptr() if acc_err is not None else None, N, L, K, D, _stream()), 'wm_vq_stats')
+    _count(1)
+
+
+def vq_onehot(idx: torch.Tensor, K: int) -> torch.Tensor:
+    """``one_hot(idx) -> float32 [..., K]`` written in one pass (``vq.py:39``)."""
+    _require_cuda(idx)
+    idx = idx.contiguous()
+    out = torch.empty(*idx.shape, K, device=idx.device, dtype=torch.float32)
+    if K % 4 != 0:
+        return out.zero_().scatter_(-1, idx.unsqueeze(-1), 1.0)
+    check(_lib.lib().wm_vq_onehot(idx.data_ptr(), out.data_ptr(), idx.numel(), K, _stream()), 'wm_vq_onehot')
+    _count(1)
+    return out
+
+
+def sample_step(logits, sample, frame, frame_stride, per_clip, topk, mask_token, dyn, seed) -> None:
+    """One draw of the iterative sampler for every position (``wm_sample_step``): ``logits [P,K]`` -> ``sample [P]``
+    and the re-masked last frame written through ``frame`` (a view of the token tensor's last frame)."""
+    _require_cuda(logits, sample)
+    logits = logits.contiguous()
+    P, K = logits.shape
+    check(_lib.lib().wm_sample_step(logits.data_ptr(), sample.data_ptr(), frame.data_ptr() if frame is not None else None,
+                                    frame_stride, per_clip, P, K, topk, mask_token, dyn.data_ptr(), seed,
+                                    _dtype_code(logits), _stream()), 'wm_sample_step')
+    _count(1)
+
+
+def loss_hist_update(ts, losses, weights, counts, alpha) -> None:
+    _require_cuda(ts, weights)
+    check(_lib.lib().wm_loss_hist_update(ts.data_ptr(), losses.data_ptr(), weights.data_ptr(), counts.data_ptr(),
+                                         ts.numel(), weights.numel(), float(alpha), _stream()), 'wm_loss_hist_update')
     _count(1)
 
 
@@ -220,6 +268,7 @@ def add_layernorm(res: torch.Tensor, delta: Optional[torch.Tensor], gamma: torch
     bias of the linear layer that produced ``delta`` (``to_out.0`` / ``net.3``), deferred to here.
     Reference: PreNorm + residual adds, local_3d_attention.py:11-17,159-161.
     """
+    _require_cuda(res)
     dim = res.shape[-1]
     if dim % 8 != 0 or dim > 2048:      # widths the kernel does not tile: stock CUDA ops (still on the device)
         total = res if delta is None else (res + delta if delta_bias is None else res + (delta + delta_bias))
@@ -288,14 +337,16 @@ class _BiasGeluFn(torch.autograd.Function):
 def bias_gelu(h: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     """``gelu(h + bias)`` with ``h = x @ W1^T`` computed WITHOUT bias (FeedForward ``net.0`` / ``net.1``,
     local_3d_attention.py:24-27).  Widths the kernel does not tile fall back to stock CUDA ops."""
+    _require_cuda(h)
     cols = h.shape[-1]
-    if not h.is_cuda or cols % 8 != 0 or cols > 2048 or h.dtype not in (torch.bfloat16, torch.float32):
+    if cols % 8 != 0 or cols > 2048 or h.dtype not in (torch.bfloat16, torch.float32):
         return torch.nn.functional.gelu(h + bias)
     return _BiasGeluFn.apply(h, bias)
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """nn.Linear forward on cuBLAS with the bias gradient reduced by ``wm_colsum``."""
-    if bias is None or not x.is_cuda or bias.shape[0] % 8 != 0 or bias.shape[0] > 2048:
+    _require_cuda(x)
+    if bias is None or bias.shape[0] % 8 != 0 or bias.shape[0] > 2048:
         return torch.nn.functional.linear(x, weight, bias)
     return _LinearFn.apply(x, weight, bias)

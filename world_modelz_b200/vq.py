@@ -61,31 +61,34 @@ class VectorQuantizerEMA(nn.Module):
 
     # -- forward -----------------------------------------------------------------------
     def forward(self, input):
+        """``-> (quantized [straight-through], encodings one-hot f32 [N,L,K], commitment_loss, perplexity)``
+        (``vq.py:25-75``).  Nearest code, gather and per-latent error come from ``wm_vq_nearest``; the per-code
+        statistics (``accumulated_error`` always, ``activation_count`` / ``cluster_size`` / ``embedding`` EMA in
+        training mode) from ONE ``wm_vq_stats`` pass over the indices -- no ``[N,L,D,K]`` distance temporary and no
+        one-hot matmul; the one-hot the API returns is written directly by ``wm_vq_onehot``."""
         L, K, D = self.num_latents, self.num_embeddings, self.embedding_dim
         flat = self._flat(input)
-        idx, ste, err = ops.vq_nearest(flat.detach().float(), self.embedding)
+        x32 = flat.detach().float().contiguous()
+        idx, ste, err = ops.vq_nearest(x32, self.embedding)
         n = flat.shape[0]
         with torch.no_grad():
-            self.accumulated_error.scatter_add_(-1, idx.t(), err.t())
-            encodings = torch.zeros(n, L, K, device=flat.device, dtype=torch.float32)
-            encodings.scatter_(-1, idx.unsqueeze(-1), 1.0)
             counts = torch.zeros(L, K, device=flat.device, dtype=torch.float32)
-            counts.scatter_add_(1, idx.t(), torch.ones(L, n, device=flat.device, dtype=torch.float32))
+            dw = torch.zeros(L, K, D, device=flat.device, dtype=torch.float32) if self.training else None
+            ops.vq_stats(x32, idx, err, counts, dw, self.accumulated_error)          # vq.py:35-36, 43-46
+            encodings = ops.vq_onehot(idx, K)                                        # vq.py:39
             quantized = self.decode(idx).reshape(input.shape)
             if self.training:
-                self._ema_update(flat.detach().float(), idx, counts)
+                self._ema_update(counts, dw)
         commitment_loss = F.mse_loss(quantized, input)
         out = _StraightThrough.apply(input, ste.to(input.dtype))
         avg = counts / n
         perplexity = torch.exp(-torch.sum(avg * torch.log(avg + 1e-10) / L))
         return out, encodings, commitment_loss, perplexity
 
-    def _ema_update(self, flat, idx, counts):
-        L, K, D = self.num_latents, self.num_embeddings, self.embedding_dim
+    def _ema_update(self, counts, dw):
+        """Cluster-size / embedding EMA with Laplace smoothing (``vq.py:47-65``) from the fused statistics."""
+        K = self.num_embeddings
         self.activation_count.add_(counts)
-        dw = torch.zeros(L, K, D, device=flat.device, dtype=torch.float32)
-        for l in range(L):
-            dw[l].index_add_(0, idx[:, l], flat[:, l])
         if self.simple_update:
             dw = dw / counts.unsqueeze(-1)
             ok = dw == dw
