@@ -1,30 +1,46 @@
-// VQ nearest-codebook search on the tensor cores: tf32 distance GEMM as a candidate filter,
-// exact fp64 re-check of the candidates (bit-exact indices, lowest index on ties).
+// VQ nearest-codebook search on the tensor cores: a split-bf16 distance GEMM as the filter, exact fp64 re-check of
+// the (rare) near-ties -- bit-exact indices, lowest index on ties.
 //
-//   d(x, e_k) = |x|^2 + |e_k|^2 - 2 x.e_k        (vq.py:30 computes the direct form in fp32)
+//   d(x, e_k) = |x|^2 + |e_k|^2 - 2 x.e_k            (vq.py:30 computes the direct form in fp32)
 //
-// A persistent CTA keeps one codebook [K, D] in shared memory (TMA, 128B swizzle, K-major = the
-// B operand), streams 128-latent tiles of x through a 2-stage TMA ring (the A operand) and
-// computes all 128 x K dot products with tcgen05.mma kind::tf32 into TMEM (K <= 512 columns).
-// Epilogue, two threads per latent row:
-//   pass 1: t_k = |e_k|^2 - 2 dot_k, row minimum
-//   pass 2: every code with t_k <= min + 2*eps is a candidate, eps = 2^-8 |x| max|e| bounding the
-//           tf32 rounding of both operands (Cauchy-Schwarz); the candidate set provably contains the
-//           exact nearest code; candidates are re-evaluated as sum_d (x_d - e_d)^2 in fp64
-//   then indices, the straight-through value x + (e - x) and sum (e - x)^2 (vq.py:34-36,70).
+// Precision of the filter.  x = x_hi + x_lo + r_x with x_hi = bf16(x), x_lo = bf16(x - x_hi), |r_x| <= 2^-17 |x| (same
+// for e).  Three bf16 MMAs accumulate  x_hi.e_hi + x_lo.e_hi + x_hi.e_lo  in fp32 (bf16 products are exact in
+// fp32), so -2 x.e is off by at most 6 * 2^-18 |x||e| plus the fp32 accumulation of 3D terms (<= 3D * 2^-24 * 2|x||e|);
+// eps = 2^-15 |x| max|e| bounds the error of the filtered distance (Cauchy-Schwarz; the split error alone is
+// 2.3e-5 |x||e|, the accumulation of the 12 K-steps at D = 64 adds ~1e-6).  Two codes closer than the window 2 eps + (key truncation) are
+// re-evaluated exactly; everything else is decided by the filter.
+//
+// Pipeline (one persistent CTA per SM keeps the whole codebook, pre-scaled by -2, as bf16 hi / lo in shared memory):
+//   warps  8-15  loader / writer, 16 lanes per latent row (coalesced): fp32 rows from global memory two tiles
+//                ahead (registers), split into the bf16 hi / lo operand tiles (128B-swizzled, K-major) + |x|^2; later,
+//                for the finished tile: merge the two code halves, gather the winner, write idx, x + (e - x), sum (e - x)^2
+//   warps  0-3   scan code half A (codes [0, K/2), TMEM columns [0, 256)), warps 4-7 half B ([256, 512)); the first warp
+//                of each group also issues its half's tcgen05.mma chain for the next tile the moment the group has
+//                drained the scores -- while one half is being scanned the tensor pipe works on the other.
+//                One thread per row: distance keys (fp32 bits with the code's column
+//                index in the low 8 bits) reduced with 3-input integer min / max to the two smallest keys
 // Replaces VectorQuantizerEMA's [N,L,D,K] distance temporary + argmin + gather (vq.py:30-36,84-87).
 #include "tc_common.cuh"
 #include "wm_common.cuh"
 
 #include <math.h>
+#include <type_traits>
+
+#ifndef WM_VQ_EXP
+#define WM_VQ_EXP 0      // timing experiments: 1 no ambiguity re-scan, 2 no MMAs, 4 no scan, 8 no output, 16 no cross-half check
+#endif
 
 namespace wm {
 namespace vq {
 
 using namespace wm::tc;
 
-constexpr int kThreads = 256;
+#if WM_VQ_EXP & 32
+__device__ unsigned long long g_vq_dbg[4];
+#endif
+
 constexpr int kTileM = 128;
+constexpr int kThreads = 16 * 32;      // 4 warps per SM sub-partition: 128 registers per thread
 
 struct Params {
     const float* x;            // [N, L, D]
@@ -35,309 +51,437 @@ struct Params {
     long N;
     int L, K, D;
     int tiles;                 // ceil(N / 128)
-    int cb_box;                // codebook rows per TMA box
 };
 
-// element (row, channel) of a [rows x 32-float slabs] tile stored with the 128B TMA swizzle
-__device__ __forceinline__ const float* sw_elem(const uint8_t* tile, int slab_bytes, int row, int ch) {
-    const int slab = ch >> 5, c = ch & 31;
-    return reinterpret_cast<const float*>(tile + slab * slab_bytes + row * 128 + ((((c >> 2) ^ (row & 7)) << 4) | ((c & 3) << 2)));
-}
-__device__ __forceinline__ float4 sw_vec4(const uint8_t* tile, int slab_bytes, int row, int ch4) {   // channels [4*ch4, 4*ch4+4)
-    const int slab = ch4 >> 3, c = ch4 & 7;
-    return *reinterpret_cast<const float4*>(tile + slab * slab_bytes + row * 128 + ((c ^ (row & 7)) << 4));
+// byte offset of 16-byte chunk c16 of row r in a [rows x 64 bf16] slab stored K-major with the 128-byte swizzle
+__device__ __forceinline__ uint32_t sw128(int r, int c16) { return (uint32_t)r * 128u + (uint32_t)((c16 ^ (r & 7)) << 4); }
+
+__device__ __forceinline__ void split_bf16(float v, uint16_t& hi, uint16_t& lo) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    hi = *reinterpret_cast<const uint16_t*>(&h);
+    lo = *reinterpret_cast<const uint16_t*>(&l);
 }
 
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// exact squared distance (fp64 accumulation of fp32 differences) between a latent row and a code, both in global memory;
+// all loads are issued before the first use (one memory round trip)
+template <int D>
+__device__ __noinline__ double exact_dist(const float* __restrict__ xr, const float* __restrict__ er) {
+    double a = 0.0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                          // two halves: 16 + 16 loads in flight at D = 64
+        float4 xv[D / 8], ev[D / 8];
+#pragma unroll
+        for (int c = 0; c < D / 8; ++c) {
+            xv[c] = __ldg(reinterpret_cast<const float4*>(xr) + h * (D / 8) + c);
+            ev[c] = __ldg(reinterpret_cast<const float4*>(er) + h * (D / 8) + c);
+        }
+#pragma unroll
+        for (int c = 0; c < D / 8; ++c) {
+            const double d0 = (double)xv[c].x - (double)ev[c].x, d1 = (double)xv[c].y - (double)ev[c].y;
+            const double d2 = (double)xv[c].z - (double)ev[c].z, d3 = (double)xv[c].w - (double)ev[c].w;
+            a = fma(d0, d0, a); a = fma(d1, d1, a); a = fma(d2, d2, a); a = fma(d3, d3, a);
+        }
+    }
+    return a;
 }
 
-__device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-                 : "memory");
+// Exact (fp64) winner among the candidates the two code halves reported, by a whole warp: r.y = best code, r.z =
+// runner-up (a candidate when r.w == 1), r.w == 2: more than two codes of that half are inside the window -> the whole
+// half.  Lanes take candidates round-robin; lowest index wins ties.  Rare path, kept out of line.
+template <int D>
+__device__ __noinline__ int settle_exact_warp(const float* __restrict__ xr, const float* __restrict__ cbl, uint4 ra, uint4 rb,
+                                              bool a_in, bool b_in, int KH, int lane) {
+    const int nA = a_in ? (ra.w == 2u ? KH : 1 + (ra.w == 1u)) : 0;
+    const int nB = b_in ? (rb.w == 2u ? KH : 1 + (rb.w == 1u)) : 0;
+    double bd = INFINITY;
+    int bk = 0x7fffffff;
+    for (int c = lane; c < nA + nB; c += 32) {
+        int k;
+        if (c < nA) k = ra.w == 2u ? c : (c == 0 ? (int)ra.y : (int)ra.z);
+        else k = rb.w == 2u ? KH + (c - nA) : (c == nA ? (int)rb.y : (int)rb.z);
+        const double dd = exact_dist<D>(xr, cbl + (long)k * D);
+        if (dd < bd || (dd == bd && k < bk)) { bd = dd; bk = k; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+        if (od < bd || (od == bd && ok < bk)) { bd = od; bk = ok; }
+    }
+    return bk;
 }
 
+template <int D>
 __global__ void __launch_bounds__(kThreads, 1)
-vq_nearest_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_cb, const Params prm) {
+vq_nearest_tc_kernel(const Params prm) {
+    constexpr int kSlabs = D / 64;                         // 64-channel (128-byte) slabs
+    constexpr int kVec = D / 4;                            // float4 per row
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int K = prm.K, D = prm.D, L = prm.L;
-    const int slabs = D / 32;
-    const int cb_slab_bytes = K * 128, x_slab_bytes = kTileM * 128;
-    uint8_t* sCB = smem;                                         // [slabs][K rows][128 B]
-    uint8_t* sX = sCB + slabs * cb_slab_bytes;                   // [2 stages][slabs][128 rows][128 B]
-    float* sNorm = reinterpret_cast<float*>(sX + 2 * slabs * x_slab_bytes);     // [K] |e_k|^2
-    float* sXch = sNorm + K;                                     // [2 halves][128] exchange (min / best)
-    double* sXd = reinterpret_cast<double*>(sXch + 2 * 128);     // [2 uses][best|second][2 halves][128]
-    int* sXi = reinterpret_cast<int*>(sXd + 2 * 512);            // [2 uses][2 halves][128]
-    float* sRed = reinterpret_cast<float*>(sXi + 2 * 256);       // [8] block reduction
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 8);
-    uint64_t* bar_cb = bars;
-    uint64_t* bar_x = bars + 1;      // [2]
-    uint64_t* bar_mma = bars + 3;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    const int K = prm.K, L = prm.L;
+    const int KH = K >> 1;                                 // codes per half
+    const int e_slab = K * 128, x_slab = kTileM * 128;
+    uint8_t* sEhi = smem;                                  // [slabs][K rows][128 B]   -2 * e, bf16 hi
+    uint8_t* sElo = sEhi + kSlabs * e_slab;                //                          -2 * e, bf16 lo
+    uint8_t* sXhi = sElo + kSlabs * e_slab;                // [2 buffers][slabs][128 rows][128 B]
+    uint8_t* sXlo = sXhi + 2 * kSlabs * x_slab;
+    float* sNorm = reinterpret_cast<float*>(sXlo + 2 * kSlabs * x_slab);     // [K]  |e_k|^2 + 1
+    float* sXn2 = sNorm + K;                               // [2][128] |x|^2
+    uint32_t* sRes = reinterpret_cast<uint32_t*>(sXn2 + 2 * kTileM);          // [2][2 halves][128] {t1, code 1, code 2, extra}
+    float* sRed = reinterpret_cast<float*>(sRes + 2 * 2 * kTileM * 4);       // [32] block reduction
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 32);
+    uint64_t* bar_xready = bars;         // [2] operand tiles of a latent tile written          (8 loader warps)
+    uint64_t* bar_xfree = bars + 2;      // [2] every MMA reading that buffer has retired       (tcgen05.commit of both halves)
+    uint64_t* bar_full = bars + 4;       // [2] scores of code half A / B computed              (tcgen05.commit)
+    uint64_t* bar_free = bars + 6;       // [2] scores of half A / B drained                    (4 scanner warps)
+    uint64_t* bar_res = bars + 8;        // [2] both halves' results of a tile are in sRes      (8 scanner warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int quad = warp & 3, half = warp >> 2;
-    const int row = quad * 32 + lane;
-    const bool leader = (lane == 0);
-    const int l = blockIdx.y;                                    // codebook / latent slot
-    const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
+    const int l = blockIdx.y;
+    const float* cbl = prm.cb + (long)l * K * D;
 
     if (tid == 0) {
-        tma_prefetch_desc(&map_x);
-        tma_prefetch_desc(&map_cb);
-        mbar_init(bar_cb, 1);
-        mbar_init(&bar_x[0], 1);
-        mbar_init(&bar_x[1], 1);
-        mbar_init(bar_mma, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_xready[i], 8);
+            mbar_init(&bar_xfree[i], 2);
+            mbar_init(&bar_full[i], 1);
+            mbar_init(&bar_free[i], 4);
+            mbar_init(&bar_res[i], 8);
+        }
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
 
-    auto issue_x_load = [&](int it, int tile) {                  // warp 0
-        if (leader) {
-            const int st = it & 1;
-            mbar_expect_tx(&bar_x[st], (uint32_t)(slabs * x_slab_bytes));
-            for (int sl = 0; sl < slabs; ++sl)
-                tma_load_2d(sX + (st * slabs + sl) * x_slab_bytes, &map_x, &bar_x[st], l * D + sl * 32, tile * kTileM);
-        }
-    };
-    const int first_tile = blockIdx.x, stride = gridDim.x;
-    if (warp == 0) {
-        if (leader) {
-            mbar_expect_tx(bar_cb, (uint32_t)(slabs * cb_slab_bytes));
-            for (int sl = 0; sl < slabs; ++sl)
-                for (int r0 = 0; r0 < K; r0 += prm.cb_box)
-                    tma_load_2d(sCB + sl * cb_slab_bytes + r0 * 128, &map_cb, bar_cb, sl * 32, l * K + r0);
-        }
-        if (first_tile < prm.tiles) issue_x_load(0, first_tile);
-        if (first_tile + stride < prm.tiles) issue_x_load(1, first_tile + stride);
-    }
-    mbar_wait(bar_cb, 0);
-    // |e_k|^2 (fp64 accumulate) and max |e_k| of this codebook
+    // ---- codebook: -2 e as bf16 hi / lo operand tiles, |e|^2 + 1 (fp64 accumulate), max |e| ---------------------------
     float emax2 = 0.f;
     for (int k = tid; k < K; k += kThreads) {
         double a = 0.0;
-        for (int c4 = 0; c4 < D / 4; ++c4) {
-            const float4 e = sw_vec4(sCB, cb_slab_bytes, k, c4);
-            a += (double)e.x * e.x + (double)e.y * e.y + (double)e.z * e.z + (double)e.w * e.w;
+        const float* er = cbl + (long)k * D;
+#pragma unroll 2
+        for (int c8 = 0; c8 < D / 8; ++c8) {               // 8 channels = one 16-byte chunk of the bf16 row
+            const float4 e0 = __ldg(reinterpret_cast<const float4*>(er + 8 * c8));
+            const float4 e1 = __ldg(reinterpret_cast<const float4*>(er + 8 * c8 + 4));
+            const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint16_t h0, l0, h1, l1;
+                split_bf16(-2.f * ev[2 * i], h0, l0);
+                split_bf16(-2.f * ev[2 * i + 1], h1, l1);
+                hi[i] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                lo[i] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                a += (double)ev[2 * i] * ev[2 * i] + (double)ev[2 * i + 1] * ev[2 * i + 1];
+            }
+            const uint32_t off = (uint32_t)(c8 >> 3) * e_slab + sw128(k, c8 & 7);
+            *reinterpret_cast<uint4*>(sEhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(sElo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
-        sNorm[k] = (float)a;
+        sNorm[k] = (float)a + 1.f;        // +1 keeps every filtered distance positive: its fp32 bits then order like integers
         emax2 = fmaxf(emax2, (float)a);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) emax2 = fmaxf(emax2, __shfl_xor_sync(0xffffffffu, emax2, o));
     if (lane == 0) sRed[warp] = emax2;
+    fence_proxy_async();                  // operand tiles (generic proxy) -> visible to tcgen05.mma
+    tc_fence_before();
     __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
     emax2 = sRed[0];
 #pragma unroll
-    for (int w = 1; w < 8; ++w) emax2 = fmaxf(emax2, sRed[w]);
+    for (int w = 1; w < 16; ++w) emax2 = fmaxf(emax2, sRed[w]);
     const float emax = sqrtf(emax2) * 1.0000002f;
 
-    const uint32_t idesc = make_idesc_tf32(K > 256 ? 256 : K);
-    const uint32_t idesc_hi = make_idesc_tf32(K > 256 ? K - 256 : 16);
-    const uint64_t dx0 = make_smem_desc(smem_u32(sX), 16, 1024, 2u);
-    const uint64_t dc0 = make_smem_desc(smem_u32(sCB), 16, 1024, 2u);
+    const int first_tile = blockIdx.x, stride = gridDim.x;
+    const int my_tiles = first_tile < prm.tiles ? (prm.tiles - first_tile + stride - 1) / stride : 0;
 
-    int it = 0;
-    for (int tile = first_tile; tile < prm.tiles; tile += stride, ++it) {
-        const int st = it & 1;
-        const uint8_t* xt = sX + st * slabs * x_slab_bytes;
-        // ---- dot products of the tile against the whole codebook -----------------------------------
-        if (warp == 0) {
-            mbar_wait(&bar_x[st], (it >> 1) & 1);
+    if (warp < 8) {
+        // =============================== scanners (+ MMA issue by the first warp of each half) =====================================================================
+        const int quad = warp & 3, half = warp >> 2;
+        const int row = quad * 32 + lane;
+        const uint32_t taddr = tmem_base + half * 256 + ((uint32_t)(quad * 32) << 16);
+        const float* nk = sNorm + half * KH;
+        const int nchunk = KH >> 4;
+        // ---- the half's MMA chain: x_hi e_hi + x_lo e_hi + x_hi e_lo over all D channels, N = K/2 columns
+        const bool issuer = quad == 0;
+        const bool leader = elect_one();
+        const uint32_t idesc = make_idesc_bf16(KH, false, false);
+        const uint64_t dxh = make_smem_desc(smem_u32(sXhi), 16, 1024, 2u), dxl = make_smem_desc(smem_u32(sXlo), 16, 1024, 2u);
+        const uint64_t deh = make_smem_desc(smem_u32(sEhi), 16, 1024, 2u), del = make_smem_desc(smem_u32(sElo), 16, 1024, 2u);
+        auto issue_tile = [&](int j) {           // called by the issuing warp once its half is free (or was never used)
+            const int b = j & 1;
+            mbar_wait(&bar_xready[b], (j >> 1) & 1);
+            if (j > 0) mbar_wait(&bar_free[half], (j - 1) & 1);           // all four warps of the group have drained tile j-1
             tc_fence_after();
-            for (int nh = 0; nh * 256 < K; ++nh) {
-                const uint32_t id = nh == 0 ? idesc : idesc_hi;
-                for (int ks = 0; ks < D / 8; ++ks) {             // 8 tf32 (32 bytes) per MMA
-                    const uint32_t sl = (uint32_t)(ks >> 2), ko = (uint32_t)((ks & 3) * 2);
-                    const uint64_t da = dx0 + (uint32_t)(((st * slabs + sl) * x_slab_bytes) >> 4) + ko;
-                    const uint64_t db = dc0 + (uint32_t)((sl * cb_slab_bytes + nh * 256 * 128) >> 4) + ko;
-                    if (leader) umma_tf32_ss(tmem_base + nh * 256, da, db, id, ks > 0);
+            if (leader) {
+                const uint32_t xoff = (uint32_t)((b * kSlabs * x_slab) >> 4);
+                const uint32_t eoff = (uint32_t)((half * KH * 128) >> 4);
+                bool first = true;
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    const uint64_t da = (p == 1 ? dxl : dxh) + xoff;
+                    const uint64_t db = (p == 2 ? del : deh) + eoff;
+#pragma unroll
+                    for (int kk = 0; kk < ((WM_VQ_EXP & 2) ? 0 : D / 16); ++kk) {
+                        const uint32_t sl = (uint32_t)(kk >> 2), ko = (uint32_t)((kk & 3) * 2);
+                        umma_bf16_ss(tmem_base + half * 256, da + sl * (uint32_t)(x_slab >> 4) + ko,
+                                     db + sl * (uint32_t)(e_slab >> 4) + ko, idesc, first ? 0u : 1u);
+                        first = false;
+                    }
                 }
+                umma_commit(&bar_full[half]);
+                umma_commit(&bar_xfree[b]);                               // (both halves' commits free operand buffer b)
             }
-            if (leader) umma_commit(bar_mma);
-        }
-        // |x|^2 of this row while the MMAs run (each half takes half of the channels)
-        mbar_wait(&bar_x[st], (it >> 1) & 1);
-        float xn2 = 0.f;
-        for (int c4 = half; c4 < D / 4; c4 += 2) {
-            const float4 v = sw_vec4(xt, x_slab_bytes, row, c4);
-            xn2 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        }
-        sXch[half * 128 + row] = xn2;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-        xn2 += sXch[(half ^ 1) * 128 + row];
-        // tf32 keeps 10 mantissa bits of each operand: |dot~ - dot| <= 2^-9 |x||e| (+ fp32 accumulation);
-        // eps bounds the error of t_k = |e_k|^2 - 2 dot_k with a 2x safety factor
-        const float eps = 0.0078125f * sqrtf(xn2) * emax + 1e-30f;
-        mbar_wait(bar_mma, it & 1);
-        tc_fence_after();
-        const int c_lo = half * (K / 2);                        // this thread's codes: [c_lo, c_lo + K/2), K % 32 == 0
-        const int nchunks = K / 32;                             // 16-column chunks per thread (<= 16)
-        // pass 1: t_k = |e_k|^2 - 2 dot_k; minimum per 16-column chunk and per row
-        float cmin[16];
-        float tmin = INFINITY;
+            __syncwarp();
+        };
+        if (issuer && my_tiles > 0) issue_tile(0);
+        for (int j = 0; j < my_tiles; ++j) {
+            const int b = j & 1;
+            const long n = ((long)(first_tile + j * stride)) * kTileM + row;
+            mbar_wait(&bar_full[half], j & 1);
+            tc_fence_after();
+            const float xn2 = sXn2[b * kTileM + row];
+            const uint64_t xx = pk2(xn2, xn2);
+            // two smallest keys of this half and the 16-column chunks they came from.  A key is the filtered distance's
+            // fp32 bits (positive, so they order like integers) with the column's position inside its chunk in the low 4
+            // bits: the comparison network sees distances truncated by 2^-19 relative, nothing more
+            uint32_t m1 = 0x7f800000u, m2 = 0x7f800000u;
+            int c1 = 0, c2 = 0;
+            uint32_t r0[16], r1[16];
+            auto scan16 = [&](const uint32_t (&r)[16], int c) {
+                uint32_t a1 = 0x7f800000u, a2 = 0x7f800000u;              // the chunk's two smallest
 #pragma unroll
-        for (int ci = 0; ci < 16; ++ci) {
-            cmin[ci] = INFINITY;
-            if (ci < nchunks) {
-                const int c = c_lo + ci * 16;
-                uint32_t r[16];
-                tmem_ld16(tmem_base + lane_sel + c, r);
-                float nk[16];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 v = *reinterpret_cast<const float4*>(sNorm + c + 4 * i);
-                    nk[4 * i] = v.x; nk[4 * i + 1] = v.y; nk[4 * i + 2] = v.z; nk[4 * i + 3] = v.w;
+                for (int i = 0; i < 8; ++i) {
+                    const float2 nn = *reinterpret_cast<const float2*>(nk + c * 16 + 2 * i);
+                    const uint64_t t2 = fadd2(fadd2(pk2u(r[2 * i], r[2 * i + 1]), xx), pk2(nn.x, nn.y));
+                    float ta, tb;
+                    upk2(t2, ta, tb);
+                    const uint32_t ka = (__float_as_uint(ta) & 0xfffffff0u) | (uint32_t)(2 * i);
+                    const uint32_t kb = (__float_as_uint(tb) & 0xfffffff0u) | (uint32_t)(2 * i + 1);
+                    const uint32_t lo = min(ka, kb), hi = max(ka, kb);
+                    a2 = (uint32_t)__vimin3_s32((int)a2, (int)hi, (int)max(a1, lo));
+                    a1 = min(a1, lo);
                 }
+                // merge (a1, a2) of chunk c into (m1, m2): the second smallest overall is min(m2, a2, max(m1, a1))
+                const bool first = a1 < m1;
+                const uint32_t loser = first ? m1 : a1;                  // max(m1, a1)
+                const int loser_c = first ? c1 : c;
+                const uint32_t rest = min(m2, a2);
+                const int rest_c = (a2 < m2) ? c : c2;
+                const bool l2 = loser < rest;
+                m2 = l2 ? loser : rest;
+                c2 = l2 ? loser_c : rest_c;
+                if (first) { m1 = a1; c1 = c; }
+            };
+            tmem_ld16(taddr, r0);
+            for (int c = 0; c < ((WM_VQ_EXP & 4) ? 0 : nchunk); c += 2) {
                 tmem_wait_ld();
-                float m0 = INFINITY, m1 = INFINITY;
-#pragma unroll
-                for (int i = 0; i < 16; i += 2) {
-                    m0 = fminf(m0, fmaf(-2.f, __uint_as_float(r[i]), nk[i]));
-                    m1 = fminf(m1, fmaf(-2.f, __uint_as_float(r[i + 1]), nk[i + 1]));
-                }
-                cmin[ci] = fminf(m0, m1);
-                tmin = fminf(tmin, cmin[ci]);
-            }
-        }
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");      // xn2 exchange reads are done
-        sXch[half * 128 + row] = tmin;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-        tmin = fminf(tmin, sXch[(half ^ 1) * 128 + row]);
-        const float thr = tmin + 2.f * eps;
-        // pass 2: only chunks that hold a candidate (t_k <= thr) are revisited.  Candidates are first
-        // ranked by their fp32 direct-form distance; fp64 is needed only for (near-)ties.
-        double best = INFINITY, second = INFINITY;
-        int best_k = 0x7fffffff;
-        // tcgen05.ld is warp-collective: whether a chunk is revisited is decided by a warp vote, and a lane
-        // that has nothing to do in it simply ends up with an empty candidate mask
-        auto scan = [&](auto zero, bool active) {                 // zero: 0.f -> fp32 arithmetic, 0.0 -> fp64
-            using acc_t = decltype(zero);
-            if (active) { best = INFINITY; second = INFINITY; best_k = 0x7fffffff; }
-#pragma unroll
-            for (int ci = 0; ci < 16; ++ci) {
-                if (ci < nchunks && __any_sync(0xffffffffu, active && cmin[ci] <= thr)) {
-                    const int c = c_lo + ci * 16;
-                    uint32_t r[16];
-                    tmem_ld16(tmem_base + lane_sel + c, r);
+                tmem_regs_ready(r0);
+                if (c + 1 < nchunk) tmem_ld16(taddr + (c + 1) * 16, r1);
+                scan16(r0, c);
+                if (c + 1 < nchunk) {
                     tmem_wait_ld();
-                    uint32_t cand = 0;
+                    tmem_regs_ready(r1);
+                    if (c + 2 < nchunk) tmem_ld16(taddr + (c + 2) * 16, r0);
+                    scan16(r1, c + 1);
+                }
+            }
+            const float t1 = __uint_as_float(m1 & 0xfffffff0u), t2nd = __uint_as_float(m2 & 0xfffffff0u);
+            const int k1 = half * KH + c1 * 16 + (int)(m1 & 15u), k2 = half * KH + c2 * 16 + (int)(m2 & 15u);
+            // window: rounding of the filter (2 eps) + the 4 key bits dropped from each of the two distances
+            const float win = 6.103515625e-5f * sqrtf(xn2) * emax + 3.9e-6f * t2nd + 1e-30f;
+            const bool close2 = !(WM_VQ_EXP & 1) && (n < prm.N) && (t2nd - t1 <= win);
+            uint32_t extra = 0;                                           // 1: the runner-up is a candidate too; 2: more than two are
+#if WM_VQ_EXP & 32
+            { const unsigned m = __ballot_sync(0xffffffffu, close2); if (lane == 0) { atomicAdd(&g_vq_dbg[2], (unsigned long long)__popc(m)); atomicAdd(&g_vq_dbg[3], m ? 1ull : 0ull); } }
+#endif
+            if (__any_sync(0xffffffffu, close2) && !((WM_VQ_EXP & 128) && (prm.N >> 40) == 0)) {
+                // rare (about one row in a thousand): count the codes of this half inside the window while the scores are
+                // still ours.  Two: the writer settles k1 against k2 exactly.  More: it re-scans the half exactly.
+                const float thr = t1 + win;
+                int cnt = 0;
+                for (int c = 0; c < nchunk; ++c) {
+                    uint32_t r[16];
+                    tmem_ld16(taddr + c * 16, r);
+                    tmem_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (fmaf(-2.f, __uint_as_float(r[i]), sNorm[c + i]) <= thr) cand |= 1u << i;
-                    if (!active) cand = 0;
-                    while (cand) {
-                        const int i = __ffs(cand) - 1;
-                        cand &= cand - 1;
-                        const int k = c + i;
-                        acc_t a = zero;
-                        for (int c4 = 0; c4 < D / 4; ++c4) {
-                            const float4 xv = sw_vec4(xt, x_slab_bytes, row, c4);
-                            const float4 ev = sw_vec4(sCB, cb_slab_bytes, k, c4);
-                            const acc_t d0 = (acc_t)xv.x - (acc_t)ev.x, d1 = (acc_t)xv.y - (acc_t)ev.y;
-                            const acc_t d2 = (acc_t)xv.z - (acc_t)ev.z, d3 = (acc_t)xv.w - (acc_t)ev.w;
-                            a = fma(d0, d0, a); a = fma(d1, d1, a); a = fma(d2, d2, a); a = fma(d3, d3, a);
-                        }
-                        const double ad = (double)a;
-                        if (ad < best) { second = best; best = ad; best_k = k; }     // ascending codes: first minimum kept
-                        else if (ad < second) second = ad;
+                    for (int i = 0; i < 16; ++i) cnt += ((__uint_as_float(r[i]) + xn2) + nk[c * 16 + i]) <= thr;
+                }
+                if (close2) extra = cnt > 2 ? 2u : 1u;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_free[half]);                    // this half may be refilled
+            if (issuer && j + 1 < my_tiles) issue_tile(j + 1);
+            uint4* res = reinterpret_cast<uint4*>(sRes) + (b * 2 + half) * kTileM + row;
+            *res = make_uint4(__float_as_uint(t1), (uint32_t)k1, (uint32_t)k2, extra);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_res[b]);
+        }
+    } else {
+        // =============================== loaders / writers (warps 8-15) ===============================================
+        // Coalesced mapping: a warp owns 16 rows; one 16-byte access per lane covers TWO whole rows (16 lanes x 16 B = one
+        // 256-byte fp32 row), so instruction i touches rows 2i, 2i+1 of the warp and a lane holds fp32 chunk `ch` (4
+        // channels) of 8 rows.  (One thread per row would put every lane on its own 128-byte line: 16x the L1 wavefronts.)
+        constexpr int kRowsPerLane = 8;
+        static_assert(D == 64, "row = 16 lanes x float4");
+        const int wrow0 = (warp - 8) * 16, sub = lane >> 4, ch = lane & 15;
+        float4 xv[kRowsPerLane];                           // tile being loaded (two tiles ahead of its output)
+        auto tile_base = [&](int j) { return ((long)(first_tile + j * stride)) * kTileM; };
+        auto load_rows = [&](int j, float4 (&dst)[kRowsPerLane]) {
+            const long n0 = tile_base(j) + wrow0 + sub;
+#pragma unroll
+            for (int i = 0; i < kRowsPerLane; ++i) {
+                const long n = n0 + 2 * i;
+                dst[i] = n < prm.N ? __ldg(reinterpret_cast<const float4*>(prm.x + (n * L + l) * (long)D) + ch)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto convert_rows = [&](int j) {                   // registers -> bf16 hi / lo operand tiles of buffer j & 1, |x|^2
+            const int b = j & 1;
+            if (j >= 2) mbar_wait(&bar_xfree[b], ((j - 2) >> 1) & 1);       // the MMAs of tile j-2 have read this buffer
+#pragma unroll
+            for (int i = 0; i < kRowsPerLane; ++i) {
+                const int row = wrow0 + 2 * i + sub;
+                const float v[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+                uint16_t h[4], lo[4];
+                float xn2 = 0.f;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    split_bf16(v[e], h[e], lo[e]);
+                    xn2 = fmaf(v[e], v[e], xn2);
+                }
+                // fp32 chunk ch (4 channels) = half `ch & 1` of the 16-byte bf16 chunk ch >> 1
+                const uint32_t off = (uint32_t)(b * kSlabs * x_slab) + sw128(row, ch >> 1) + (uint32_t)(ch & 1) * 8u;
+                *reinterpret_cast<uint2*>(sXhi + off) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+                *reinterpret_cast<uint2*>(sXlo + off) = make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 16), (uint32_t)lo[2] | ((uint32_t)lo[3] << 16));
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) xn2 += __shfl_xor_sync(0xffffffffu, xn2, o);     // over the row's 16 lanes
+                if (ch == 0) sXn2[b * kTileM + row] = xn2;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_xready[b]);
+        };
+        auto output_rows = [&](int j) {                    // merge the halves, gather the winner, write the outputs
+            const int b = j & 1;
+            float4 xo[kRowsPerLane];
+            load_rows(j, xo);                              // re-read (L2 hit), in flight while waiting for the scanners
+            mbar_wait(&bar_res[b], (j >> 1) & 1);
+            const bool want_q = !(WM_VQ_EXP & 8) && (prm.quantized != nullptr || prm.sq_err != nullptr);
+            uint32_t redo = 0;                             // rows of this warp (bit = row - wrow0) whose winner needs the exact path
+#pragma unroll
+            for (int i = 0; i < kRowsPerLane; ++i) {
+                const int row = wrow0 + 2 * i + sub;
+                const long n = tile_base(j) + row;
+                const bool valid = n < prm.N;
+                const uint4 ra = reinterpret_cast<const uint4*>(sRes)[(b * 2 + 0) * kTileM + row];
+                const uint4 rb = reinterpret_cast<const uint4*>(sRes)[(b * 2 + 1) * kTileM + row];
+                const float ta = __uint_as_float(ra.x), tb = __uint_as_float(rb.x);
+                const float xn2 = sXn2[b * kTileM + row];
+                int best = ta <= tb ? (int)ra.y : (int)rb.y;
+                const float win = 6.103515625e-5f * sqrtf(xn2) * emax + 3.9e-6f * fmaxf(ta, tb) + 1e-30f;
+                const bool a_in = ta <= tb + win, b_in = tb <= ta + win;   // does the half hold a candidate for the row minimum?
+                const bool need = valid && !(WM_VQ_EXP & 16) && ((a_in && b_in) || (a_in && ra.w) || (b_in && rb.w));
+                redo |= need ? (1u << (2 * i + sub)) : 0u;  // settled exactly after the loop (rare); the row is rewritten then
+                if (valid && ch == 0) prm.idx[n * L + l] = (int64_t)best;
+                if (want_q) {
+                    const float4 ev = __ldg(reinterpret_cast<const float4*>(cbl + (long)(valid ? best : 0) * D) + ch);
+                    const float d0 = ev.x - xo[i].x, d1 = ev.y - xo[i].y, d2 = ev.z - xo[i].z, d3 = ev.w - xo[i].w;
+                    float err = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
+                    if (prm.quantized != nullptr && valid)
+                        reinterpret_cast<float4*>(prm.quantized + (n * L + l) * (long)D)[ch] =
+                            make_float4(xo[i].x + d0, xo[i].y + d1, xo[i].z + d2, xo[i].w + d3);
+                    if (prm.sq_err != nullptr) {
+#pragma unroll
+                        for (int o = 8; o > 0; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
+                        if (ch == 0 && valid) prm.sq_err[n * L + l] = err;
                     }
                 }
             }
-        };
-        auto merge_halves = [&](int slot_parity) {                 // combine with the other half of the row
-            double* xd = sXd + slot_parity * 512;
-            int* xi = sXi + slot_parity * 256;
-            xd[half * 128 + row] = best;
-            xd[256 + half * 128 + row] = second;
-            xi[half * 128 + row] = best_k;
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-            const double ob = xd[(half ^ 1) * 128 + row], os = xd[256 + (half ^ 1) * 128 + row];
-            const int ok = xi[(half ^ 1) * 128 + row];
-            if (ob < best || (ob == best && ok < best_k)) { second = fmin(best, os); best = ob; best_k = ok; }
-            else second = fmin(second, ob);
-        };
-        scan(0.f, true);
-        merge_halves(0);
-        // fp32 direct form is within (D+2) 2^-24 relative of the exact distance: 4x safety band
-        const double band = 4.0 * (double)(D + 2) * 5.9604645e-8;
-        const bool ambiguous = second <= best * (1.0 + band) + 1e-37;
-        if (__any_sync(0xffffffffu, ambiguous)) {                  // both warps of the quadrant see the same rows
-            scan(0.0, ambiguous);
-            merge_halves(1);
-        }
-        tc_fence_before();
-        __syncthreads();                                           // every TMEM read of this tile is done
-        // ---- epilogue: index, straight-through value, squared error ---------------------------------
-        const long n = (long)tile * kTileM + row;
-        if (n < prm.N) {
-            if (half == 0) prm.idx[n * L + l] = (int64_t)best_k;
-            float err = 0.f;
-            for (int c4 = half; c4 < D / 4; c4 += 2) {
-                const float4 xv = sw_vec4(xt, x_slab_bytes, row, c4);
-                const float4 ev = sw_vec4(sCB, cb_slab_bytes, best_k, c4);
-                const float d0 = ev.x - xv.x, d1 = ev.y - xv.y, d2 = ev.z - xv.z, d3 = ev.w - xv.w;
-                err = fmaf(d0, d0, err); err = fmaf(d1, d1, err); err = fmaf(d2, d2, err); err = fmaf(d3, d3, err);
-                if (prm.quantized != nullptr)
-                    *reinterpret_cast<float4*>(prm.quantized + (n * L + l) * (long)D + c4 * 4) =
-                        make_float4(xv.x + d0, xv.y + d1, xv.z + d2, xv.w + d3);
+            // ---- rare: rows whose candidates lie inside the filter's window are settled exactly by the whole warp and rewritten
+            redo = __reduce_or_sync(0xffffffffu, redo);
+#if WM_VQ_EXP & 64
+            redo &= (uint32_t)(prm.N >> 40);               // timing experiment: never run the exact path (all code kept)
+#endif
+#if WM_VQ_EXP & 32
+            if (lane == 0) { atomicAdd(&g_vq_dbg[0], (unsigned long long)__popc(redo)); atomicAdd(&g_vq_dbg[1], 16ull); }
+#endif
+            while (redo) {
+                const int rr = __ffs(redo) - 1;
+                redo &= redo - 1;
+                const int row = wrow0 + rr;
+                const long n = tile_base(j) + row;
+                const uint4 ra = reinterpret_cast<const uint4*>(sRes)[(b * 2 + 0) * kTileM + row];
+                const uint4 rb = reinterpret_cast<const uint4*>(sRes)[(b * 2 + 1) * kTileM + row];
+                const float ta = __uint_as_float(ra.x), tb = __uint_as_float(rb.x);
+                const float win = 6.103515625e-5f * sqrtf(sXn2[b * kTileM + row]) * emax + 3.9e-6f * fmaxf(ta, tb) + 1e-30f;
+                const float* xr = prm.x + (n * L + l) * (long)D;
+                const int best = settle_exact_warp<D>(xr, cbl, ra, rb, ta <= tb + win, tb <= ta + win, KH, lane);
+                if (lane == 0) prm.idx[n * L + l] = (int64_t)best;
+                if (want_q && lane < 16) {
+                    const float4 xq = __ldg(reinterpret_cast<const float4*>(xr) + lane);
+                    const float4 ev = __ldg(reinterpret_cast<const float4*>(cbl + (long)best * D) + lane);
+                    const float d0 = ev.x - xq.x, d1 = ev.y - xq.y, d2 = ev.z - xq.z, d3 = ev.w - xq.w;
+                    float err = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
+                    if (prm.quantized != nullptr)
+                        reinterpret_cast<float4*>(prm.quantized + (n * L + l) * (long)D)[lane] = make_float4(xq.x + d0, xq.y + d1, xq.z + d2, xq.w + d3);
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) err += __shfl_xor_sync(0x0000ffffu, err, o);
+                    if (prm.sq_err != nullptr && lane == 0) prm.sq_err[n * L + l] = err;
+                }
+                __syncwarp();
             }
-            if (prm.sq_err != nullptr) {
-                sXch[half * 128 + row] = err;
-            }
+        };
+        // software pipeline: load two tiles ahead of the output
+        if (my_tiles > 0) { load_rows(0, xv); convert_rows(0); }
+        if (my_tiles > 1) { load_rows(1, xv); convert_rows(1); }
+        for (int j = 0; j < my_tiles; ++j) {
+            if (j + 2 < my_tiles) load_rows(j + 2, xv);    // global loads in flight across the output of tile j
+            output_rows(j);
+            if (j + 2 < my_tiles) convert_rows(j + 2);
         }
-        __syncthreads();                                           // x stage fully consumed
-        if (prm.sq_err != nullptr && half == 0 && n < prm.N)
-            prm.sq_err[n * L + l] = sXch[row] + sXch[128 + row];
-        if (warp == 0 && tile + 2 * stride < prm.tiles) issue_x_load(it + 2, tile + 2 * stride);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
-static int cb_box_rows(int K) { return K % 256 == 0 ? 256 : K % 128 == 0 ? 128 : K % 64 == 0 ? 64 : 32; }
+static size_t smem_bytes(int K, int D) {
+    const int slabs = D / 64;
+    return 1024 + 2ul * slabs * K * 128 + 4ul * slabs * kTileM * 128 + (size_t)K * 4 + 2 * kTileM * 4 + 2 * 2 * kTileM * 16 + 128 + 256;
+}
 
 }  // namespace vq
 
+#if WM_VQ_EXP & 32
+extern "C" __attribute__((visibility("default"))) int wm_vq_debug_read(unsigned long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, vq::g_vq_dbg, sizeof(unsigned long long) * 4);
+}
+#endif
+
 bool vq_tc_supported(long N, int L, int K, int D) {
-    if (D % 32 != 0 || D > 128 || K % 32 != 0 || K > 512 || K < 32) return false;
-    const size_t smem = 1024 + (size_t)K * D * 4 + 2ul * 128 * D * 4 + (size_t)K * 4 + 16384;
-    return smem <= 227ul * 1024 && N >= 1 && L <= 65535;
+    if (D != 64) return false;                             // one 64-channel (128-byte) operand slab; the codebook's hi / lo
+                                                           // tiles of a 128-channel code would not fit next to the latents
+    if (K % 32 != 0 || K > 512 || K < 32) return false;    // two halves of <= 256 codes, multiples of 16
+    return vq::smem_bytes(K, D) <= 227ul * 1024 && N >= 1 && L <= 65535;
 }
 
 int vq_nearest_tc(const void* x, const void* cb, int64_t* idx, void* quantized, float* sq_err, long N, int L, int K,
                   int D, cudaStream_t st) {
     using namespace vq;
-    CUtensorMap mx, mc;
-    // x viewed as [N rows, L*D cols] (row stride L*D floats); the kernel offsets columns by l*D
-    const int box = cb_box_rows(K);
-    if (int rc = make_tensor_map_2d_f32(&mx, x, (uint64_t)L * D, (uint64_t)N, (uint64_t)L * D * 4, 128)) return rc;
-    if (int rc = make_tensor_map_2d_f32(&mc, cb, (uint64_t)D, (uint64_t)L * K, (uint64_t)D * 4, (uint32_t)box)) return rc;
     Params prm{static_cast<const float*>(x), static_cast<const float*>(cb), idx, static_cast<float*>(quantized), sq_err,
-               N, L, K, D, (int)((N + kTileM - 1) / kTileM), box};
-    const size_t smem = 1024 + (size_t)K * D * 4 + 2ul * 128 * D * 4 + (size_t)K * 4 + 16384;
-    WM_CUDA_CHECK(cudaFuncSetAttribute(vq_nearest_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int ctas = prm.tiles < 148 ? prm.tiles : 148;
-    if (L > 1 && ctas > 148 / L) ctas = 148 / L > 0 ? 148 / L : 1;
-    vq_nearest_tc_kernel<<<dim3((unsigned)ctas, (unsigned)L), kThreads, smem, st>>>(mx, mc, prm);
+               N, L, K, D, (int)((N + kTileM - 1) / kTileM)};
+    const size_t smem = smem_bytes(K, D);
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int ctas = prm.tiles < sms ? prm.tiles : sms;
+    if (L > 1 && ctas > sms / L) ctas = sms / L > 0 ? sms / L : 1;
+    const dim3 grid((unsigned)ctas, (unsigned)L);
+    WM_CUDA_CHECK(cudaFuncSetAttribute(vq_nearest_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vq_nearest_tc_kernel<64><<<grid, kThreads, smem, st>>>(prm);
     WM_CUDA_CHECK(cudaGetLastError());
     return WM_OK;
 }
