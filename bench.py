@@ -2,7 +2,8 @@
 """Benchmark of the local-3D-attention / VQ denoiser hot path (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path: the unmodified modules from
+                                                             # /root/reference when that tree exists, else the oracle port
 
 A *step* is one denoiser training step (corruption, forward, CE, backward, gradient
 all-reduce, AdamW) over one batch of synthetic clips of BASELINE config 3: 16 frames x
@@ -36,7 +37,7 @@ UNIT = 'clips/s'
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--clips-per-gpu', type=int, default=32)
@@ -62,10 +63,49 @@ def peaks():
 
 
 # ------------------------------------------------------------------------ CPU reference arm
-def cpu_train_sample(steps, warmup, clips):
-    """Reference CPU path: the oracle's train_step (fp32, all host threads) on `clips` clips."""
+REF_DIR = '/root/reference/vq-video-diffusion'
+# measured in the build container (8-core Xeon, this commit): seconds per 1-clip config-3 train step
+PORT_VS_REFERENCE = 'oracle port 2.2 s/step vs unmodified reference modules 5.7 s/step on the 8-core build box'
+
+
+def _reference_step_fn(clips):
+    """One config-3 training step on the UNMODIFIED reference modules (local_3d_attention.py + a Linear head + AdamW, which
+    is all main.py:25-36,266-283,433 does), imported read-only from /root/reference.  None when that tree is absent
+    (it does not exist on the GPU box)."""
+    if not os.path.isdir(REF_DIR):
+        return None
+    try:
+        sys.path.insert(0, REF_DIR)
+        from local_3d_attention import Local3dAttentionTransformer   # noqa
+    except Exception:
+        return None
+    finally:
+        if REF_DIR in sys.path:
+            sys.path.remove(REF_DIR)
+    torch.manual_seed(42)
+    kw = dict(C3)
+    kw['num_classes'] = C3['num_classes'] + 1
+    tr = Local3dAttentionTransformer(**kw)
+    head = torch.nn.Linear(C3['dim'], C3['num_classes'])
+    opt = torch.optim.AdamW(list(tr.parameters()) + list(head.parameters()), lr=1e-4, weight_decay=1e-7)
+    from oracle import local3d as O
+
+    def step(tokens, r, gen):
+        corrupted, target = O.corrupt_last_frame(tokens, r, C3['num_classes'], gen=gen)
+        opt.zero_grad()
+        logits = head(tr(corrupted)[:, -1])
+        loss = torch.nn.functional.cross_entropy(logits.reshape(-1, C3['num_classes']), target.reshape(-1))
+        loss.backward()
+        opt.step()
+    return step
+
+
+def cpu_train_sample(steps, warmup, clips, allow_reference=True):
+    """Reference CPU path on `clips` clips per step, fp32, all host threads: the reference's own modules when
+    /root/reference is importable, else the oracle's train_step.  Returns (seconds, steps, kind)."""
     from oracle import local3d as O
     torch.set_num_threads(os.cpu_count() or 1)
+    ref_step = _reference_step_fn(clips) if allow_reference else None
     cfg = O.DenoiserConfig(**C3)
     p = O.init_denoiser_params(cfg, seed=42)
     state = {}
@@ -75,12 +115,15 @@ def cpu_train_sample(steps, warmup, clips):
         tokens = torch.randint(0, cfg.num_classes, (clips, *cfg.data_shape), generator=g)
         r = torch.rand(clips, generator=g)
         t0 = time.perf_counter()
-        corrupted, target = O.corrupt_last_frame(tokens, r, cfg.num_classes, gen=g)
-        O.train_step(p, state, it + 1, corrupted, target, cfg)
+        if ref_step is not None:
+            ref_step(tokens, r, g)
+        else:
+            corrupted, target = O.corrupt_last_frame(tokens, r, cfg.num_classes, gen=g)
+            O.train_step(p, state, it + 1, corrupted, target, cfg)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    return sum(times), len(times)
+    return sum(times), len(times), ('reference' if ref_step is not None else 'port')
 
 
 def run_reference(args):
@@ -88,14 +131,17 @@ def run_reference(args):
     if rank != 0:
         return
     clips = 1
-    total, n = cpu_train_sample(args.steps, min(args.warmup, 1), clips)
+    steps = min(args.steps, 40)                  # bounded sample: the whole run must end within a few minutes
+    total, n, kind = cpu_train_sample(steps, min(args.warmup, 1), clips)
     value = clips * n / total
     cores = os.cpu_count() or 1
-    sample = f'{n} steps x {clips} clip(s) of config 3, fp32, oracle port of the reference modules on {cores} host threads'
+    what = 'the unmodified reference modules (/root/reference)' if kind == 'reference' else \
+        f'the oracle port of the reference modules ({PORT_VS_REFERENCE})'
+    sample = f'{n} steps x {clips} clip(s) of config 3, fp32, {what} on {cores} host threads'
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': n,
             'warmup': min(args.warmup, 1), 'ms_per_step': 1e3 * total / n, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic', 'config': config_dict(args.gpus, clips),
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
@@ -186,7 +232,7 @@ def micro_benchmarks(dev, clips, hbm_gbs, tf_peak):
                    'tensor_cores': ops.uses_tensor_cores(S, H, W, heads, d, ext)}
     # roofline of the dominant kernel of the path: attention forward+backward, HBM-bound algorithmically
     ach = bytes_fb / ((t_f + t_b) * 1e-3) / 1e9
-    out['roofline'] = {'kernel': 'local-3D attention core fwd+bwd (3 launches)', 'bound': 'hbm', 'achieved': ach,
+    out['roofline'] = {'kernel': 'local-3D attention core fwd+bwd (l3d_fwd_tc + fix-up scan, delta, dQ, dK/dV)', 'bound': 'hbm', 'achieved': ach,
                        'peak': hbm_gbs, 'unit': 'GB/s', 'frac': ach / hbm_gbs, 'traffic': None,
                        'algorithmic_bytes_per_launch_set': bytes_fb,
                        'note': 'algorithmic bytes = 12*inner*2 B + 12*heads B per token (q,k,v,o,dO read; o,dq,dk,dv written)'}
@@ -209,35 +255,71 @@ def micro_benchmarks(dev, clips, hbm_gbs, tf_peak):
     t_v = time_kernel(lambda: ops.vq_nearest(x, cb), 5)
     out['vq'] = {'shape': f'{n} latents x 64 vs 512 codes (fp32, bit-exact indices)', 'ms': t_v,
                  'latents_per_s': n / (t_v * 1e-3), 'algorithmic_gbs': n * 524 / (t_v * 1e-3) / 1e9,
-                 'kernel': 'tf32 tcgen05 filter + exact re-check'}
+                 'kernel': 'split-bf16 tcgen05 filter (3 products) + exact settlement of near-ties'}
+    ach_v = n * 524 / (t_v * 1e-3) / 1e9
+    out['roofline_vq'] = {'kernel': 'vq_nearest_tc_kernel', 'bound': 'hbm', 'achieved': ach_v, 'peak': hbm_gbs, 'unit': 'GB/s',
+                          'frac': ach_v / hbm_gbs, 'traffic': None,
+                          'note': 'algorithmic bytes = 4D read + 4D straight-through value + 8 index + 4 error = 524 B per latent (D = 64)'}
     return out
 
 
-def sampling_benchmark(dev, model, clips):
-    """Config 5 per GPU: mask/replace sampling of the next frame (30 denoiser forwards) for `clips` clips,
-    then VQ decode of the sampled latents (codebook gather, 512 x 64)."""
+def config4_transformer_benchmark(dev, tf_peak, clips=1, iters=3):
+    """BASELINE config 4 (X1): Local3dAttentionTransformer at the sparse_diffusion sizing -- 32x32x32 tokens, dim 512,
+    4 heads x 128, depth 8, mlp 1024, window 5x7x7 (minecraft/sparse_diffusion.py:233,250-253,362 on
+    minecraft/main2.py:20,31) -- forward + backward of a mean loss, bf16, `clips` clip(s)."""
+    import world_modelz_b200 as wm
+    torch.manual_seed(4)
+    m = wm.Local3dAttentionTransformer(data_shape=(32, 32, 32), dim=512, num_classes=1024, extents=(2, 3, 3), depth=8,
+                                       heads=4, dim_head=128, mlp_dim=1024).to(dev).bfloat16()
+    tokens = torch.randint(0, 1024, (clips, 32, 32, 32), device=dev)
+
+    def step():
+        for p in m.parameters():
+            p.grad = None
+        m(tokens).float().mean().backward()
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    # per token-layer: 4 projections + 2 MLP GEMMs (2 flop/MAC) + attention core 4*Wn*inner; x3 for fwd+bwd
+    flop_clip = 3.0 * 32768 * 8 * (2 * (4 * 512 * 512 + 2 * 512 * 1024) + 4 * 245 * 512)
+    del m
+    return {'shape': f'{clips} x 32x32x32 tokens, dim 512, 4 heads x 128, depth 8, mlp 1024, window 245', 'fwd_bwd_ms': ms,
+            'clips_per_s': clips / (ms * 1e-3), 'tokens_per_s': clips * 32768 / (ms * 1e-3),
+            'model_tflops': clips * flop_clip / (ms * 1e-3) / 1e12, 'model_tflop_per_clip': flop_clip / 1e12,
+            'frac_of_bf16_peak': clips * flop_clip / (ms * 1e-3) / 1e12 / tf_peak}
+
+
+def sampling_benchmark(dev, model, clips, world):
+    """Config 5, this rank's shard: `clips` clips x num_steps = 4 new frames (main.py:161 eval_timesteps), each denoised in
+    30 mask/replace iterations (one wm_sample_step + one denoiser forward per iteration, captured once), every frame
+    decoded by the VQ auto-encoder (codebook gather + conv decoder, 64x64 output).  Clips are independent: the 64-clip
+    job is batch-sharded over the ranks with no collective; the caller reduces the time with MAX over ranks."""
     import world_modelz_b200 as wm
     K = C3['num_classes']
-    vq = wm.VectorQuantizerEMA(64, K).to(dev)
+    torch.manual_seed(7)
+    ae = wm.VqAutoEncoder(64, K, downscale_steps=2, hidden_planes=128, in_channels=1).to(dev).eval()
     tokens = torch.randint(0, K, (clips, *C3['data_shape']), device=dev)
-    tokens[:, -1] = K
     model.eval()
-    out = {}
-    for graph in (False, True):
-        wm.sample_next_frame(model, tokens, iterations=2, use_cuda_graph=graph)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        frame = wm.sample_next_frame(model, tokens, iterations=30, use_cuda_graph=graph)
-        latents = vq.decode(frame)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        out['cuda_graph' if graph else 'eager'] = {'ms_per_frame': ms, 'clips_per_s': clips / (ms * 1e-3)}
+    num_steps = 4
+    wm.sample_frames(model, tokens, num_steps=1, iterations=30, decoder=ae, use_cuda_graph=True)        # capture + warm-up
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    frames, decoded = wm.sample_frames(model, tokens, num_steps=num_steps, iterations=30, decoder=ae, use_cuda_graph=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
     model.train()
-    out.update({'clips': clips, 'iterations': 30, 'decoded_latents_shape': list(latents.shape),
-                'tokens_ok': bool((frame >= 0).all().item() and (frame < K).all().item())})
-    return out
+    ok = bool((frames >= 0).all().item() and (frames < K).all().item() and torch.isfinite(decoded[-1]).all().item())
+    return ms, {'clips_per_gpu': clips, 'frames_per_clip': num_steps, 'iterations': 30,
+                'decoded_frame_shape': list(decoded[-1].shape), 'tokens_ok': ok}
 
 
 class StdoutGuard:
@@ -367,6 +449,17 @@ def run_b200(args):
     ms_e2e, _, _ = timed(run_e2e, args.steps)
     dbg(f'timed e2e arm: {ms_e2e:.1f} ms')
 
+    # --- config 5 on EVERY rank: 8 clips per GPU, batch-sharded, no collective; time = max over ranks ---------------
+    samp = None
+    if not args.no_micro:
+        sync_all()
+        samp_ms, samp = sampling_benchmark(dev, model, 8, world)
+        t_ms = torch.tensor([samp_ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        samp.update({'global_clips': 8 * world, 'ms': t_ms.item(),
+                     'clips_per_s': 8 * world / (t_ms.item() * 1e-3),
+                     'frames_per_s': 8 * world * samp['frames_per_clip'] / (t_ms.item() * 1e-3)})
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -389,21 +482,29 @@ def run_b200(args):
     if not args.no_micro:
         micro = micro_benchmarks(dev, B, hbm_gbs, tf_peak)
         line['roofline'] = micro.pop('roofline')
-        traffic_file = os.path.join(ROOT, 'profiles', 'ncu_traffic_r1.json')
-        if os.path.exists(traffic_file):      # dram__bytes_read+write of the three attention kernels, ncu --set full, same shape
+        # DRAM traffic is not measurable inside an un-profiled run: it comes from the committed `ncu --set full` capture of
+        # the same kernels at the same shape, labelled with the commit it was taken at
+        traffic_file = os.path.join(ROOT, 'profiles', 'ncu_traffic_r2.json')
+        if os.path.exists(traffic_file):
             tr = json.load(open(traffic_file))
             if tr.get('clips') == B:
                 line['roofline']['traffic'] = tr['fwd_bwd_dram_bytes']
                 line['roofline']['traffic_source'] = tr['source']
+                line['roofline']['traffic_commit'] = tr.get('commit')
+            if 'vq_dram_bytes' in tr:
+                micro['roofline_vq']['traffic'] = tr['vq_dram_bytes']
+                micro['roofline_vq']['traffic_commit'] = tr.get('commit')
         line.update(micro)
-        line['sampling_config5'] = sampling_benchmark(dev, model, 8)
+        line['sampling_config5'] = samp
+        line['transformer_config4'] = config4_transformer_benchmark(dev, tf_peak)
     else:
         line['roofline'] = None
     if world == 1 and not args.no_cpu_baseline:
-        total, n = cpu_train_sample(2, 1, 1)
+        total, n, kind = cpu_train_sample(6, 1, 1)
         cores = os.cpu_count() or 1
-        line['cpu_baseline'] = {'value': n / total, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                                'sample': f'{n} steps x 1 clip of config 3, fp32, oracle port on {cores} host threads'}
+        what = 'unmodified reference modules' if kind == 'reference' else f'oracle port ({PORT_VS_REFERENCE})'
+        line['cpu_baseline'] = {'value': n / total, 'unit': UNIT, 'cores': cores, 'kind': kind,
+                                'sample': f'{n} steps x 1 clip of config 3, fp32, {what} on {cores} host threads'}
     else:
         line['cpu_baseline'] = None
     guard.release()

@@ -59,7 +59,7 @@ def attn_forward(q, k, v, heads: int, extents: Sequence[int], scale: float, flag
     check(_lib.lib().wm_l3d_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(),
                                      B, S, H, W, heads, C // heads, *[int(e) for e in extents], float(scale),
                                      _dtype_code(q), flags, _stream()), 'wm_l3d_attn_fwd')
-    _count(1)
+    _count(2 if q.dtype == torch.bfloat16 and not (flags & FLAG_SIMT) else 1)     # tensor-core forward + its fix-up scan
     return out, lse
 
 
