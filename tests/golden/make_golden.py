@@ -226,6 +226,40 @@ def main():
                         decoded=dec.numpy(), recon=recon.numpy(), latent_loss=latent_loss.item(), ppl=ppl.item(),
                         z_train=z_train.numpy(), cfg=np.array([16, 64, 2, 32, 1]), **sd0)
 
+    # ---- 7. sparse-context denoiser (minecraft/sparse_diffusion.py:75-111 cannot be imported: minerl): the reference's
+    #         dense Transformer (minecraft/transformer.py) under the wrapper's attribute names ----
+    sys.path.insert(0, '/root/reference/minecraft')
+    import importlib
+    ref_tr = importlib.import_module('transformer')
+    sys.path.pop(0)
+
+    class RefSparse(torch.nn.Module):
+        def __init__(self, shape, dim, num_classes, depth, dim_head, mlp_dim, heads):
+            super().__init__()
+            S, H, W = shape
+            self.pos_emb_s = torch.nn.Embedding(S, dim)
+            self.pos_emb_h = torch.nn.Embedding(H, dim)
+            self.pos_emb_w = torch.nn.Embedding(W, dim)
+            self.embedding = torch.nn.Embedding(num_classes + 1, dim)
+            self.transformer = ref_tr.Transformer(dim=dim, depth=depth, heads=heads, dim_head=dim_head, mlp_dim=mlp_dim)
+            self.logit_proj = torch.nn.Linear(dim, num_classes)
+
+    torch.manual_seed(9)
+    shape, dim, K, depth, dh, mlp, heads = (4, 6, 6), 32, 20, 2, 16, 48, 2
+    sp = RefSparse(shape, dim, K, depth, dh, mlp, heads)
+    idx = torch.stack([torch.randperm(4 * 6 * 6)[:24] for _ in range(3)])
+    tok = torch.randint(0, K + 1, (3, 24))
+    tgt = torch.randint(0, K, (3, 24))
+    W_, H_ = shape[2], shape[1]
+    pos = sp.pos_emb_s(idx.div(H_ * W_, rounding_mode='trunc')) + sp.pos_emb_h(idx.div(W_, rounding_mode='trunc') % H_) \
+        + sp.pos_emb_w(idx % W_)                                                     # sparse_diffusion.py:100-105
+    logits = sp.logit_proj(sp.transformer(sp.embedding(tok) + pos))                  # :107-111
+    loss = torch.nn.functional.cross_entropy(logits.reshape(-1, K), tgt.reshape(-1))
+    loss.backward()
+    np.savez_compressed(os.path.join(HERE, 'sparse_small.npz'), tokens=tok.numpy(), indices=idx.numpy(), target=tgt.numpy(),
+                        logits=logits.detach().numpy(), loss=loss.item(), cfg=np.array([*shape, dim, K, depth, dh, mlp, heads]),
+                        **sd_np(sp), **{'grad/' + k: v.grad.numpy() for k, v in sp.named_parameters()})
+
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')

@@ -282,3 +282,21 @@ def test_graphed_sampler_reuses_one_capture():
     assert len(m.__dict__['_wm_sample_graphs']) == 1
     # the frames before the last one are inputs only: the sampler must not have modified the caller's tensor
     assert (tokens[:, -1] == 16).all()
+
+
+def test_sparse_context_model_against_reference_fixture():
+    """minecraft/sparse_diffusion.py:75-111 on the GPU: logits, loss and all parameter gradients of the drop-in
+    VqSparseDiffusionModel against the fixture written by the reference's dense Transformer (fp32)."""
+    from world_modelz_b200.sparse_diffusion import VqSparseDiffusionModel
+    f = load('sparse_small.npz')
+    c = [int(v) for v in f['cfg']]
+    m = VqSparseDiffusionModel(shape=tuple(c[0:3]), dim=c[3], num_classes=c[4], depth=c[5], dim_head=c[6], mlp_dim=c[7],
+                               heads=c[8]).to(DEV)
+    m.load_state_dict(state_dict_of(f))
+    logits = m(torch.from_numpy(f['tokens']).to(DEV), torch.from_numpy(f['indices']).to(DEV))
+    np.testing.assert_allclose(logits.detach().cpu().numpy(), f['logits'], rtol=1e-4, atol=2e-5)
+    loss = torch.nn.functional.cross_entropy(logits.reshape(-1, c[4]), torch.from_numpy(f['target']).to(DEV).reshape(-1))
+    assert abs(loss.item() - float(f['loss'])) < 1e-5
+    loss.backward()
+    for k, p in m.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), f['grad/' + k], rtol=2e-4, atol=5e-6, err_msg=k)

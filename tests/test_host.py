@@ -266,3 +266,31 @@ def test_bench_stdout_guard_keeps_native_banners_off_stdout(tmp_path):
     assert res.returncode == 0, res.stderr
     assert res.stdout.strip() == '{"ok": 1}'
     assert 'NCCL version banner' in res.stderr and 'guarded python print' in res.stderr
+
+
+def test_sparse_model_surface_and_position_samplers():
+    """VqSparseDiffusionModel keeps the reference's state_dict keys (strict load of its checkpoint); the position
+    samplers (sparse_diffusion.py:31-72) return unique in-window positions without per-sample loops."""
+    from world_modelz_b200.sparse_diffusion import VqSparseDiffusionModel, sample_flat_positions, sample_time_dependent
+    f = load('sparse_small.npz')
+    c = [int(v) for v in f['cfg']]
+    m = VqSparseDiffusionModel(shape=tuple(c[0:3]), dim=c[3], num_classes=c[4], depth=c[5], dim_head=c[6], mlp_dim=c[7],
+                               heads=c[8])
+    ref = state_dict_of(f)
+    assert set(m.state_dict()) == set(ref)
+    m.load_state_dict(ref)
+    torch.manual_seed(0)
+    p = sample_flat_positions(5, 100, 8, 6, 6, 'cpu')
+    assert p.shape == (5, 100) and p.min() >= 0 and p.max() < 288
+    flat = p.reshape(-1)
+    assert flat[:288].unique().numel() == 288                      # the first permutation-sized run has no repeats
+    t = torch.tensor([0.0, 0.3, 1.0, 0.6])
+    q = sample_time_dependent(4, 50, 8, 6, 6, t, 'cpu', o=torch.tensor([0.0, 0.99, 0.5, 0.2]))
+    assert q.shape == (4, 50)
+    for i in range(4):
+        assert q[i].unique().numel() == 50                         # without replacement
+    # t = 0: the window is min_sample_window = ceil(50 / 36) = 2 frames, starting at frame 0 (o = 0)
+    assert q[0].max() < 2 * 36
+    # window length grows with t (sparse_diffusion.py:58-59): floor(2 + t * 7), clamped to 6 frames
+    frames = [(q[i].div(36, rounding_mode='trunc')).unique().numel() for i in range(4)]
+    assert frames[0] <= 2 and frames[1] <= 4 and frames[2] <= 6

@@ -170,3 +170,20 @@ def test_vq_config2_latents():
     f = load('vq_c2_latents.npz')
     idx = OV.encode(f['latents'], f['embedding']).reshape(2, 16, 16)
     assert np.array_equal(idx, f['encode'])
+
+
+def test_sparse_denoiser_oracle_against_reference_fixture():
+    """oracle/sparse.py vs the reference's dense Transformer under the VqSparseDiffusionModel wrapper
+    (minecraft/sparse_diffusion.py:75-111): logits, loss and every parameter gradient."""
+    from oracle import sparse as OS
+    f = load('sparse_small.npz')
+    c = [int(v) for v in f['cfg']]
+    shape, dim, K, depth, dh, mlp, heads = tuple(c[0:3]), c[3], c[4], c[5], c[6], c[7], c[8]
+    p = {k: v.clone().requires_grad_(True) for k, v in state_dict_of(f).items()}
+    logits = OS.sparse_denoiser_forward(p, torch.from_numpy(f['tokens']), torch.from_numpy(f['indices']), shape, depth, heads)
+    np.testing.assert_allclose(logits.detach().numpy(), f['logits'], rtol=1e-4, atol=2e-5)
+    loss = torch.nn.functional.cross_entropy(logits.reshape(-1, K), torch.from_numpy(f['target']).reshape(-1))
+    assert abs(loss.item() - float(f['loss'])) < 1e-5
+    loss.backward()
+    for k, v in p.items():
+        np.testing.assert_allclose(v.grad.numpy(), f['grad/' + k], rtol=2e-4, atol=2e-6, err_msg=k)
