@@ -21,6 +21,17 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+    }
+    return cached[dev];
+}
+
 namespace {
 
 int check_attn(const AttnShape& s, int dtype, const void* const* ptrs, int nptrs) {

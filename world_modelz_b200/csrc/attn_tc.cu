@@ -27,8 +27,10 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include <mutex>
 #include <type_traits>
+#include <unordered_map>
 
 namespace wm {
 namespace tc {
@@ -51,8 +53,33 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
+// Descriptor cache: the library owns nothing but these -- encoded CUtensorMaps keyed on (pointer, shape,
+// box, swizzle).  A training step or a sampling loop presents the same few activations again and again (the caching
+// allocator hands the same blocks back), so eager launches skip the ~1-2 us driver call per map.  Mutex-guarded,
+// bounded (cleared when full); the map itself is passed to the kernel by value, so eviction is harmless.
+struct MapKey {
+    const void* base;
+    int v[11];
+    bool operator==(const MapKey& o) const { return base == o.base && memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = std::hash<const void*>()(k.base);
+        for (int i = 0; i < 11; ++i) h = h * 1000003u ^ (size_t)k.v[i];
+        return h;
+    }
+};
+static std::mutex g_map_mutex;
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+
 int make_tensor_map_5d(CUtensorMap* out, const void* base, int B, int S, int H, int W, int C, int box_c, int box_w,
                        int box_h, int box_s, int swizzle_bytes) {
+    const MapKey key{base, {B, S, H, W, C, box_c, box_w, box_h, box_s, swizzle_bytes, 5}};
+    {
+        std::lock_guard<std::mutex> lock(g_map_mutex);
+        auto it = g_map_cache.find(key);
+        if (it != g_map_cache.end()) { *out = it->second; return WM_OK; }
+    }
     EncodeTiledFn fn = encode_tiled_fn();
     if (fn == nullptr) return fail(WM_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)S, (cuuint64_t)B};
@@ -67,22 +94,9 @@ int make_tensor_map_5d(CUtensorMap* out, const void* base, int B, int S, int H, 
     if (r != CUDA_SUCCESS)
         return fail(WM_ECUDA, "cuTensorMapEncodeTiled failed (%d) for box (%d,%d,%d,%d) of [%d,%d,%d,%d,%d]", (int)r,
                     box_c, box_w, box_h, box_s, B, S, H, W, C);
-    return WM_OK;
-}
-
-// 2-D fp32 tensor map: [rows, cols] with an arbitrary row stride; box = (32 floats = 128 B, box_rows), 128B swizzle
-int make_tensor_map_2d_f32(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
-                           uint32_t box_rows) {
-    EncodeTiledFn fn = encode_tiled_fn();
-    if (fn == nullptr) return fail(WM_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)row_stride_bytes};
-    const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(WM_ECUDA, "cuTensorMapEncodeTiled (2-D fp32) failed (%d)", (int)r);
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    if (g_map_cache.size() >= 1024) g_map_cache.clear();
+    g_map_cache.emplace(key, *out);
     return WM_OK;
 }
 
@@ -134,7 +148,7 @@ bool make_plan(const AttnShape& s, Mode mode, Plan& best) {
         // heads per CTA (forward kernel): walk as many heads as possible while keeping the grid >= 4 CTAs per SM
         int hpc = 1;
         for (int h = s.heads; h >= 1; --h)
-            if (s.heads % h == 0 && (double)s.B * tiles * (s.heads / h) >= 4.0 * 148) { hpc = h; break; }
+            if (s.heads % h == 0 && (double)s.B * tiles * (s.heads / h) >= 4.0 * sm_count()) { hpc = h; break; }
         for (int nchunk = 1; nchunk <= p.hH; ++nchunk) {
             p.ch = (p.hH + nchunk - 1) / nchunk;
             p.nchunk = (p.hH + p.ch - 1) / p.ch;

@@ -522,7 +522,7 @@ using namespace wm;
 
 extern "C" int wm_reduce_blocks(long rows) {
     long b = (rows + 63) / 64;
-    if (b > 148L * 4) b = 148L * 4;
+    if (b > (long)sm_count() * 4) b = (long)sm_count() * 4;
     if (b < 1) b = 1;
     return (int)b;
 }
@@ -576,7 +576,7 @@ template <typename T>
 int launch_bias_gelu_fwd(const void* h, const void* bias, void* y, long rows, int C, cudaStream_t st) {
     const int lanes = 256 / (C / 8) > 0 ? 256 / (C / 8) : 1;
     long blocks = (rows + 4L * lanes - 1) / (4L * lanes);          // four rows per thread
-    if (blocks > 148L * 8) blocks = 148L * 8;
+    if (blocks > (long)sm_count() * 8) blocks = (long)sm_count() * 8;
     if (blocks < 1) blocks = 1;
     bias_gelu_fwd_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const T*>(h), static_cast<const T*>(bias),
                                                               static_cast<T*>(y), rows, C);

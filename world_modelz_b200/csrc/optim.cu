@@ -74,9 +74,7 @@ extern "C" int wm_adamw_step_norm(float* master, void* shadow, const void* grad,
     if (!master || !grad || !exp_avg || !exp_avg_sq || !dyn) return fail(WM_EINVAL, "wm_adamw_step: null pointer");
     if (grad_dtype != WM_DTYPE_BF16 && grad_dtype != WM_DTYPE_FP32) return fail(WM_EINVAL, "wm_adamw_step: grad dtype %d", grad_dtype);
     long blocks = (n + 255) / 256;
-    int sms = 148, dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (blocks > (long)sms * 16) blocks = (long)sms * 16;
+    if (blocks > (long)sm_count() * 16) blocks = (long)sm_count() * 16;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (grad_dtype == WM_DTYPE_BF16)
         adamw_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(master, static_cast<__nv_bfloat16*>(shadow),

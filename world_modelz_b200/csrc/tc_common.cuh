@@ -278,8 +278,5 @@ __device__ __forceinline__ uint32_t pack_bf16_2(uint64_t v) {   // (lo, hi) fp32
 int make_tensor_map_5d(CUtensorMap* out, const void* base, int B, int S, int H, int W, int C, int box_c, int box_w,
                        int box_h, int box_s, int swizzle_bytes);
 
-int make_tensor_map_2d_f32(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
-                           uint32_t box_rows);
-
 }  // namespace tc
 }  // namespace wm

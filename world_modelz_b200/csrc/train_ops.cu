@@ -179,9 +179,7 @@ extern "C" int wm_vq_stats(const void* x, const int64_t* idx, const float* sq_er
     if (N == 0) return WM_OK;
     if (!idx || !counts || (dw && !x)) return fail(WM_EINVAL, "wm_vq_stats: null pointer");
     if (L > 65535) return fail(WM_EUNSUPPORTED, "wm_vq_stats: L=%d", L);
-    int sms = 148;
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count();
     const size_t small = (size_t)2 * K * sizeof(float), full = small + (size_t)K * D * sizeof(float);
     const int dw_in_smem = (dw != nullptr && full <= 200 * 1024) ? 1 : 0;
     const size_t smem = dw_in_smem ? full : small;
@@ -201,7 +199,7 @@ extern "C" int wm_vq_onehot(const int64_t* idx, float* encodings, long rows, int
     if (rows == 0) return WM_OK;
     if (!idx || !encodings || !aligned16(encodings)) return fail(WM_EINVAL, "wm_vq_onehot: null or misaligned pointer");
     long blocks = (rows * (K / 4) + 255) / 256;
-    if (blocks > 148L * 32) blocks = 148L * 32;
+    if (blocks > (long)sm_count() * 32) blocks = (long)sm_count() * 32;
     vq_onehot_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(idx, encodings, rows, K);
     WM_CUDA_CHECK(cudaGetLastError());
     return WM_OK;

@@ -247,7 +247,8 @@ extern "C" int wm_vq_distance(const void* x, const void* codebook, float* dist, 
     if (N == 0) return WM_OK;
     if (!x || !codebook || !dist) return fail(WM_EINVAL, "wm_vq_distance: null pointer");
     const long total = N * L * (long)K;
-    const unsigned grid = (unsigned)((total + 255) / 256 < 148L * 32 ? (total + 255) / 256 : 148L * 32);
+    const long cap = (long)sm_count() * 32;
+    const unsigned grid = (unsigned)((total + 255) / 256 < cap ? (total + 255) / 256 : cap);
     vq_distance_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(x),
                                                                static_cast<const float*>(codebook), dist, N, L, K, D,
                                                                normalize ? 1.f / (float)D : 1.f);

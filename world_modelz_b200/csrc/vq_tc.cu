@@ -475,8 +475,7 @@ int vq_nearest_tc(const void* x, const void* cb, int64_t* idx, void* quantized, 
     Params prm{static_cast<const float*>(x), static_cast<const float*>(cb), idx, static_cast<float*>(quantized), sq_err,
                N, L, K, D, (int)((N + kTileM - 1) / kTileM)};
     const size_t smem = smem_bytes(K, D);
-    int sms = 148, dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count();
     int ctas = prm.tiles < sms ? prm.tiles : sms;
     if (L > 1 && ctas > sms / L) ctas = sms / L > 0 ? sms / L : 1;
     const dim3 grid((unsigned)ctas, (unsigned)L);

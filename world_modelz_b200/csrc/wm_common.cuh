@@ -36,6 +36,8 @@ struct AttnShape {
     __host__ __device__ int window() const { return wS() * wH() * wW(); }
 };
 
+int sm_count();                                  // multiprocessors of the current device (cached per device)
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- kernel families (defined in attn_simt.cu / attn_tc.cu) ----------------------------
