@@ -58,7 +58,7 @@ extern "C" {
 #define WM_API
 #endif
 
-#define WM_B200_VERSION 110          /* major*100 + minor */
+#define WM_B200_VERSION 120          /* major*100 + minor */
 
 /* dtype of q/k/v/o and their gradients */
 #define WM_DTYPE_BF16 0              /* tensor-core path (tcgen05), fp32 accumulate   */
@@ -96,6 +96,19 @@ WM_API int wm_l3d_attn_bwd(const void* q, const void* k, const void* v, const vo
                     const void* dout, void* dq, void* dk, void* dv, float* delta,
                     int B, int S, int H, int W, int heads, int dim_head,
                     int eS, int eH, int eW, float scale, int dtype, int flags, void* stream);
+
+/* The same two calls for operands that live side by side in the output of a MERGED projection (to_k and to_v
+ * of local_3d_attention.py:106-107 evaluated as one GEMM over the normalised input, N = 2*heads*dim_head): k and v
+ * (and dk, dv) are channel slices whose consecutive tokens are ld_kv elements apart, q (and dq) ld_q elements;
+ * 0 means heads*dim_head (contiguous).  o, dout, lse and delta are always contiguous.  Strides must be multiples
+ * of 16 bytes.  The slices are read by TMA / written by the kernels in place: no split or concatenation copies. */
+WM_API int wm_l3d_attn_fwd_ld(const void* q, const void* k, const void* v, void* o, float* lse,
+                       long ld_q, long ld_kv, int B, int S, int H, int W, int heads, int dim_head,
+                       int eS, int eH, int eW, float scale, int dtype, int flags, void* stream);
+WM_API int wm_l3d_attn_bwd_ld(const void* q, const void* k, const void* v, const void* o, const float* lse,
+                       const void* dout, void* dq, void* dk, void* dv, float* delta,
+                       long ld_q, long ld_kv, int B, int S, int H, int W, int heads, int dim_head,
+                       int eS, int eH, int eW, float scale, int dtype, int flags, void* stream);
 
 /* Nearest codebook entry per latent (vq.py:30-36).
  *   x         [N, L, D] fp32        codebook [L, K, D] fp32

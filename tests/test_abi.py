@@ -34,7 +34,7 @@ def test_header_symbols_exported():
 def test_version_and_argument_errors():
     _lib = _ensure_built()
     L = _lib.lib()
-    assert L.wm_version() == 110
+    assert L.wm_version() == 120
     # null pointers / bad shapes are rejected before any CUDA call
     rc = L.wm_l3d_attn_fwd(None, None, None, None, None, 1, 4, 4, 4, 2, 16, 1, 1, 1, 0.25, _lib.DTYPE_FP32, 0, None)
     assert rc == -1 and b'null pointer' in L.wm_last_error()
@@ -44,6 +44,11 @@ def test_version_and_argument_errors():
     assert rc == -1 and b'aligned' in L.wm_last_error()
     rc = L.wm_l3d_attn_fwd(16, 16, 16, 16, 16, 1, 4, 4, 4, 2, 16, 1, 1, 1, 0.25, 7, 0, None)
     assert rc == -1 and b'dtype' in L.wm_last_error()
+    # token strides of the merged-projection variants: at least heads*dim_head, multiples of 16 bytes
+    rc = L.wm_l3d_attn_fwd_ld(16, 16, 16, 16, 16, 0, 24, 1, 4, 4, 4, 2, 16, 1, 1, 1, 0.25, _lib.DTYPE_FP32, 0, None)
+    assert rc == -1 and b'token strides' in L.wm_last_error()
+    rc = L.wm_l3d_attn_bwd_ld(*([16] * 10), 0, 66, 1, 4, 4, 4, 2, 16, 1, 1, 1, 0.25, _lib.DTYPE_FP32, 0, None)
+    assert rc == -1 and b'16 bytes' in L.wm_last_error()
     rc = L.wm_vq_nearest(16, 16, 16, None, None, 8, 1, 4, 6, _lib.DTYPE_FP32, 0, None)
     assert rc == -2 and b'multiple of 4' in L.wm_last_error()
     rc = L.wm_vq_nearest(16, 16, 16, None, None, 8, 1, 4, 8, _lib.DTYPE_BF16, 0, None)

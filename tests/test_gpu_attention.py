@@ -248,3 +248,29 @@ def test_bf16_extreme_logits_recentre_the_softmax_reference(gain):
     _close(l_tc, l_si, 1e-3, 1e-4, 'lse')
     ref = O.attention_core(q.float(), k.float(), v.float(), heads, ext)
     _close(o_tc, ref, 2e-2, 6e-3, 'out vs oracle')
+
+
+@pytest.mark.parametrize('dtype,flags', [(torch.bfloat16, 0), (torch.bfloat16, ops.FLAG_SIMT), (torch.float32, 0)])
+@pytest.mark.parametrize('shape,heads,ext', [
+    ((2, 4, 16, 16, 64), 2, (1, 2, 2)),     # config-3 head width
+    ((1, 5, 10, 9, 256), 2, (2, 3, 3)),     # config-4 head width, ragged tiles
+])
+def test_merged_kv_projection_operands_match_separate_tensors(shape, heads, ext, dtype, flags):
+    """wm_l3d_attn_*_ld on the two channel halves of ONE [.., 2*inner] buffer (merged to_k / to_v GEMM) gives the same
+    bits as the contiguous entry points on copies of the halves, forward and backward (dK | dV side by side)."""
+    g = torch.Generator().manual_seed(5)
+    C = shape[-1]
+    q = torch.randn(shape, generator=g).to(DEV, dtype).requires_grad_(True)
+    kv = torch.randn(*shape[:-1], 2 * C, generator=g).to(DEV, dtype).requires_grad_(True)
+    do = torch.randn(shape, generator=g).to(DEV, dtype)
+    out = ops.local3d_attention_kv(q, kv, heads, ext, flags=flags)
+    out.backward(do)
+    q2 = q.detach().clone().requires_grad_(True)
+    k2 = kv.detach()[..., :C].contiguous().requires_grad_(True)
+    v2 = kv.detach()[..., C:].contiguous().requires_grad_(True)
+    ref = ops.local3d_attention(q2, k2, v2, heads, ext, flags=flags)
+    ref.backward(do)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    assert torch.equal(q.grad, q2.grad)
+    assert torch.equal(kv.grad[..., :C], k2.grad) and torch.equal(kv.grad[..., C:], v2.grad)

@@ -8,13 +8,14 @@ q, k, v = (torch.randn(B, S, H, W, heads * d, device='cuda', generator=g).bfloat
 for _ in range(3):
     ops.attn_forward(q, k, v, heads, ext, d ** -0.5)
 torch.cuda.synchronize()
-buf = (ctypes.c_longlong * (64 * 16))()
+buf = (ctypes.c_longlong * (64 * 32))()
 rc = _lib.lib().wm_debug_read(buf)
 import numpy as np
-a = np.array(buf[:], dtype=np.int64).reshape(64, 16)
+a = np.array(buf[:], dtype=np.int64).reshape(64, 32)
 t0 = a[0, 0]
 names = {0: 'pv:top', 1: 'pv:kv ok', 4: 'pv:p ok', 5: 'pv:issued', 2: 's:top', 3: 's:p ok', 6: 's:inputs ok', 7: 's:issued',
-         14: 'cmp:HEAD top', 15: 'cmp:geometry done', 8: 'cmp:top', 9: 'cmp:o ok', 10: 'cmp:s ok', 13: 'cmp:math done', 11: 'cmp:st waited', 12: 'cmp:arrived'}
+         14: 'cmp:HEAD top', 15: 'cmp:geometry done', 8: 'cmp:top', 9: 'cmp:o ok', 10: 'cmp:s ok', 13: 'cmp:math done', 11: 'cmp:st waited', 12: 'cmp:arrived',
+         16: 'q0:arr', 17: 'q1:arr', 18: 'q2:arr', 19: 'q3:arr', 20: 'q0:top', 21: 'q1:top', 22: 'q2:top', 23: 'q3:top'}
 print('rc', rc)
 for t in range(0, 14 if len(sys.argv) < 2 else 0):
     ev = sorted((a[t, s] - t0, names[s]) for s in names if a[t, s] != 0)

@@ -41,6 +41,10 @@ def lib() -> ctypes.CDLL:
     L.wm_l3d_attn_fwd.argtypes = [c_void_p] * 5 + [c_int] * 9 + [c_float, c_int, c_int, c_void_p]
     L.wm_l3d_attn_bwd.restype = c_int
     L.wm_l3d_attn_bwd.argtypes = [c_void_p] * 10 + [c_int] * 9 + [c_float, c_int, c_int, c_void_p]
+    L.wm_l3d_attn_fwd_ld.restype = c_int
+    L.wm_l3d_attn_fwd_ld.argtypes = [c_void_p] * 5 + [c_long, c_long] + [c_int] * 9 + [c_float, c_int, c_int, c_void_p]
+    L.wm_l3d_attn_bwd_ld.restype = c_int
+    L.wm_l3d_attn_bwd_ld.argtypes = [c_void_p] * 10 + [c_long, c_long] + [c_int] * 9 + [c_float, c_int, c_int, c_void_p]
     L.wm_vq_nearest.restype = c_int
     L.wm_vq_nearest.argtypes = [c_void_p] * 5 + [c_long, c_int, c_int, c_int, c_int, c_int, c_void_p]
     L.wm_vq_distance.restype = c_int
@@ -79,6 +83,7 @@ def check(rc: int, what: str) -> None:
 
 
 EXPORTS = ('wm_version', 'wm_last_error', 'wm_l3d_attn_uses_tensor_cores', 'wm_l3d_attn_fwd', 'wm_l3d_attn_bwd',
+           'wm_l3d_attn_fwd_ld', 'wm_l3d_attn_bwd_ld',
            'wm_vq_nearest', 'wm_vq_distance', 'wm_adamw_step', 'wm_adamw_step_norm', 'wm_vq_stats', 'wm_vq_onehot',
            'wm_sample_step', 'wm_loss_hist_update', 'wm_reduce_blocks', 'wm_add_layernorm_fwd',
            'wm_add_layernorm_bwd', 'wm_colsum', 'wm_bias_gelu_fwd', 'wm_bias_gelu_bwd')

@@ -63,27 +63,56 @@ extern "C" int wm_l3d_attn_uses_tensor_cores(int S, int H, int W, int heads, int
     return attn_tc_supported(s) ? 1 : 0;
 }
 
-extern "C" int wm_l3d_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S, int H,
-                               int W, int heads, int dim_head, int eS, int eH, int eW, float scale, int dtype,
-                               int flags, void* stream) {
+namespace {
+int check_ld(AttnShape& s, long ld_q, long ld_kv, int dtype) {
+    const long esz = dtype == WM_DTYPE_BF16 ? 2 : 4;
+    if ((ld_q != 0 && ld_q < s.inner()) || (ld_kv != 0 && ld_kv < s.inner()) || ld_q > 0x7fffffffL || ld_kv > 0x7fffffffL)
+        return fail(WM_EINVAL, "token strides ld_q=%ld, ld_kv=%ld must be 0 or >= heads*dim_head=%d", ld_q, ld_kv, s.inner());
+    if ((ld_q * esz) % 16 != 0 || (ld_kv * esz) % 16 != 0)
+        return fail(WM_EINVAL, "token strides must be multiples of 16 bytes (ld_q=%ld, ld_kv=%ld elements)", ld_q, ld_kv);
+    s.ldq = (int)ld_q;
+    s.ldkv = (int)ld_kv;
+    return WM_OK;
+}
+}  // namespace
+
+extern "C" int wm_l3d_attn_fwd_ld(const void* q, const void* k, const void* v, void* o, float* lse, long ld_q, long ld_kv,
+                                  int B, int S, int H, int W, int heads, int dim_head, int eS, int eH, int eW,
+                                  float scale, int dtype, int flags, void* stream) {
     AttnShape s{B, S, H, W, heads, dim_head, eS, eH, eW, scale};
     const void* ptrs[] = {q, k, v, o, lse};
     if (int rc = check_attn(s, dtype, ptrs, 5)) return rc;
+    if (int rc = check_ld(s, ld_q, ld_kv, dtype)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == WM_DTYPE_BF16 && !(flags & WM_FLAG_SIMT) && attn_tc_supported(s))
         return attn_fwd_tc(q, k, v, o, lse, s, st);
     return attn_fwd_simt(q, k, v, o, lse, s, dtype, st);
 }
 
-extern "C" int wm_l3d_attn_bwd(const void* q, const void* k, const void* v, const void* o, const float* lse,
-                               const void* dout, void* dq, void* dk, void* dv, float* delta, int B, int S, int H,
+extern "C" int wm_l3d_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S, int H,
                                int W, int heads, int dim_head, int eS, int eH, int eW, float scale, int dtype,
                                int flags, void* stream) {
+    return wm_l3d_attn_fwd_ld(q, k, v, o, lse, 0, 0, B, S, H, W, heads, dim_head, eS, eH, eW, scale, dtype, flags, stream);
+}
+
+extern "C" int wm_l3d_attn_bwd_ld(const void* q, const void* k, const void* v, const void* o, const float* lse,
+                                  const void* dout, void* dq, void* dk, void* dv, float* delta, long ld_q, long ld_kv,
+                                  int B, int S, int H, int W, int heads, int dim_head, int eS, int eH, int eW,
+                                  float scale, int dtype, int flags, void* stream) {
     AttnShape s{B, S, H, W, heads, dim_head, eS, eH, eW, scale};
     const void* ptrs[] = {q, k, v, o, lse, dout, dq, dk, dv, delta};
     if (int rc = check_attn(s, dtype, ptrs, 10)) return rc;
+    if (int rc = check_ld(s, ld_q, ld_kv, dtype)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == WM_DTYPE_BF16 && !(flags & WM_FLAG_SIMT) && attn_tc_supported(s))
         return attn_bwd_tc(q, k, v, o, lse, dout, dq, dk, dv, delta, s, st);
     return attn_bwd_simt(q, k, v, o, lse, dout, dq, dk, dv, delta, s, dtype, st);
+}
+
+extern "C" int wm_l3d_attn_bwd(const void* q, const void* k, const void* v, const void* o, const float* lse,
+                               const void* dout, void* dq, void* dk, void* dv, float* delta, int B, int S, int H,
+                               int W, int heads, int dim_head, int eS, int eH, int eW, float scale, int dtype,
+                               int flags, void* stream) {
+    return wm_l3d_attn_bwd_ld(q, k, v, o, lse, dout, dq, dk, dv, delta, 0, 0, B, S, H, W, heads, dim_head, eS, eH, eW,
+                              scale, dtype, flags, stream);
 }

@@ -101,16 +101,16 @@ __device__ __forceinline__ void fwd_item(const T* __restrict__ q, const T* __res
                                          T* __restrict__ o, float* __restrict__ lse, const AttnShape& sh, const Item& it,
                                          float* qs, float* ps, int lane) {
     const int Wn = sh.window(), d = sh.d;
-    const long inner = sh.inner();
+    const long inner = sh.inner(), ldq = sh.q_ld(), ldkv = sh.kv_ld();
     const long hoff = (long)it.head * d;
-    for (int c = lane; c < d; c += 32) qs[c] = to_f(q[it.tok * inner + hoff + c]);
+    for (int c = lane; c < d; c += 32) qs[c] = to_f(q[it.tok * ldq + hoff + c]);
     __syncwarp();
 
     float mx = -INFINITY;
     for (int j = lane; j < Wn; j += 32) {
         const long kt = neighbour(sh, it, j);
         float sc = -INFINITY;
-        if (kt >= 0) sc = dot_row(qs, k + kt * inner + hoff, d) * sh.scale;
+        if (kt >= 0) sc = dot_row(qs, k + kt * ldkv + hoff, d) * sh.scale;
         ps[j] = sc;
         mx = fmaxf(mx, sc);
     }
@@ -133,7 +133,7 @@ __device__ __forceinline__ void fwd_item(const T* __restrict__ q, const T* __res
         const float p = ps[j];
         if (p == 0.f) continue;                          // warp-uniform
         const long kt = neighbour(sh, it, j);
-        const T* vrow = v + kt * inner + hoff;
+        const T* vrow = v + kt * ldkv + hoff;
 #pragma unroll
         for (int i = 0; i < kMaxChanPerLane; ++i) {
             const int c = lane + 32 * i;
@@ -200,12 +200,12 @@ l3d_bwd_dq_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T
     float* dss = dos + d;
     Item it;
     if (!decode_item(sh, (long)blockIdx.x * kWarpsPerBlock + warp, it)) return;
-    const long inner = sh.inner();
+    const long inner = sh.inner(), ldq = sh.q_ld(), ldkv = sh.kv_ld();
     const long hoff = (long)it.head * d;
-    const long row = it.tok * inner + hoff;
+    const long row = it.tok * inner + hoff, qrow_off = it.tok * ldq + hoff;
     float dl = 0.f;
     for (int c = lane; c < d; c += 32) {
-        qs[c] = to_f(q[row + c]);
+        qs[c] = to_f(q[qrow_off + c]);
         const float g = to_f(dout[row + c]);
         dos[c] = g;
         dl = fmaf(g, to_f(o[row + c]), dl);
@@ -219,9 +219,9 @@ l3d_bwd_dq_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T
         const long kt = neighbour(sh, it, j);
         float ds = 0.f;
         if (kt >= 0) {
-            const float sc = dot_row(qs, k + kt * inner + hoff, d) * sh.scale;
+            const float sc = dot_row(qs, k + kt * ldkv + hoff, d) * sh.scale;
             const float p = expf(sc - L);
-            const float dp = dot_row(dos, v + kt * inner + hoff, d);
+            const float dp = dot_row(dos, v + kt * ldkv + hoff, d);
             ds = p * (dp - dl) * sh.scale;
         }
         dss[j] = ds;
@@ -235,7 +235,7 @@ l3d_bwd_dq_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T
         const long kt = neighbour(sh, it, j);
         if (kt < 0) continue;                            // warp-uniform
         const float ds = dss[j];
-        const T* krow = k + kt * inner + hoff;
+        const T* krow = k + kt * ldkv + hoff;
 #pragma unroll
         for (int i = 0; i < kMaxChanPerLane; ++i) {
             const int c = lane + 32 * i;
@@ -245,7 +245,7 @@ l3d_bwd_dq_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T
 #pragma unroll
     for (int i = 0; i < kMaxChanPerLane; ++i) {
         const int c = lane + 32 * i;
-        if (c < d) from_f(dq + row + c, acc[i]);
+        if (c < d) from_f(dq + qrow_off + c, acc[i]);
     }
 }
 
@@ -265,9 +265,9 @@ l3d_bwd_dkv_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const 
     float* dss = ps + Wn;
     Item it;                                            // here the item is a KEY token
     if (!decode_item(sh, (long)blockIdx.x * kWarpsPerBlock + warp, it)) return;
-    const long inner = sh.inner();
+    const long inner = sh.inner(), ldq = sh.q_ld(), ldkv = sh.kv_ld();
     const long hoff = (long)it.head * d;
-    const long row = it.tok * inner + hoff;
+    const long row = it.tok * ldkv + hoff;
     for (int c = lane; c < d; c += 32) {
         ks[c] = to_f(k[row + c]);
         vs[c] = to_f(v[row + c]);
@@ -279,7 +279,7 @@ l3d_bwd_dkv_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const 
         const long qt = neighbour(sh, it, j);
         float p = 0.f, ds = 0.f;
         if (qt >= 0) {
-            const float sc = dot_row(ks, q + qt * inner + hoff, d) * sh.scale;
+            const float sc = dot_row(ks, q + qt * ldq + hoff, d) * sh.scale;
             p = expf(sc - lse[qt * sh.heads + it.head]);
             const float dp = dot_row(vs, dout + qt * inner + hoff, d);
             ds = p * (dp - delta[qt * sh.heads + it.head]) * sh.scale;
@@ -297,7 +297,7 @@ l3d_bwd_dkv_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const 
         if (qt < 0) continue;                            // warp-uniform
         const float p = ps[j], ds = dss[j];
         const T* dorow = dout + qt * inner + hoff;
-        const T* qrow = q + qt * inner + hoff;
+        const T* qrow = q + qt * ldq + hoff;
 #pragma unroll
         for (int i = 0; i < kMaxChanPerLane; ++i) {
             const int c = lane + 32 * i;

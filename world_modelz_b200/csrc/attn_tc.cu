@@ -72,9 +72,9 @@ struct MapKeyHash {
 static std::mutex g_map_mutex;
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
 
-int make_tensor_map_5d(CUtensorMap* out, const void* base, int B, int S, int H, int W, int C, int box_c, int box_w,
-                       int box_h, int box_s, int swizzle_bytes) {
-    const MapKey key{base, {B, S, H, W, C, box_c, box_w, box_h, box_s, swizzle_bytes, 5}};
+int make_tensor_map_5d(CUtensorMap* out, const void* base, int B, int S, int H, int W, int C, long ld, int box_c,
+                       int box_w, int box_h, int box_s, int swizzle_bytes) {
+    const MapKey key{base, {B, S, H, W, C, box_c, box_w, box_h, box_s, swizzle_bytes, (int)ld}};
     {
         std::lock_guard<std::mutex> lock(g_map_mutex);
         auto it = g_map_cache.find(key);
@@ -83,8 +83,8 @@ int make_tensor_map_5d(CUtensorMap* out, const void* base, int B, int S, int H, 
     EncodeTiledFn fn = encode_tiled_fn();
     if (fn == nullptr) return fail(WM_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)S, (cuuint64_t)B};
-    const cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H,
-                                   (cuuint64_t)C * 2 * W * H * S};
+    const cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * W, (cuuint64_t)ld * 2 * W * H,
+                                   (cuuint64_t)ld * 2 * W * H * S};      // ld: elements between consecutive tokens (>= C)
     const cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_s, 1u};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -189,12 +189,14 @@ bool make_plan(const AttnShape& s, Mode mode, Plan& best) {
 }
 
 #if WM_EXPERIMENT == 7
-__device__ long long g_dbg[64 * 16];
-#define DBG(slot) do { if (dbg_on && t < 64) g_dbg[t * 16 + (slot)] = clock64(); } while (0)
-#define DBGT(slot, tt) do { if (dbg_on && (tt) < 64) g_dbg[(tt) * 16 + (slot)] = clock64(); } while (0)
+__device__ long long g_dbg[64 * 32];
+#define DBG(slot) do { if (dbg_on && t < 64) g_dbg[t * 32 + (slot)] = clock64(); } while (0)
+#define DBGT(slot, tt) do { if (dbg_on && (tt) < 64) g_dbg[(tt) * 32 + (slot)] = clock64(); } while (0)
+#define DBGQ(slot) do { if (dbg_blk && lane == 0 && t < 64) g_dbg[t * 32 + (slot)] = clock64(); } while (0)
 #else
 #define DBG(slot) do { } while (0)
 #define DBGT(slot, tt) do { } while (0)
+#define DBGQ(slot) do { } while (0)
 #endif
 
 // ------------------------------------------------------------------------------ kernel
@@ -252,9 +254,13 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     uint64_t* bar_q = bars;           // [2]  Q tile of a head landed
     uint64_t* bar_kv = bars + 2;      // [4]  K/V block landed
     uint64_t* bar_s = bars + 6;       // [2]  S buffer computed            (tcgen05.commit)
-    uint64_t* bar_p = bars + 8;       // [2]  P buffer written, S buffer drained (8 compute warps)
+    uint64_t* bar_p = bars + 8;       // [2]  P buffer written             (the 4 warps of the team that owns the buffer)
     uint64_t* bar_o = bars + 10;      // [2]  O += P V of a step retired   (tcgen05.commit)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* bar_sfree = bars + 12;  // [2]  S buffer drained             (the 4 warps of the team; long before P is complete)
+    uint64_t* bar_head = bars + 14;   // [2]  last O += P V of a head retired (tcgen05.commit), per head parity
+    uint64_t* bar_l = bars + 16;      // [2]  the other team's share of a head's row sums is in shared memory (its 4 warps)
+    uint64_t* bar_ofree = bars + 18;  // [2]  a head's O accumulator has been read out (the 4 warps of its epilogue team)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
     // ---- which brick / head group ----------------------------------------------------------
     const int tw_i = blockIdx.x % pl.tilesW, th_i = blockIdx.x / pl.tilesW;
@@ -286,8 +292,12 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int i = 0; i < 4; ++i) mbar_init(&bar_kv[i], 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bar_s[i], 1);
-            mbar_init(&bar_p[i], 4 * NPART);       // one arrival per compute warp (hundreds of arrivals on one word serialise)
+            mbar_init(&bar_p[i], 4);               // one arrival per compute warp of the owning team
+            mbar_init(&bar_sfree[i], 4);
             mbar_init(&bar_o[i], 1);
+            mbar_init(&bar_head[i], 1);
+            mbar_init(&bar_l[i], 4);
+            mbar_init(&bar_ofree[i], 4);
         }
         fence_barrier_init();
     }
@@ -399,7 +409,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                              db + (uint32_t)kk * (uint32_t)((16 * G::kRowBytes) >> 4), idesc_o, (accumulate || kk > 0) ? 1u : 0u);
             umma_commit(bar);
         };
-        auto issue_o_mma = [&](int t, int stage, int hd, bool accumulate) {   // O[hd&1] += P[t&1] V_t
+        auto issue_o_mma = [&](int t, int stage, int hd, bool accumulate, bool head_end) {   // O[hd&1] += P[t&1] V_t
             if (leader) {
                 const uint32_t tmem_o = tmem_base + (pl.obufs == 2 ? (hd & 1) : 0) * D;
                 const uint32_t ta = tmem_p0 + (t & 1) * p_cols;                          // A = P from tensor memory
@@ -412,6 +422,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     default: issue_o_chain(std::integral_constant<int, 16>{}, tmem_o, ta, db, accumulate, bar); break;
                 }
 #undef WM_O_CASE
+                if (head_end) umma_commit(&bar_head[hd & 1]);
             }
             __syncwarp();
         };
@@ -467,7 +478,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             }
             for (int t = 0; t + 2 < nsteps; ++t) {
                 DBG(2);
-                mbar_wait(&bar_p[t & 1], (t >> 1) & 1);                  // S buffer t&1 drained
+                mbar_wait(&bar_sfree[t & 1], (t >> 1) & 1);              // S buffer t&1 drained
                 DBG(3);
                 wait_inputs(c2, c2.hd != prev_hd);
                 DBG(6);
@@ -488,23 +499,30 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 kv_par ^= 1u << stage;
                 DBG(1);
                 mbar_wait(&bar_p[t & 1], (t >> 1) & 1);
+                if (head_start && cur.hd >= pl.obufs) {      // the accumulator's previous head (cur.hd - obufs) has been read out
+                    const int h = cur.hd - pl.obufs;
+                    mbar_wait(&bar_ofree[h & 1], (h >> 1) & 1);
+                }
                 tc_fence_after();
                 DBG(4);
-                issue_o_mma(t, stage, cur.hd, !head_start);
-                DBG(5);
+                const int hd_now = cur.hd;
                 advance(cur);
+                issue_o_mma(t, stage, hd_now, !head_start, cur.hd != hd_now);
+                DBG(5);
                 if (++stage == nstage) stage = 0;
             }
         }
     } else {
         // =============================== compute warps ==========================================
-        // Two threads per query row: warps w and w+4 share TMEM lane quadrant w&3 and split the
-        // quadrant's live key columns (in groups of 8) between them.
-        constexpr int CP = D / NPART;                  // O columns per thread in rescale / epilogue
-        const int quad = warp & 3, part = warp >> 2;
+        // Two TEAMS of four warps (one per TMEM lane quadrant).  Team b owns S / P buffer b, i.e. the steps t with
+        // t & 1 == b, and one of its threads handles a whole query row of such a step.  The two warps of an SM
+        // sub-partition (w, w + 4: same quadrant, different teams) are therefore always in different steps: while
+        // one sits in the fixed latencies around a step (TMEM store drain, hand-off to the issuing warps, S MMA of its
+        // next step) the other one is in its element math.  The S buffer is handed back the moment its last
+        // tcgen05.ld has returned (bar_sfree), long before the step's P is complete (bar_p).
+        const int quad = warp & 3, team = warp >> 2;
         const int row = quad * 32 + lane;              // query row of the brick == TMEM lane
         const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
-        auto quad_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * NPART) : "memory"); };
         const int plane_mask = (1 << pl.lgPlane) - 1;
         const int qs = row >> pl.lgPlane, qh = (row & plane_mask) >> pl.lgTW, qw = row & (pl.tW - 1);
         const bool q_valid = (s0 + qs < sh.S) && (h0 + qh < sh.H) && (w0 + qw < sh.W);
@@ -518,87 +536,106 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         // inside [2^-100, 2^100], i.e. for logits within about +-69 nats -- no max pass, no O rescale, and the two
         // threads of a row never have to agree on anything.  A row whose sum leaves that range (or is inf / NaN) gets
         // LSE = NaN here and is recomputed exactly by l3d_fwd_fixup_kernel, launched right behind this kernel.
-        float l_part = 0.f;            // this thread's share of the running sum of P
-        // exchange slot: [parity][part][row]; parity alternates so that a slot is rewritten only
-        // after a later quad_sync has proven every reader of its previous contents done
-        auto xslot = [&](int parity) { return sX + ((parity & 1) * 4) * 128; };
-        // O / l -> bf16 and the LSE of head `hd`; called once that head's last P V has retired
+        float l_part = 0.f;            // this thread's share (its team's steps) of the running sum of P
+        // Head epilogue without a rendezvous between the teams (they must stay out of step).  The team that owns the
+        // LAST step of a head only deposits its share of the row sums (shared memory + bar_l) and moves on; the other
+        // team -- whose own work on that head ended a step earlier -- writes the whole row: it picks the deposit up,
+        // reads all D columns of O once the head's last P V has retired (bar_head), releases the accumulator to the
+        // P V issuer (bar_ofree) and stores O / l and the LSE.  It does so after its first step of the NEXT head, so
+        // that the wait for the retiring MMAs overlaps its own math.
+        auto xslot = [&](int hd) { return sX + (hd & 3) * 128; };      // four slots: see the reuse argument at bar_ofree
+        auto deposit_l = [&](int hd, float l_mine) {
+            xslot(hd)[row] = l_mine;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_l[hd & 1]);
+        };
         auto finish_head = [&](int hd, float l_mine) {
-            const uint32_t tmem_o = tmem_base + (pl.obufs == 2 ? (hd & 1) : 0) * D;
-            float* x = xslot(hd);
-            x[part * 128 + row] = l_mine;
-            uint32_t r[CP];
-#pragma unroll
-            for (int c = 0; c < CP; c += 16) tmem_ld16(tmem_o + lane_sel + part * CP + c, *reinterpret_cast<uint32_t(*)[16]>(&r[c]));
-            quad_sync();
-            const float l_run = x[row] + x[128 + row];
+            mbar_wait(&bar_l[hd & 1], (hd >> 1) & 1);
+            const float l_run = l_mine + xslot(hd)[row];
             const bool ok = l_run >= 7.8886091e-31f && l_run <= 1.2676506e30f;       // [2^-100, 2^100]; false for NaN
             const float inv_l = 1.f / l_run;
-            const int cb = (head0 + hd) * D;
-            __nv_bfloat16* orow = prm.o + tok * (long)sh.inner() + cb + part * CP;
-            tmem_wait_ld();
-            if (q_valid) {
+            mbar_wait(&bar_head[hd & 1], (hd >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tmem_o = tmem_base + (pl.obufs == 2 ? (hd & 1) : 0) * D + lane_sel;
+            __nv_bfloat16* orow = prm.o + tok * (long)sh.inner() + (head0 + hd) * D;
+            const float lse_out = ok ? lg2(l_run) * 0.6931471805599453f : __int_as_float(0x7fc00000);
 #pragma unroll
-                for (int c = 0; c < CP; c += 8) {
-                    uint32_t pk[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        pk[i] = pack_bf16(__uint_as_float(r[c + 2 * i]) * inv_l, __uint_as_float(r[c + 2 * i + 1]) * inv_l);
-                    *reinterpret_cast<uint4*>(orow + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            for (int c0 = 0; c0 < D; c0 += 32) {           // 32 columns at a time: bounded register footprint at D = 128
+                uint32_t r[32];
+                tmem_ld32(tmem_o + c0, r);
+                tmem_wait_ld();
+                if (c0 + 32 == D) {                        // the accumulator has been read out
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_ofree[hd & 1]);
                 }
-                if (part == 0) prm.lse[tok * sh.heads + head0 + hd] = ok ? lg2(l_run) * 0.6931471805599453f : __int_as_float(0x7fc00000);
+                if (q_valid) {
+#pragma unroll
+                    for (int c = 0; c < 32; c += 8) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            pk[i] = pack_bf16(__uint_as_float(r[c + 2 * i]) * inv_l, __uint_as_float(r[c + 2 * i + 1]) * inv_l);
+                        *reinterpret_cast<uint4*>(orow + c0 + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
             }
+            if (q_valid) prm.lse[tok * sh.heads + head0 + hd] = lse_out;
         };
+        // does this team own the last step of head hd?  (steps are numbered across heads: head hd ends with step
+        // (hd + 1) * nblocks - 1)
+        auto owns_last = [&](int hd) { return (((hd + 1) * nblocks - 1) & 1) == team; };
 
         const int ngroups = ncols_pad >> 3;
-        int dlo0 = 0, dhi0 = ngroups, dlo1 = 0, dhi1 = ngroups;   // 8-column groups of P buffer 0 / 1 that may be non-zero
-        bool seen_o = false, seen_s = false;   // next step's barriers already seen complete by this step's probes
-        uint32_t dbg_flag = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0 && tid == 0);
+        int dlo = 0, dhi = ngroups;            // 8-column groups of this team's P buffer that may be non-zero
+        uint32_t dbg_flag = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0 && (tid & 127) == 0);     // one thread per team
         asm volatile("" : "+r"(dbg_flag));
         const bool dbg_on = dbg_flag != 0;
         (void)dbg_on;
+        uint32_t dbg_blk_flag = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0);
+        asm volatile("" : "+r"(dbg_blk_flag));
+        const bool dbg_blk = dbg_blk_flag != 0;
+        (void)dbg_blk;
         const uint64_t cc = pk2(pl.scale_log2, pl.scale_log2), zz = pk2(0.f, 0.f);
+        const uint32_t tmem_s = tmem_s0 + team * ncols_pad + lane_sel;
+        const uint32_t tmem_p = tmem_p0 + team * p_cols + lane_sel;
+        auto s_drained = [&]() {               // every tcgen05.ld of this step's S has returned: the issuer may refill the buffer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_sfree[team]);
+        };
 
         int t = 0;
         for (int hd = 0; hd < pl.hpc; ++hd) {
             DBGT(14, t);
-            // ---- head start: the previous head is finished AFTER this head's first step (its O buffer is not reused yet) ----
             const float prev_l = l_part;
-            bool drain_prev = hd > 0;
-            if (hd > 0 && pl.obufs == 1) {           // single O accumulator: drain it before this head's first P V can be issued
-                mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);
-                tc_fence_after();
-                finish_head(hd - 1, prev_l);
-                drain_prev = false;
-            }
+            bool drain_prev = hd > 0 && !owns_last(hd - 1);      // the previous head's epilogue is this team's, still to be done
             l_part = 0.f;
             for (int chunk = chunk_first; chunk <= chunk_last; ++chunk) {
-                // ---- live column range of this quadrant / thread in this h-chunk (warp-uniform) ----
+                // ---- live column range of this quadrant in this h-chunk (warp-uniform) ----
                 // the quadrant's rows see halo rows [w_qh_lo, w_qh_hi + 2 eH]; rows outside the grid are never live
                 const int kh0 = chunk * pl.ch;
                 const int ua = max(max(w_qh_lo, kh0), khg_lo), ub = min(min(w_qh_hi + 2 * sh.eH, kh0 + pl.ch - 1), khg_hi);
                 const bool chunk_live = ub >= ua;
                 const int g_lo = chunk_live ? ((ua - kh0) * pl.hW) >> 3 : 0;
                 const int g_hi = chunk_live ? min(((ub - kh0 + 1) * pl.hW + 7) >> 3, ngroups) : 0;
-                // the two threads of a row split [g_lo, g_hi) at an even group (16-column loads)
-                const int gm = min(g_lo + ((((g_hi - g_lo) + 2) >> 2) << 1), g_hi);
-                const int ga = part ? gm : g_lo, gb = part ? g_hi : gm;
-                const int n16 = (gb - ga) >> 1;
+                const int n16 = (g_hi - g_lo) >> 1;
+                const bool rem8 = ((g_hi - g_lo) & 1) != 0;
                 DBGT(15, t);
                 for (int ks = ks_first; ks <= ks_last; ++ks, ++t) {
+                    if ((t & 1) != team) continue;
                     DBG(8);
-                    const int buf = t & 1;
-                    const uint32_t tmem_s = tmem_s0 + buf * ncols_pad + lane_sel;
-                    const uint32_t tmem_p = tmem_p0 + buf * p_cols + lane_sel;
+                    // single O accumulator: this head's first P V waits for the read-out (bar_ofree) -- do it right away
+                    if (drain_prev && pl.obufs == 1) {
+                        finish_head(hd - 1, prev_l);
+                        drain_prev = false;
+                    }
                     // warp-uniform: can any of this quadrant's queries see this block?
                     const bool live = chunk_live && (ks >= w_qs) && (ks <= w_qs + 2 * sh.eS);
-                    // Both barriers of this step were probed during the previous one (a satisfied try_wait still costs
-                    // ~100 cycles); every warp observes every phase, live step or not (parity waits are unambiguous then).
-                    if (t >= 2 && !seen_o) mbar_wait(&bar_o[buf], ((t - 2) >> 1) & 1);     // P buffer free: P V of step t-2 retired
+                    DBGQ(20 + quad);
+                    if (t >= 2) mbar_wait(&bar_o[team], ((t - 2) >> 1) & 1);     // P buffer free: P V of step t-2 retired
                     DBG(9);
-                    if (!seen_s) mbar_wait(&bar_s[buf], (t >> 1) & 1);                     // S_t computed
-                    seen_o = seen_s = false;
-                    const int dl = buf ? dlo1 : dlo0, dh = buf ? dhi1 : dhi0;
+                    mbar_wait(&bar_s[team], (t >> 1) & 1);                       // S_t computed
                     int nl = 0, nh = 0;
                     if (live) {
                         tc_fence_after();
@@ -628,30 +665,30 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                         };
                         // two register sets: the TMEM load of the next 16 columns is in flight while these are processed
                         uint32_t r0[16], r1[16];
-                        int g = ga;
+                        int g = g_lo;
                         if (n16 > 0) tmem_ld16(tmem_s + g * 8, r0);
-                        // probe the two barriers of the next step: the answers arrive under the math
-                        bool pr_o = t < 1, pr_s = false;
+                        else if (!rem8) s_drained();
                         for (int i = 0; i < n16; i += 2) {
                             tmem_wait_ld();
                             tmem_regs_ready(r0);
                             if (i + 1 < n16) tmem_ld16(tmem_s + (g + 2) * 8, r1);
+                            else if (!rem8) s_drained();
                             cols16(r0, g);
                             g += 2;
                             if (i + 1 < n16) {
                                 tmem_wait_ld();
                                 tmem_regs_ready(r1);
                                 if (i + 2 < n16) tmem_ld16(tmem_s + (g + 2) * 8, r0);
-                                if (t >= 1 && !pr_o) pr_o = mbar_test(&bar_o[buf ^ 1], ((t - 1) >> 1) & 1);
-                                if (t + 1 < nsteps && !pr_s) pr_s = mbar_test(&bar_s[buf ^ 1], ((t + 1) >> 1) & 1);
+                                else if (!rem8) s_drained();
                                 cols16(r1, g);
                                 g += 2;
                             }
                         }
-                        if (g < gb) {                 // odd group count of the quadrant: 8 columns left for part 1
+                        if (rem8) {                   // odd group count: 8 columns left
                             uint32_t r8[8];
                             tmem_ld8(tmem_s + g * 8, r8);
                             tmem_wait_ld();
+                            s_drained();
                             uint32_t pk[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
@@ -669,38 +706,36 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                         upk2(acc0, a0, a1);
                         upk2(acc1, a2, a3);
                         l_part += (a0 + a1) + (a2 + a3);
-                        if (t >= 1 && !pr_o) pr_o = mbar_test(&bar_o[buf ^ 1], ((t - 1) >> 1) & 1);
-                        if (t + 1 < nsteps && !pr_s) pr_s = mbar_test(&bar_s[buf ^ 1], ((t + 1) >> 1) & 1);
-                        seen_o = __all_sync(0xffffffffu, pr_o) && t >= 1;
-                        seen_s = __all_sync(0xffffffffu, pr_s);
+#else
+                        s_drained();
 #endif
                         // Columns outside the quadrant's live range must be zero in the P operand.  They stay zero from step
                         // to step: only what an earlier step left non-zero outside today's range is cleared (normally nothing).
-                        for (int gz = dl + part; gz < min(dh, g_lo); gz += NPART) tmem_st4(tmem_p + gz * 4, 0u, 0u, 0u, 0u);
-                        for (int gz = max(dl, g_hi) + part; gz < dh; gz += NPART) tmem_st4(tmem_p + gz * 4, 0u, 0u, 0u, 0u);
+                        for (int gz = dlo; gz < min(dhi, g_lo); ++gz) tmem_st4(tmem_p + gz * 4, 0u, 0u, 0u, 0u);
+                        for (int gz = max(dlo, g_hi); gz < dhi; ++gz) tmem_st4(tmem_p + gz * 4, 0u, 0u, 0u, 0u);
                         nl = g_lo; nh = g_hi;
                     } else {
-                        for (int gz = dl + part; gz < dh; gz += NPART) tmem_st4(tmem_p + gz * 4, 0u, 0u, 0u, 0u);
+                        s_drained();
+                        for (int gz = dlo; gz < dhi; ++gz) tmem_st4(tmem_p + gz * 4, 0u, 0u, 0u, 0u);
                     }
-                    if (buf) { dlo1 = nl; dhi1 = nh; } else { dlo0 = nl; dhi0 = nh; }
+                    dlo = nl; dhi = nh;
                     DBG(11);
                     tmem_wait_st();               // P is in tensor memory
-                    tc_fence_before();            // ... and our tcgen05.ld of S_t are complete before the issuers reuse the buffers
+                    tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_p[buf]);
+                    if (lane == 0) mbar_arrive(&bar_p[team]);
                     DBG(12);
-                    if (drain_prev && pl.obufs == 2) {   // epilogue of the previous head, off the critical path
-                        mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);     // its last P V has retired
-                        tc_fence_after();
+                    DBGQ(16 + quad);
+                    if (drain_prev) {             // epilogue of the previous head, off the critical path (two O accumulators)
                         finish_head(hd - 1, prev_l);
                         drain_prev = false;
                     }
                 }
             }
+            if (drain_prev) finish_head(hd - 1, prev_l);      // this team had no step in this head
+            if (owns_last(hd)) deposit_l(hd, l_part);
         }
-        mbar_wait(&bar_o[(nsteps - 1) & 1], ((nsteps - 1) >> 1) & 1);
-        tc_fence_after();
-        finish_head(pl.hpc - 1, l_part);
+        if (!owns_last(pl.hpc - 1)) finish_head(pl.hpc - 1, l_part);
     }
 
     tc_fence_before();
@@ -718,9 +753,9 @@ static int launch_fwd(const void* q, const void* k, const void* v, void* o, floa
     using G = Geo<D>;
     CUtensorMap mq, mk, mv;
     const int C = s.inner();
-    if (int rc = make_tensor_map_5d(&mq, q, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.tW, pl.tH, pl.tS, G::kSwizzleBytes)) return rc;
-    if (int rc = make_tensor_map_5d(&mk, k, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
-    if (int rc = make_tensor_map_5d(&mv, v, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
+    if (int rc = make_tensor_map_5d(&mq, q, s.B, s.S, s.H, s.W, C, s.q_ld(), G::kSlabCh, pl.tW, pl.tH, pl.tS, G::kSwizzleBytes)) return rc;
+    if (int rc = make_tensor_map_5d(&mk, k, s.B, s.S, s.H, s.W, C, s.kv_ld(), G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
+    if (int rc = make_tensor_map_5d(&mv, v, s.B, s.S, s.H, s.W, C, s.kv_ld(), G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
     FwdParams prm{s, pl, static_cast<__nv_bfloat16*>(o), lse};
     WM_CUDA_CHECK(cudaFuncSetAttribute(l3d_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
     const dim3 grid((unsigned)(pl.tilesW * pl.tilesH), (unsigned)pl.tilesS, (unsigned)(s.B * (s.heads / pl.hpc)));
@@ -734,7 +769,7 @@ static int launch_fwd(const void* q, const void* k, const void* v, void* o, floa
 
 #if WM_EXPERIMENT == 7
 extern "C" __attribute__((visibility("default"))) int wm_debug_read(long long* out) {
-    return (int)cudaMemcpyFromSymbol(out, tc::g_dbg, sizeof(long long) * 64 * 16);
+    return (int)cudaMemcpyFromSymbol(out, tc::g_dbg, sizeof(long long) * 64 * 32);
 }
 #endif
 

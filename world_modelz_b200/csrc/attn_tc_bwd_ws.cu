@@ -75,6 +75,7 @@ struct BwdWsParams {
     const float* delta;
     __nv_bfloat16* out1;     // dQ kernel: dq.   dK/dV kernel: dv
     __nv_bfloat16* out2;     //                  dK/dV kernel: dk
+    long ld_out;             // elements between consecutive tokens of the outputs
 };
 
 constexpr int kWsThreads = 352;        // 8 compute warps + (S,dP) issuer + accumulate issuer + TMA loader
@@ -403,7 +404,7 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             }
         };
         auto finish_head = [&](int hd) {            // accumulators of head `hd` -> bf16 -> global
-            const long row_off = row_tok * (long)sh.inner() + (head0 + hd) * D + half * (D / 2);
+            const long row_off = row_tok * prm.ld_out + (head0 + hd) * D + half * (D / 2);
 #pragma unroll
             for (int which = 0; which < (kDKV ? 2 : 1); ++which) {
                 __nv_bfloat16* dst = (which == 0 ? prm.out1 : prm.out2) + row_off;
@@ -641,16 +642,17 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
 }
 
 template <int D, int MODE>
-static int launch_ws(const void* a1, const void* a2, const void* b1, const void* b2, const float* lse,
-                     const float* delta, void* out1, void* out2, const AttnShape& s, const Plan& pl, cudaStream_t st) {
+static int launch_ws(const void* a1, const void* a2, const void* b1, const void* b2, const long (&ld)[4], const float* lse,
+                     const float* delta, void* out1, void* out2, long ld_out, const AttnShape& s, const Plan& pl,
+                     cudaStream_t st) {
     using G = Geo<D>;
     CUtensorMap ma1, ma2, mb1, mb2;
     const int C = s.inner();
-    if (int rc = make_tensor_map_5d(&ma1, a1, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.tW, pl.tH, pl.tS, G::kSwizzleBytes)) return rc;
-    if (int rc = make_tensor_map_5d(&ma2, a2, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.tW, pl.tH, pl.tS, G::kSwizzleBytes)) return rc;
-    if (int rc = make_tensor_map_5d(&mb1, b1, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
-    if (int rc = make_tensor_map_5d(&mb2, b2, s.B, s.S, s.H, s.W, C, G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
-    BwdWsParams prm{s, pl, lse, delta, static_cast<__nv_bfloat16*>(out1), static_cast<__nv_bfloat16*>(out2)};
+    if (int rc = make_tensor_map_5d(&ma1, a1, s.B, s.S, s.H, s.W, C, ld[0], G::kSlabCh, pl.tW, pl.tH, pl.tS, G::kSwizzleBytes)) return rc;
+    if (int rc = make_tensor_map_5d(&ma2, a2, s.B, s.S, s.H, s.W, C, ld[1], G::kSlabCh, pl.tW, pl.tH, pl.tS, G::kSwizzleBytes)) return rc;
+    if (int rc = make_tensor_map_5d(&mb1, b1, s.B, s.S, s.H, s.W, C, ld[2], G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
+    if (int rc = make_tensor_map_5d(&mb2, b2, s.B, s.S, s.H, s.W, C, ld[3], G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
+    BwdWsParams prm{s, pl, lse, delta, static_cast<__nv_bfloat16*>(out1), static_cast<__nv_bfloat16*>(out2), ld_out};
     WM_CUDA_CHECK(cudaFuncSetAttribute(l3d_bwd_ws_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
     const dim3 grid((unsigned)(pl.tilesW * pl.tilesH), (unsigned)pl.tilesS, (unsigned)(s.B * (s.heads / pl.hpc)));
     if (grid.y > 65535u || grid.z > 65535u) return fail(WM_EUNSUPPORTED, "grid too large for the tensor-core kernel");
@@ -676,8 +678,10 @@ static int launch_bwd_d(const void* q, const void* k, const void* v, const void*
                                                                       static_cast<const __nv_bfloat16*>(dout), delta,
                                                                       items, s.d);
     WM_CUDA_CHECK(cudaGetLastError());
-    if (int rc = launch_ws<D, kBwdDQws>(q, dout, k, v, lse, delta, dq, nullptr, s, pq, st)) return rc;     // rows: queries
-    return launch_ws<D, kBwdDKVws>(k, v, q, dout, lse, delta, dv, dk, s, pkv, st);                         // rows: keys
+    const long in = s.inner(), lq = s.q_ld(), lkv = s.kv_ld();
+    const long ld_dq[4] = {lq, in, lkv, lkv}, ld_dkv[4] = {lkv, lkv, lq, in};
+    if (int rc = launch_ws<D, kBwdDQws>(q, dout, k, v, ld_dq, lse, delta, dq, nullptr, lq, s, pq, st)) return rc;     // rows: queries
+    return launch_ws<D, kBwdDKVws>(k, v, q, dout, ld_dkv, lse, delta, dv, dk, lkv, s, pkv, st);                       // rows: keys
 }
 
 int launch_bwd_tc(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout,

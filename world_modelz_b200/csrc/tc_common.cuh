@@ -274,9 +274,10 @@ __device__ __forceinline__ uint32_t pack_bf16_2(uint64_t v) {   // (lo, hi) fp32
 }
 
 // ------------------------------------------------------------------ host: tensor maps
-// [B,S,H,W,C] bf16 tensor viewed as a 5-D TMA tensor (C innermost); box = (c, w, h, s, 1).
-int make_tensor_map_5d(CUtensorMap* out, const void* base, int B, int S, int H, int W, int C, int box_c, int box_w,
-                       int box_h, int box_s, int swizzle_bytes);
+// [B,S,H,W,C] bf16 tensor viewed as a 5-D TMA tensor (C innermost, `ld` elements from one token to the next);
+// box = (c, w, h, s, 1).
+int make_tensor_map_5d(CUtensorMap* out, const void* base, int B, int S, int H, int W, int C, long ld, int box_c,
+                       int box_w, int box_h, int box_s, int swizzle_bytes);
 
 }  // namespace tc
 }  // namespace wm

@@ -28,7 +28,11 @@ struct AttnShape {
     int B, S, H, W, heads, d;       // d = dim_head
     int eS, eH, eW;                 // window extents; window = (2e+1) per axis
     float scale;
+    int ldq = 0, ldkv = 0;          // elements between consecutive tokens of q (and dq) / of k, v, dk, dv; 0 = heads*d.
+                                    // A merged projection writes q | k | v side by side: its slices are addressed in place.
     __host__ __device__ int inner() const { return heads * d; }
+    __host__ __device__ long q_ld() const { return ldq ? ldq : heads * d; }
+    __host__ __device__ long kv_ld() const { return ldkv ? ldkv : heads * d; }
     __host__ __device__ long tokens() const { return (long)B * S * H * W; }
     __host__ __device__ int wS() const { return 2 * eS + 1; }
     __host__ __device__ int wH() const { return 2 * eH + 1; }

@@ -107,8 +107,10 @@ class Local3dAttention(nn.Module):
         if x.dim() != 5 or q.shape[:-1] != x.shape[:-1]:
             raise ValueError(f'expected x, q of shape [B,S,H,W,dim], got {tuple(x.shape)} and {tuple(q.shape)}')
         w_o = self.to_out[0].weight
-        core = ops.local3d_attention(self.to_q(q), self.to_k(x), torch.nn.functional.linear(x, self.to_v.weight),
-                                     self.heads, self.extents, self.scale, self.kernel_flags)
+        # to_k and to_v read the same normalised input: ONE GEMM with N = 2*inner; the kernels take the two channel
+        # halves of its output in place, and backward hands dK | dV back as one operand (one dgrad, one wgrad)
+        kv = torch.nn.functional.linear(x, torch.cat((self.to_k.weight, self.to_v.weight), dim=0))
+        core = ops.local3d_attention_kv(self.to_q(q), kv, self.heads, self.extents, self.scale, self.kernel_flags)
         bias = torch.addmv(self.to_out[0].bias, w_o, self.to_v.bias)      # W_o b_v + b_o, one GEMV
         return torch.nn.functional.linear(core, w_o).reshape(q.shape), bias
 

@@ -106,6 +106,58 @@ def local3d_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: 
     return _Local3dAttentionFn.apply(q, k, v, heads, tuple(extents), scale, flags)
 
 
+class _Local3dAttentionKvFn(torch.autograd.Function):
+    """Attention core over a MERGED key/value projection: ``kv [B,S,H,W,2*inner]`` is the output of one GEMM with
+    ``cat(to_k.weight, to_v.weight)``; the kernels address its two channel halves in place (``wm_l3d_attn_*_ld``,
+    token stride ``2*inner``), and backward writes dK | dV side by side into one buffer, which is then the single
+    gradient operand of that GEMM's dgrad and wgrad -- no split / cat copies, no ``dxk + dxv`` add."""
+
+    @staticmethod
+    def forward(ctx, q, kv, heads, extents, scale, flags):
+        _require_cuda(q, kv)
+        B, S, H, W, C = q.shape
+        if kv.shape[-1] != 2 * C or kv.shape[:-1] != q.shape[:-1]:
+            raise ValueError(f'kv must be [B,S,H,W,2*inner] next to q {tuple(q.shape)}, got {tuple(kv.shape)}')
+        q, kv = q.contiguous(), kv.contiguous()
+        esz = q.element_size()
+        out = torch.empty_like(q)
+        lse = torch.empty(B, S, H, W, heads, device=q.device, dtype=torch.float32)
+        check(_lib.lib().wm_l3d_attn_fwd_ld(q.data_ptr(), kv.data_ptr(), kv.data_ptr() + C * esz, out.data_ptr(),
+                                            lse.data_ptr(), 0, 2 * C, B, S, H, W, heads, C // heads,
+                                            *[int(e) for e in extents], float(scale), _dtype_code(q), flags, _stream()),
+              'wm_l3d_attn_fwd_ld')
+        _count(2 if q.dtype == torch.bfloat16 and not (flags & FLAG_SIMT) else 1)
+        ctx.save_for_backward(q, kv, out, lse)
+        ctx.cfg = (heads, tuple(int(e) for e in extents), float(scale), flags)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, kv, out, lse = ctx.saved_tensors
+        heads, extents, scale, flags = ctx.cfg
+        B, S, H, W, C = q.shape
+        esz = q.element_size()
+        dout = dout.contiguous()
+        dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+        delta = torch.empty_like(lse)
+        check(_lib.lib().wm_l3d_attn_bwd_ld(q.data_ptr(), kv.data_ptr(), kv.data_ptr() + C * esz, out.data_ptr(),
+                                            lse.data_ptr(), dout.data_ptr(), dq.data_ptr(), dkv.data_ptr(),
+                                            dkv.data_ptr() + C * esz, delta.data_ptr(), 0, 2 * C, B, S, H, W, heads,
+                                            C // heads, *extents, scale, _dtype_code(q), flags, _stream()),
+              'wm_l3d_attn_bwd_ld')
+        _count(3)
+        return dq, dkv, None, None, None, None
+
+
+def local3d_attention_kv(q: torch.Tensor, kv: torch.Tensor, heads: int, extents: Sequence[int],
+                         scale: Optional[float] = None, flags: int = 0) -> torch.Tensor:
+    """``local3d_attention(q, kv[..., :inner], kv[..., inner:])`` without materialising the two halves
+    (reference ``local_3d_attention.py:106-107`` as one projection)."""
+    if scale is None:
+        scale = (q.shape[-1] // heads) ** -0.5
+    return _Local3dAttentionKvFn.apply(q, kv, heads, tuple(extents), scale, flags)
+
+
 # ------------------------------------------------------------------------------------ VQ
 def vq_nearest(x: torch.Tensor, codebook: torch.Tensor, want_quantized: bool = True,
                want_err: bool = True, flags: int = 0) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
