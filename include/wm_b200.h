@@ -28,6 +28,8 @@
  *   wm_sample_step
  *       replaces one draw of the mask/replace sampler: top_k_logits + softmax + multinomial + re-masking
  *       (vq-video-diffusion/main.py:39-43, 80-109).
+ *   wm_embed_pos_fwd
+ *       replaces embedding(img_z) + get_pos_embedding(...) (vq-video-diffusion/local_3d_attention.py:143-157).
  *   wm_loss_hist_update
  *       replaces LossAwareSamplerEma.update_with_losses (vq-video-diffusion/importance_sampling.py:35-41).
  *
@@ -204,6 +206,15 @@ WM_API int wm_colsum(const void* a, void* out, float* workspace, long rows, int 
 WM_API int wm_bias_gelu_fwd(const void* h, const void* bias, void* y, long rows, int cols, int dtype, void* stream);
 WM_API int wm_bias_gelu_bwd(const void* dy, const void* h, const void* bias, void* dh, void* dbias, float* workspace,
                             long rows, int cols, int dtype, void* stream);
+
+/* x[b,s,h,w,:] = table[tokens[b,s,h,w]] + ((pos_s[s] + pos_h[h]) + pos_w[w]): the token embedding plus the three
+ * axis position embeddings of Local3dAttentionTransformer.forward (vq-video-diffusion/local_3d_attention.py:149-157)
+ * in one pass -- no gathered temporary, no broadcast adds; the sums round to the storage type in the order of the
+ * stock ops they replace.  tokens int64 [B,S,H,W] (clamped to [0, num_rows)), table [num_rows, dim], pos_* [>= S|H|W, dim],
+ * out [B,S,H,W,dim]; dim a multiple of 8. */
+WM_API int wm_embed_pos_fwd(const int64_t* tokens, const void* table, const void* pos_s, const void* pos_h,
+                     const void* pos_w, void* out, long B, int S, int H, int W, int dim, int num_rows, int dtype,
+                     void* stream);
 
 #ifdef __cplusplus
 }

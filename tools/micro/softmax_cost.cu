@@ -130,8 +130,10 @@ static void run(const char* name, long long* d_out) {
         long long mx = 0;
         for (int w = 0; w < warps; ++w) mx = h[w] > mx ? h[w] : mx;
         const double per_warp = (double)mx / iters;
-        printf("%-44s warps/SMSP %d: %7.1f cycles per unit per warp, %7.1f per unit per sub-partition\n", name, warps / 4,
+        printf("%-44s warps/SMSP %d: %7.1f cycles per unit per warp, %7.1f per unit per sub-partition   per warp:", name, warps / 4,
                per_warp, per_warp / (warps / 4));
+        for (int w = 0; w < warps; ++w) printf(" %.0f", (double)h[w] / iters);
+        printf("\n");
     }
 }
 

@@ -61,6 +61,8 @@ def lib() -> ctypes.CDLL:
     L.wm_sample_step.argtypes = [c_void_p] * 3 + [c_long, c_long, c_long, c_int, c_int, c_int, c_void_p, c_uint64, c_int, c_void_p]
     L.wm_loss_hist_update.restype = c_int
     L.wm_loss_hist_update.argtypes = [c_void_p] * 4 + [c_int, c_int, c_float, c_void_p]
+    L.wm_embed_pos_fwd.restype = c_int
+    L.wm_embed_pos_fwd.argtypes = [c_void_p] * 6 + [c_long, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
     L.wm_reduce_blocks.restype = c_int
     L.wm_reduce_blocks.argtypes = [c_long]
     L.wm_add_layernorm_fwd.restype = c_int
@@ -85,5 +87,5 @@ def check(rc: int, what: str) -> None:
 EXPORTS = ('wm_version', 'wm_last_error', 'wm_l3d_attn_uses_tensor_cores', 'wm_l3d_attn_fwd', 'wm_l3d_attn_bwd',
            'wm_l3d_attn_fwd_ld', 'wm_l3d_attn_bwd_ld',
            'wm_vq_nearest', 'wm_vq_distance', 'wm_adamw_step', 'wm_adamw_step_norm', 'wm_vq_stats', 'wm_vq_onehot',
-           'wm_sample_step', 'wm_loss_hist_update', 'wm_reduce_blocks', 'wm_add_layernorm_fwd',
+           'wm_sample_step', 'wm_loss_hist_update', 'wm_embed_pos_fwd', 'wm_reduce_blocks', 'wm_add_layernorm_fwd',
            'wm_add_layernorm_bwd', 'wm_colsum', 'wm_bias_gelu_fwd', 'wm_bias_gelu_bwd')

@@ -224,7 +224,10 @@ struct FwdParams {
 // step t+1.  All hand-offs are mbarriers; there is no CTA-wide barrier inside the loop.  A CTA walks
 // `hpc` heads of its brick back to back.  The window / border mask is part of the score MMA
 // (build_mask_tiles in attn_tc.cuh), so the element loop is: scale, 2^x, sum, pack.
-template <int D>
+// NK > 0: the kernel is compiled for blocks of exactly 16 * NK key columns (one P V chain instead of a 16-way switch of
+// unrolled chains: the issuing warps' code shrinks by ~10x, which matters to the instruction caches they share with the
+// compute warps); NK == 0: any block width.
+template <int D, int NK>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv_k,
                   const __grid_constant__ CUtensorMap map_kv_v, const FwdParams prm) {
@@ -415,13 +418,17 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 const uint32_t ta = tmem_p0 + (t & 1) * p_cols;                          // A = P from tensor memory
                 const uint64_t db = dv0 + stage * stage_step;
                 uint64_t* bar = &bar_o[t & 1];
+                if constexpr (NK > 0) {
+                    issue_o_chain(std::integral_constant<int, NK>{}, tmem_o, ta, db, accumulate, bar);
+                } else {
 #define WM_O_CASE(n) case n: issue_o_chain(std::integral_constant<int, n>{}, tmem_o, ta, db, accumulate, bar); break;
-                switch (nk_o) {
-                    WM_O_CASE(1) WM_O_CASE(2) WM_O_CASE(3) WM_O_CASE(4) WM_O_CASE(5) WM_O_CASE(6) WM_O_CASE(7) WM_O_CASE(8)
-                    WM_O_CASE(9) WM_O_CASE(10) WM_O_CASE(11) WM_O_CASE(12) WM_O_CASE(13) WM_O_CASE(14) WM_O_CASE(15)
-                    default: issue_o_chain(std::integral_constant<int, 16>{}, tmem_o, ta, db, accumulate, bar); break;
-                }
+                    switch (nk_o) {
+                        WM_O_CASE(1) WM_O_CASE(2) WM_O_CASE(3) WM_O_CASE(4) WM_O_CASE(5) WM_O_CASE(6) WM_O_CASE(7) WM_O_CASE(8)
+                        WM_O_CASE(9) WM_O_CASE(10) WM_O_CASE(11) WM_O_CASE(12) WM_O_CASE(13) WM_O_CASE(14) WM_O_CASE(15)
+                        default: issue_o_chain(std::integral_constant<int, 16>{}, tmem_o, ta, db, accumulate, bar); break;
+                    }
 #undef WM_O_CASE
+                }
                 if (head_end) umma_commit(&bar_head[hd & 1]);
             }
             __syncwarp();
@@ -747,7 +754,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
 }
 
-template <int D>
+template <int D, int NK>
 static int launch_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const AttnShape& s,
                       const Plan& pl, cudaStream_t st) {
     using G = Geo<D>;
@@ -757,10 +764,10 @@ static int launch_fwd(const void* q, const void* k, const void* v, void* o, floa
     if (int rc = make_tensor_map_5d(&mk, k, s.B, s.S, s.H, s.W, C, s.kv_ld(), G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
     if (int rc = make_tensor_map_5d(&mv, v, s.B, s.S, s.H, s.W, C, s.kv_ld(), G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
     FwdParams prm{s, pl, static_cast<__nv_bfloat16*>(o), lse};
-    WM_CUDA_CHECK(cudaFuncSetAttribute(l3d_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
+    WM_CUDA_CHECK(cudaFuncSetAttribute(l3d_fwd_tc_kernel<D, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
     const dim3 grid((unsigned)(pl.tilesW * pl.tilesH), (unsigned)pl.tilesS, (unsigned)(s.B * (s.heads / pl.hpc)));
     if (grid.y > 65535u || grid.z > 65535u) return fail(WM_EUNSUPPORTED, "grid too large for the tensor-core kernel");
-    l3d_fwd_tc_kernel<D><<<grid, kFwdThreads, pl.smem_bytes, st>>>(mq, mk, mv, prm);
+    l3d_fwd_tc_kernel<D, NK><<<grid, kFwdThreads, pl.smem_bytes, st>>>(mq, mk, mv, prm);
     WM_CUDA_CHECK(cudaGetLastError());
     return WM_OK;
 }
@@ -782,11 +789,14 @@ int attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse
     tc::Plan pl;
     if (!tc::make_plan(s, tc::kFwd, pl)) return fail(WM_EUNSUPPORTED, "no tensor-core tiling for this shape");
     int rc;
-    switch (s.d) {
-        case 32: rc = tc::launch_fwd<32>(q, k, v, o, lse, s, pl, st); break;
-        case 64: rc = tc::launch_fwd<64>(q, k, v, o, lse, s, pl, st); break;
-        default: rc = tc::launch_fwd<128>(q, k, v, o, lse, s, pl, st); break;
-    }
+    const int nk = pl.ncols_pad / 16;
+    // block widths of the named configurations get their own instantiation (3x5x5 window, 2x8x8 brick: 144 columns;
+    // 5x7x7: 112), everything else the generic kernel
+    if (s.d == 32 && nk == 9) rc = tc::launch_fwd<32, 9>(q, k, v, o, lse, s, pl, st);
+    else if (s.d == 128 && nk == 7) rc = tc::launch_fwd<128, 7>(q, k, v, o, lse, s, pl, st);
+    else if (s.d == 32) rc = tc::launch_fwd<32, 0>(q, k, v, o, lse, s, pl, st);
+    else if (s.d == 64) rc = tc::launch_fwd<64, 0>(q, k, v, o, lse, s, pl, st);
+    else rc = tc::launch_fwd<128, 0>(q, k, v, o, lse, s, pl, st);
     if (rc) return rc;
     // rows whose softmax left the range of the max-free formulation (LSE = NaN) are recomputed exactly
     return attn_fwd_fixup(q, k, v, o, lse, s, st);

@@ -168,6 +168,58 @@ __global__ void loss_hist_update_kernel(const float* __restrict__ ts, const floa
     counts[b] = c;
 }
 
+// ------------------------------------------------------------------------------ token + position embedding
+// x[b,s,h,w,:] = E[token] + ((Ps[s] + Ph[h]) + Pw[w])  -- Local3dAttentionTransformer.forward's first line
+// (local_3d_attention.py:149-157) in one pass: no gathered [B,S,H,W,dim] temporary, no broadcast add.  The three
+// sums round to the storage type one after the other, exactly like the chain of stock ops they replace.
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ float round_to(float v, const __nv_bfloat16*) { return __bfloat162float(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ float round_to(float v, const float*) { return v; }
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+    uint4 v;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = v;
+}
+__device__ __forceinline__ void store8(float* p, const float (&f)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+embed_pos_kernel(const int64_t* __restrict__ tokens, const T* __restrict__ table, const T* __restrict__ ps,
+                 const T* __restrict__ ph, const T* __restrict__ pw, T* __restrict__ out, long ntok, int S, int H, int W,
+                 int dim, int num_rows) {
+    const int vecs = dim >> 3;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntok * vecs) return;
+    const long tok = i / vecs;
+    const int c = (int)(i - tok * vecs) * 8;
+    const int w = (int)(tok % W), h = (int)((tok / W) % H), s = (int)((tok / ((long)W * H)) % S);
+    long row = tokens[tok];
+    row = row < 0 ? 0 : (row >= num_rows ? num_rows - 1 : row);
+    float e[8], a[8], b2[8], c2[8], r[8];
+    load8(table + row * dim + c, e);
+    load8(ps + (long)s * dim + c, a);
+    load8(ph + (long)h * dim + c, b2);
+    load8(pw + (long)w * dim + c, c2);
+    const T* tag = nullptr;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = e[k] + round_to(round_to(a[k] + b2[k], tag) + c2[k], tag);
+    store8(out + tok * dim + c, r);
+}
+
 }  // namespace
 }  // namespace wm
 
@@ -230,6 +282,33 @@ extern "C" int wm_loss_hist_update(const float* ts, const float* losses, float* 
     if (!ts || !losses || !weights || !counts) return fail(WM_EINVAL, "wm_loss_hist_update: null pointer");
     loss_hist_update_kernel<<<(buckets + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(ts, losses, weights, counts, B,
                                                                                                  buckets, alpha);
+    WM_CUDA_CHECK(cudaGetLastError());
+    return WM_OK;
+}
+
+extern "C" int wm_embed_pos_fwd(const int64_t* tokens, const void* table, const void* pos_s, const void* pos_h,
+                                const void* pos_w, void* out, long B, int S, int H, int W, int dim, int num_rows, int dtype,
+                                void* stream) {
+    if (B < 0 || S <= 0 || H <= 0 || W <= 0 || dim <= 0 || num_rows <= 0)
+        return fail(WM_EINVAL, "wm_embed_pos_fwd: bad shape B=%ld S=%d H=%d W=%d dim=%d rows=%d", B, S, H, W, dim, num_rows);
+    if (B == 0) return WM_OK;
+    if (!tokens || !table || !pos_s || !pos_h || !pos_w || !out) return fail(WM_EINVAL, "wm_embed_pos_fwd: null pointer");
+    if (dim % 8 != 0) return fail(WM_EUNSUPPORTED, "wm_embed_pos_fwd: dim=%d must be a multiple of 8", dim);
+    if (dtype != WM_DTYPE_BF16 && dtype != WM_DTYPE_FP32) return fail(WM_EINVAL, "wm_embed_pos_fwd: dtype %d", dtype);
+    const void* ptrs[] = {table, pos_s, pos_h, pos_w, out};
+    for (const void* q : ptrs)
+        if (!aligned16(q)) return fail(WM_EINVAL, "wm_embed_pos_fwd: pointers must be 16-byte aligned");
+    const long ntok = B * S * H * W, items = ntok * (dim / 8);
+    const unsigned blocks = (unsigned)((items + 255) / 256);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == WM_DTYPE_BF16)
+        embed_pos_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(tokens, static_cast<const __nv_bfloat16*>(table),
+            static_cast<const __nv_bfloat16*>(pos_s), static_cast<const __nv_bfloat16*>(pos_h),
+            static_cast<const __nv_bfloat16*>(pos_w), static_cast<__nv_bfloat16*>(out), ntok, S, H, W, dim, num_rows);
+    else
+        embed_pos_kernel<float><<<blocks, 256, 0, st>>>(tokens, static_cast<const float*>(table), static_cast<const float*>(pos_s),
+            static_cast<const float*>(pos_h), static_cast<const float*>(pos_w), static_cast<float*>(out), ntok, S, H, W, dim,
+            num_rows);
     WM_CUDA_CHECK(cudaGetLastError());
     return WM_OK;
 }

@@ -34,8 +34,7 @@ class VqVideoDiffusionModel(nn.Module):
         self.logit_proj = nn.Linear(dim, num_classes)
 
     def forward(self, x):
-        feats = self.transformer(x)
-        return self.logit_proj(feats[:, -1])                                  # last frame only
+        return self.logit_proj(self.transformer.forward_last_frame(x))       # == transformer(x)[:, -1]
 
 
 def corrupt_last_frame(tokens: torch.Tensor, r: torch.Tensor, num_embeddings: int,

@@ -93,8 +93,8 @@ class Local3dAttention(nn.Module):
         out = ops.local3d_attention(q, k, v, self.heads, self.extents, self.scale, self.kernel_flags)
         return out.reshape(-1, self.heads, 1, out.shape[-1] // self.heads)
 
-    def forward_deferred_bias(self, x, q):
-        """``(y, bias)`` with ``forward(x, q) == y + bias``.  Softmax rows sum to one, so ``to_v``'s bias passes through
+    def forward_deferred_bias(self, x, q, q_projected=None):
+        """``(y, bias)`` with ``forward(x, q) == y + bias`` (``q_projected``: ``to_q(q)`` when the caller already has it).  Softmax rows sum to one, so ``to_v``'s bias passes through
         the attention core unchanged: ``attn(q, k, v + b_v) = attn(q, k, v) + b_v``, and with the output projection
         the whole module equals ``attn(q, k, x W_v^T) W_o^T + (W_o b_v + b_o)``.  The caller adds that [dim] vector in
         its fused residual-add + LayerNorm kernel; autograd routes its gradient (reduced by that kernel's backward) to
@@ -110,7 +110,8 @@ class Local3dAttention(nn.Module):
         # to_k and to_v read the same normalised input: ONE GEMM with N = 2*inner; the kernels take the two channel
         # halves of its output in place, and backward hands dK | dV back as one operand (one dgrad, one wgrad)
         kv = torch.nn.functional.linear(x, torch.cat((self.to_k.weight, self.to_v.weight), dim=0))
-        core = ops.local3d_attention_kv(self.to_q(q), kv, self.heads, self.extents, self.scale, self.kernel_flags)
+        qp = q_projected if q_projected is not None else self.to_q(q)
+        core = ops.local3d_attention_kv(qp, kv, self.heads, self.extents, self.scale, self.kernel_flags)
         bias = torch.addmv(self.to_out[0].bias, w_o, self.to_v.bias)      # W_o b_v + b_o, one GEMV
         return torch.nn.functional.linear(core, w_o).reshape(q.shape), bias
 
@@ -149,16 +150,35 @@ class Local3dAttentionTransformer(nn.Module):
                + self.pos_emb_w.weight[None, None, :w, :])
         return pos.unsqueeze(0).expand(batch_shape[0], -1, -1, -1, -1)
 
-    def forward(self, img_z):
-        """``x = attn(LN(x), q=x) + x; x = ff(LN(x)) + x`` per layer (reference ``:159-161``), scheduled so
-        that every residual add is fused with the LayerNorm that follows it (``wm_add_layernorm_*``)."""
-        x = self.embedding(img_z) + self.get_pos_embedding(img_z.shape)
+    def _blocks(self, img_z):
+        """The residual stream before the last MLP branch is added, that branch's output and its deferred bias."""
+        _, s, h, w = img_z.shape
+        x = ops.embed_pos(img_z, self.embedding.weight, self.pos_emb_s.weight[:s], self.pos_emb_h.weight[:h],
+                          self.pos_emb_w.weight[:w])
         pending = pending_bias = None                # branch output (and its deferred bias) not yet added to the stream
         for attn, ff in self.layers:
             x, xn = ops.add_layernorm(x, pending, attn.norm.weight, attn.norm.bias, attn.norm.eps, pending_bias)
-            a, a_bias = attn.fn.forward_deferred_bias(xn, q=x)
+            # to_q reads the residual stream itself (reference :160, q=x): the stream goes THROUGH the projection node, so
+            # that its gradient is folded into the projection's dgrad GEMM instead of a separate full-size add
+            qp, x = ops.linear_passthrough(x, attn.fn.to_q.weight)
+            a, a_bias = attn.fn.forward_deferred_bias(xn, q=x, q_projected=qp)
             x, xn = ops.add_layernorm(x, a, ff.norm.weight, ff.norm.bias, ff.norm.eps, a_bias)
             pending, pending_bias = ff.fn.forward_deferred_bias(xn)
+        return x, pending, pending_bias
+
+    @staticmethod
+    def _close(x, pending, pending_bias):
         if pending is None:
             return x
         return x + pending if pending_bias is None else x + (pending + pending_bias.to(pending.dtype))
+
+    def forward(self, img_z):
+        """``x = attn(LN(x), q=x) + x; x = ff(LN(x)) + x`` per layer (reference ``:159-161``), scheduled so
+        that every residual add is fused with the LayerNorm that follows it (``wm_add_layernorm_*``)."""
+        return self._close(*self._blocks(img_z))
+
+    def forward_last_frame(self, img_z):
+        """``forward(img_z)[:, -1]``: the only part of the output the denoiser head reads (``main.py:35``).  The final
+        residual add (element-wise) is done on that frame alone -- same values, 1/S of the traffic."""
+        x, pending, pending_bias = self._blocks(img_z)
+        return self._close(x[:, -1], None if pending is None else pending[:, -1], pending_bias)

@@ -251,6 +251,82 @@ def loss_hist_update(ts, losses, weights, counts, alpha) -> None:
     _count(1)
 
 
+class _EmbedPosFn(torch.autograd.Function):
+    """``embedding(tokens) + ((pos_s + pos_h) + pos_w)`` in one kernel (``wm_embed_pos_fwd``); the backward reduces the
+    incoming gradient over the batch once and hands the table gradient to the stock embedding backward."""
+
+    @staticmethod
+    def forward(ctx, tokens, table, ps, ph, pw):
+        _require_cuda(tokens, table)
+        B, S, H, W = tokens.shape
+        dim = table.shape[1]
+        tokens = tokens.contiguous()
+        table, ps, ph, pw = (t.contiguous() for t in (table, ps, ph, pw))
+        out = torch.empty(B, S, H, W, dim, device=table.device, dtype=table.dtype)
+        check(_lib.lib().wm_embed_pos_fwd(tokens.data_ptr(), table.data_ptr(), ps.data_ptr(), ph.data_ptr(), pw.data_ptr(),
+                                          out.data_ptr(), B, S, H, W, dim, table.shape[0], _dtype_code(table), _stream()),
+              'wm_embed_pos_fwd')
+        _count(1)
+        ctx.save_for_backward(tokens)
+        ctx.rows = (table.shape[0], ps.shape[0], ph.shape[0], pw.shape[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (tokens,) = ctx.saved_tensors
+        n, ns, nh, nw = ctx.rows
+        B, S, H, W = tokens.shape
+        dout = dout.contiguous()
+        dtable = torch.ops.aten.embedding_dense_backward(dout, tokens, n, -1, False)
+        g = dout.sum(dim=0)                                   # [S,H,W,dim]: the one pass over the full gradient
+        dps = torch.zeros(ns, g.shape[-1], device=g.device, dtype=g.dtype)
+        dph = torch.zeros(nh, g.shape[-1], device=g.device, dtype=g.dtype)
+        dpw = torch.zeros(nw, g.shape[-1], device=g.device, dtype=g.dtype)
+        dps[:S] = g.sum(dim=(1, 2))
+        dph[:H] = g.sum(dim=(0, 2))
+        dpw[:W] = g.sum(dim=(0, 1))
+        return None, dtable, dps, dph, dpw
+
+
+def embed_pos(tokens: torch.Tensor, table: torch.Tensor, pos_s: torch.Tensor, pos_h: torch.Tensor,
+              pos_w: torch.Tensor) -> torch.Tensor:
+    """Token embedding + the three axis position embeddings (``local_3d_attention.py:143-157``) -> ``[B,S,H,W,dim]``."""
+    _require_cuda(tokens, table)
+    if table.shape[1] % 8 != 0 or table.dtype not in (torch.bfloat16, torch.float32):
+        _, s, h, w = tokens.shape
+        pos = pos_s[:s, None, None, :] + pos_h[None, :h, None, :] + pos_w[None, None, :w, :]
+        return torch.nn.functional.embedding(tokens, table) + pos.unsqueeze(0)
+    return _EmbedPosFn.apply(tokens, table, pos_s, pos_h, pos_w)
+
+
+class _ProjPassFn(torch.autograd.Function):
+    """``(x @ W^T, x)``: a bias-free projection whose input also continues down another branch (``to_q`` reads the
+    residual stream, ``local_3d_attention.py:160``).  Routing the stream THROUGH this node lets the backward fold the
+    stream's gradient into the projection's dgrad GEMM (``beta = 1``) instead of a separate full-size add."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        ctx.save_for_backward(x, weight)
+        return torch.nn.functional.linear(x, weight), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dpass):
+        x, weight = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        x2 = x.reshape(-1, x.shape[-1])
+        dw = dy2.t() @ x2
+        if dpass is None:
+            dx = (dy2 @ weight).view(x.shape)
+        else:
+            dx = torch.addmm(dpass.reshape(-1, x.shape[-1]), dy2, weight).view(x.shape)
+        return dx, dw
+
+
+def linear_passthrough(x: torch.Tensor, weight: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    _require_cuda(x)
+    return _ProjPassFn.apply(x, weight)
+
+
 # ------------------------------------------------------- layer-level kernels (LayerNorm, bias grads)
 def _rows(t: torch.Tensor) -> int:
     return t.numel() // t.shape[-1]
