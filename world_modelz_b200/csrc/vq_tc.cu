@@ -17,8 +17,11 @@
 //   warps  0-3   scan code half A (codes [0, K/2), TMEM columns [0, 256)), warps 4-7 half B ([256, 512)); the first warp
 //                of each group also issues its half's tcgen05.mma chain for the next tile the moment the group has
 //                drained the scores -- while one half is being scanned the tensor pipe works on the other.
-//                One thread per row: distance keys (fp32 bits with the code's column
-//                index in the low 8 bits) reduced with 3-input integer min / max to the two smallest keys
+//                One thread per row: distance keys (the score's fp32 bits shifted left by four, the code's position
+//                inside its 16-column chunk below them: one IMAD per score) reduced with 3-input integer min / max
+//                to the two smallest keys.  |x|^2 + |e_k|^2 + 2 arrive WITH the score: a thirteenth K = 16 MMA step
+//                multiplies [1 1 1 | split3(|x|^2 + 2)] with [split3(|e_k|^2) | 1 1 1] (three bf16 terms carry an fp32
+//                value exactly), so the scanners add nothing and read no shared memory
 // Replaces VectorQuantizerEMA's [N,L,D,K] distance temporary + argmin + gather (vq.py:30-36,84-87).
 #include "tc_common.cuh"
 #include "wm_common.cuh"
@@ -56,11 +59,46 @@ struct Params {
 // byte offset of 16-byte chunk c16 of row r in a [rows x 64 bf16] slab stored K-major with the 128-byte swizzle
 __device__ __forceinline__ uint32_t sw128(int r, int c16) { return (uint32_t)r * 128u + (uint32_t)((c16 ^ (r & 7)) << 4); }
 
+// 1-D bulk copy global -> shared (TMA engine, no tensor map), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr uint32_t kKeyBase = 0x08000000u;      // -(bits(1.0f) << 4) mod 2^32: key = (bits(t) - bits(1.0f)) * 16 + position
+constexpr float kHugeNorm = 1.0e9f;             // |x|^2 + max|e|^2 below this keeps every score under 2^32 (28 key bits of exponent + mantissa)
+
+__device__ __forceinline__ uint32_t vmin3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("min.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));      // ptxas fuses the pair into one 3-input VIMNMX3
+    asm("min.u32 %0, %1, %2;" : "=r"(d) : "r"(d), "r"(c));
+    return d;
+}
+
+// Two codes whose FILTERED scores differ by more than this are ordered like their exact distances.  The filter's score is
+// |x|^2 + |e|^2 + 2 - 2 x.e with x.e from three bf16 products (split error <= 6 * 2^-18 |x||e| ~ 2.3e-5 |x||e|) and every
+// term accumulated in fp32 by the tensor core: 13 K-steps, each adding a rounding of at most 2^-23 of the running sum,
+// which is bounded by (|x| + |e|)^2 + 2 <= 2 (|x|^2 + |e|^2) + 2.  Twice the per-score bound, with slack:
+__device__ __forceinline__ float filter_window(float xn2, float emax) {
+    return 6.103515625e-5f * sqrtf(xn2) * emax + 8.0e-6f * (xn2 + emax * emax + 1.f) + 1e-30f;
+}
+
 __device__ __forceinline__ void split_bf16(float v, uint16_t& hi, uint16_t& lo) {
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
     const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
     hi = *reinterpret_cast<const uint16_t*>(&h);
     lo = *reinterpret_cast<const uint16_t*>(&l);
+}
+
+// v = h + m + l exactly (three bf16 terms hold the 24 significant bits of an fp32 value)
+__device__ __forceinline__ void split3_bf16(float v, uint16_t (&out)[3]) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+    out[0] = *reinterpret_cast<const uint16_t*>(&h);
+    out[1] = *reinterpret_cast<const uint16_t*>(&m);
+    out[2] = *reinterpret_cast<const uint16_t*>(&l);
 }
 
 // exact squared distance (fp64 accumulation of fp32 differences) between a latent row and a code, both in global memory;
@@ -86,30 +124,73 @@ __device__ __noinline__ double exact_dist(const float* __restrict__ xr, const fl
     return a;
 }
 
-// Exact (fp64) winner among the candidates the two code halves reported, by a whole warp: r.y = best code, r.z =
-// runner-up (a candidate when r.w == 1), r.w == 2: more than two codes of that half are inside the window -> the whole
-// half.  Lanes take candidates round-robin; lowest index wins ties.  Rare path, kept out of line.
+// Undecided rows (two or more codes inside the filter's error window -- about one row in a thousand on Gaussian data)
+// leave the filter kernel with a NEGATIVE idx that packs their candidates: per code half the best code, the runner-up
+// and whether the runner-up (w = 1) or more than two codes (w = 2: the whole half) lie inside the window.
+__device__ __forceinline__ long pack_candidates(uint32_t k1a, uint32_t k2a, uint32_t wa, uint32_t k1b, uint32_t k2b, uint32_t wb,
+                                                bool a_in, bool b_in) {
+    const uint64_t m = (uint64_t)(k1a & 511u) | ((uint64_t)(k2a & 511u) << 9) | ((uint64_t)(wa & 3u) << 18) |
+                       ((uint64_t)(k1b & 511u) << 20) | ((uint64_t)(k2b & 511u) << 29) | ((uint64_t)(wb & 3u) << 38) |
+                       ((uint64_t)(a_in ? 1u : 0u) << 40) | ((uint64_t)(b_in ? 1u : 0u) << 41) | (1ull << 63);
+    return (long)m;
+}
+
+// Second kernel, launched right behind the filter: a warp settles each undecided row exactly (fp64 distances to its
+// candidates, lowest index on ties) and rewrites idx / quantized / sq_err.  Keeping this out of the filter
+// kernel matters: with the fp64 path inlined there, its mere presence (registers, code size) cost the filter 17 %.
 template <int D>
-__device__ __noinline__ int settle_exact_warp(const float* __restrict__ xr, const float* __restrict__ cbl, uint4 ra, uint4 rb,
-                                              bool a_in, bool b_in, int KH, int lane) {
-    const int nA = a_in ? (ra.w == 2u ? KH : 1 + (ra.w == 1u)) : 0;
-    const int nB = b_in ? (rb.w == 2u ? KH : 1 + (rb.w == 1u)) : 0;
-    double bd = INFINITY;
-    int bk = 0x7fffffff;
-    for (int c = lane; c < nA + nB; c += 32) {
-        int k;
-        if (c < nA) k = ra.w == 2u ? c : (c == 0 ? (int)ra.y : (int)ra.z);
-        else k = rb.w == 2u ? KH + (c - nA) : (c == nA ? (int)rb.y : (int)rb.z);
-        const double dd = exact_dist<D>(xr, cbl + (long)k * D);
-        if (dd < bd || (dd == bd && k < bk)) { bd = dd; bk = k; }
-    }
+__global__ void __launch_bounds__(256)
+vq_settle_kernel(const Params prm) {
+    const int lane = threadIdx.x & 31;
+    const long items = prm.N * prm.L;
+    const long base = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+    if (base >= items) return;
+    const long mine = base + lane;
+    const int64_t marker = mine < items ? prm.idx[mine] : 0;
+    unsigned todo = __ballot_sync(0xffffffffu, marker < 0);
+    while (todo) {
+        const int j = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const long item = base + j;                       // = n * L + l
+        const int l = (int)(item % prm.L);
+        const float* xr = prm.x + item * (long)D;
+        const float* cbl = prm.cb + (long)l * prm.K * D;
+        // candidates: per code half its best code, its runner-up (w == 1) or the whole half (w == 2)
+        const uint64_t m = (uint64_t)__shfl_sync(0xffffffffu, (long long)marker, j);
+        const int KH = prm.K >> 1;
+        const uint32_t k1a = m & 511u, k2a = (m >> 9) & 511u, wa = (m >> 18) & 3u;
+        const uint32_t k1b = (m >> 20) & 511u, k2b = (m >> 29) & 511u, wb = (m >> 38) & 3u;
+        const int nA = ((m >> 40) & 1u) ? (wa == 2u ? KH : 1 + (wa == 1u)) : 0;
+        const int nB = ((m >> 41) & 1u) ? (wb == 2u ? KH : 1 + (wb == 1u)) : 0;
+        double bd = INFINITY;
+        int bk = 0x7fffffff;
+        for (int c = lane; c < nA + nB; c += 32) {
+            int k;
+            if (c < nA) k = wa == 2u ? c : (c == 0 ? (int)k1a : (int)k2a);
+            else k = wb == 2u ? KH + (c - nA) : (c == nA ? (int)k1b : (int)k2b);
+            const double dd = exact_dist<D>(xr, cbl + (long)k * D);
+            if (dd < bd || (dd == bd && k < bk)) { bd = dd; bk = k; }
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double od = __shfl_xor_sync(0xffffffffu, bd, o);
-        const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-        if (od < bd || (od == bd && ok < bk)) { bd = od; bk = ok; }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            if (od < bd || (od == bd && ok < bk)) { bd = od; bk = ok; }
+        }
+        if (lane == 0) prm.idx[item] = (int64_t)bk;
+        if ((prm.quantized != nullptr || prm.sq_err != nullptr) && lane < D / 4) {
+            const float4 xq = __ldg(reinterpret_cast<const float4*>(xr) + lane);
+            const float4 ev = __ldg(reinterpret_cast<const float4*>(cbl + (long)bk * D) + lane);
+            const float d0 = ev.x - xq.x, d1 = ev.y - xq.y, d2 = ev.z - xq.z, d3 = ev.w - xq.w;
+            float err = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
+            if (prm.quantized != nullptr)
+                reinterpret_cast<float4*>(prm.quantized + item * (long)D)[lane] = make_float4(xq.x + d0, xq.y + d1, xq.z + d2, xq.w + d3);
+#pragma unroll
+            for (int o = D / 8; o > 0; o >>= 1) err += __shfl_xor_sync((1u << (D / 4)) - 1u, err, o);
+            if (prm.sq_err != nullptr && lane == 0) prm.sq_err[item] = err;
+        }
+        __syncwarp();
     }
-    return bk;
 }
 
 template <int D>
@@ -121,14 +202,23 @@ vq_nearest_tc_kernel(const Params prm) {
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int K = prm.K, L = prm.L;
     const int KH = K >> 1;                                 // codes per half
-    const int e_slab = K * 128, x_slab = kTileM * 128;
+    const int e_slab = K * 128;
     uint8_t* sEhi = smem;                                  // [slabs][K rows][128 B]   -2 * e, bf16 hi
     uint8_t* sElo = sEhi + kSlabs * e_slab;                //                          -2 * e, bf16 lo
-    uint8_t* sXhi = sElo + kSlabs * e_slab;                // [2 buffers][slabs][128 rows][128 B]
-    uint8_t* sXlo = sXhi + 2 * kSlabs * x_slab;
-    float* sNorm = reinterpret_cast<float*>(sXlo + 2 * kSlabs * x_slab);     // [K]  |e_k|^2 + 1
-    float* sXn2 = sNorm + K;                               // [2][128] |x|^2
-    uint32_t* sRes = reinterpret_cast<uint32_t*>(sXn2 + 2 * kTileM);          // [2][2 halves][128] {t1, code 1, code 2, extra}
+    // Latent tiles: two 32 KB buffers.  A tile arrives as fp32 rows (cp.async.bulk, 256 B per row) and is converted IN
+    // PLACE into the bf16 hi / lo operand tiles: the 8-row swizzle atoms of hi and lo alternate (hi atom g at g * 2048,
+    // lo atom g at g * 2048 + 1024; descriptors with SBO = 2048), so the 16 rows a loader warp owns occupy the same
+    // 4 KB as fp32 data and as operands -- the warp reads them all, then overwrites them.
+    uint8_t* sX = sElo + kSlabs * e_slab;                  // [2 buffers][32 KB]
+    constexpr int kXBuf = kTileM * D * 4;
+    static_assert(kXBuf == 2 * kTileM * 128, "fp32 tile and the hi + lo operand tiles must have the same size");
+    // operands of the norm step (K = 16 channels, no swizzle: 8-row x 16-byte core matrices, the two 8-channel columns
+    // LBO apart): x side [1 1 1 h m l 0 0 | 0..], h + m + l = |x|^2 + 2;  e side [h m l 1 1 1 0 0 | 0..], h + m + l = |e_k|^2
+    uint8_t* sXe = sX + 2 * kXBuf;                         // [2 buffers][2 columns][128 rows][16 B]
+    uint8_t* sEe = sXe + 2 * 2 * kTileM * 16;              // [2 columns][K rows][16 B]
+    float* sXn2 = reinterpret_cast<float*>(sEe + 2 * K * 16);               // [3][128] |x|^2 (tile j in slot j % 3: tile j+2 is
+                                                                              // converted while tiles j and j+1 still need theirs)
+    uint32_t* sRes = reinterpret_cast<uint32_t*>(sXn2 + 3 * kTileM);          // [2][2 halves][128] {t1, code 1, code 2, extra}
     float* sRed = reinterpret_cast<float*>(sRes + 2 * 2 * kTileM * 4);       // [32] block reduction
     uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 32);
     uint64_t* bar_xready = bars;         // [2] operand tiles of a latent tile written          (8 loader warps)
@@ -136,7 +226,9 @@ vq_nearest_tc_kernel(const Params prm) {
     uint64_t* bar_full = bars + 4;       // [2] scores of code half A / B computed              (tcgen05.commit)
     uint64_t* bar_free = bars + 6;       // [2] scores of half A / B drained                    (4 scanner warps)
     uint64_t* bar_res = bars + 8;        // [2] both halves' results of a tile are in sRes      (8 scanner warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* bar_xload = bars + 10;     // [2] fp32 rows of a latent tile landed                 (cp.async.bulk complete_tx)
+    uint64_t* bar_resfree = bars + 12;   // [2] the writers have consumed a tile's sRes entries     (8 writer warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int l = blockIdx.y;
@@ -146,6 +238,8 @@ vq_nearest_tc_kernel(const Params prm) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bar_xready[i], 8);
             mbar_init(&bar_xfree[i], 2);
+            mbar_init(&bar_xload[i], 1);
+            mbar_init(&bar_resfree[i], 8);
             mbar_init(&bar_full[i], 1);
             mbar_init(&bar_free[i], 4);
             mbar_init(&bar_res[i], 8);
@@ -178,9 +272,19 @@ vq_nearest_tc_kernel(const Params prm) {
             *reinterpret_cast<uint4*>(sEhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<uint4*>(sElo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
-        sNorm[k] = (float)a + 1.f;        // +1 keeps every filtered distance positive: its fp32 bits then order like integers
+        {   // e side of the norm step
+            const float nrm = (float)a;
+            uint16_t h3[3];
+            split3_bf16(nrm, h3);
+            const uint32_t off = (uint32_t)(k >> 3) * 128u + (uint32_t)(k & 7) * 16u;
+            *reinterpret_cast<uint4*>(sEe + off) = make_uint4((uint32_t)h3[0] | ((uint32_t)h3[1] << 16), (uint32_t)h3[2] | (0x3F80u << 16),
+                                                              0x3F803F80u, 0u);
+            *reinterpret_cast<uint4*>(sEe + K * 16 + off) = make_uint4(0u, 0u, 0u, 0u);
+        }
         emax2 = fmaxf(emax2, (float)a);
     }
+    for (int i = tid; i < 2 * kTileM; i += kThreads)
+        *reinterpret_cast<uint4*>(sXe + (i / kTileM) * (2 * kTileM * 16) + kTileM * 16 + (i % kTileM) * 16) = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) emax2 = fmaxf(emax2, __shfl_xor_sync(0xffffffffu, emax2, o));
     if (lane == 0) sRed[warp] = emax2;
@@ -202,21 +306,22 @@ vq_nearest_tc_kernel(const Params prm) {
         const int quad = warp & 3, half = warp >> 2;
         const int row = quad * 32 + lane;
         const uint32_t taddr = tmem_base + half * 256 + ((uint32_t)(quad * 32) << 16);
-        const float* nk = sNorm + half * KH;
         const int nchunk = KH >> 4;
         // ---- the half's MMA chain: x_hi e_hi + x_lo e_hi + x_hi e_lo over all D channels, N = K/2 columns
         const bool issuer = quad == 0;
         const bool leader = elect_one();
         const uint32_t idesc = make_idesc_bf16(KH, false, false);
-        const uint64_t dxh = make_smem_desc(smem_u32(sXhi), 16, 1024, 2u), dxl = make_smem_desc(smem_u32(sXlo), 16, 1024, 2u);
+        const uint64_t dxh = make_smem_desc(smem_u32(sX), 16, 2048, 2u), dxl = make_smem_desc(smem_u32(sX + 1024), 16, 2048, 2u);
         const uint64_t deh = make_smem_desc(smem_u32(sEhi), 16, 1024, 2u), del = make_smem_desc(smem_u32(sElo), 16, 1024, 2u);
+        const uint64_t dxe = make_smem_desc(smem_u32(sXe), (uint32_t)kTileM * 16u, 128u, 0u);      // norm step: no swizzle
+        const uint64_t dee = make_smem_desc(smem_u32(sEe), (uint32_t)K * 16u, 128u, 0u);
         auto issue_tile = [&](int j) {           // called by the issuing warp once its half is free (or was never used)
             const int b = j & 1;
             mbar_wait(&bar_xready[b], (j >> 1) & 1);
             if (j > 0) mbar_wait(&bar_free[half], (j - 1) & 1);           // all four warps of the group have drained tile j-1
             tc_fence_after();
             if (leader) {
-                const uint32_t xoff = (uint32_t)((b * kSlabs * x_slab) >> 4);
+                const uint32_t xoff = (uint32_t)((b * kXBuf) >> 4);
                 const uint32_t eoff = (uint32_t)((half * KH * 128) >> 4);
                 bool first = true;
 #pragma unroll
@@ -226,11 +331,14 @@ vq_nearest_tc_kernel(const Params prm) {
 #pragma unroll
                     for (int kk = 0; kk < ((WM_VQ_EXP & 2) ? 0 : D / 16); ++kk) {
                         const uint32_t sl = (uint32_t)(kk >> 2), ko = (uint32_t)((kk & 3) * 2);
-                        umma_bf16_ss(tmem_base + half * 256, da + sl * (uint32_t)(x_slab >> 4) + ko,
-                                     db + sl * (uint32_t)(e_slab >> 4) + ko, idesc, first ? 0u : 1u);
+                        umma_bf16_ss(tmem_base + half * 256, da + ko, db + sl * (uint32_t)(e_slab >> 4) + ko, idesc, first ? 0u : 1u);
                         first = false;
                     }
                 }
+                // + (|x|^2 + 2) + |e_k|^2: the norm step
+                if (!(WM_VQ_EXP & 2))
+                    umma_bf16_ss(tmem_base + half * 256, dxe + (uint32_t)((b * 2 * kTileM * 16) >> 4),
+                                 dee + (uint32_t)((half * KH * 16) >> 4), idesc, 1u);
                 umma_commit(&bar_full[half]);
                 umma_commit(&bar_xfree[b]);                               // (both halves' commits free operand buffer b)
             }
@@ -242,26 +350,21 @@ vq_nearest_tc_kernel(const Params prm) {
             const long n = ((long)(first_tile + j * stride)) * kTileM + row;
             mbar_wait(&bar_full[half], j & 1);
             tc_fence_after();
-            const float xn2 = sXn2[b * kTileM + row];
-            const uint64_t xx = pk2(xn2, xn2);
-            // two smallest keys of this half and the 16-column chunks they came from.  A key is the filtered distance's
-            // fp32 bits (positive, so they order like integers) with the column's position inside its chunk in the low 4
-            // bits: the comparison network sees distances truncated by 2^-19 relative, nothing more
-            uint32_t m1 = 0x7f800000u, m2 = 0x7f800000u;
+            const float xn2 = sXn2[(j % 3) * kTileM + row];
+            // two smallest keys of this half and the 16-column chunks they came from.  A score t = |x - e|^2 + 2 (>= 1, so
+            // its fp32 bits order like integers) becomes the key (bits(t) - bits(1)) * 16 + position-in-chunk: one IMAD,
+            // no bits dropped; t < 2^32 is the writer's business (kHugeNorm)
+            uint32_t m1 = 0xffffffffu, m2 = 0xffffffffu;
             int c1 = 0, c2 = 0;
             uint32_t r0[16], r1[16];
             auto scan16 = [&](const uint32_t (&r)[16], int c) {
-                uint32_t a1 = 0x7f800000u, a2 = 0x7f800000u;              // the chunk's two smallest
+                uint32_t a1 = 0xffffffffu, a2 = 0xffffffffu;              // the chunk's two smallest
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float2 nn = *reinterpret_cast<const float2*>(nk + c * 16 + 2 * i);
-                    const uint64_t t2 = fadd2(fadd2(pk2u(r[2 * i], r[2 * i + 1]), xx), pk2(nn.x, nn.y));
-                    float ta, tb;
-                    upk2(t2, ta, tb);
-                    const uint32_t ka = (__float_as_uint(ta) & 0xfffffff0u) | (uint32_t)(2 * i);
-                    const uint32_t kb = (__float_as_uint(tb) & 0xfffffff0u) | (uint32_t)(2 * i + 1);
+                    const uint32_t ka = r[2 * i] * 16u + (kKeyBase + (uint32_t)(2 * i));
+                    const uint32_t kb = r[2 * i + 1] * 16u + (kKeyBase + (uint32_t)(2 * i + 1));
                     const uint32_t lo = min(ka, kb), hi = max(ka, kb);
-                    a2 = (uint32_t)__vimin3_s32((int)a2, (int)hi, (int)max(a1, lo));
+                    a2 = vmin3(a2, hi, max(a1, lo));
                     a1 = min(a1, lo);
                 }
                 // merge (a1, a2) of chunk c into (m1, m2): the second smallest overall is min(m2, a2, max(m1, a1))
@@ -288,18 +391,14 @@ vq_nearest_tc_kernel(const Params prm) {
                     scan16(r1, c + 1);
                 }
             }
-            const float t1 = __uint_as_float(m1 & 0xfffffff0u), t2nd = __uint_as_float(m2 & 0xfffffff0u);
+            const float t1 = __uint_as_float((m1 >> 4) + 0x3f800000u), t2nd = __uint_as_float((m2 >> 4) + 0x3f800000u);
             const int k1 = half * KH + c1 * 16 + (int)(m1 & 15u), k2 = half * KH + c2 * 16 + (int)(m2 & 15u);
-            // window: rounding of the filter (2 eps) + the 4 key bits dropped from each of the two distances
-            const float win = 6.103515625e-5f * sqrtf(xn2) * emax + 3.9e-6f * t2nd + 1e-30f;
+            const float win = filter_window(xn2, emax);
             const bool close2 = !(WM_VQ_EXP & 1) && (n < prm.N) && (t2nd - t1 <= win);
             uint32_t extra = 0;                                           // 1: the runner-up is a candidate too; 2: more than two are
-#if WM_VQ_EXP & 32
-            { const unsigned m = __ballot_sync(0xffffffffu, close2); if (lane == 0) { atomicAdd(&g_vq_dbg[2], (unsigned long long)__popc(m)); atomicAdd(&g_vq_dbg[3], m ? 1ull : 0ull); } }
-#endif
-            if (__any_sync(0xffffffffu, close2) && !((WM_VQ_EXP & 128) && (prm.N >> 40) == 0)) {
+            if (__any_sync(0xffffffffu, close2)) {
                 // rare (about one row in a thousand): count the codes of this half inside the window while the scores are
-                // still ours.  Two: the writer settles k1 against k2 exactly.  More: it re-scans the half exactly.
+                // still ours.  Two: k1 is settled against k2 exactly.  More: the whole half is.
                 const float thr = t1 + win;
                 int cnt = 0;
                 for (int c = 0; c < nchunk; ++c) {
@@ -307,7 +406,7 @@ vq_nearest_tc_kernel(const Params prm) {
                     tmem_ld16(taddr + c * 16, r);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) cnt += ((__uint_as_float(r[i]) + xn2) + nk[c * 16 + i]) <= thr;
+                    for (int i = 0; i < 16; ++i) cnt += __uint_as_float(r[i]) <= thr;
                 }
                 if (close2) extra = cnt > 2 ? 2u : 1u;
             }
@@ -315,6 +414,7 @@ vq_nearest_tc_kernel(const Params prm) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_free[half]);                    // this half may be refilled
             if (issuer && j + 1 < my_tiles) issue_tile(j + 1);
+            if (j >= 2) mbar_wait(&bar_resfree[b], ((j - 2) >> 1) & 1);    // tile j-2's results have been written out
             uint4* res = reinterpret_cast<uint4*>(sRes) + (b * 2 + half) * kTileM + row;
             *res = make_uint4(__float_as_uint(t1), (uint32_t)k1, (uint32_t)k2, extra);
             __syncwarp();
@@ -328,9 +428,8 @@ vq_nearest_tc_kernel(const Params prm) {
         constexpr int kRowsPerLane = 8;
         static_assert(D == 64, "row = 16 lanes x float4");
         const int wrow0 = (warp - 8) * 16, sub = lane >> 4, ch = lane & 15;
-        float4 xv[kRowsPerLane];                           // tile being loaded (two tiles ahead of its output)
         auto tile_base = [&](int j) { return ((long)(first_tile + j * stride)) * kTileM; };
-        auto load_rows = [&](int j, float4 (&dst)[kRowsPerLane]) {
+        auto load_rows = [&](int j, float4 (&dst)[kRowsPerLane]) {      // output path: re-read of the tile (L2 hit)
             const long n0 = tile_base(j) + wrow0 + sub;
 #pragma unroll
             for (int i = 0; i < kRowsPerLane; ++i) {
@@ -339,9 +438,31 @@ vq_nearest_tc_kernel(const Params prm) {
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        auto convert_rows = [&](int j) {                   // registers -> bf16 hi / lo operand tiles of buffer j & 1, |x|^2
+        // fp32 rows of tile j -> buffer j & 1, one 256-byte bulk copy per row (rows are L * D floats apart), all on one
+        // mbarrier: 32 KB in flight per SM without a register or an instruction slot spent on it
+        const int ltid = tid - 8 * 32;
+        auto issue_tile_load = [&](int j) {
             const int b = j & 1;
             if (j >= 2) mbar_wait(&bar_xfree[b], ((j - 2) >> 1) & 1);       // the MMAs of tile j-2 have read this buffer
+            const long base = tile_base(j);
+            const long left = prm.N - base;
+            const int valid = left < kTileM ? (int)left : kTileM;
+            if (ltid == 0) mbar_expect_tx(&bar_xload[b], (uint32_t)valid * (uint32_t)(D * 4));
+            if (ltid < valid)
+                bulk_load(sX + b * kXBuf + ltid * (D * 4), prm.x + ((base + ltid) * L + l) * (long)D, D * 4, &bar_xload[b]);
+        };
+        auto convert_rows = [&](int j) {                   // fp32 rows (shared) -> bf16 hi / lo operand tiles in place, |x|^2
+            const int b = j & 1;
+            uint8_t* buf = sX + b * kXBuf;
+            mbar_wait(&bar_xload[b], (j >> 1) & 1);
+            float4 xv[kRowsPerLane];
+#pragma unroll
+            for (int i = 0; i < kRowsPerLane; ++i) {
+                const int row = wrow0 + 2 * i + sub;
+                xv[i] = (tile_base(j) + row < prm.N) ? *reinterpret_cast<const float4*>(buf + row * (D * 4) + ch * 16)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncwarp();                                  // every fp32 value of this warp's 16 rows is in registers
 #pragma unroll
             for (int i = 0; i < kRowsPerLane; ++i) {
                 const int row = wrow0 + 2 * i + sub;
@@ -353,13 +474,19 @@ vq_nearest_tc_kernel(const Params prm) {
                     split_bf16(v[e], h[e], lo[e]);
                     xn2 = fmaf(v[e], v[e], xn2);
                 }
-                // fp32 chunk ch (4 channels) = half `ch & 1` of the 16-byte bf16 chunk ch >> 1
-                const uint32_t off = (uint32_t)(b * kSlabs * x_slab) + sw128(row, ch >> 1) + (uint32_t)(ch & 1) * 8u;
-                *reinterpret_cast<uint2*>(sXhi + off) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
-                *reinterpret_cast<uint2*>(sXlo + off) = make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 16), (uint32_t)lo[2] | ((uint32_t)lo[3] << 16));
+                // fp32 chunk ch (4 channels) = half `ch & 1` of the 16-byte bf16 chunk ch >> 1; hi atom, lo atom 1 KB behind it
+                const uint32_t off = (uint32_t)(row >> 3) * 2048u + sw128(row & 7, ch >> 1) + (uint32_t)(ch & 1) * 8u;
+                *reinterpret_cast<uint2*>(buf + off) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+                *reinterpret_cast<uint2*>(buf + off + 1024) = make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 16), (uint32_t)lo[2] | ((uint32_t)lo[3] << 16));
 #pragma unroll
                 for (int o = 8; o > 0; o >>= 1) xn2 += __shfl_xor_sync(0xffffffffu, xn2, o);     // over the row's 16 lanes
-                if (ch == 0) sXn2[b * kTileM + row] = xn2;
+                if (ch == 0) {
+                    sXn2[(j % 3) * kTileM + row] = xn2;
+                    uint16_t h3[3];
+                    split3_bf16(xn2 + 2.f, h3);     // + 2: every score stays >= 1 under the filter's error
+                    *reinterpret_cast<uint4*>(sXe + b * (2 * kTileM * 16) + (row >> 3) * 128 + (row & 7) * 16) =
+                        make_uint4(0x3F803F80u, 0x3F80u | ((uint32_t)h3[0] << 16), (uint32_t)h3[1] | ((uint32_t)h3[2] << 16), 0u);
+                }
             }
             fence_proxy_async();
             __syncwarp();
@@ -371,77 +498,66 @@ vq_nearest_tc_kernel(const Params prm) {
             load_rows(j, xo);                              // re-read (L2 hit), in flight while waiting for the scanners
             mbar_wait(&bar_res[b], (j >> 1) & 1);
             const bool want_q = !(WM_VQ_EXP & 8) && (prm.quantized != nullptr || prm.sq_err != nullptr);
-            uint32_t redo = 0;                             // rows of this warp (bit = row - wrow0) whose winner needs the exact path
+            // three passes over the lane's 8 rows, so that the 8 codebook gathers are in flight together (a load that
+            // follows a store to another global array is not hoisted by the compiler: one row at a time costs 8 round trips)
+            long best[kRowsPerLane];                       // winner, or (negative) the packed candidates of an undecided row
+            const long n_first = tile_base(j) + wrow0 + sub;
 #pragma unroll
             for (int i = 0; i < kRowsPerLane; ++i) {
                 const int row = wrow0 + 2 * i + sub;
-                const long n = tile_base(j) + row;
-                const bool valid = n < prm.N;
+                const bool valid = n_first + 2 * i < prm.N;
                 const uint4 ra = reinterpret_cast<const uint4*>(sRes)[(b * 2 + 0) * kTileM + row];
                 const uint4 rb = reinterpret_cast<const uint4*>(sRes)[(b * 2 + 1) * kTileM + row];
                 const float ta = __uint_as_float(ra.x), tb = __uint_as_float(rb.x);
-                const float xn2 = sXn2[b * kTileM + row];
-                int best = ta <= tb ? (int)ra.y : (int)rb.y;
-                const float win = 6.103515625e-5f * sqrtf(xn2) * emax + 3.9e-6f * fmaxf(ta, tb) + 1e-30f;
+                const float xn2 = sXn2[(j % 3) * kTileM + row];
+                best[i] = valid ? (ta <= tb ? (long)ra.y : (long)rb.y) : 0;
+                const float win = filter_window(xn2, emax);
+                const bool huge = !(xn2 + emax * emax < kHugeNorm);       // scores may leave the key range (or are not finite): settle exactly
                 const bool a_in = ta <= tb + win, b_in = tb <= ta + win;   // does the half hold a candidate for the row minimum?
-                const bool need = valid && !(WM_VQ_EXP & 16) && ((a_in && b_in) || (a_in && ra.w) || (b_in && rb.w));
-                redo |= need ? (1u << (2 * i + sub)) : 0u;  // settled exactly after the loop (rare); the row is rewritten then
-                if (valid && ch == 0) prm.idx[n * L + l] = (int64_t)best;
+                const bool need = valid && !(WM_VQ_EXP & 16) && (huge || (a_in && b_in) || (a_in && ra.w) || (b_in && rb.w));
+                if (need)                                   // undecided: settled exactly by vq_settle_kernel, which rewrites the row
+                    best[i] = pack_candidates(ra.y, ra.z, huge ? 2u : ra.w, rb.y, rb.z, huge ? 2u : rb.w, huge || a_in, huge || b_in);
+            }
+            float4 ev[kRowsPerLane];
+            if (want_q) {
+#pragma unroll
+                for (int i = 0; i < kRowsPerLane; ++i) ev[i] = __ldg(reinterpret_cast<const float4*>(cbl + (best[i] < 0 ? 0 : best[i]) * D) + ch);
+            }
+#pragma unroll
+            for (int i = 0; i < kRowsPerLane; ++i) {
+                const long n = n_first + 2 * i;
+                const bool valid = n < prm.N;
+                const long o = n * L + l;
+                if (valid && ch == 0) prm.idx[o] = (int64_t)best[i];
                 if (want_q) {
-                    const float4 ev = __ldg(reinterpret_cast<const float4*>(cbl + (long)(valid ? best : 0) * D) + ch);
-                    const float d0 = ev.x - xo[i].x, d1 = ev.y - xo[i].y, d2 = ev.z - xo[i].z, d3 = ev.w - xo[i].w;
+                    const float d0 = ev[i].x - xo[i].x, d1 = ev[i].y - xo[i].y, d2 = ev[i].z - xo[i].z, d3 = ev[i].w - xo[i].w;
                     float err = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
                     if (prm.quantized != nullptr && valid)
-                        reinterpret_cast<float4*>(prm.quantized + (n * L + l) * (long)D)[ch] =
+                        reinterpret_cast<float4*>(prm.quantized + o * (long)D)[ch] =
                             make_float4(xo[i].x + d0, xo[i].y + d1, xo[i].z + d2, xo[i].w + d3);
                     if (prm.sq_err != nullptr) {
 #pragma unroll
-                        for (int o = 8; o > 0; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
-                        if (ch == 0 && valid) prm.sq_err[n * L + l] = err;
+                        for (int sh = 8; sh > 0; sh >>= 1) err += __shfl_xor_sync(0xffffffffu, err, sh);
+                        if (ch == 0 && valid) prm.sq_err[o] = err;
                     }
                 }
             }
-            // ---- rare: rows whose candidates lie inside the filter's window are settled exactly by the whole warp and rewritten
-            redo = __reduce_or_sync(0xffffffffu, redo);
-#if WM_VQ_EXP & 64
-            redo &= (uint32_t)(prm.N >> 40);               // timing experiment: never run the exact path (all code kept)
-#endif
-#if WM_VQ_EXP & 32
-            if (lane == 0) { atomicAdd(&g_vq_dbg[0], (unsigned long long)__popc(redo)); atomicAdd(&g_vq_dbg[1], 16ull); }
-#endif
-            while (redo) {
-                const int rr = __ffs(redo) - 1;
-                redo &= redo - 1;
-                const int row = wrow0 + rr;
-                const long n = tile_base(j) + row;
-                const uint4 ra = reinterpret_cast<const uint4*>(sRes)[(b * 2 + 0) * kTileM + row];
-                const uint4 rb = reinterpret_cast<const uint4*>(sRes)[(b * 2 + 1) * kTileM + row];
-                const float ta = __uint_as_float(ra.x), tb = __uint_as_float(rb.x);
-                const float win = 6.103515625e-5f * sqrtf(sXn2[b * kTileM + row]) * emax + 3.9e-6f * fmaxf(ta, tb) + 1e-30f;
-                const float* xr = prm.x + (n * L + l) * (long)D;
-                const int best = settle_exact_warp<D>(xr, cbl, ra, rb, ta <= tb + win, tb <= ta + win, KH, lane);
-                if (lane == 0) prm.idx[n * L + l] = (int64_t)best;
-                if (want_q && lane < 16) {
-                    const float4 xq = __ldg(reinterpret_cast<const float4*>(xr) + lane);
-                    const float4 ev = __ldg(reinterpret_cast<const float4*>(cbl + (long)best * D) + lane);
-                    const float d0 = ev.x - xq.x, d1 = ev.y - xq.y, d2 = ev.z - xq.z, d3 = ev.w - xq.w;
-                    float err = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
-                    if (prm.quantized != nullptr)
-                        reinterpret_cast<float4*>(prm.quantized + (n * L + l) * (long)D)[lane] = make_float4(xq.x + d0, xq.y + d1, xq.z + d2, xq.w + d3);
-#pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) err += __shfl_xor_sync(0x0000ffffu, err, o);
-                    if (prm.sq_err != nullptr && lane == 0) prm.sq_err[n * L + l] = err;
-                }
-                __syncwarp();
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_resfree[b]);   // this warp's sRes entries of tile j may be overwritten
         };
-        // software pipeline: load two tiles ahead of the output
-        if (my_tiles > 0) { load_rows(0, xv); convert_rows(0); }
-        if (my_tiles > 1) { load_rows(1, xv); convert_rows(1); }
+        // Software pipeline.  The conversion of tile j+2 must not wait for the output of tile j (that would close a loop
+        // scan -> output -> convert -> MMA -> scan over two tiles and serialise the four phases): tile j+2 is converted
+        // FIRST -- its fp32 rows landed during the previous iteration -- then the copy of tile j+3 is started (its buffer
+        // is free once the MMAs of tile j+1 have retired), then tile j is written out.
+        if (my_tiles > 0) issue_tile_load(0);
+        if (my_tiles > 1) issue_tile_load(1);
+        if (my_tiles > 0) convert_rows(0);
+        if (my_tiles > 1) convert_rows(1);
+        if (my_tiles > 2) issue_tile_load(2);
         for (int j = 0; j < my_tiles; ++j) {
-            if (j + 2 < my_tiles) load_rows(j + 2, xv);    // global loads in flight across the output of tile j
-            output_rows(j);
             if (j + 2 < my_tiles) convert_rows(j + 2);
+            if (j + 3 < my_tiles) issue_tile_load(j + 3);
+            output_rows(j);
         }
     }
     tc_fence_before();
@@ -451,7 +567,8 @@ vq_nearest_tc_kernel(const Params prm) {
 
 static size_t smem_bytes(int K, int D) {
     const int slabs = D / 64;
-    return 1024 + 2ul * slabs * K * 128 + 4ul * slabs * kTileM * 128 + (size_t)K * 4 + 2 * kTileM * 4 + 2 * 2 * kTileM * 16 + 128 + 256;
+    return 1024 + 2ul * slabs * K * 128 + 4ul * slabs * kTileM * 128 + 2ul * 2 * kTileM * 16 + 2ul * K * 16 + 3 * kTileM * 4 +
+           2 * 2 * kTileM * 16 + 128 + 256;
 }
 
 }  // namespace vq
@@ -481,6 +598,9 @@ int vq_nearest_tc(const void* x, const void* cb, int64_t* idx, void* quantized, 
     const dim3 grid((unsigned)ctas, (unsigned)L);
     WM_CUDA_CHECK(cudaFuncSetAttribute(vq_nearest_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     vq_nearest_tc_kernel<64><<<grid, kThreads, smem, st>>>(prm);
+    WM_CUDA_CHECK(cudaGetLastError());
+    const long items = N * L;
+    vq_settle_kernel<64><<<(unsigned)((items + 255) / 256), 256, 0, st>>>(prm);
     WM_CUDA_CHECK(cudaGetLastError());
     return WM_OK;
 }
