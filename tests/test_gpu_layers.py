@@ -134,3 +134,47 @@ def test_bias_gelu_forward_backward(dtype, rtol, atol, rows, cols):
     torch.testing.assert_close(out.float().cpu(), ref.detach(), rtol=rtol, atol=atol)
     torch.testing.assert_close(d_h.grad.float().cpu(), r_h.grad, rtol=rtol, atol=atol)
     torch.testing.assert_close(d_b.grad.float().cpu(), r_b.grad, rtol=rtol, atol=atol * max(1.0, rows ** 0.5))
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('shape,dim,rows', [((2, 3, 5, 7), 64, 19), ((3, 16, 16, 16), 256, 513), ((1, 1, 2, 2), 8, 4)])
+def test_embed_pos_matches_the_stock_op_chain_bit_for_bit(dtype, shape, dim, rows):
+    """wm_embed_pos_fwd == embedding(tokens) + ((pos_s + pos_h) + pos_w) of local_3d_attention.py:143-157, rounded to the
+    storage type in the same order; gradients of the table and of the three position tables against autograd."""
+    g = torch.Generator().manual_seed(dim + rows)
+    B, S, H, W = shape
+    tokens = torch.randint(0, rows, shape, generator=g).to(DEV)
+    mk = lambda n: torch.randn(n, dim, generator=g).to(DEV, dtype).requires_grad_(True)
+    table, ps, ph, pw = mk(rows), mk(S), mk(H), mk(W)
+    out = ops.embed_pos(tokens, table, ps, ph, pw)
+    wgt = torch.randn(*shape, dim, generator=g).to(DEV, dtype)
+    (out.float() * wgt.float()).sum().backward()
+    got = [t.grad.clone() for t in (table, ps, ph, pw)]
+    for t in (table, ps, ph, pw):
+        t.grad = None
+    pos = ps[:, None, None, :] + ph[None, :, None, :] + pw[None, None, :, :]
+    ref = F.embedding(tokens, table) + pos.unsqueeze(0).expand(B, -1, -1, -1, -1)
+    (ref.float() * wgt.float()).sum().backward()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    tol = dict(rtol=1e-5, atol=1e-4) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-1)
+    for a, t in zip(got, (table, ps, ph, pw)):
+        torch.testing.assert_close(a.float(), t.grad.float(), **tol)
+
+
+def test_projection_passthrough_folds_the_stream_gradient_into_the_dgrad():
+    """ops.linear_passthrough(x, W) == (x @ W^T, x); its backward is one GEMM with beta = 1 (dgrad + stream gradient)."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, 4, 5, 64, generator=g).to(DEV, torch.bfloat16).requires_grad_(True)
+    w = (torch.randn(96, 64, generator=g) * 0.1).to(DEV, torch.bfloat16).requires_grad_(True)
+    gy = torch.randn(2, 3, 4, 5, 96, generator=g).to(DEV, torch.bfloat16)
+    gx = torch.randn(2, 3, 4, 5, 64, generator=g).to(DEV, torch.bfloat16)
+    y, xp = ops.linear_passthrough(x, w)
+    ((y.float() * gy.float()).sum() + (xp.float() * gx.float()).sum()).backward()
+    dx, dw = x.grad.clone(), w.grad.clone()
+    x.grad = w.grad = None
+    y2 = F.linear(x, w)
+    ((y2.float() * gy.float()).sum() + (x.float() * gx.float()).sum()).backward()
+    assert torch.equal(y, y2) and torch.equal(xp, x)
+    torch.testing.assert_close(dx.float(), x.grad.float(), rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(dw.float(), w.grad.float(), rtol=2e-2, atol=2e-1)

@@ -196,28 +196,33 @@ __device__ __forceinline__ void store8(float* p, const float (&f)[8]) {
     *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
 }
 
+// A group of dim/8 consecutive threads writes one token row (16 bytes per thread); token coordinates are decoded once per
+// row in 32-bit arithmetic, position rows come from L1/L2.
 template <typename T>
 __global__ void __launch_bounds__(256)
 embed_pos_kernel(const int64_t* __restrict__ tokens, const T* __restrict__ table, const T* __restrict__ ps,
                  const T* __restrict__ ph, const T* __restrict__ pw, T* __restrict__ out, long ntok, int S, int H, int W,
                  int dim, int num_rows) {
     const int vecs = dim >> 3;
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ntok * vecs) return;
-    const long tok = i / vecs;
-    const int c = (int)(i - tok * vecs) * 8;
-    const int w = (int)(tok % W), h = (int)((tok / W) % H), s = (int)((tok / ((long)W * H)) % S);
-    long row = tokens[tok];
-    row = row < 0 ? 0 : (row >= num_rows ? num_rows - 1 : row);
-    float e[8], a[8], b2[8], c2[8], r[8];
-    load8(table + row * dim + c, e);
-    load8(ps + (long)s * dim + c, a);
-    load8(ph + (long)h * dim + c, b2);
-    load8(pw + (long)w * dim + c, c2);
+    const int rows_per_block = 256 / vecs;                 // host guarantees vecs <= 256
+    const int r = threadIdx.x / vecs, c = (threadIdx.x - r * vecs) * 8;
+    if (r >= rows_per_block) return;
     const T* tag = nullptr;
+    for (long tok = (long)blockIdx.x * rows_per_block + r; tok < ntok; tok += (long)gridDim.x * rows_per_block) {
+        const unsigned in_clip = (unsigned)(tok % ((long)S * H * W));
+        const unsigned w = in_clip % (unsigned)W, hs = in_clip / (unsigned)W;
+        const unsigned h = hs % (unsigned)H, s = hs / (unsigned)H;
+        long row = tokens[tok];
+        row = row < 0 ? 0 : (row >= num_rows ? num_rows - 1 : row);
+        float e[8], a[8], b2[8], c2[8], o[8];
+        load8(table + row * dim + c, e);
+        load8(ps + (long)s * dim + c, a);
+        load8(ph + (long)h * dim + c, b2);
+        load8(pw + (long)w * dim + c, c2);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) r[k] = e[k] + round_to(round_to(a[k] + b2[k], tag) + c2[k], tag);
-    store8(out + tok * dim + c, r);
+        for (int k = 0; k < 8; ++k) o[k] = e[k] + round_to(round_to(a[k] + b2[k], tag) + c2[k], tag);
+        store8(out + tok * dim + c, o);
+    }
 }
 
 }  // namespace
@@ -298,8 +303,12 @@ extern "C" int wm_embed_pos_fwd(const int64_t* tokens, const void* table, const 
     const void* ptrs[] = {table, pos_s, pos_h, pos_w, out};
     for (const void* q : ptrs)
         if (!aligned16(q)) return fail(WM_EINVAL, "wm_embed_pos_fwd: pointers must be 16-byte aligned");
-    const long ntok = B * S * H * W, items = ntok * (dim / 8);
-    const unsigned blocks = (unsigned)((items + 255) / 256);
+    if (dim > 2048) return fail(WM_EUNSUPPORTED, "wm_embed_pos_fwd: dim=%d", dim);
+    const long ntok = B * S * H * W;
+    const int rows_per_block = 256 / (dim / 8);
+    long want = (ntok + rows_per_block - 1) / rows_per_block;
+    const long cap = (long)sm_count() * 16;
+    const unsigned blocks = (unsigned)(want < cap ? want : cap);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == WM_DTYPE_BF16)
         embed_pos_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(tokens, static_cast<const __nv_bfloat16*>(table),
