@@ -78,6 +78,7 @@ struct BwdWsParams {
     long ld_out;             // elements between consecutive tokens of the outputs
 };
 
+constexpr int kMaxItemsPerCta = 64;    // rows of the per-CTA work table (2 KB of the fixed shared-memory budget)
 constexpr int kWsThreads = 352;        // 8 compute warps + (S,dP) issuer + accumulate issuer + TMA loader
 
 template <int D, int MODE>
@@ -123,23 +124,61 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     const int gA = (ncols_pad >> 4) >= 2 ? (ncols_pad >> 5) : 0;   // 16-column groups in half A (0: a single half)
     const int nA = gA * 16;
 
-    const int tw_i = blockIdx.x % pl.tilesW, th_i = blockIdx.x / pl.tilesW;
-    const int ts_i = blockIdx.y;
+    // Persistent CTAs.  A CTA serves ONE (h, w) brick position -- its masks, border ranges and live column ranges depend on
+    // nothing else -- and walks the work items (batch element, s position, head group) of that position back to back:
+    // TMEM, barriers and mask tiles are set up once, and the loader runs ahead across item boundaries, so the pipeline
+    // never drains between bricks (a one-item CTA spent ~16 % of its life in prologue and drain).
+    const int nclass = pl.tilesH * pl.tilesW;
+    const int cls = (int)blockIdx.x % nclass, rank = (int)blockIdx.x / nclass;
+    const int nrank = ((int)gridDim.x - cls + nclass - 1) / nclass;          // CTAs sharing this brick position
+    const int tw_i = cls % pl.tilesW, th_i = cls / pl.tilesW;
     const int hgroups = sh.heads / pl.hpc;
-    const int hg = blockIdx.z % hgroups, b = blockIdx.z / hgroups;
-    const int head0 = hg * pl.hpc;
-    const int s0 = ts_i * pl.tS, h0 = th_i * pl.tH, w0 = tw_i * pl.tW;
-
-    const int ks_first = max(0, sh.eS - s0), ks_last = min(pl.hS - 1, sh.S - 1 - s0 + sh.eS);
+    const int n_items = sh.B * pl.tilesS * hgroups;
+    const int h0 = th_i * pl.tH, w0 = tw_i * pl.tW;
     const int khg_lo = max(0, sh.eH - h0), khg_hi = min(pl.hH - 1, sh.H - 1 - h0 + sh.eH);
     int chunk_first = 0, chunk_last = 0;
     for (int c = 0; c < pl.nchunk; ++c) {
         if (khg_lo >= (c + 1) * pl.ch) chunk_first = c + 1;
         if (khg_hi >= c * pl.ch) chunk_last = c;
     }
-    const int nplanes = ks_last - ks_first + 1;
-    const int nblocks = nplanes * (chunk_last - chunk_first + 1);
-    const int nsteps = nblocks * pl.hpc;
+    // a step = (item, head, h-chunk, plane); H counts heads across items (buffer / barrier parities run on it)
+    // The items of this CTA live in a small shared-memory table {b, s0, head0, ks_first, ks_last}; a cursor is five
+    // integers (slot, head, plane, chunk, H), so that the three or four cursors a warp keeps cost few registers.
+    struct Item { int b, s0, head0, ks_first, ks_last, pad0, pad1, pad2; };
+    Item* sItems = reinterpret_cast<Item*>(bars + 16);                  // [kMaxItemsPerCta], inside the fixed part of the budget
+    const int my_items = rank < n_items ? (n_items - rank + nrank - 1) / nrank : 0;
+    if (tid < my_items) {
+        const int item = rank + tid * nrank;
+        const int hg = item % hgroups, ts_i = (item / hgroups) % pl.tilesS;
+        Item it;
+        it.b = item / (hgroups * pl.tilesS);
+        it.s0 = ts_i * pl.tS;
+        it.head0 = hg * pl.hpc;
+        it.ks_first = max(0, sh.eS - it.s0);
+        it.ks_last = min(pl.hS - 1, sh.S - 1 - it.s0 + sh.eS);
+        it.pad0 = it.pad1 = it.pad2 = 0;
+        sItems[tid] = it;
+    }
+    __syncthreads();
+    struct Cursor { int slot, hd, ks, chunk, H; };
+    auto next_head = [&](Cursor& c) {                 // first step of the head after c's
+        ++c.H;
+        if (++c.hd == pl.hpc) { c.hd = 0; ++c.slot; }
+        c.ks = sItems[min(c.slot, my_items - 1)].ks_first;
+        c.chunk = chunk_first;
+    };
+    auto advance = [&](Cursor& c) {
+        if (++c.ks > sItems[c.slot].ks_last) {
+            c.ks = sItems[c.slot].ks_first;
+            if (++c.chunk > chunk_last) next_head(c);
+        }
+    };
+    auto is_head_start = [&](const Cursor& c) { return c.ks == sItems[c.slot].ks_first && c.chunk == chunk_first; };
+    int nsteps = 0;
+    for (int i = 0; i < my_items; ++i)
+        nsteps += (sItems[i].ks_last - sItems[i].ks_first + 1) * (chunk_last - chunk_first + 1) * pl.hpc;
+    const int nheads = my_items * pl.hpc;
+    const Cursor first = {0, 0, my_items > 0 ? sItems[0].ks_first : 0, chunk_first, 0};
 
     if (tid == 0) {
         tma_prefetch_desc(&map_a1); tma_prefetch_desc(&map_a2); tma_prefetch_desc(&map_b1); tma_prefetch_desc(&map_b2);
@@ -177,22 +216,17 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     const uint32_t tmem_pa = tmem_t2 + ncols_pad;                           // A operand buffers: [2][ncols_pad / 2]
     const int pa_cols = ncols_pad >> 1;
 
-    struct Cursor { int hd, ks, chunk; };
-    auto advance = [&](Cursor& c) {
-        if (++c.ks > ks_last) {
-            c.ks = ks_first;
-            if (++c.chunk > chunk_last) { c.chunk = chunk_first; ++c.hd; }
-        }
-    };
-
     if (warp >= 8) {
         // =============================== issuing warps (warp-uniform code; instructions on one elected lane) =========
         const bool leader = elect_one();      // each of these warps is converged here
-        auto a_buf = [&](int hd) { return sA + (pl.rowbuf == 2 ? (hd & 1) : 0) * 2 * row_tile_bytes; };
-        auto issue_row_load = [&](int hd) {
+        auto a_buf = [&](int H) { return sA + (pl.rowbuf == 2 ? (H & 1) : 0) * 2 * row_tile_bytes; };
+        auto issue_row_load = [&](const Cursor& c) {      // row tiles of c's head
             if (leader) {
+                const int hd = c.H;
+                const Item it = sItems[c.slot];
+                const int s0 = it.s0, b = it.b;
                 uint64_t* bar = &bar_a[hd & 1];
-                const int cb = (head0 + hd) * D;
+                const int cb = (it.head0 + c.hd) * D;
                 mbar_expect_tx(bar, 2u * (uint32_t)row_tile_bytes);
 #pragma unroll
                 for (int sl = 0; sl < G::kSlabs; ++sl) {
@@ -203,7 +237,9 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         };
         auto issue_block_load = [&](int stage, const Cursor& c) {
             if (leader) {
-                const int cb = (head0 + c.hd) * D;
+                const Item it = sItems[c.slot];
+                const int s0 = it.s0, b = it.b;
+                const int cb = (it.head0 + c.hd) * D;
                 uint8_t* dst = sB + stage * 2 * blk_tile_bytes;
                 mbar_expect_tx(&bar_b[stage], 2u * G::kSlabs * (uint32_t)ncols * G::kRowBytes);
 #pragma unroll
@@ -291,28 +327,35 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             }
             __syncwarp();
         };
-        uint32_t dbg_flag = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0) && leader;
+        uint32_t dbg_flag = (blockIdx.x == 1) && leader;
         asm volatile("" : "+r"(dbg_flag));
         const bool dbg_on = dbg_flag != 0;
         (void)dbg_on;
-        Cursor cur = {0, ks_first, chunk_first};
+        Cursor cur = first;
 
         if (warp == 10) {
             // ---- TMA loader: row tiles one head ahead, halo blocks nstage steps ahead -------------------------------
             Cursor ld = cur;
             int ld_t = 0, ld_stage = 0;
-            issue_row_load(0);
+            issue_row_load(cur);
             for (; ld_t < nstage && ld_t < nsteps; ++ld_t) {
                 issue_block_load(ld_stage, ld);
                 advance(ld);
                 if (++ld_stage == nstage) ld_stage = 0;
             }
             for (int t = 0; t < nsteps; ++t) {
-                const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
-                if (head_start && pl.rowbuf == 2 && cur.hd + 1 < pl.hpc) {
-                    // the buffer of head hd-1: its last (S, dP) was drained when every thread arrived for step t-1
+                const bool head_start = is_head_start(cur);
+                if (head_start && pl.rowbuf == 2 && cur.H + 1 < nheads) {
+                    // two row buffers: the next head's tiles go into the buffer of head H-1, whose last (S, dP) was drained
+                    // when every thread arrived for step t-1
                     if (t > 0) mbar_wait(&bar_p[(t - 1) & 1], ((t - 1) >> 1) & 1);
-                    issue_row_load(cur.hd + 1);
+                    Cursor nh = cur;
+                    next_head(nh);
+                    issue_row_load(nh);
+                } else if (head_start && pl.rowbuf == 1 && t > 0) {
+                    // one row buffer: this head's tiles, once the previous head's last (S, dP) has been drained
+                    mbar_wait(&bar_p[(t - 1) & 1], ((t - 1) >> 1) & 1);
+                    issue_row_load(cur);
                 }
                 if (t >= 1 && ld_t < nsteps) {   // the stage of step t-1 is free once its accumulating MMAs have retired
                     mbar_wait(&bar_acc[(t - 1) & 1], ((t - 1) >> 1) & 1);
@@ -342,13 +385,13 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                 }
                 mbar_wait(&bar_b[st_nxt], (b_par >> st_nxt) & 1u);
                 b_par ^= 1u << st_nxt;
-                if (nxt.hd != cur.hd) mbar_wait(&bar_a[nxt.hd & 1], (nxt.hd >> 1) & 1);
+                if (nxt.H != cur.H) mbar_wait(&bar_a[nxt.H & 1], (nxt.H >> 1) & 1);
                 tc_fence_after();
-                if (gA > 0) issue_t_mma(st_nxt, nxt.hd, nxt.chunk, 0);
+                if (gA > 0) issue_t_mma(st_nxt, nxt.H, nxt.chunk, 0);
                 DBGW(2);
                 mbar_wait(&bar_p[t & 1], (t >> 1) & 1);
                 tc_fence_after();
-                issue_t_mma(st_nxt, nxt.hd, nxt.chunk, 1);
+                issue_t_mma(st_nxt, nxt.H, nxt.chunk, 1);
                 DBGW(3);
                 cur = nxt;
                 advance(nxt);
@@ -358,7 +401,7 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             // ---- accumulating MMAs of step t, once all of its dS / P is written -------------------------------------
             int st_cur = 0;
             for (int t = 0; t < nsteps; ++t) {
-                const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
+                const bool head_start = is_head_start(cur);
                 mbar_wait(&bar_p[t & 1], (t >> 1) & 1);
                 tc_fence_after();
                 DBGW(4);
@@ -376,14 +419,19 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
         const int plane_mask = (1 << pl.lgPlane) - 1;
         const int rs = row >> pl.lgPlane, rh = (row & plane_mask) >> pl.lgTW, rw = row & (pl.tW - 1);
-        const bool row_valid = (s0 + rs < sh.S) && (h0 + rh < sh.H) && (w0 + rw < sh.W);
+        const bool hw_valid = (h0 + rh < sh.H) && (w0 + rw < sh.W);
+        // (item-dependent) is this row a token of the grid, and which
+        auto valid_of = [&](const Cursor& c) { return hw_valid && (sItems[c.slot].s0 + rs < sh.S); };
+        auto tok_of = [&](const Cursor& c) {
+            return (((long)sItems[c.slot].b * sh.S + (sItems[c.slot].s0 + rs)) * sh.H + (h0 + rh)) * sh.W + (w0 + rw);
+        };
         const int w_rs = (quad * 32) >> pl.lgPlane;
         const int w_rh_lo = ((quad * 32) & plane_mask) >> pl.lgTW, w_rh_hi = ((quad * 32 + 31) & plane_mask) >> pl.lgTW;
-        const long row_tok = (((long)b * sh.S + (s0 + rs)) * sh.H + (h0 + rh)) * sh.W + (w0 + rw);
         constexpr float kLog2e = 1.4426950408889634f;
 
         auto load_colvec = [&](const Cursor& c, float& lse2, float& dl) {     // dK/dV kernel: one halo column per thread
-            const int gs = s0 - sh.eS + c.ks;
+            const Item it = sItems[c.slot];
+            const int gs = it.s0 - sh.eS + c.ks;
             const int col = ctid;
             lse2 = 0.f;
             dl = 0.f;
@@ -391,7 +439,7 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                 const int khl = col / pl.hW, kw = col - khl * pl.hW;
                 const int gh = h0 - sh.eH + c.chunk * pl.ch + khl, gw = w0 - sh.eW + kw;
                 if (gs >= 0 && gs < sh.S && gh >= 0 && gh < sh.H && gw >= 0 && gw < sh.W) {
-                    const long idx = ((((long)b * sh.S + gs) * sh.H + gh) * sh.W + gw) * sh.heads + head0 + c.hd;
+                    const long idx = ((((long)it.b * sh.S + gs) * sh.H + gh) * sh.W + gw) * sh.heads + it.head0 + c.hd;
                     lse2 = __ldg(prm.lse + idx);          // raw: scaled in store_colvec, a whole step later, so that
                     dl = __ldg(prm.delta + idx);          // the load latency is never waited for at the top of a step
                 }
@@ -403,8 +451,9 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                 sCol[(buf * 2 + 1) * ncols_pad + ctid] = -dl_raw * sh.scale;
             }
         };
-        auto finish_head = [&](int hd) {            // accumulators of head `hd` -> bf16 -> global
-            const long row_off = row_tok * prm.ld_out + (head0 + hd) * D + half * (D / 2);
+        auto finish_head = [&](const Cursor& c) {   // accumulators of c's head -> bf16 -> global
+            const bool row_valid = valid_of(c);
+            const long row_off = tok_of(c) * prm.ld_out + (sItems[c.slot].head0 + c.hd) * D + half * (D / 2);
 #pragma unroll
             for (int which = 0; which < (kDKV ? 2 : 1); ++which) {
                 __nv_bfloat16* dst = (which == 0 ? prm.out1 : prm.out2) + row_off;
@@ -425,15 +474,16 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             }
         };
 
-        Cursor cur{0, ks_first, chunk_first};
+        Cursor cur = first;
         Cursor nxt = cur;
         advance(nxt);
+        Cursor done_head = cur;                                          // the head whose accumulators are drained next
         float row_lse2 = 0.f, row_delta = 0.f;
         float ahead_lse = 0.f, ahead_delta = 0.f;                        // dQ kernel: raw values of the next head, in flight
         if constexpr (!kDKV) {
-            if (row_valid) {
-                ahead_lse = __ldg(prm.lse + row_tok * sh.heads + head0);
-                ahead_delta = __ldg(prm.delta + row_tok * sh.heads + head0);
+            if (valid_of(cur)) {
+                ahead_lse = __ldg(prm.lse + tok_of(cur) * sh.heads + sItems[0].head0);
+                ahead_delta = __ldg(prm.delta + tok_of(cur) * sh.heads + sItems[0].head0);
             }
         }
         if constexpr (kDKV) {
@@ -451,14 +501,14 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         const int ngroups = ncols_pad >> 4;
         const uint32_t zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
-        uint32_t dbg_flag = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0 && tid == 0);
+        uint32_t dbg_flag = (blockIdx.x == 1 && tid == 0);
         asm volatile("" : "+r"(dbg_flag));
         const bool dbg_on = dbg_flag != 0;
         (void)dbg_on;
         for (int t = 0; t < nsteps; ++t) {
             DBGW(8);
             const int buf = t & 1;
-            const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
+            const bool head_start = is_head_start(cur);
             float nxt_lse2 = 0.f, nxt_dl = 0.f;
             if constexpr (kDKV) {
                 if (t + 1 < nsteps) load_colvec(nxt, nxt_lse2, nxt_dl);      // global loads in flight during the waits
@@ -467,9 +517,14 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                     asm volatile("" : "+f"(ahead_lse), "+f"(ahead_delta));   // first use of the loads issued one head ago
                     row_lse2 = -ahead_lse * kLog2e;          // kept negated: the addends of the two FFMA2 below
                     row_delta = -ahead_delta * sh.scale;
-                    if (row_valid && cur.hd + 1 < pl.hpc) {
-                        ahead_lse = __ldg(prm.lse + row_tok * sh.heads + head0 + cur.hd + 1);
-                        ahead_delta = __ldg(prm.delta + row_tok * sh.heads + head0 + cur.hd + 1);
+                    if (cur.H + 1 < nheads) {                // the next head may belong to the next work item
+                        Cursor nh = cur;
+                        next_head(nh);
+                        ahead_lse = ahead_delta = 0.f;
+                        if (valid_of(nh)) {
+                            ahead_lse = __ldg(prm.lse + tok_of(nh) * sh.heads + sItems[nh.slot].head0 + nh.hd);
+                            ahead_delta = __ldg(prm.delta + tok_of(nh) * sh.heads + sItems[nh.slot].head0 + nh.hd);
+                        }
                     }
                 }
             }
@@ -620,7 +675,8 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                 // math, lets the wait for the previous head's last MMAs overlap that math.
                 mbar_wait(&bar_acc[(t - 1) & 1], ((t - 1) >> 1) & 1);
                 tc_fence_after();
-                finish_head(cur.hd - 1);
+                finish_head(done_head);
+                done_head = cur;
             }
             tmem_wait_st();
             tc_fence_before();
@@ -633,7 +689,7 @@ l3d_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         }
         mbar_wait(&bar_acc[(nsteps - 1) & 1], ((nsteps - 1) >> 1) & 1);
         tc_fence_after();
-        finish_head(pl.hpc - 1);
+        finish_head(done_head);
     }
 
     tc_fence_before();
@@ -654,8 +710,13 @@ static int launch_ws(const void* a1, const void* a2, const void* b1, const void*
     if (int rc = make_tensor_map_5d(&mb2, b2, s.B, s.S, s.H, s.W, C, ld[3], G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
     BwdWsParams prm{s, pl, lse, delta, static_cast<__nv_bfloat16*>(out1), static_cast<__nv_bfloat16*>(out2), ld_out};
     WM_CUDA_CHECK(cudaFuncSetAttribute(l3d_bwd_ws_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
-    const dim3 grid((unsigned)(pl.tilesW * pl.tilesH), (unsigned)pl.tilesS, (unsigned)(s.B * (s.heads / pl.hpc)));
-    if (grid.y > 65535u || grid.z > 65535u) return fail(WM_EUNSUPPORTED, "grid too large for the tensor-core kernel");
+    // Grid (see the kernel's work decomposition): one persistent CTA per SM when there is more than one work item per SM
+    // and its items fit the per-CTA table, else one CTA per item.  Measured on the same box against one CTA per item:
+    // config 3 dQ 276 -> 246 us, dK/dV 382 -> 349; config 4 dQ 362 -> 309, dK/dV 547 -> 514.
+    const long items = (long)pl.tilesW * pl.tilesH * pl.tilesS * s.B * (s.heads / pl.hpc);
+    if (items > 0x7fffffffL) return fail(WM_EUNSUPPORTED, "grid too large for the tensor-core kernel");
+    const bool fits = (items + sm_count() - 1) / sm_count() + pl.tilesH * pl.tilesW <= kMaxItemsPerCta;      // per-CTA item table
+    const unsigned grid = (unsigned)(items > (long)sm_count() && fits ? (long)sm_count() : items);
     l3d_bwd_ws_kernel<D, MODE><<<grid, kWsThreads, pl.smem_bytes, st>>>(ma1, ma2, mb1, mb2, prm);
     WM_CUDA_CHECK(cudaGetLastError());
     return WM_OK;
