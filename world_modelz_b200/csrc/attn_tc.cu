@@ -265,25 +265,44 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     uint64_t* bar_ofree = bars + 18;  // [2]  a head's O accumulator has been read out (the 4 warps of its epilogue team)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
-    // ---- which brick / head group ----------------------------------------------------------
-    const int tw_i = blockIdx.x % pl.tilesW, th_i = blockIdx.x / pl.tilesW;
-    const int ts_i = blockIdx.y;
+    // ---- work: persistent CTAs (see attn_tc_bwd_ws.cu) --------------------------------------------------------------
+    // A CTA serves ONE (h, w) brick position -- masks, border ranges and live column ranges depend on nothing else -- and
+    // walks the work items (batch element, s position, head group) of that position back to back.
+    const int nclass = pl.tilesH * pl.tilesW;
+    const int cls = (int)blockIdx.x % nclass, rank = (int)blockIdx.x / nclass;
+    const int nrank = ((int)gridDim.x - cls + nclass - 1) / nclass;          // CTAs sharing this brick position
+    const int tw_i = cls % pl.tilesW, th_i = cls / pl.tilesW;
     const int hgroups = sh.heads / pl.hpc;
-    const int hg = blockIdx.z % hgroups, b = blockIdx.z / hgroups;
-    const int head0 = hg * pl.hpc;
-    const int s0 = ts_i * pl.tS, h0 = th_i * pl.tH, w0 = tw_i * pl.tW;
+    const int n_items = sh.B * pl.tilesS * hgroups;
+    const int h0 = th_i * pl.tH, w0 = tw_i * pl.tW;
 
-    // block iteration space: planes and h-chunks that intersect the grid
-    const int ks_first = max(0, sh.eS - s0), ks_last = min(pl.hS - 1, sh.S - 1 - s0 + sh.eS);
+    // block iteration space: h-chunks that intersect the grid (planes: per item)
     const int khg_lo = max(0, sh.eH - h0), khg_hi = min(pl.hH - 1, sh.H - 1 - h0 + sh.eH);
     int chunk_first = 0, chunk_last = 0;
     for (int c = 0; c < pl.nchunk; ++c) {           // nchunk is tiny; avoids integer divisions
         if (khg_lo >= (c + 1) * pl.ch) chunk_first = c + 1;
         if (khg_hi >= c * pl.ch) chunk_last = c;
     }
-    const int nplanes = ks_last - ks_first + 1;
-    const int nblocks = nplanes * (chunk_last - chunk_first + 1);
-    const int nsteps = nblocks * pl.hpc;
+    const int nchunks_live = chunk_last - chunk_first + 1;
+    struct Item { int b, s0, head0, ks_first, ks_last, pad0, pad1, pad2; };
+    Item* sItems = reinterpret_cast<Item*>(sX + 4 * 128);               // [kMaxItemsPerCta] rows of 32 bytes, behind the four row-sum slots
+    const int my_items = rank < n_items ? (n_items - rank + nrank - 1) / nrank : 0;
+    if (tid < my_items) {
+        const int item = rank + tid * nrank;
+        const int hg = item % hgroups, ts_i = (item / hgroups) % pl.tilesS;
+        Item it;
+        it.b = item / (hgroups * pl.tilesS);
+        it.s0 = ts_i * pl.tS;
+        it.head0 = hg * pl.hpc;
+        it.ks_first = max(0, sh.eS - it.s0);
+        it.ks_last = min(pl.hS - 1, sh.S - 1 - it.s0 + sh.eS);
+        it.pad0 = it.pad1 = it.pad2 = 0;
+        sItems[tid] = it;
+    }
+    __syncthreads();
+    int nsteps = 0;
+    for (int i = 0; i < my_items; ++i) nsteps += (sItems[i].ks_last - sItems[i].ks_first + 1) * nchunks_live * pl.hpc;
+    const int nheads = my_items * pl.hpc;
 
     // ---- one-time setup ----------------------------------------------------------------------
     if (tid == 0) {
@@ -329,14 +348,22 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const uint32_t tmem_p0 = tmem_s0 + 2 * ncols_pad;
     const int p_cols = ncols_pad >> 1;
 
-    // a step = (head, plane, h-chunk); steps run head-major, then chunk, then plane
-    struct Cursor { int hd, ks, chunk; };
+    // a step = (item, head, h-chunk, plane); H counts heads across items (buffer / barrier parities run on it)
+    struct Cursor { int slot, hd, ks, chunk, H; };
+    auto next_head = [&](Cursor& c) {                 // first step of the head after c's
+        ++c.H;
+        if (++c.hd == pl.hpc) { c.hd = 0; ++c.slot; }
+        c.ks = sItems[min(c.slot, my_items - 1)].ks_first;
+        c.chunk = chunk_first;
+    };
     auto advance = [&](Cursor& c) {
-        if (++c.ks > ks_last) {
-            c.ks = ks_first;
-            if (++c.chunk > chunk_last) { c.chunk = chunk_first; ++c.hd; }
+        if (++c.ks > sItems[c.slot].ks_last) {
+            c.ks = sItems[c.slot].ks_first;
+            if (++c.chunk > chunk_last) next_head(c);
         }
     };
+    auto is_head_start = [&](const Cursor& c) { return c.ks == sItems[c.slot].ks_first && c.chunk == chunk_first; };
+    const Cursor first = {0, 0, my_items > 0 ? sItems[0].ks_first : 0, chunk_first, 0};
 
     if (warp >= kDriverWarp) {
         // =============================== issuing warps ===========================================
@@ -345,19 +372,22 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         // themselves are predicated on one elected lane.  One thread pays 20-70 cycles per tcgen05.mma it issues, so
         // the per-step chains (3 score MMAs, ncols/16 P V MMAs, 2 TMA boxes) are spread over three warps.
         const bool leader = elect_one();      // each of these warps is converged here
-        auto q_buf = [&](int hd) { return sQ + (pl.rowbuf == 2 ? (hd & 1) : 0) * q_tile_bytes; };
-        auto issue_q_load = [&](int hd) {
+        auto q_buf = [&](int H) { return sQ + (pl.rowbuf == 2 ? (H & 1) : 0) * q_tile_bytes; };
+        auto issue_q_load = [&](const Cursor& c) {        // Q tile of c's head
             if (leader) {
-                uint64_t* bar = &bar_q[hd & 1];
+                const Item it = sItems[c.slot];
+                uint64_t* bar = &bar_q[c.H & 1];
                 mbar_expect_tx(bar, (uint32_t)q_tile_bytes);
 #pragma unroll
                 for (int sl = 0; sl < G::kSlabs; ++sl)
-                    tma_load_5d(q_buf(hd) + sl * q_slab_bytes, &map_q, bar, (head0 + hd) * D + sl * G::kSlabCh, w0, h0, s0, b);
+                    tma_load_5d(q_buf(c.H) + sl * q_slab_bytes, &map_q, bar, (it.head0 + c.hd) * D + sl * G::kSlabCh, w0, h0, it.s0, it.b);
             }
         };
         auto issue_kv_load = [&](int stage, const Cursor& c) {
             if (leader) {
-                const int cb = (head0 + c.hd) * D;
+                const Item it = sItems[c.slot];
+                const int s0 = it.s0, b = it.b;
+                const int cb = (it.head0 + c.hd) * D;
                 uint8_t* dst = sKV + stage * 2 * kv_tile_bytes;
                 mbar_expect_tx(&bar_kv[stage], 2u * G::kSlabs * (uint32_t)ncols * G::kRowBytes);
 #pragma unroll
@@ -387,7 +417,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         auto issue_s_mma = [&](int t, int stage, const Cursor& c) {     // S[t&1] = Q_hd K_t^T + R C_chunk^T
             if (leader) {
                 const uint32_t tmem_s = tmem_s0 + (t & 1) * ncols_pad;
-                const uint64_t da0 = dq0 + (c.hd & 1) * q_buf_step, db0 = dk0 + stage * stage_step;
+                const uint64_t da0 = dq0 + (c.H & 1) * q_buf_step, db0 = dk0 + stage * stage_step;
 #pragma unroll
                 for (int kk = 0; kk < ((WM_SKEL & 4) ? 0 : D / 16); ++kk) {
                     const uint32_t off = (uint32_t)(((kk * 16) / G::kSlabCh) * 1 /*slab*/);
@@ -412,7 +442,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                              db + (uint32_t)kk * (uint32_t)((16 * G::kRowBytes) >> 4), idesc_o, (accumulate || kk > 0) ? 1u : 0u);
             umma_commit(bar);
         };
-        auto issue_o_mma = [&](int t, int stage, int hd, bool accumulate, bool head_end) {   // O[hd&1] += P[t&1] V_t
+        auto issue_o_mma = [&](int t, int stage, int hd, bool accumulate, bool head_end) {   // O[H&1] += P[t&1] V_t  (hd: head counter H)
             if (leader) {
                 const uint32_t tmem_o = tmem_base + (pl.obufs == 2 ? (hd & 1) : 0) * D;
                 const uint32_t ta = tmem_p0 + (t & 1) * p_cols;                          // A = P from tensor memory
@@ -433,28 +463,34 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             }
             __syncwarp();
         };
-        uint32_t dbg_flag = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0) && leader;
+        uint32_t dbg_flag = (blockIdx.x == 1) && leader;
         asm volatile("" : "+r"(dbg_flag));
         const bool dbg_on = dbg_flag != 0;
         (void)dbg_on;
-        Cursor cur = {0, ks_first, chunk_first};
+        Cursor cur = first;
 
         if (warp == kDriverWarp + 2) {
             // ---- TMA loader: K/V blocks nstage steps ahead, Q one head ahead ---------------------------------------
             Cursor ld = cur;
             int ld_t = 0, ld_stage = 0;
-            issue_q_load(0);
+            issue_q_load(cur);
             for (; ld_t < nstage && ld_t < nsteps; ++ld_t) {
                 issue_kv_load(ld_stage, ld);
                 advance(ld);
                 if (++ld_stage == nstage) ld_stage = 0;
             }
             for (int t = 0; t < nsteps; ++t) {
-                const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
+                const bool head_start = is_head_start(cur);
                 // O += P V of step t-1 has retired: its K/V stage is free, and (the compute warps had to see S_{t-1} before
                 // they released that step) every S MMA of the head that ended with step t-1 has retired as well
                 if (t >= 1) mbar_wait(&bar_o[(t - 1) & 1], ((t - 1) >> 1) & 1);
-                if (head_start && cur.hd + 1 < pl.hpc) issue_q_load(cur.hd + 1);     // hpc > 1 implies two Q buffers
+                if (head_start && pl.rowbuf == 2 && cur.H + 1 < nheads) {            // two Q buffers: the next head's tile
+                    Cursor nh = cur;
+                    next_head(nh);
+                    issue_q_load(nh);
+                } else if (head_start && pl.rowbuf == 1 && t >= 1) {
+                    issue_q_load(cur);                                              // one Q buffer: this head's tile, now that it is free
+                }
                 if (t >= 1 && ld_t < nsteps) {
                     if (WM_SKEL & 8) { if (leader) mbar_arrive(&bar_kv[ld_stage]); } else
                     issue_kv_load(ld_stage, ld);          // == stage of step t-1
@@ -471,15 +507,15 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             auto wait_inputs = [&](const Cursor& c, bool new_head) {
                 mbar_wait(&bar_kv[stage], (kv_par >> stage) & 1u);
                 kv_par ^= 1u << stage;
-                if (new_head) mbar_wait(&bar_q[c.hd & 1], (c.hd >> 1) & 1);
+                if (new_head) mbar_wait(&bar_q[c.H & 1], (c.H >> 1) & 1);
                 tc_fence_after();
             };
             Cursor c2 = cur;
             int prev_hd = -1;
             for (int u = 0; u < 2 && u < nsteps; ++u) {                  // S_0, S_1
-                wait_inputs(c2, c2.hd != prev_hd);
+                wait_inputs(c2, c2.H != prev_hd);
                 issue_s_mma(u, stage, c2);
-                prev_hd = c2.hd;
+                prev_hd = c2.H;
                 advance(c2);
                 if (++stage == nstage) stage = 0;
             }
@@ -487,11 +523,11 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 DBG(2);
                 mbar_wait(&bar_sfree[t & 1], (t >> 1) & 1);              // S buffer t&1 drained
                 DBG(3);
-                wait_inputs(c2, c2.hd != prev_hd);
+                wait_inputs(c2, c2.H != prev_hd);
                 DBG(6);
                 issue_s_mma(t + 2, stage, c2);
                 DBG(7);
-                prev_hd = c2.hd;
+                prev_hd = c2.H;
                 advance(c2);
                 if (++stage == nstage) stage = 0;
             }
@@ -501,20 +537,20 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             int stage = 0;
             for (int t = 0; t < nsteps; ++t) {
                 DBG(0);
-                const bool head_start = (cur.ks == ks_first) && (cur.chunk == chunk_first);
+                const bool head_start = is_head_start(cur);
                 mbar_wait(&bar_kv[stage], (kv_par >> stage) & 1u);       // V block (long since there: S_t came from its K)
                 kv_par ^= 1u << stage;
                 DBG(1);
                 mbar_wait(&bar_p[t & 1], (t >> 1) & 1);
-                if (head_start && cur.hd >= pl.obufs) {      // the accumulator's previous head (cur.hd - obufs) has been read out
-                    const int h = cur.hd - pl.obufs;
+                if (head_start && cur.H >= pl.obufs) {       // the accumulator's previous head (H - obufs) has been read out
+                    const int h = cur.H - pl.obufs;
                     mbar_wait(&bar_ofree[h & 1], (h >> 1) & 1);
                 }
                 tc_fence_after();
                 DBG(4);
-                const int hd_now = cur.hd;
+                const int hd_now = cur.H;
                 advance(cur);
-                issue_o_mma(t, stage, hd_now, !head_start, cur.hd != hd_now);
+                issue_o_mma(t, stage, hd_now, !head_start, cur.H != hd_now);
                 DBG(5);
                 if (++stage == nstage) stage = 0;
             }
@@ -532,11 +568,10 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
         const int plane_mask = (1 << pl.lgPlane) - 1;
         const int qs = row >> pl.lgPlane, qh = (row & plane_mask) >> pl.lgTW, qw = row & (pl.tW - 1);
-        const bool q_valid = (s0 + qs < sh.S) && (h0 + qh < sh.H) && (w0 + qw < sh.W);
+        const bool hw_valid = (h0 + qh < sh.H) && (w0 + qw < sh.W);
         // warp-uniform ranges (identical for all warps of a quadrant)
         const int w_qs = (quad * 32) >> pl.lgPlane;
         const int w_qh_lo = ((quad * 32) & plane_mask) >> pl.lgTW, w_qh_hi = ((quad * 32 + 31) & plane_mask) >> pl.lgTW;
-        const long tok = (((long)b * sh.S + (s0 + qs)) * sh.H + (h0 + qh)) * sh.W + (w0 + qw);
 
         // Softmax without a running maximum.  P = 2^(s*scale*log2e) is taken relative to the FIXED exponent 0: bf16 P, the
         // fp32 row sums and the fp32 accumulation of P V keep full relative precision as long as the row sum stays
@@ -556,7 +591,11 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_l[hd & 1]);
         };
-        auto finish_head = [&](int hd, float l_mine) {
+        auto finish_head = [&](int hd, float l_mine) {          // hd: head counter H (across items)
+            const Item it = sItems[hd / pl.hpc];
+            const int head = it.head0 + hd % pl.hpc;
+            const bool q_valid = hw_valid && (it.s0 + qs < sh.S);
+            const long tok = (((long)it.b * sh.S + (it.s0 + qs)) * sh.H + (h0 + qh)) * sh.W + (w0 + qw);
             mbar_wait(&bar_l[hd & 1], (hd >> 1) & 1);
             const float l_run = l_mine + xslot(hd)[row];
             const bool ok = l_run >= 7.8886091e-31f && l_run <= 1.2676506e30f;       // [2^-100, 2^100]; false for NaN
@@ -564,7 +603,7 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             mbar_wait(&bar_head[hd & 1], (hd >> 1) & 1);
             tc_fence_after();
             const uint32_t tmem_o = tmem_base + (pl.obufs == 2 ? (hd & 1) : 0) * D + lane_sel;
-            __nv_bfloat16* orow = prm.o + tok * (long)sh.inner() + (head0 + hd) * D;
+            __nv_bfloat16* orow = prm.o + tok * (long)sh.inner() + head * D;
             const float lse_out = ok ? lg2(l_run) * 0.6931471805599453f : __int_as_float(0x7fc00000);
 #pragma unroll
             for (int c0 = 0; c0 < D; c0 += 32) {           // 32 columns at a time: bounded register footprint at D = 128
@@ -587,19 +626,16 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     }
                 }
             }
-            if (q_valid) prm.lse[tok * sh.heads + head0 + hd] = lse_out;
+            if (q_valid) prm.lse[tok * sh.heads + head] = lse_out;
         };
-        // does this team own the last step of head hd?  (steps are numbered across heads: head hd ends with step
-        // (hd + 1) * nblocks - 1)
-        auto owns_last = [&](int hd) { return (((hd + 1) * nblocks - 1) & 1) == team; };
 
         const int ngroups = ncols_pad >> 3;
         int dlo = 0, dhi = ngroups;            // 8-column groups of this team's P buffer that may be non-zero
-        uint32_t dbg_flag = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0 && (tid & 127) == 0);     // one thread per team
+        uint32_t dbg_flag = (blockIdx.x == 1 && (tid & 127) == 0);     // one thread per team
         asm volatile("" : "+r"(dbg_flag));
         const bool dbg_on = dbg_flag != 0;
         (void)dbg_on;
-        uint32_t dbg_blk_flag = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0);
+        uint32_t dbg_blk_flag = (blockIdx.x == 1);
         asm volatile("" : "+r"(dbg_blk_flag));
         const bool dbg_blk = dbg_blk_flag != 0;
         (void)dbg_blk;
@@ -613,10 +649,13 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         };
 
         int t = 0;
-        for (int hd = 0; hd < pl.hpc; ++hd) {
+        bool owned_last_prev = false;            // did this team own the last step of the previous head?
+        for (int hd = 0; hd < nheads; ++hd) {    // hd: head counter across this CTA's items
             DBGT(14, t);
+            const int ks_first = sItems[hd / pl.hpc].ks_first, ks_last = sItems[hd / pl.hpc].ks_last;
+            const bool owns_last = ((t + (ks_last - ks_first + 1) * nchunks_live - 1) & 1) == team;     // of THIS head
             const float prev_l = l_part;
-            bool drain_prev = hd > 0 && !owns_last(hd - 1);      // the previous head's epilogue is this team's, still to be done
+            bool drain_prev = hd > 0 && !owned_last_prev;        // the previous head's epilogue is this team's, still to be done
             l_part = 0.f;
             for (int chunk = chunk_first; chunk <= chunk_last; ++chunk) {
                 // ---- live column range of this quadrant in this h-chunk (warp-uniform) ----
@@ -740,9 +779,10 @@ l3d_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                 }
             }
             if (drain_prev) finish_head(hd - 1, prev_l);      // this team had no step in this head
-            if (owns_last(hd)) deposit_l(hd, l_part);
+            if (owns_last) deposit_l(hd, l_part);
+            owned_last_prev = owns_last;
         }
-        if (!owns_last(pl.hpc - 1)) finish_head(pl.hpc - 1, l_part);
+        if (nheads > 0 && !owned_last_prev) finish_head(nheads - 1, l_part);
     }
 
     tc_fence_before();
@@ -765,8 +805,12 @@ static int launch_fwd(const void* q, const void* k, const void* v, void* o, floa
     if (int rc = make_tensor_map_5d(&mv, v, s.B, s.S, s.H, s.W, C, s.kv_ld(), G::kSlabCh, pl.hW, pl.ch, 1, G::kSwizzleBytes)) return rc;
     FwdParams prm{s, pl, static_cast<__nv_bfloat16*>(o), lse};
     WM_CUDA_CHECK(cudaFuncSetAttribute(l3d_fwd_tc_kernel<D, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
-    const dim3 grid((unsigned)(pl.tilesW * pl.tilesH), (unsigned)pl.tilesS, (unsigned)(s.B * (s.heads / pl.hpc)));
-    if (grid.y > 65535u || grid.z > 65535u) return fail(WM_EUNSUPPORTED, "grid too large for the tensor-core kernel");
+    // persistent grid when there is more than one work item per SM (see the kernel's work decomposition), else one CTA per item
+    const long items = (long)pl.tilesW * pl.tilesH * pl.tilesS * s.B * (s.heads / pl.hpc);
+    if (items > 0x7fffffffL) return fail(WM_EUNSUPPORTED, "grid too large for the tensor-core kernel");
+    const bool fits = (items + sm_count() - 1) / sm_count() + pl.tilesH * pl.tilesW <= kMaxItemsPerCta;      // per-CTA item table
+    const bool every_position_served = pl.tilesH * pl.tilesW <= sm_count();                                  // a CTA serves ONE brick position
+    const unsigned grid = (unsigned)(items > (long)sm_count() && fits && every_position_served ? (long)sm_count() : items);
     l3d_fwd_tc_kernel<D, NK><<<grid, kFwdThreads, pl.smem_bytes, st>>>(mq, mk, mv, prm);
     WM_CUDA_CHECK(cudaGetLastError());
     return WM_OK;

@@ -28,6 +28,7 @@ struct Plan {
     float scale_log2;
 };
 
+constexpr int kMaxItemsPerCta = 64;  // rows of the per-CTA work table of the persistent kernels (2 KB of shared memory)
 constexpr int kFwdThreads = 352;     // fwd: 8 compute warps + S issuer + P V issuer + TMA loader
 constexpr int kSmemLimit = 227 * 1024;
 

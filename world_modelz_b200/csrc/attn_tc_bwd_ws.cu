@@ -78,7 +78,6 @@ struct BwdWsParams {
     long ld_out;             // elements between consecutive tokens of the outputs
 };
 
-constexpr int kMaxItemsPerCta = 64;    // rows of the per-CTA work table (2 KB of the fixed shared-memory budget)
 constexpr int kWsThreads = 352;        // 8 compute warps + (S,dP) issuer + accumulate issuer + TMA loader
 
 template <int D, int MODE>
@@ -716,7 +715,8 @@ static int launch_ws(const void* a1, const void* a2, const void* b1, const void*
     const long items = (long)pl.tilesW * pl.tilesH * pl.tilesS * s.B * (s.heads / pl.hpc);
     if (items > 0x7fffffffL) return fail(WM_EUNSUPPORTED, "grid too large for the tensor-core kernel");
     const bool fits = (items + sm_count() - 1) / sm_count() + pl.tilesH * pl.tilesW <= kMaxItemsPerCta;      // per-CTA item table
-    const unsigned grid = (unsigned)(items > (long)sm_count() && fits ? (long)sm_count() : items);
+    const bool every_position_served = pl.tilesH * pl.tilesW <= sm_count();       // a CTA serves ONE brick position
+    const unsigned grid = (unsigned)(items > (long)sm_count() && fits && every_position_served ? (long)sm_count() : items);
     l3d_bwd_ws_kernel<D, MODE><<<grid, kWsThreads, pl.smem_bytes, st>>>(ma1, ma2, mb1, mb2, prm);
     WM_CUDA_CHECK(cudaGetLastError());
     return WM_OK;
