@@ -49,13 +49,13 @@ namespace tc {
 __global__ void __launch_bounds__(256)
 l3d_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
                  float* __restrict__ delta, long items, int d) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;       // (token, head)
-    if (i >= items) return;
-    const uint4* po = reinterpret_cast<const uint4*>(o + i * d);
-    const uint4* pg = reinterpret_cast<const uint4*>(dout + i * d);
+    // d / 8 consecutive lanes share one (token, head): every load instruction of a warp covers 512 contiguous bytes
+    const int lanes = d >> 3;                                            // 4, 8 or 16 (d = 32, 64, 128)
+    const long chunk = (long)blockIdx.x * blockDim.x + threadIdx.x;      // 16-byte chunk of the [items, d] tensors
+    const long i = chunk / lanes;
     float acc = 0.f;
-    for (int c = 0; c < d / 8; ++c) {
-        const uint4 a = __ldg(po + c), g = __ldg(pg + c);
+    if (i < items) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(o) + chunk), g = __ldg(reinterpret_cast<const uint4*>(dout) + chunk);
         const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
         const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&g);
 #pragma unroll
@@ -65,7 +65,8 @@ l3d_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __res
             acc = fmaf(fa.y, fg.y, acc);
         }
     }
-    delta[i] = acc;
+    for (int sft = lanes >> 1; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+    if (i < items && (threadIdx.x & (lanes - 1)) == 0) delta[i] = acc;
 }
 
 struct BwdWsParams {
@@ -735,7 +736,7 @@ static int launch_bwd_d(const void* q, const void* k, const void* v, const void*
     if (!make_plan(s, kBwdDQws, pq) || !make_plan(s, kBwdDKVws, pkv))
         return fail(WM_EUNSUPPORTED, "no tensor-core backward tiling for this shape");
     const long items = s.tokens() * s.heads;
-    l3d_delta_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(o),
+    l3d_delta_kernel<<<(unsigned)((items * (s.d / 8) + 255) / 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(o),
                                                                       static_cast<const __nv_bfloat16*>(dout), delta,
                                                                       items, s.d);
     WM_CUDA_CHECK(cudaGetLastError());
