@@ -253,8 +253,8 @@ def loss_hist_update(ts, losses, weights, counts, alpha) -> None:
 
 
 class _EmbedPosFn(torch.autograd.Function):
-    """``embedding(tokens) + ((pos_s + pos_h) + pos_w)`` in one kernel (``wm_embed_pos_fwd``); the backward reduces the
-    incoming gradient over the batch once and hands the table gradient to the stock embedding backward."""
+    """``embedding(tokens) + ((pos_s + pos_h) + pos_w)`` in one kernel (``wm_embed_pos_fwd``); the backward is one
+    one-hot GEMM (see ``backward``)."""
 
     @staticmethod
     def forward(ctx, tokens, table, ps, ph, pw):
@@ -274,19 +274,44 @@ class _EmbedPosFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
+        """All four gradients are ONE GEMM: ``onehot^T @ dout`` with a ``[tokens, rows + S + H + W]`` matrix that has four
+        ones per row (the token's table row and its three position rows).  Products by 1.0 are exact and the GEMM
+        accumulates in fp32, so this equals the stock embedding backward + broadcast reductions -- without the radix
+        sort, the segment scan and the three full-size reductions (≈ 0.25 ms -> ≈ 0.08 ms at config 3)."""
         (tokens,) = ctx.saved_tensors
         n, ns, nh, nw = ctx.rows
         B, S, H, W = tokens.shape
-        dout = dout.contiguous()
-        dtable = torch.ops.aten.embedding_dense_backward(dout, tokens, n, -1, False)
-        g = dout.sum(dim=0)                                   # [S,H,W,dim]: the one pass over the full gradient
-        dps = torch.zeros(ns, g.shape[-1], device=g.device, dtype=g.dtype)
-        dph = torch.zeros(nh, g.shape[-1], device=g.device, dtype=g.dtype)
-        dpw = torch.zeros(nw, g.shape[-1], device=g.device, dtype=g.dtype)
-        dps[:S] = g.sum(dim=(1, 2))
-        dph[:H] = g.sum(dim=(0, 2))
-        dpw[:W] = g.sum(dim=(0, 1))
-        return None, dtable, dps, dph, dpw
+        if ns != S or nh != H or nw != W:
+            raise RuntimeError('embed_pos: position tables must be sliced to the grid (pos_s[:S], pos_h[:H], pos_w[:W])')
+        dim = dout.shape[-1]
+        ntok = tokens.numel()
+        cols = (n + S + H + W + 7) // 8 * 8
+        idx = torch.empty(ntok, 4, device=dout.device, dtype=torch.int64)
+        idx[:, 0] = tokens.reshape(-1).clamp(0, n - 1)
+        idx[:, 1:] = _pos_rows(B, S, H, W, n, dout.device)
+        onehot = torch.zeros(ntok, cols, device=dout.device, dtype=dout.dtype)
+        onehot.scatter_(1, idx, 1.0)
+        g = onehot.t() @ dout.reshape(ntok, dim)
+        return None, g[:n], g[n:n + S], g[n + S:n + S + H], g[n + S + H:n + S + H + W]
+
+
+_pos_rows_cache = {}
+
+
+def _pos_rows(B, S, H, W, n, device):
+    """``[B*S*H*W, 3]`` int64: the one-hot columns of a token's three position rows (constant per shape, cached)."""
+    key = (B, S, H, W, n, str(device))
+    t = _pos_rows_cache.get(key)
+    if t is None:
+        s = torch.arange(S, device=device).view(S, 1, 1).expand(S, H, W)
+        h = torch.arange(H, device=device).view(1, H, 1).expand(S, H, W)
+        w = torch.arange(W, device=device).view(1, 1, W).expand(S, H, W)
+        one = torch.stack((n + s, n + S + h, n + S + H + w), dim=-1).reshape(1, S * H * W, 3)
+        t = one.expand(B, -1, -1).reshape(B * S * H * W, 3).contiguous()
+        if len(_pos_rows_cache) > 16:
+            _pos_rows_cache.clear()
+        _pos_rows_cache[key] = t
+    return t
 
 
 def embed_pos(tokens: torch.Tensor, table: torch.Tensor, pos_s: torch.Tensor, pos_h: torch.Tensor,
