@@ -274,3 +274,29 @@ def test_merged_kv_projection_operands_match_separate_tensors(shape, heads, ext,
     assert torch.equal(out, ref)
     assert torch.equal(q.grad, q2.grad)
     assert torch.equal(kv.grad[..., :C], k2.grad) and torch.equal(kv.grad[..., C:], v2.grad)
+
+
+@pytest.mark.parametrize('shape,heads,ext', [
+    ((5, 16, 16, 16, 256), 8, (1, 2, 2)),      # config-3 widths: 160 work items > 148 SMs, some CTAs walk two items
+    ((32, 16, 16, 16, 256), 8, (1, 2, 2)),     # the benchmarked shape: 6-7 items per persistent CTA, s-border and interior mixed
+    ((3, 12, 40, 24, 64), 2, (1, 2, 2)),       # many brick positions (5 x 3), ragged in s, one head per item
+])
+def test_persistent_grid_matches_the_exact_kernels(shape, heads, ext):
+    """Shapes with more work items than SMs run the tensor-core kernels on their persistent grid (a CTA walks several
+    (batch, s position, head group) items of one brick position): forward and all gradients against the exact SIMT
+    kernels on the same inputs, everywhere."""
+    g = torch.Generator().manual_seed(11)
+    q = (torch.randn(shape, generator=g) * 0.5).to(DEV, torch.bfloat16)
+    k = (torch.randn(shape, generator=g) * 0.5).to(DEV, torch.bfloat16)
+    v = torch.randn(shape, generator=g).to(DEV, torch.bfloat16)
+    do = torch.randn(shape, generator=g).to(DEV, torch.bfloat16)
+    scale = (shape[-1] // heads) ** -0.5
+    assert ops.uses_tensor_cores(*shape[1:4], heads, shape[-1] // heads, ext)
+    o_tc, lse_tc = ops.attn_forward(q, k, v, heads, ext, scale)
+    o_si, lse_si = ops.attn_forward(q, k, v, heads, ext, scale, ops.FLAG_SIMT)
+    _close(o_tc, o_si, 2e-2, 4e-3, 'out')
+    _close(lse_tc, lse_si, 1e-3, 1e-4, 'lse')
+    g_tc = ops.attn_backward(q, k, v, o_tc, lse_tc, do, heads, ext, scale)
+    g_si = ops.attn_backward(q, k, v, o_si, lse_si, do, heads, ext, scale, ops.FLAG_SIMT)
+    for name, a, b in zip(('dq', 'dk', 'dv'), g_tc, g_si):
+        _close(a, b, 2e-2, 1e-2, name)
