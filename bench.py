@@ -450,16 +450,39 @@ def run_b200(args):
     dbg(f'timed e2e arm: {ms_e2e:.1f} ms')
 
     # --- config 5 on EVERY rank: 8 clips per GPU, batch-sharded, no collective; time = max over ranks ---------------
-    samp = None
+    samp = samp_pruned = pruned = None
     if not args.no_micro:
-        sync_all()
-        samp_ms, samp = sampling_benchmark(dev, model, 8, world)
-        t_ms = torch.tensor([samp_ms], device=dev)
-        if world > 1:
-            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-        samp.update({'global_clips': 8 * world, 'ms': t_ms.item(),
-                     'clips_per_s': 8 * world / (t_ms.item() * 1e-3),
-                     'frames_per_s': 8 * world * samp['frames_per_clip'] / (t_ms.item() * 1e-3)})
+        def sampling_arm():
+            sync_all()
+            samp_ms, info = sampling_benchmark(dev, model, 8, world)
+            t_ms = torch.tensor([samp_ms], device=dev)
+            if world > 1:
+                dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+            info.update({'global_clips': 8 * world, 'ms': t_ms.item(),
+                         'clips_per_s': 8 * world / (t_ms.item() * 1e-3),
+                         'frames_per_s': 8 * world * info['frames_per_clip'] / (t_ms.item() * 1e-3)})
+            return info
+        samp = sampling_arm()
+        # --- opt-in receptive-field cone (NOT the headline): the same step / sampling loop evaluating only the rows the
+        # last frame depends on (Local3dAttentionTransformer.last_frame_cone); identical loss and gradients (tests)
+        model.prune_receptive_field = True
+        samp_pruned = sampling_arm()
+        model_p = wm.VqVideoDiffusionModel(**C3).to(dev)
+        model_p.prune_receptive_field = True
+        trainer_p = wm.DenoiserTrainer(model_p, lr=1e-4, weight_decay=1e-7, compute_dtype=torch.bfloat16,
+                                       use_cuda_graph=not args.no_graph)
+
+        def step_pruned(i):
+            trainer_p.step(dev_tokens[i % n_batches], dev_r[i % n_batches])
+        for i in range(3):
+            step_pruned(i)
+        ms_p, _, _ = timed(step_pruned, args.steps)
+        pruned = {'ms_per_step': ms_p / args.steps, 'clips_per_s': world * B * args.steps / (ms_p * 1e-3),
+                  'frames_per_layer': [C3['data_shape'][0] - c for c in model_p.transformer.last_frame_cone(C3['data_shape'][0])[:-1]],
+                  'note': 'opt-in (model.prune_receptive_field): layers run on the last frame\'s dependency cone only; '
+                          'same loss and parameter gradients as the full step; not used for value / e2e'}
+        model.prune_receptive_field = False
+        del trainer_p, model_p
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -496,6 +519,7 @@ def run_b200(args):
                 micro['roofline_vq']['traffic_commit'] = tr.get('commit')
         line.update(micro)
         line['sampling_config5'] = samp
+        line['receptive_field_cone'] = {'train_step': pruned, 'sampling_config5': samp_pruned}
         line['transformer_config4'] = config4_transformer_benchmark(dev, tf_peak)
     else:
         line['roofline'] = None

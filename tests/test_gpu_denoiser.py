@@ -18,11 +18,17 @@ def _small(f):
     return kw, O.DenoiserConfig(**kw)
 
 
-def test_denoiser_against_reference_fixture_fp32():
+@pytest.mark.parametrize('prune', [False, True])
+def test_denoiser_against_reference_fixture_fp32(prune):
+    """prune=True: the opt-in receptive-field cone (4 frames, depth 2, extents (1, ., .): layers see frames 1.., 2..)
+    must give the reference's logits, loss and parameter gradients -- including the exact zeros of the position rows
+    and embedding rows only dead frames touch."""
     f = load('denoiser_small.npz')
     kw, _ = _small(f)
     m = wm.VqVideoDiffusionModel(**kw).to(DEV)
     m.load_state_dict(state_dict_of(f))
+    m.prune_receptive_field = prune
+    assert m.transformer.last_frame_cone(4) == [1, 2, 3]
     tokens = torch.from_numpy(f['tokens']).to(DEV)
     target = torch.from_numpy(f['target']).to(DEV)
     feats = m.transformer(tokens)
@@ -84,8 +90,9 @@ def _rel_close(a, b, rtol, atol_frac, what):
                                                f'{(a - b).abs().max().item():.3e} scale={b.abs().max().item():.3e}')
 
 
-def test_bf16_config3_step_matches_oracle():
-    """The benchmarked path itself: bf16, BASELINE config-3 shape, fused deferred-bias schedule, CUDA graphs.  One clip,
+@pytest.mark.parametrize('prune', [False, True])
+def test_bf16_config3_step_matches_oracle(prune):
+    """The benchmarked path itself (prune=True: the same through the opt-in receptive-field cone, 5/4/3/2 frames per layer): bf16, BASELINE config-3 shape, fused deferred-bias schedule, CUDA graphs.  One clip,
     r = 0 (no corruption, so that the oracle sees the same inputs): loss and every parameter gradient against the
     fp32 CPU oracle (bf16 bar: rtol 2e-2 plus a scale-relative atol; gradients are sums over 4096 tokens of bf16
     products, so a small fraction of near-zero elements may exceed it)."""
@@ -93,6 +100,7 @@ def test_bf16_config3_step_matches_oracle():
     p = O.init_denoiser_params(cfg, seed=42)
     m = wm.VqVideoDiffusionModel(**C3).to(DEV)
     m.load_state_dict(p)
+    m.prune_receptive_field = prune
     tr = wm.DenoiserTrainer(m, lr=1e-4, weight_decay=1e-7, compute_dtype=torch.bfloat16, use_cuda_graph=True)
     tokens = torch.randint(0, 512, (1, 16, 16, 16), generator=torch.Generator().manual_seed(7))
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
@@ -200,6 +208,30 @@ def _chi2_same_distribution(a, b, K):
     keep = (ca + cb) > 0
     stat = (((ca * (nb / na).sqrt() - cb * (na / nb).sqrt()) ** 2) / (ca + cb))[keep].sum().item()
     return stat / max(1, int(keep.sum()) - 1)
+
+
+def test_pruned_forward_equals_full_forward_multi_clip():
+    """Several clips (the frame slices are strided copies then), short and long cones, fp32 and bf16: logits and
+    parameter gradients of the pruned evaluation against the full one on the same device."""
+    for dtype, tol in ((torch.float32, 2e-5), (torch.bfloat16, 3e-2)):
+        for S, depth, e_s in ((6, 2, 1), (3, 2, 1), (7, 1, 2), (5, 3, 0)):
+            torch.manual_seed(S)
+            m = wm.VqVideoDiffusionModel(data_shape=(S, 8, 8), dim=32, num_classes=24, extents=(e_s, 1, 2), depth=depth,
+                                         heads=2, dim_head=16, mlp_dim=48).to(DEV).to(dtype)
+            tokens = torch.randint(0, 25, (3, S, 8, 8), device=DEV)
+            target = torch.randint(0, 24, (3, 8, 8), device=DEV)
+            res = []
+            for prune in (False, True):
+                m.prune_receptive_field = prune
+                m.zero_grad(set_to_none=True)
+                logits = m(tokens)
+                torch.nn.functional.cross_entropy(logits.float().reshape(-1, 24), target.reshape(-1)).backward()
+                res.append((logits.detach().float(), {k: q.grad.detach().float() for k, q in m.named_parameters()}))
+            scale = res[0][0].abs().max().item()
+            assert (res[0][0] - res[1][0]).abs().max().item() <= tol * scale, (dtype, S, depth, e_s)
+            for k, g in res[0][1].items():
+                gs = g.abs().max().item() + 1e-12
+                assert (g - res[1][1][k]).abs().max().item() <= tol * gs, (dtype, S, depth, e_s, k)
 
 
 @pytest.mark.parametrize('graph,topk', [(False, -1), (True, -1), (True, 3), (False, 3)])

@@ -294,3 +294,25 @@ def test_sparse_model_surface_and_position_samplers():
     # window length grows with t (sparse_diffusion.py:58-59): floor(2 + t * 7), clamped to 6 frames
     frames = [(q[i].div(36, rounding_mode='trunc')).unique().numel() for i in range(4)]
     assert frames[0] <= 2 and frames[1] <= 4 and frames[2] <= 6
+
+
+def test_last_frame_cone_is_the_reference_models_dependency_cone():
+    """Local3dAttentionTransformer.last_frame_cone against the reference's semantics (the oracle's CPU denoiser): tokens
+    in frames below cone[0] cannot change the last frame's logits, a token in frame cone[0] can."""
+    import world_modelz_b200 as wm
+    from oracle import local3d as O
+    for S, depth, e_s in ((7, 2, 1), (6, 1, 2), (4, 3, 1)):
+        kw = dict(data_shape=(S, 4, 4), dim=16, num_classes=10, extents=(e_s, 1, 1), depth=depth, heads=2, dim_head=8, mlp_dim=16)
+        cfg = O.DenoiserConfig(**kw)
+        p = O.init_denoiser_params(cfg, seed=S)
+        cone = wm.VqVideoDiffusionModel(**kw).transformer.last_frame_cone(S)
+        assert cone[-1] == S - 1 and cone[0] == max(0, S - 1 - depth * e_s) and all(b - a in (0, e_s) or a == 0 for a, b in zip(cone, cone[1:]))
+        tokens = torch.randint(0, 10, (1, S, 4, 4), generator=torch.Generator().manual_seed(0))
+        base = O.denoiser_forward(p, tokens, cfg)
+        if cone[0] > 0:
+            dead = tokens.clone()
+            dead[:, :cone[0]] = (dead[:, :cone[0]] + 3) % 10
+            assert torch.equal(O.denoiser_forward(p, dead, cfg), base)
+        live = tokens.clone()
+        live[:, cone[0]] = (live[:, cone[0]] + 3) % 10
+        assert not torch.equal(O.denoiser_forward(p, live, cfg), base)

@@ -32,9 +32,14 @@ class VqVideoDiffusionModel(nn.Module):
             data_shape=data_shape, dim=dim, num_classes=num_classes + 1,      # +1: the mask token
             extents=extents, depth=depth, heads=heads, dim_head=dim_head, mlp_dim=mlp_dim, dropout=dropout)
         self.logit_proj = nn.Linear(dim, num_classes)
+        # opt-in (not part of the reference's surface): evaluate only the rows the last frame depends on -- see
+        # Local3dAttentionTransformer.last_frame_cone.  Off by default: every number quoted as the reference's metric
+        # is measured on the full 16-frame computation.
+        self.prune_receptive_field = False
 
     def forward(self, x):
-        return self.logit_proj(self.transformer.forward_last_frame(x))       # == transformer(x)[:, -1]
+        feats = self.transformer.forward_last_frame(x, self.prune_receptive_field)   # == transformer(x)[:, -1]
+        return ops.linear(feats, self.logit_proj.weight, self.logit_proj.bias)   # nn.Linear; bias gradient by wm_colsum
 
 
 def corrupt_last_frame(tokens: torch.Tensor, r: torch.Tensor, num_embeddings: int,
@@ -360,7 +365,8 @@ class _SamplerState:
 
 def _sampler_state(model, tokens, iterations, seed):
     cache = model.__dict__.setdefault('_wm_sample_graphs', {})
-    key = (tuple(tokens.shape), str(tokens.device), model.training, iterations)
+    key = (tuple(tokens.shape), str(tokens.device), model.training, iterations,
+           bool(getattr(model, 'prune_receptive_field', False)))
     if key not in cache:
         cache[key] = _SamplerState(model, tokens.shape, tokens.device, iterations, seed)
     return cache[key]

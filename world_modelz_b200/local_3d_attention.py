@@ -93,8 +93,9 @@ class Local3dAttention(nn.Module):
         out = ops.local3d_attention(q, k, v, self.heads, self.extents, self.scale, self.kernel_flags)
         return out.reshape(-1, self.heads, 1, out.shape[-1] // self.heads)
 
-    def forward_deferred_bias(self, x, q, q_projected=None):
-        """``(y, bias)`` with ``forward(x, q) == y + bias`` (``q_projected``: ``to_q(q)`` when the caller already has it).  Softmax rows sum to one, so ``to_v``'s bias passes through
+    def forward_deferred_bias(self, x, q, q_projected=None, drop_frames=0):
+        """``(y, bias)`` with ``forward(x, q) == y + bias`` (``q_projected``: ``to_q(q)`` when the caller already has it;
+        ``drop_frames``: return ``y[:, drop_frames:]`` only -- the output projection then runs on those frames alone).  Softmax rows sum to one, so ``to_v``'s bias passes through
         the attention core unchanged: ``attn(q, k, v + b_v) = attn(q, k, v) + b_v``, and with the output projection
         the whole module equals ``attn(q, k, x W_v^T) W_o^T + (W_o b_v + b_o)``.  The caller adds that [dim] vector in
         its fused residual-add + LayerNorm kernel; autograd routes its gradient (reduced by that kernel's backward) to
@@ -103,7 +104,7 @@ class Local3dAttention(nn.Module):
         deferrable = (x.is_cuda and isinstance(self.to_out, nn.Sequential)
                       and (not self.training or self.to_out[1].p == 0.0))
         if not deferrable:
-            return self.forward(x, q), None
+            return self.forward(x, q)[:, drop_frames:], None
         if x.dim() != 5 or q.shape[:-1] != x.shape[:-1]:
             raise ValueError(f'expected x, q of shape [B,S,H,W,dim], got {tuple(x.shape)} and {tuple(q.shape)}')
         w_o = self.to_out[0].weight
@@ -113,6 +114,9 @@ class Local3dAttention(nn.Module):
         qp = q_projected if q_projected is not None else self.to_q(q)
         core = ops.local3d_attention_kv(qp, kv, self.heads, self.extents, self.scale, self.kernel_flags)
         bias = torch.addmv(self.to_out[0].bias, w_o, self.to_v.bias)      # W_o b_v + b_o, one GEMV
+        if drop_frames:
+            core = core.reshape(*q.shape[:-1], -1)[:, drop_frames:]
+            return torch.nn.functional.linear(core, w_o), bias
         return torch.nn.functional.linear(core, w_o).reshape(q.shape), bias
 
     def forward(self, x, q):
@@ -150,18 +154,37 @@ class Local3dAttentionTransformer(nn.Module):
                + self.pos_emb_w.weight[None, None, :w, :])
         return pos.unsqueeze(0).expand(batch_shape[0], -1, -1, -1, -1)
 
-    def _blocks(self, img_z):
-        """The residual stream before the last MLP branch is added, that branch's output and its deferred bias."""
+    def last_frame_cone(self, s):
+        """``lo[i]``: the first frame the input of layer ``i`` has to cover for the LAST frame of the transformer's
+        output to be exact (``lo[depth] = s - 1``).  A query sees ``extents[0]`` frames on either side, so the last
+        frame depends on ``depth * extents[0]`` frames before it and on nothing earlier: frames below ``lo[i]`` are
+        dead inputs of layer ``i`` for ``forward(img_z)[:, -1]`` -- their contribution to it and to its gradient is
+        exactly zero."""
+        depth = len(self.layers)
+        e_s = self.layers[0][0].fn.extents[0] if depth else 0
+        return [max(0, s - 1 - (depth - i) * e_s) for i in range(depth + 1)]
+
+    def _blocks(self, img_z, cone=None):
+        """The residual stream before the last MLP branch is added, that branch's output and its deferred bias.  With a
+        ``cone`` (``last_frame_cone``) only frames ``>= cone[i]`` enter layer ``i``: the attention of a slice that does
+        not start at frame 0 is wrong on its first ``extents[0]`` frames (their earlier neighbours are missing), which
+        are exactly the frames ``cone[i + 1]`` drops before the branch is added."""
         _, s, h, w = img_z.shape
-        x = ops.embed_pos(img_z, self.embedding.weight, self.pos_emb_s.weight[:s], self.pos_emb_h.weight[:h],
+        lo = cone[0] if cone is not None else 0
+        if lo:
+            img_z = img_z[:, lo:].contiguous()
+        x = ops.embed_pos(img_z, self.embedding.weight, self.pos_emb_s.weight[lo:s], self.pos_emb_h.weight[:h],
                           self.pos_emb_w.weight[:w])
         pending = pending_bias = None                # branch output (and its deferred bias) not yet added to the stream
-        for attn, ff in self.layers:
+        for i, (attn, ff) in enumerate(self.layers):
             x, xn = ops.add_layernorm(x, pending, attn.norm.weight, attn.norm.bias, attn.norm.eps, pending_bias)
             # to_q reads the residual stream itself (reference :160, q=x): the stream goes THROUGH the projection node, so
             # that its gradient is folded into the projection's dgrad GEMM instead of a separate full-size add
             qp, x = ops.linear_passthrough(x, attn.fn.to_q.weight)
-            a, a_bias = attn.fn.forward_deferred_bias(xn, q=x, q_projected=qp)
+            drop = cone[i + 1] - cone[i] if cone is not None else 0
+            a, a_bias = attn.fn.forward_deferred_bias(xn, q=x, q_projected=qp, drop_frames=drop)
+            if drop:
+                x, a = x[:, drop:].contiguous(), a.contiguous()
             x, xn = ops.add_layernorm(x, a, ff.norm.weight, ff.norm.bias, ff.norm.eps, a_bias)
             pending, pending_bias = ff.fn.forward_deferred_bias(xn)
         return x, pending, pending_bias
@@ -177,8 +200,13 @@ class Local3dAttentionTransformer(nn.Module):
         that every residual add is fused with the LayerNorm that follows it (``wm_add_layernorm_*``)."""
         return self._close(*self._blocks(img_z))
 
-    def forward_last_frame(self, img_z):
+    def forward_last_frame(self, img_z, prune_receptive_field=False):
         """``forward(img_z)[:, -1]``: the only part of the output the denoiser head reads (``main.py:35``).  The final
-        residual add (element-wise) is done on that frame alone -- same values, 1/S of the traffic."""
-        x, pending, pending_bias = self._blocks(img_z)
-        return self._close(x[:, -1], None if pending is None else pending[:, -1], pending_bias)
+        residual add (element-wise) is done on that frame alone -- same values, 1/S of the traffic.
+        ``prune_receptive_field`` (opt-in): run every layer on ``last_frame_cone`` only, i.e. skip the rows whose
+        contribution to that frame and to every parameter gradient is exactly zero (same values up to the summation
+        order of the GEMMs; at depth 4, extents (1, ., .), 16 frames: 5, 4, 3, 2 frames instead of 16 per layer)."""
+        x, pending, pending_bias = self._blocks(img_z, self.last_frame_cone(img_z.shape[1]) if prune_receptive_field else None)
+        if pending is None:
+            return x[:, -1]
+        return ops.last_frame_close(x, pending, pending_bias)

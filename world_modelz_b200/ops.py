@@ -325,6 +325,48 @@ def embed_pos(tokens: torch.Tensor, table: torch.Tensor, pos_s: torch.Tensor, po
     return _EmbedPosFn.apply(tokens, table, pos_s, pos_h, pos_w)
 
 
+def _colsum(t2d: torch.Tensor) -> torch.Tensor:
+    """Column sums of a contiguous ``[rows, cols]`` tensor with ``wm_colsum`` (stock reductions of a tall, narrow matrix
+    run on a handful of CTAs: ~20 us for 8192 x 256)."""
+    rows, cols = t2d.shape
+    out = torch.empty(cols, device=t2d.device, dtype=t2d.dtype)
+    ws = torch.empty(_lib.lib().wm_reduce_blocks(rows) * cols, device=t2d.device, dtype=torch.float32)
+    check(_lib.lib().wm_colsum(t2d.data_ptr(), out.data_ptr(), ws.data_ptr(), rows, cols, _dtype_code(t2d), _stream()),
+          'wm_colsum')
+    _count(2)
+    return out
+
+
+class _LastFrameCloseFn(torch.autograd.Function):
+    """``x[:, -1] + (pending[:, -1] + bias)``: the last residual add of the transformer, on the only frame the denoiser
+    head reads (``main.py:35``).  Backward: the gradients of ``x`` and ``pending`` are the SAME tensor (zero but for the last
+    frame) -- one fill and one copy instead of two of each -- and the bias gradient is a ``wm_colsum``."""
+
+    @staticmethod
+    def forward(ctx, x, pending, bias):
+        ctx.shape = x.shape
+        ctx.has_bias = bias is not None
+        last = pending[:, -1] if bias is None else pending[:, -1] + bias.to(pending.dtype)
+        return x[:, -1] + last
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        g = torch.zeros(ctx.shape, device=dout.device, dtype=dout.dtype)
+        g[:, -1] = dout
+        dbias = None
+        if ctx.has_bias:
+            cols = dout.shape[-1]
+            d2 = dout.reshape(-1, cols)
+            dbias = _colsum(d2) if (cols % 8 == 0 and cols <= 2048) else d2.sum(0)
+        return g, g, dbias
+
+
+def last_frame_close(x: torch.Tensor, pending: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    _require_cuda(x, pending)
+    return _LastFrameCloseFn.apply(x, pending, bias)
+
+
 class _ProjPassFn(torch.autograd.Function):
     """``(x @ W^T, x)``: a bias-free projection whose input also continues down another branch (``to_q`` reads the
     residual stream, ``local_3d_attention.py:160``).  Routing the stream THROUGH this node lets the backward fold the
