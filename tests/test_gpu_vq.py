@@ -126,7 +126,8 @@ def test_full_size_properties():
     assert torch.equal(ste2, codes)
 
 
-@pytest.mark.parametrize('N,L,K,D', [(1000, 1, 512, 64), (257, 2, 96, 32), (4096, 1, 256, 128), (130, 3, 32, 96)])
+@pytest.mark.parametrize('N,L,K,D', [(1000, 1, 512, 64), (257, 2, 96, 32), (4096, 1, 256, 128), (130, 3, 32, 96),
+                                     (40000, 2, 192, 64), (700, 1, 64, 64), (20000, 1, 448, 64), (333, 1, 96, 64)])
 def test_tensor_core_filter_matches_exact_simt_kernel(N, L, K, D):
     """tf32 tcgen05 candidate filter + fp64 re-check vs the fp32 SIMT kernel + fp64 re-scan: same indices
     (both are the exact-arithmetic argmin), also with duplicated / nearly duplicated codes."""

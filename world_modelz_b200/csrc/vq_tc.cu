@@ -39,11 +39,23 @@ namespace vq {
 using namespace wm::tc;
 
 #if WM_VQ_EXP & 32
-__device__ unsigned long long g_vq_dbg[4];
+// timeline of CTA (0, 0): clock64 at the hand-offs of the first 64 tiles (tools/vq_timeline.py)
+__device__ unsigned long long g_vq_dbg[64 * 16];
+#define VQ_TL(tile, ev)                                                                                   \
+    do {                                                                                                  \
+        if (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && (tile) < 64)                 \
+            g_vq_dbg[(tile) * 16 + (ev)] = (unsigned long long)clock64();                                 \
+    } while (0)
+#else
+#define VQ_TL(tile, ev) do { } while (0)
+#endif
+
+#ifndef WM_VQ_ISSUER_WARP
+#define WM_VQ_ISSUER_WARP 1   // 1: a seventeenth warp issues the MMA chains; 0: the first scanner warp of each group does (16 warps, 128 registers)
 #endif
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 16 * 32;      // 4 warps per SM sub-partition: 128 registers per thread
+constexpr int kThreads = (16 + WM_VQ_ISSUER_WARP) * 32;      // 8 scanner, 8 loader / writer warps, 1 MMA issuer: 120 registers per thread
 
 struct Params {
     const float* x;            // [N, L, D]
@@ -80,7 +92,40 @@ __device__ __forceinline__ uint32_t vmin3(uint32_t a, uint32_t b, uint32_t c) {
 // term accumulated in fp32 by the tensor core: 13 K-steps, each adding a rounding of at most 2^-23 of the running sum,
 // which is bounded by (|x| + |e|)^2 + 2 <= 2 (|x|^2 + |e|^2) + 2.  Twice the per-score bound, with slack:
 __device__ __forceinline__ float filter_window(float xn2, float emax) {
-    return 6.103515625e-5f * sqrtf(xn2) * emax + 8.0e-6f * (xn2 + emax * emax + 1.f) + 1e-30f;
+    float r;                                              // one MUFU; its relative error (2^-22) is inside the 2^-10 slack of the factor
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(xn2));
+    return 6.11e-5f * r * emax + 8.0e-6f * (xn2 + emax * emax + 1.f) + 1e-30f;
+}
+
+// hi / lo split of two values with the packed conversion (F2FP on the ALU; the scalar cvt is a quarter-rate XU instruction)
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// Sum of p[i] over the 16 lanes that share lane bit 4, for 8 values at once: 8 shuffles instead of 32.  The butterfly
+// exchanges half of the remaining values per stage, so the additions form the same tree as four xor-shuffles per value;
+// afterwards the lanes ch = 2 i and 2 i + 1 (ch = lane & 15) hold the total of value i.
+__device__ __forceinline__ float reduce8_over16(const float (&p)[8], int ch) {
+    float q[4], r[2];
+    const bool b8 = ch & 8, b4 = ch & 4, b2 = ch & 2;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float mine = b8 ? p[k + 4] : p[k], other = b8 ? p[k] : p[k + 4];
+        q[k] = mine + __shfl_xor_sync(0xffffffffu, other, 8);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float mine = b4 ? q[k + 2] : q[k], other = b4 ? q[k] : q[k + 2];
+        r[k] = mine + __shfl_xor_sync(0xffffffffu, other, 4);
+    }
+    const float mine = b2 ? r[1] : r[0], other = b2 ? r[0] : r[1];
+    float t = mine + __shfl_xor_sync(0xffffffffu, other, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    return t;                                             // value index ((ch >> 1) & 1) + 2 ((ch >> 2) & 1) + 4 ((ch >> 3) & 1) = ch >> 1
 }
 
 __device__ __forceinline__ void split_bf16(float v, uint16_t& hi, uint16_t& lo) {
@@ -222,13 +267,13 @@ vq_nearest_tc_kernel(const Params prm) {
     float* sRed = reinterpret_cast<float*>(sRes + 2 * 2 * kTileM * 4);       // [32] block reduction
     uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 32);
     uint64_t* bar_xready = bars;         // [2] operand tiles of a latent tile written          (8 loader warps)
-    uint64_t* bar_xfree = bars + 2;      // [2] every MMA reading that buffer has retired       (tcgen05.commit of both halves)
-    uint64_t* bar_full = bars + 4;       // [2] scores of code half A / B computed              (tcgen05.commit)
-    uint64_t* bar_free = bars + 6;       // [2] scores of half A / B drained                    (4 scanner warps)
-    uint64_t* bar_res = bars + 8;        // [2] both halves' results of a tile are in sRes      (8 scanner warps)
-    uint64_t* bar_xload = bars + 10;     // [2] fp32 rows of a latent tile landed                 (cp.async.bulk complete_tx)
-    uint64_t* bar_resfree = bars + 12;   // [2] the writers have consumed a tile's sRes entries     (8 writer warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* bar_xfree = bars + 2;      // [2] every MMA reading that buffer has retired       (tcgen05.commit behind the tile's last chain)
+    uint64_t* bar_full = bars + 4;       // [4] scores of a code quarter computed               (tcgen05.commit)
+    uint64_t* bar_free = bars + 8;       // [4] scores of a code quarter drained                (4 scanner warps)
+    uint64_t* bar_res = bars + 12;       // [2] both halves' results of a tile are in sRes      (8 scanner warps)
+    uint64_t* bar_xload = bars + 14;     // [2] fp32 rows of a latent tile landed                 (cp.async.bulk complete_tx)
+    uint64_t* bar_resfree = bars + 16;   // [2] the writers have consumed a tile's sRes entries     (8 writer warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int l = blockIdx.y;
@@ -237,12 +282,14 @@ vq_nearest_tc_kernel(const Params prm) {
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bar_xready[i], 8);
-            mbar_init(&bar_xfree[i], 2);
+            mbar_init(&bar_xfree[i], WM_VQ_ISSUER_WARP ? 1 : 2);
             mbar_init(&bar_xload[i], 1);
             mbar_init(&bar_resfree[i], 8);
+            mbar_init(&bar_res[i], 8);
+        }
+        for (int i = 0; i < 4; ++i) {
             mbar_init(&bar_full[i], 1);
             mbar_init(&bar_free[i], 4);
-            mbar_init(&bar_res[i], 8);
         }
         fence_barrier_init();
     }
@@ -295,62 +342,82 @@ vq_nearest_tc_kernel(const Params prm) {
     const uint32_t tmem_base = *tmem_slot;
     emax2 = sRed[0];
 #pragma unroll
-    for (int w = 1; w < 16; ++w) emax2 = fmaxf(emax2, sRed[w]);
+    for (int w = 1; w < kThreads / 32; ++w) emax2 = fmaxf(emax2, sRed[w]);
     const float emax = sqrtf(emax2) * 1.0000002f;
 
     const int first_tile = blockIdx.x, stride = gridDim.x;
     const int my_tiles = first_tile < prm.tiles ? (prm.tiles - first_tile + stride - 1) / stride : 0;
 
-    if (warp < 8) {
-        // =============================== scanners (+ MMA issue by the first warp of each half) =====================================================================
-        const int quad = warp & 3, half = warp >> 2;
-        const int row = quad * 32 + lane;
-        const uint32_t taddr = tmem_base + half * 256 + ((uint32_t)(quad * 32) << 16);
-        const int nchunk = KH >> 4;
-        // ---- the half's MMA chain: x_hi e_hi + x_lo e_hi + x_hi e_lo over all D channels, N = K/2 columns
-        const bool issuer = quad == 0;
-        const bool leader = elect_one();
-        const uint32_t idesc = make_idesc_bf16(KH, false, false);
+    const int KQ = KH >> 1;                                // codes per quarter = N of one MMA chain (tensor-memory columns [q * 128, q * 128 + KQ))
+    // One MMA chain: scores of code quarter q for the latent tile in operand buffer b -- x_hi e_hi + x_lo e_hi + x_hi e_lo over all D
+    // channels, then the norm step (+ |x|^2 + 2 + |e_k|^2).  Called by one elected thread.
+    auto issue_chain = [&](int b, int q, bool last_of_tile) {
+        const uint32_t idesc = make_idesc_bf16(KQ, false, false);
         const uint64_t dxh = make_smem_desc(smem_u32(sX), 16, 2048, 2u), dxl = make_smem_desc(smem_u32(sX + 1024), 16, 2048, 2u);
         const uint64_t deh = make_smem_desc(smem_u32(sEhi), 16, 1024, 2u), del = make_smem_desc(smem_u32(sElo), 16, 1024, 2u);
         const uint64_t dxe = make_smem_desc(smem_u32(sXe), (uint32_t)kTileM * 16u, 128u, 0u);      // norm step: no swizzle
         const uint64_t dee = make_smem_desc(smem_u32(sEe), (uint32_t)K * 16u, 128u, 0u);
-        auto issue_tile = [&](int j) {           // called by the issuing warp once its half is free (or was never used)
+        const uint32_t xoff = (uint32_t)((b * kXBuf) >> 4);
+        const uint32_t eoff = (uint32_t)((q * KQ * 128) >> 4);
+        const uint32_t dst = tmem_base + (uint32_t)q * 128u;
+        bool first = true;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const uint64_t da = (p == 1 ? dxl : dxh) + xoff;
+            const uint64_t db = (p == 2 ? del : deh) + eoff;
+#pragma unroll
+            for (int kk = 0; kk < ((WM_VQ_EXP & 2) ? 0 : D / 16); ++kk) {
+                const uint32_t sl = (uint32_t)(kk >> 2), ko = (uint32_t)((kk & 3) * 2);
+                umma_bf16_ss(dst, da + ko, db + sl * (uint32_t)(e_slab >> 4) + ko, idesc, first ? 0u : 1u);
+                first = false;
+            }
+        }
+        if (!(WM_VQ_EXP & 2))
+            umma_bf16_ss(dst, dxe + (uint32_t)((b * 2 * kTileM * 16) >> 4), dee + (uint32_t)((q * KQ * 16) >> 4), idesc, 1u);
+        umma_commit(&bar_full[q]);
+        if (last_of_tile) umma_commit(&bar_xfree[b]);      // every MMA (of this issuer) reading operand buffer b has been issued
+    };
+#if WM_VQ_ISSUER_WARP
+    if (warp == 16) {
+        // =============================== MMA issuer (its own warp: the issuing thread blocks while the tensor pipe's queue is full -- 3 300
+        // cycles per tile when a scanner warp did this between two scans).  Per tile four chains, one per code quarter, in the
+        // order 0, 2, 1, 3: each scanner group gets its first quarter first. ===========================================================
+        const bool leader = elect_one();
+        for (int j = 0; j < my_tiles; ++j) {
             const int b = j & 1;
             mbar_wait(&bar_xready[b], (j >> 1) & 1);
-            if (j > 0) mbar_wait(&bar_free[half], (j - 1) & 1);           // all four warps of the group have drained tile j-1
-            tc_fence_after();
-            if (leader) {
-                const uint32_t xoff = (uint32_t)((b * kXBuf) >> 4);
-                const uint32_t eoff = (uint32_t)((half * KH * 128) >> 4);
-                bool first = true;
-#pragma unroll
-                for (int p = 0; p < 3; ++p) {
-                    const uint64_t da = (p == 1 ? dxl : dxh) + xoff;
-                    const uint64_t db = (p == 2 ? del : deh) + eoff;
-#pragma unroll
-                    for (int kk = 0; kk < ((WM_VQ_EXP & 2) ? 0 : D / 16); ++kk) {
-                        const uint32_t sl = (uint32_t)(kk >> 2), ko = (uint32_t)((kk & 3) * 2);
-                        umma_bf16_ss(tmem_base + half * 256, da + ko, db + sl * (uint32_t)(e_slab >> 4) + ko, idesc, first ? 0u : 1u);
-                        first = false;
-                    }
-                }
-                // + (|x|^2 + 2) + |e_k|^2: the norm step
-                if (!(WM_VQ_EXP & 2))
-                    umma_bf16_ss(tmem_base + half * 256, dxe + (uint32_t)((b * 2 * kTileM * 16) >> 4),
-                                 dee + (uint32_t)((half * KH * 16) >> 4), idesc, 1u);
-                umma_commit(&bar_full[half]);
-                umma_commit(&bar_xfree[b]);                               // (both halves' commits free operand buffer b)
+            VQ_TL(j, 9);
+#pragma unroll 1
+            for (int qi = 0; qi < 4; ++qi) {
+                const int q = ((qi & 1) << 1) | (qi >> 1);
+                if (j > 0) mbar_wait(&bar_free[q], (j - 1) & 1);          // the quarter's four scanner warps have drained tile j-1
+                tc_fence_after();
+                if (leader) issue_chain(b, q, qi == 3);
+                __syncwarp();
             }
+            VQ_TL(j, 10);
+        }
+    } else
+#endif
+    if (warp < 8) {
+        // =============================== scanners ===============================================================================================
+        // Group A (warps 0-3) scans code quarters 0 and 1, group B (warps 4-7) quarters 2 and 3, one thread per row.  A quarter is handed
+        // back to the issuer the moment its last tcgen05.ld has returned: its next tile's chain runs while the group scans the other quarter.
+        const int quad = warp & 3, half = warp >> 2;
+        const int row = quad * 32 + lane;
+        const int nq = KQ >> 4;                            // 16-column chunks per quarter
+#if !WM_VQ_ISSUER_WARP
+        const bool leader = elect_one();
+        if (quad == 0 && my_tiles > 0) {                   // the group's first warp issues its two quarters' chains
+            mbar_wait(&bar_xready[0], 0);
+            tc_fence_after();
+            if (leader) { issue_chain(0, half * 2, false); issue_chain(0, half * 2 + 1, true); }
             __syncwarp();
-        };
-        if (issuer && my_tiles > 0) issue_tile(0);
+        }
+#endif
         for (int j = 0; j < my_tiles; ++j) {
             const int b = j & 1;
             const long n = ((long)(first_tile + j * stride)) * kTileM + row;
-            mbar_wait(&bar_full[half], j & 1);
-            tc_fence_after();
-            const float xn2 = sXn2[(j % 3) * kTileM + row];
             // two smallest keys of this half and the 16-column chunks they came from.  A score t = |x - e|^2 + 2 (>= 1, so
             // its fp32 bits order like integers) becomes the key (bits(t) - bits(1)) * 16 + position-in-chunk: one IMAD,
             // no bits dropped; t < 2^32 is the writer's business (kHugeNorm)
@@ -378,47 +445,63 @@ vq_nearest_tc_kernel(const Params prm) {
                 c2 = l2 ? loser_c : rest_c;
                 if (first) { m1 = a1; c1 = c; }
             };
-            tmem_ld16(taddr, r0);
-            for (int c = 0; c < ((WM_VQ_EXP & 4) ? 0 : nchunk); c += 2) {
-                tmem_wait_ld();
-                tmem_regs_ready(r0);
-                if (c + 1 < nchunk) tmem_ld16(taddr + (c + 1) * 16, r1);
-                scan16(r0, c);
-                if (c + 1 < nchunk) {
-                    tmem_wait_ld();
-                    tmem_regs_ready(r1);
-                    if (c + 2 < nchunk) tmem_ld16(taddr + (c + 2) * 16, r0);
-                    scan16(r1, c + 1);
+#pragma unroll 1
+            for (int qq = 0; qq < 2; ++qq) {
+                const int q = half * 2 + qq;
+                const uint32_t taddr = tmem_base + (uint32_t)q * 128u + ((uint32_t)(quad * 32) << 16);
+                const int cbase = qq * nq;
+                mbar_wait(&bar_full[q], j & 1);
+                tc_fence_after();
+                if (quad == 0 && qq == 0) VQ_TL(j, half ? 12 : 7);
+                auto release = [&]() {                     // every score of the quarter is in registers
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_free[q]);
+#if !WM_VQ_ISSUER_WARP
+                    if (quad == 0 && j + 1 < my_tiles) {   // next tile's chain for this quarter, before this warp scans its last chunk
+                        mbar_wait(&bar_xready[(j + 1) & 1], ((j + 1) >> 1) & 1);
+                        mbar_wait(&bar_free[q], j & 1);
+                        tc_fence_after();
+                        if (leader) issue_chain((j + 1) & 1, q, qq == 1);
+                        __syncwarp();
+                    }
+#endif
+                };
+                if (!(WM_VQ_EXP & 4)) {
+                    tmem_ld16(taddr, r0);
+                    for (int c = 0; c < nq; c += 2) {
+                        tmem_wait_ld();
+                        tmem_regs_ready(r0);
+                        if (c + 1 < nq) tmem_ld16(taddr + (c + 1) * 16, r1);
+                        else release();
+                        scan16(r0, cbase + c);
+                        if (c + 1 < nq) {
+                            tmem_wait_ld();
+                            tmem_regs_ready(r1);
+                            if (c + 2 < nq) tmem_ld16(taddr + (c + 2) * 16, r0);
+                            else release();
+                            scan16(r1, cbase + c + 1);
+                        }
+                    }
+                } else {
+                    release();
                 }
             }
+            if (quad == 0) VQ_TL(j, half ? 13 : 8);
+            const float xn2 = sXn2[(j % 3) * kTileM + row];
             const float t1 = __uint_as_float((m1 >> 4) + 0x3f800000u), t2nd = __uint_as_float((m2 >> 4) + 0x3f800000u);
             const int k1 = half * KH + c1 * 16 + (int)(m1 & 15u), k2 = half * KH + c2 * 16 + (int)(m2 & 15u);
             const float win = filter_window(xn2, emax);
+            // the runner-up inside the window (about one row in a thousand): the scores are gone by now (the quarters were handed back), so
+            // the whole half becomes the candidate set of the exact settlement
             const bool close2 = !(WM_VQ_EXP & 1) && (n < prm.N) && (t2nd - t1 <= win);
-            uint32_t extra = 0;                                           // 1: the runner-up is a candidate too; 2: more than two are
-            if (__any_sync(0xffffffffu, close2)) {
-                // rare (about one row in a thousand): count the codes of this half inside the window while the scores are
-                // still ours.  Two: k1 is settled against k2 exactly.  More: the whole half is.
-                const float thr = t1 + win;
-                int cnt = 0;
-                for (int c = 0; c < nchunk; ++c) {
-                    uint32_t r[16];
-                    tmem_ld16(taddr + c * 16, r);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) cnt += __uint_as_float(r[i]) <= thr;
-                }
-                if (close2) extra = cnt > 2 ? 2u : 1u;
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_free[half]);                    // this half may be refilled
-            if (issuer && j + 1 < my_tiles) issue_tile(j + 1);
+            const uint32_t extra = close2 ? 2u : 0u;
             if (j >= 2) mbar_wait(&bar_resfree[b], ((j - 2) >> 1) & 1);    // tile j-2's results have been written out
             uint4* res = reinterpret_cast<uint4*>(sRes) + (b * 2 + half) * kTileM + row;
             *res = make_uint4(__float_as_uint(t1), (uint32_t)k1, (uint32_t)k2, extra);
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_res[b]);
+            if (quad == 0 && half == 0) VQ_TL(j, 11);
         }
     } else {
         // =============================== loaders / writers (warps 8-15) ===============================================
@@ -444,17 +527,23 @@ vq_nearest_tc_kernel(const Params prm) {
         auto issue_tile_load = [&](int j) {
             const int b = j & 1;
             if (j >= 2) mbar_wait(&bar_xfree[b], ((j - 2) >> 1) & 1);       // the MMAs of tile j-2 have read this buffer
+            if (warp == 8) VQ_TL(j, 3);
             const long base = tile_base(j);
             const long left = prm.N - base;
             const int valid = left < kTileM ? (int)left : kTileM;
             if (ltid == 0) mbar_expect_tx(&bar_xload[b], (uint32_t)valid * (uint32_t)(D * 4));
-            if (ltid < valid)
+            if (L == 1) {                                  // rows back to back: ONE copy (a bulk copy issues per thread, ~60 cycles each)
+                if (ltid == 0) bulk_load(sX + b * kXBuf, prm.x + base * (long)D, (uint32_t)valid * (uint32_t)(D * 4), &bar_xload[b]);
+            } else if (ltid < valid) {
                 bulk_load(sX + b * kXBuf + ltid * (D * 4), prm.x + ((base + ltid) * L + l) * (long)D, D * 4, &bar_xload[b]);
+            }
         };
         auto convert_rows = [&](int j) {                   // fp32 rows (shared) -> bf16 hi / lo operand tiles in place, |x|^2
             const int b = j & 1;
             uint8_t* buf = sX + b * kXBuf;
+            if (warp == 8) VQ_TL(j, 0);
             mbar_wait(&bar_xload[b], (j >> 1) & 1);
+            if (warp == 8) VQ_TL(j, 1);
             float4 xv[kRowsPerLane];
 #pragma unroll
             for (int i = 0; i < kRowsPerLane; ++i) {
@@ -463,24 +552,23 @@ vq_nearest_tc_kernel(const Params prm) {
                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             __syncwarp();                                  // every fp32 value of this warp's 16 rows is in registers
+            float part[kRowsPerLane];
 #pragma unroll
             for (int i = 0; i < kRowsPerLane; ++i) {
                 const int row = wrow0 + 2 * i + sub;
-                const float v[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
-                uint16_t h[4], lo[4];
-                float xn2 = 0.f;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    split_bf16(v[e], h[e], lo[e]);
-                    xn2 = fmaf(v[e], v[e], xn2);
-                }
+                uint32_t h01, l01, h23, l23;
+                split_bf16x2(xv[i].x, xv[i].y, h01, l01);
+                split_bf16x2(xv[i].z, xv[i].w, h23, l23);
+                part[i] = fmaf(xv[i].w, xv[i].w, fmaf(xv[i].z, xv[i].z, fmaf(xv[i].y, xv[i].y, xv[i].x * xv[i].x)));
                 // fp32 chunk ch (4 channels) = half `ch & 1` of the 16-byte bf16 chunk ch >> 1; hi atom, lo atom 1 KB behind it
                 const uint32_t off = (uint32_t)(row >> 3) * 2048u + sw128(row & 7, ch >> 1) + (uint32_t)(ch & 1) * 8u;
-                *reinterpret_cast<uint2*>(buf + off) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
-                *reinterpret_cast<uint2*>(buf + off + 1024) = make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 16), (uint32_t)lo[2] | ((uint32_t)lo[3] << 16));
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) xn2 += __shfl_xor_sync(0xffffffffu, xn2, o);     // over the row's 16 lanes
-                if (ch == 0) {
+                *reinterpret_cast<uint2*>(buf + off) = make_uint2(h01, h23);
+                *reinterpret_cast<uint2*>(buf + off + 1024) = make_uint2(l01, l23);
+            }
+            {   // |x|^2 of the 8 rows in 8 shuffles; lanes ch = 2 i write row i's norm operands
+                const float xn2 = reduce8_over16(part, ch);
+                if ((ch & 1) == 0) {
+                    const int row = wrow0 + 2 * (ch >> 1) + sub;
                     sXn2[(j % 3) * kTileM + row] = xn2;
                     uint16_t h3[3];
                     split3_bf16(xn2 + 2.f, h3);     // + 2: every score stays >= 1 under the filter's error
@@ -491,59 +579,70 @@ vq_nearest_tc_kernel(const Params prm) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_xready[b]);
+            if (warp == 8) VQ_TL(j, 2);
         };
-        auto output_rows = [&](int j) {                    // merge the halves, gather the winner, write the outputs
+        auto output_rows = [&](int j, const float4 (&xo)[kRowsPerLane]) {      // merge the halves, gather the winner, write the outputs
             const int b = j & 1;
-            float4 xo[kRowsPerLane];
-            load_rows(j, xo);                              // re-read (L2 hit), in flight while waiting for the scanners
+            if (warp == 8) VQ_TL(j, 4);
             mbar_wait(&bar_res[b], (j >> 1) & 1);
+            if (warp == 8) VQ_TL(j, 5);
             const bool want_q = !(WM_VQ_EXP & 8) && (prm.quantized != nullptr || prm.sq_err != nullptr);
-            // three passes over the lane's 8 rows, so that the 8 codebook gathers are in flight together (a load that
-            // follows a store to another global array is not hoisted by the compiler: one row at a time costs 8 round trips)
-            long best[kRowsPerLane];                       // winner, or (negative) the packed candidates of an undecided row
+            // Pass 1, ONE row per lane (lane r and r + 16 both take row r of the warp's 16; all 16 lanes of a row doing it for
+            // their 8 rows was 16-fold redundant work): merge the halves, decide, write idx -- one coalesced store per warp.
             const long n_first = tile_base(j) + wrow0 + sub;
-#pragma unroll
-            for (int i = 0; i < kRowsPerLane; ++i) {
-                const int row = wrow0 + 2 * i + sub;
-                const bool valid = n_first + 2 * i < prm.N;
+            int bk;                                        // winner, or -1: undecided (its packed candidates go to idx)
+            {
+                const int row = wrow0 + ch;
+                const long n = tile_base(j) + row;
+                const bool valid = n < prm.N;
                 const uint4 ra = reinterpret_cast<const uint4*>(sRes)[(b * 2 + 0) * kTileM + row];
                 const uint4 rb = reinterpret_cast<const uint4*>(sRes)[(b * 2 + 1) * kTileM + row];
                 const float ta = __uint_as_float(ra.x), tb = __uint_as_float(rb.x);
                 const float xn2 = sXn2[(j % 3) * kTileM + row];
-                best[i] = valid ? (ta <= tb ? (long)ra.y : (long)rb.y) : 0;
+                bk = valid ? (ta <= tb ? (int)ra.y : (int)rb.y) : 0;
                 const float win = filter_window(xn2, emax);
                 const bool huge = !(xn2 + emax * emax < kHugeNorm);       // scores may leave the key range (or are not finite): settle exactly
                 const bool a_in = ta <= tb + win, b_in = tb <= ta + win;   // does the half hold a candidate for the row minimum?
                 const bool need = valid && !(WM_VQ_EXP & 16) && (huge || (a_in && b_in) || (a_in && ra.w) || (b_in && rb.w));
-                if (need)                                   // undecided: settled exactly by vq_settle_kernel, which rewrites the row
-                    best[i] = pack_candidates(ra.y, ra.z, huge ? 2u : ra.w, rb.y, rb.z, huge ? 2u : rb.w, huge || a_in, huge || b_in);
+                long out = (long)bk;
+                if (need) {                                 // undecided: settled exactly by vq_settle_kernel, which rewrites the row
+                    out = pack_candidates(ra.y, ra.z, huge ? 2u : ra.w, rb.y, rb.z, huge ? 2u : rb.w, huge || a_in, huge || b_in);
+                    bk = -1;
+                }
+                if (valid && sub == 0) prm.idx[n * L + l] = (int64_t)out;
             }
+            int best[kRowsPerLane];
+#pragma unroll
+            for (int i = 0; i < kRowsPerLane; ++i) best[i] = __shfl_sync(0xffffffffu, bk, 2 * i + sub);
+            if (warp == 8) VQ_TL(j, 15);
             float4 ev[kRowsPerLane];
             if (want_q) {
 #pragma unroll
                 for (int i = 0; i < kRowsPerLane; ++i) ev[i] = __ldg(reinterpret_cast<const float4*>(cbl + (best[i] < 0 ? 0 : best[i]) * D) + ch);
             }
+            float errp[kRowsPerLane];
 #pragma unroll
             for (int i = 0; i < kRowsPerLane; ++i) {
                 const long n = n_first + 2 * i;
                 const bool valid = n < prm.N;
                 const long o = n * L + l;
-                if (valid && ch == 0) prm.idx[o] = (int64_t)best[i];
+                errp[i] = 0.f;
                 if (want_q) {
                     const float d0 = ev[i].x - xo[i].x, d1 = ev[i].y - xo[i].y, d2 = ev[i].z - xo[i].z, d3 = ev[i].w - xo[i].w;
-                    float err = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
+                    errp[i] = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
                     if (prm.quantized != nullptr && valid)
                         reinterpret_cast<float4*>(prm.quantized + o * (long)D)[ch] =
                             make_float4(xo[i].x + d0, xo[i].y + d1, xo[i].z + d2, xo[i].w + d3);
-                    if (prm.sq_err != nullptr) {
-#pragma unroll
-                        for (int sh = 8; sh > 0; sh >>= 1) err += __shfl_xor_sync(0xffffffffu, err, sh);
-                        if (ch == 0 && valid) prm.sq_err[o] = err;
-                    }
                 }
+            }
+            if (want_q && prm.sq_err != nullptr) {        // the 8 rows' errors in 8 shuffles; lanes ch = 2 i hold row i's
+                const float err = reduce8_over16(errp, ch);
+                const long n = n_first + 2 * (ch >> 1);
+                if ((ch & 1) == 0 && n < prm.N) prm.sq_err[n * L + l] = err;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_resfree[b]);   // this warp's sRes entries of tile j may be overwritten
+            if (warp == 8) VQ_TL(j, 6);
         };
         // Software pipeline.  The conversion of tile j+2 must not wait for the output of tile j (that would close a loop
         // scan -> output -> convert -> MMA -> scan over two tiles and serialise the four phases): tile j+2 is converted
@@ -557,7 +656,9 @@ vq_nearest_tc_kernel(const Params prm) {
         for (int j = 0; j < my_tiles; ++j) {
             if (j + 2 < my_tiles) convert_rows(j + 2);
             if (j + 3 < my_tiles) issue_tile_load(j + 3);
-            output_rows(j);
+            float4 xo[kRowsPerLane];
+            load_rows(j, xo);                              // re-read of tile j for its output (L2 hit)
+            output_rows(j, xo);
         }
     }
     tc_fence_before();
@@ -575,14 +676,14 @@ static size_t smem_bytes(int K, int D) {
 
 #if WM_VQ_EXP & 32
 extern "C" __attribute__((visibility("default"))) int wm_vq_debug_read(unsigned long long* out) {
-    return (int)cudaMemcpyFromSymbol(out, vq::g_vq_dbg, sizeof(unsigned long long) * 4);
+    return (int)cudaMemcpyFromSymbol(out, vq::g_vq_dbg, sizeof(unsigned long long) * 64 * 16);
 }
 #endif
 
 bool vq_tc_supported(long N, int L, int K, int D) {
     if (D != 64) return false;                             // one 64-channel (128-byte) operand slab; the codebook's hi / lo
                                                            // tiles of a 128-channel code would not fit next to the latents
-    if (K % 32 != 0 || K > 512 || K < 32) return false;    // two halves of <= 256 codes, multiples of 16
+    if (K % 64 != 0 || K > 512 || K < 64) return false;    // four quarters of <= 128 codes, multiples of 16
     return vq::smem_bytes(K, D) <= 227ul * 1024 && N >= 1 && L <= 65535;
 }
 
