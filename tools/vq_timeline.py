@@ -17,12 +17,12 @@ cb = torch.randn(1, 512, 64, device='cuda', generator=g)
 for _ in range(3):
     ops.vq_nearest(x, cb)
 torch.cuda.synchronize()
-buf = (ctypes.c_ulonglong * (64 * 16))()
+buf = (ctypes.c_ulonglong * (64 * 24))()
 L = _lib.lib()
 L.wm_vq_debug_read.argtypes = [ctypes.POINTER(ctypes.c_ulonglong)]
 assert L.wm_vq_debug_read(buf) == 0
-names = ['cv0', 'land', 'xrdy', 'xfree', 'out0', 'res', 'outE', 'A.full', 'A.scanE', 'iss.xrdy', 'iss.done', 'A.post', 'B.full', 'B.scanE', '-', 'out.p1']
-t0 = min(buf[20 * 16 + e] for e in range(16) if buf[20 * 16 + e])
+names = ['cv0', 'land', 'xrdy', 'xfree', 'out0', 'res', 'outE', 'A.full', 'A.scanE', 'iss.xrdy', 'iss.done', 'A.post', 'B.full', 'B.scanE', 'out.r0', 'out.p1', 'out.r7']
+t0 = min(buf[20 * 24 + e] for e in range(17) if buf[20 * 24 + e])
 print('tile ' + ' '.join(f'{s:>8}' for s in names))
 for j in range(20, 30):
-    print(f'{j:4d} ' + ' '.join(f'{(buf[j * 16 + e] - t0) if buf[j * 16 + e] else -1:8d}' for e in range(16)))
+    print(f'{j:4d} ' + ' '.join(f'{(buf[j * 24 + e] - t0) if buf[j * 24 + e] else -1:8d}' for e in range(17)))

@@ -10,18 +10,27 @@
 // 2.3e-5 |x||e|, the accumulation of the 12 K-steps at D = 64 adds ~1e-6).  Two codes closer than the window 2 eps + (key truncation) are
 // re-evaluated exactly; everything else is decided by the filter.
 //
-// Pipeline (one persistent CTA per SM keeps the whole codebook, pre-scaled by -2, as bf16 hi / lo in shared memory):
-//   warps  8-15  loader / writer, 16 lanes per latent row (coalesced): fp32 rows from global memory two tiles
-//                ahead (registers), split into the bf16 hi / lo operand tiles (128B-swizzled, K-major) + |x|^2; later,
-//                for the finished tile: merge the two code halves, gather the winner, write idx, x + (e - x), sum (e - x)^2
-//   warps  0-3   scan code half A (codes [0, K/2), TMEM columns [0, 256)), warps 4-7 half B ([256, 512)); the first warp
-//                of each group also issues its half's tcgen05.mma chain for the next tile the moment the group has
-//                drained the scores -- while one half is being scanned the tensor pipe works on the other.
-//                One thread per row: distance keys (the score's fp32 bits shifted left by four, the code's position
-//                inside its 16-column chunk below them: one IMAD per score) reduced with 3-input integer min / max
-//                to the two smallest keys.  |x|^2 + |e_k|^2 + 2 arrive WITH the score: a thirteenth K = 16 MMA step
-//                multiplies [1 1 1 | split3(|x|^2 + 2)] with [split3(|e_k|^2) | 1 1 1] (three bf16 terms carry an fp32
-//                value exactly), so the scanners add nothing and read no shared memory
+// Pipeline (one persistent CTA per SM keeps the whole codebook, pre-scaled by -2, as bf16 hi / lo in shared memory; 17 warps):
+//   warps  8-15  loader / writer, 16 lanes per latent row (coalesced).  A tile's fp32 rows arrive by ONE cp.async.bulk three
+//                tiles ahead and are split in place into the bf16 hi / lo operand tiles (128B-swizzled, K-major) + |x|^2; later,
+//                for the finished tile: merge the two code halves and decide (one row per lane), write idx, gather the
+//                winners, write x + (e - x) and sum (e - x)^2.  These warps take 112 registers (setmaxnreg): a tile's
+//                re-read rows + gathered codes are 64 of them, and at 96 the row loop reloaded spills at ~300 cycles each
+//   warp   16    MMA issuer: per tile four tcgen05.mma chains, one per code QUARTER (N = K/4 columns of tensor memory each),
+//                each issued as soon as the scanners have handed that quarter back.  The issuing thread blocks while the
+//                tensor pipe's queue is full (3 300 cycles per tile when a scanner warp did this between two scans), and
+//                sleeps between barrier probes (spinning probes were a fifth of all issued instructions)
+//   warps  0-3   scan code quarters 0, 1 (codes [0, K/2)), warps 4-7 quarters 2, 3; 80 registers.  A quarter goes back to the
+//                issuer the moment its last tcgen05.ld has returned, so its next chain runs while the group scans the other
+//                quarter: the scanners never wait for the tensor pipe.
+//                One thread per row: distance keys (the score's fp32 bits times 16, the code's position inside its
+//                16-column chunk below them: one IMAD per score -- with the factor passed as a kernel parameter, or ptxas
+//                turns it into an LEA on the ALU pipe that the min / max instructions already saturate) reduced with
+//                3-input integer min / max to the two smallest keys.  |x|^2 + |e_k|^2 + 2 arrive WITH the score: a
+//                thirteenth K = 16 MMA step multiplies [1 1 1 | split3(|x|^2 + 2)] with [split3(|e_k|^2) | 1 1 1] (three bf16
+//                terms carry an fp32 value exactly), so the scanners add nothing and read no shared memory.  A runner-up
+//                inside the error window marks the whole half for the exact settlement (the scores are gone by then)
+// Timeline of the hand-offs: tools/vq_timeline.py (library built with -DWM_VQ_EXP=32).
 // Replaces VectorQuantizerEMA's [N,L,D,K] distance temporary + argmin + gather (vq.py:30-36,84-87).
 #include "tc_common.cuh"
 #include "wm_common.cuh"
@@ -30,7 +39,7 @@
 #include <type_traits>
 
 #ifndef WM_VQ_EXP
-#define WM_VQ_EXP 0      // timing experiments: 1 no ambiguity re-scan, 2 no MMAs, 4 no scan, 8 no output, 16 no cross-half check
+#define WM_VQ_EXP 0      // timing experiments: 1 no ambiguity flag, 2 no MMAs, 4 no scan, 8 no output, 16 no cross-half check, 32 timeline
 #endif
 
 namespace wm {
@@ -40,16 +49,24 @@ using namespace wm::tc;
 
 #if WM_VQ_EXP & 32
 // timeline of CTA (0, 0): clock64 at the hand-offs of the first 64 tiles (tools/vq_timeline.py)
-__device__ unsigned long long g_vq_dbg[64 * 16];
+__device__ unsigned long long g_vq_dbg[64 * 24];
 #define VQ_TL(tile, ev)                                                                                   \
     do {                                                                                                  \
         if (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && (tile) < 64)                 \
-            g_vq_dbg[(tile) * 16 + (ev)] = (unsigned long long)clock64();                                 \
+            g_vq_dbg[(tile) * 24 + (ev)] = (unsigned long long)clock64();                                 \
     } while (0)
 #else
 #define VQ_TL(tile, ev) do { } while (0)
 #endif
 
+#ifndef WM_VQ_TUNE
+#define WM_VQ_TUNE 3          // bit 0: the issuer warp sleeps between barrier probes; bit 1: keys by IMAD (FMA pipe) instead of LEA (ALU pipe);
+                              // bit 2: the gather of a tile's winners is in flight across the conversion of the tile two ahead (measured: 0.285 vs
+                              // 0.279 ms -- the re-read of x then waits behind the conversion); bit 3: with bit 2, re-read x first (spills)
+#endif
+#ifndef WM_VQ_REGS
+#define WM_VQ_REGS 1          // 1: the scanner warps hand 16 registers per thread to the writer warps (setmaxnreg: 80 / 112 instead of 96 / 96)
+#endif
 #ifndef WM_VQ_ISSUER_WARP
 #define WM_VQ_ISSUER_WARP 1   // 1: a seventeenth warp issues the MMA chains; 0: the first scanner warp of each group does (16 warps, 128 registers)
 #endif
@@ -66,6 +83,7 @@ struct Params {
     long N;
     int L, K, D;
     int tiles;                 // ceil(N / 128)
+    uint32_t key_mul;          // 16, as a kernel parameter: a multiplier the compiler cannot see keeps the key an IMAD (FMA pipe)
 };
 
 // byte offset of 16-byte chunk c16 of row r in a [rows x 64 bf16] slab stored K-major with the 128-byte swizzle
@@ -79,6 +97,16 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 
 constexpr uint32_t kKeyBase = 0x08000000u;      // -(bits(1.0f) << 4) mod 2^32: key = (bits(t) - bits(1.0f)) * 16 + position
 constexpr float kHugeNorm = 1.0e9f;             // |x|^2 + max|e|^2 below this keeps every score under 2^32 (28 key bits of exponent + mantissa)
+
+// A wait that gives its issue slots away: the MMA issuer spends most of its life waiting, on a sub-partition it shares with two
+// scanner and two writer warps (spinning probes were a fifth of all instructions the kernel issued).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+#if WM_VQ_TUNE & 1
+    while (!mbar_test(bar, parity)) __nanosleep(32);
+#else
+    mbar_wait(bar, parity);
+#endif
+}
 
 __device__ __forceinline__ uint32_t vmin3(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d;
@@ -180,61 +208,79 @@ __device__ __forceinline__ long pack_candidates(uint32_t k1a, uint32_t k2a, uint
     return (long)m;
 }
 
-// Second kernel, launched right behind the filter: a warp settles each undecided row exactly (fp64 distances to its
-// candidates, lowest index on ties) and rewrites idx / quantized / sq_err.  Keeping this out of the filter
-// kernel matters: with the fp64 path inlined there, its mere presence (registers, code size) cost the filter 17 %.
+// Second kernel, launched right behind the filter: undecided rows are settled exactly (fp64 distances to their candidates,
+// lowest index on ties) and idx / quantized / sq_err rewritten.  Keeping this out of the filter kernel matters: with the
+// fp64 path inlined there, its mere presence (registers, code size) cost the filter 17 %.
+// One wave of blocks; a block scans its slice of idx in rounds of kSettleRound items (coalesced), queues the marked rows in
+// shared memory and then spreads them over its warps -- with a warp per 32 consecutive rows the few warps that met a marked
+// row set the time of each of seven waves (38 us for ~2 000 rows; 16 us of it just to get every warp scheduled once).
+constexpr int kSettleThreads = 256;
+constexpr int kSettleRound = kSettleThreads * 8;
+
 template <int D>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void settle_row(const Params& prm, long item, int lane) {
+    const uint64_t m = (uint64_t)prm.idx[item];
+    const int l = (int)(item % prm.L);
+    const float* xr = prm.x + item * (long)D;
+    const float* cbl = prm.cb + (long)l * prm.K * D;
+    // candidates: per code half its best code, its runner-up (w == 1) or the whole half (w == 2)
+    const int KH = prm.K >> 1;
+    const uint32_t k1a = m & 511u, k2a = (m >> 9) & 511u, wa = (m >> 18) & 3u;
+    const uint32_t k1b = (m >> 20) & 511u, k2b = (m >> 29) & 511u, wb = (m >> 38) & 3u;
+    const int nA = ((m >> 40) & 1u) ? (wa == 2u ? KH : 1 + (wa == 1u)) : 0;
+    const int nB = ((m >> 41) & 1u) ? (wb == 2u ? KH : 1 + (wb == 1u)) : 0;
+    double bd = INFINITY;
+    int bk = 0x7fffffff;
+    for (int c = lane; c < nA + nB; c += 32) {
+        int k;
+        if (c < nA) k = wa == 2u ? c : (c == 0 ? (int)k1a : (int)k2a);
+        else k = wb == 2u ? KH + (c - nA) : (c == nA ? (int)k1b : (int)k2b);
+        const double dd = exact_dist<D>(xr, cbl + (long)k * D);
+        if (dd < bd || (dd == bd && k < bk)) { bd = dd; bk = k; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+        if (od < bd || (od == bd && ok < bk)) { bd = od; bk = ok; }
+    }
+    __syncwarp();                                         // every lane has read the marker before it is overwritten
+    if (lane == 0) prm.idx[item] = (int64_t)bk;
+    if ((prm.quantized != nullptr || prm.sq_err != nullptr) && lane < D / 4) {
+        const float4 xq = __ldg(reinterpret_cast<const float4*>(xr) + lane);
+        const float4 ev = __ldg(reinterpret_cast<const float4*>(cbl + (long)bk * D) + lane);
+        const float d0 = ev.x - xq.x, d1 = ev.y - xq.y, d2 = ev.z - xq.z, d3 = ev.w - xq.w;
+        float err = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
+        if (prm.quantized != nullptr)
+            reinterpret_cast<float4*>(prm.quantized + item * (long)D)[lane] = make_float4(xq.x + d0, xq.y + d1, xq.z + d2, xq.w + d3);
+#pragma unroll
+        for (int o = D / 8; o > 0; o >>= 1) err += __shfl_xor_sync((1u << (D / 4)) - 1u, err, o);
+        if (prm.sq_err != nullptr && lane == 0) prm.sq_err[item] = err;
+    }
+    __syncwarp();
+}
+
+template <int D>
+__global__ void __launch_bounds__(kSettleThreads)
 vq_settle_kernel(const Params prm) {
-    const int lane = threadIdx.x & 31;
+    __shared__ unsigned short queue[kSettleRound];
+    __shared__ unsigned queued;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long items = prm.N * prm.L;
-    const long base = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
-    if (base >= items) return;
-    const long mine = base + lane;
-    const int64_t marker = mine < items ? prm.idx[mine] : 0;
-    unsigned todo = __ballot_sync(0xffffffffu, marker < 0);
-    while (todo) {
-        const int j = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const long item = base + j;                       // = n * L + l
-        const int l = (int)(item % prm.L);
-        const float* xr = prm.x + item * (long)D;
-        const float* cbl = prm.cb + (long)l * prm.K * D;
-        // candidates: per code half its best code, its runner-up (w == 1) or the whole half (w == 2)
-        const uint64_t m = (uint64_t)__shfl_sync(0xffffffffu, (long long)marker, j);
-        const int KH = prm.K >> 1;
-        const uint32_t k1a = m & 511u, k2a = (m >> 9) & 511u, wa = (m >> 18) & 3u;
-        const uint32_t k1b = (m >> 20) & 511u, k2b = (m >> 29) & 511u, wb = (m >> 38) & 3u;
-        const int nA = ((m >> 40) & 1u) ? (wa == 2u ? KH : 1 + (wa == 1u)) : 0;
-        const int nB = ((m >> 41) & 1u) ? (wb == 2u ? KH : 1 + (wb == 1u)) : 0;
-        double bd = INFINITY;
-        int bk = 0x7fffffff;
-        for (int c = lane; c < nA + nB; c += 32) {
-            int k;
-            if (c < nA) k = wa == 2u ? c : (c == 0 ? (int)k1a : (int)k2a);
-            else k = wb == 2u ? KH + (c - nA) : (c == nA ? (int)k1b : (int)k2b);
-            const double dd = exact_dist<D>(xr, cbl + (long)k * D);
-            if (dd < bd || (dd == bd && k < bk)) { bd = dd; bk = k; }
-        }
+    const long rounds = (items + kSettleRound - 1) / kSettleRound;
+    for (long r = blockIdx.x; r < rounds; r += gridDim.x) {
+        const long base = r * kSettleRound;
+        if (tid == 0) queued = 0;
+        __syncthreads();
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
-            const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-            if (od < bd || (od == bd && ok < bk)) { bd = od; bk = ok; }
+        for (int u = 0; u < kSettleRound / kSettleThreads; ++u) {
+            const int off = u * kSettleThreads + tid;
+            if (base + off < items && prm.idx[base + off] < 0) queue[atomicAdd(&queued, 1u)] = (unsigned short)off;
         }
-        if (lane == 0) prm.idx[item] = (int64_t)bk;
-        if ((prm.quantized != nullptr || prm.sq_err != nullptr) && lane < D / 4) {
-            const float4 xq = __ldg(reinterpret_cast<const float4*>(xr) + lane);
-            const float4 ev = __ldg(reinterpret_cast<const float4*>(cbl + (long)bk * D) + lane);
-            const float d0 = ev.x - xq.x, d1 = ev.y - xq.y, d2 = ev.z - xq.z, d3 = ev.w - xq.w;
-            float err = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
-            if (prm.quantized != nullptr)
-                reinterpret_cast<float4*>(prm.quantized + item * (long)D)[lane] = make_float4(xq.x + d0, xq.y + d1, xq.z + d2, xq.w + d3);
-#pragma unroll
-            for (int o = D / 8; o > 0; o >>= 1) err += __shfl_xor_sync((1u << (D / 4)) - 1u, err, o);
-            if (prm.sq_err != nullptr && lane == 0) prm.sq_err[item] = err;
-        }
-        __syncwarp();
+        __syncthreads();
+        const unsigned n = queued;
+        for (unsigned e = warp; e < n; e += kSettleThreads / 32) settle_row<D>(prm, base + queue[e], lane);
+        __syncthreads();
     }
 }
 
@@ -385,12 +431,12 @@ vq_nearest_tc_kernel(const Params prm) {
         const bool leader = elect_one();
         for (int j = 0; j < my_tiles; ++j) {
             const int b = j & 1;
-            mbar_wait(&bar_xready[b], (j >> 1) & 1);
+            mbar_wait_relaxed(&bar_xready[b], (j >> 1) & 1);
             VQ_TL(j, 9);
 #pragma unroll 1
             for (int qi = 0; qi < 4; ++qi) {
                 const int q = ((qi & 1) << 1) | (qi >> 1);
-                if (j > 0) mbar_wait(&bar_free[q], (j - 1) & 1);          // the quarter's four scanner warps have drained tile j-1
+                if (j > 0) mbar_wait_relaxed(&bar_free[q], (j - 1) & 1);  // the quarter's four scanner warps have drained tile j-1
                 tc_fence_after();
                 if (leader) issue_chain(b, q, qi == 3);
                 __syncwarp();
@@ -403,6 +449,9 @@ vq_nearest_tc_kernel(const Params prm) {
         // =============================== scanners ===============================================================================================
         // Group A (warps 0-3) scans code quarters 0 and 1, group B (warps 4-7) quarters 2 and 3, one thread per row.  A quarter is handed
         // back to the issuer the moment its last tcgen05.ld has returned: its next tile's chain runs while the group scans the other quarter.
+#if WM_VQ_REGS && WM_VQ_ISSUER_WARP
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+#endif
         const int quad = warp & 3, half = warp >> 2;
         const int row = quad * 32 + lane;
         const int nq = KQ >> 4;                            // 16-column chunks per quarter
@@ -424,12 +473,18 @@ vq_nearest_tc_kernel(const Params prm) {
             uint32_t m1 = 0xffffffffu, m2 = 0xffffffffu;
             int c1 = 0, c2 = 0;
             uint32_t r0[16], r1[16];
+#if WM_VQ_TUNE & 2
+            const uint32_t sixteen = prm.key_mul;          // opaque to the compiler: the key becomes an IMAD (FMA pipe), not an LEA on the
+                                                           // ALU pipe, which the 3-input min / max instructions already saturate
+#else
+            const uint32_t sixteen = 16u;
+#endif
             auto scan16 = [&](const uint32_t (&r)[16], int c) {
                 uint32_t a1 = 0xffffffffu, a2 = 0xffffffffu;              // the chunk's two smallest
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const uint32_t ka = r[2 * i] * 16u + (kKeyBase + (uint32_t)(2 * i));
-                    const uint32_t kb = r[2 * i + 1] * 16u + (kKeyBase + (uint32_t)(2 * i + 1));
+                    const uint32_t ka = r[2 * i] * sixteen + (kKeyBase + (uint32_t)(2 * i));
+                    const uint32_t kb = r[2 * i + 1] * sixteen + (kKeyBase + (uint32_t)(2 * i + 1));
                     const uint32_t lo = min(ka, kb), hi = max(ka, kb);
                     a2 = vmin3(a2, hi, max(a1, lo));
                     a1 = min(a1, lo);
@@ -508,17 +563,24 @@ vq_nearest_tc_kernel(const Params prm) {
         // Coalesced mapping: a warp owns 16 rows; one 16-byte access per lane covers TWO whole rows (16 lanes x 16 B = one
         // 256-byte fp32 row), so instruction i touches rows 2i, 2i+1 of the warp and a lane holds fp32 chunk `ch` (4
         // channels) of 8 rows.  (One thread per row would put every lane on its own 128-byte line: 16x the L1 wavefronts.)
+#if WM_VQ_REGS && WM_VQ_ISSUER_WARP
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");     // xo + ev of a tile are 64 registers; at 96 the row loop reloaded spills
+#endif
         constexpr int kRowsPerLane = 8;
         static_assert(D == 64, "row = 16 lanes x float4");
         const int wrow0 = (warp - 8) * 16, sub = lane >> 4, ch = lane & 15;
         auto tile_base = [&](int j) { return ((long)(first_tile + j * stride)) * kTileM; };
+        // Rows are addressed as (tile pointer) + 32-bit offset and bounds are a 32-bit row count: eight 64-bit row indices per lane
+        // spilled to local memory, and every reload in the output loop was a ~300-cycle stall (the L1 is all but carved away).
+        const int LD = L * D;                              // floats between consecutive latent rows of this codebook slot
+        auto rows_left = [&](int j) { const long left = prm.N - tile_base(j); return left < kTileM ? (int)left : kTileM; };
         auto load_rows = [&](int j, float4 (&dst)[kRowsPerLane]) {      // output path: re-read of the tile (L2 hit)
-            const long n0 = tile_base(j) + wrow0 + sub;
+            const float* xt = prm.x + (tile_base(j) * L + l) * (long)D + ch * 4;
+            const int nv = rows_left(j);
 #pragma unroll
             for (int i = 0; i < kRowsPerLane; ++i) {
-                const long n = n0 + 2 * i;
-                dst[i] = n < prm.N ? __ldg(reinterpret_cast<const float4*>(prm.x + (n * L + l) * (long)D) + ch)
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int r = wrow0 + sub + 2 * i;
+                dst[i] = r < nv ? __ldg(reinterpret_cast<const float4*>(xt + r * LD)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
         // fp32 rows of tile j -> buffer j & 1, one 256-byte bulk copy per row (rows are L * D floats apart), all on one
@@ -581,24 +643,25 @@ vq_nearest_tc_kernel(const Params prm) {
             if (lane == 0) mbar_arrive(&bar_xready[b]);
             if (warp == 8) VQ_TL(j, 2);
         };
-        auto output_rows = [&](int j, const float4 (&xo)[kRowsPerLane]) {      // merge the halves, gather the winner, write the outputs
+        const bool want_q = !(WM_VQ_EXP & 8) && (prm.quantized != nullptr || prm.sq_err != nullptr);
+        // Output, first part: wait for the scanners, merge the halves, decide, write idx, start the gather of the winners.
+        // ONE row per lane here (lane r and r + 16 both take row r of the warp's 16; all 16 lanes of a row doing it for their
+        // 8 rows was 16-fold redundant work), the winners then go to the lanes that own the rows by shuffle.
+        auto output_decide = [&](int j, float4 (&ev)[kRowsPerLane]) {
             const int b = j & 1;
             if (warp == 8) VQ_TL(j, 4);
             mbar_wait(&bar_res[b], (j >> 1) & 1);
             if (warp == 8) VQ_TL(j, 5);
-            const bool want_q = !(WM_VQ_EXP & 8) && (prm.quantized != nullptr || prm.sq_err != nullptr);
-            // Pass 1, ONE row per lane (lane r and r + 16 both take row r of the warp's 16; all 16 lanes of a row doing it for
-            // their 8 rows was 16-fold redundant work): merge the halves, decide, write idx -- one coalesced store per warp.
-            const long n_first = tile_base(j) + wrow0 + sub;
             int bk;                                        // winner, or -1: undecided (its packed candidates go to idx)
             {
                 const int row = wrow0 + ch;
-                const long n = tile_base(j) + row;
-                const bool valid = n < prm.N;
+                const bool valid = row < rows_left(j);
                 const uint4 ra = reinterpret_cast<const uint4*>(sRes)[(b * 2 + 0) * kTileM + row];
                 const uint4 rb = reinterpret_cast<const uint4*>(sRes)[(b * 2 + 1) * kTileM + row];
                 const float ta = __uint_as_float(ra.x), tb = __uint_as_float(rb.x);
                 const float xn2 = sXn2[(j % 3) * kTileM + row];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_resfree[b]);   // this warp's sRes entries of tile j may be overwritten
                 bk = valid ? (ta <= tb ? (int)ra.y : (int)rb.y) : 0;
                 const float win = filter_window(xn2, emax);
                 const bool huge = !(xn2 + emax * emax < kHugeNorm);       // scores may leave the key range (or are not finite): settle exactly
@@ -609,56 +672,73 @@ vq_nearest_tc_kernel(const Params prm) {
                     out = pack_candidates(ra.y, ra.z, huge ? 2u : ra.w, rb.y, rb.z, huge ? 2u : rb.w, huge || a_in, huge || b_in);
                     bk = -1;
                 }
-                if (valid && sub == 0) prm.idx[n * L + l] = (int64_t)out;
+                if (valid && sub == 0) prm.idx[tile_base(j) * L + l + row * L] = (int64_t)out;
             }
-            int best[kRowsPerLane];
-#pragma unroll
-            for (int i = 0; i < kRowsPerLane; ++i) best[i] = __shfl_sync(0xffffffffu, bk, 2 * i + sub);
-            if (warp == 8) VQ_TL(j, 15);
-            float4 ev[kRowsPerLane];
             if (want_q) {
 #pragma unroll
-                for (int i = 0; i < kRowsPerLane; ++i) ev[i] = __ldg(reinterpret_cast<const float4*>(cbl + (best[i] < 0 ? 0 : best[i]) * D) + ch);
+                for (int i = 0; i < kRowsPerLane; ++i) {
+                    const int best = __shfl_sync(0xffffffffu, bk, 2 * i + sub);
+                    ev[i] = __ldg(reinterpret_cast<const float4*>(cbl + (best < 0 ? 0 : best) * D) + ch);
+                }
             }
+            if (warp == 8) VQ_TL(j, 15);
+        };
+        // Output, second part: x + (e - x), sum (e - x)^2
+        auto output_write = [&](int j, const float4 (&ev)[kRowsPerLane], const float4 (&xo)[kRowsPerLane]) {
+            const int nv = rows_left(j);
+            const long o0 = tile_base(j) * L + l;          // output slot of the tile's first row
+            float* qt = prm.quantized != nullptr ? prm.quantized + o0 * (long)D + ch * 4 : nullptr;
             float errp[kRowsPerLane];
 #pragma unroll
             for (int i = 0; i < kRowsPerLane; ++i) {
-                const long n = n_first + 2 * i;
-                const bool valid = n < prm.N;
-                const long o = n * L + l;
+                const int r = wrow0 + sub + 2 * i;
+                const bool valid = r < nv;
                 errp[i] = 0.f;
                 if (want_q) {
                     const float d0 = ev[i].x - xo[i].x, d1 = ev[i].y - xo[i].y, d2 = ev[i].z - xo[i].z, d3 = ev[i].w - xo[i].w;
                     errp[i] = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
-                    if (prm.quantized != nullptr && valid)
-                        reinterpret_cast<float4*>(prm.quantized + o * (long)D)[ch] =
-                            make_float4(xo[i].x + d0, xo[i].y + d1, xo[i].z + d2, xo[i].w + d3);
+                    if (qt != nullptr && valid)
+                        *reinterpret_cast<float4*>(qt + r * LD) = make_float4(xo[i].x + d0, xo[i].y + d1, xo[i].z + d2, xo[i].w + d3);
                 }
+                if (i == 0 && warp == 8) VQ_TL(j, 14);
             }
+            if (warp == 8) VQ_TL(j, 16);
             if (want_q && prm.sq_err != nullptr) {        // the 8 rows' errors in 8 shuffles; lanes ch = 2 i hold row i's
                 const float err = reduce8_over16(errp, ch);
-                const long n = n_first + 2 * (ch >> 1);
-                if ((ch & 1) == 0 && n < prm.N) prm.sq_err[n * L + l] = err;
+                const int r = wrow0 + sub + 2 * (ch >> 1);
+                if ((ch & 1) == 0 && r < nv) prm.sq_err[o0 + r * L] = err;
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_resfree[b]);   // this warp's sRes entries of tile j may be overwritten
             if (warp == 8) VQ_TL(j, 6);
         };
-        // Software pipeline.  The conversion of tile j+2 must not wait for the output of tile j (that would close a loop
-        // scan -> output -> convert -> MMA -> scan over two tiles and serialise the four phases): tile j+2 is converted
-        // FIRST -- its fp32 rows landed during the previous iteration -- then the copy of tile j+3 is started (its buffer
-        // is free once the MMAs of tile j+1 have retired), then tile j is written out.
+        // Software pipeline.  Tile j's results arrive, its winners are decided and the gather of their codes is started; the
+        // conversion of tile j+2 (its fp32 rows landed during the previous iteration) and the copy of tile j+3 (its buffer is
+        // free once the MMAs of tile j+1 have retired) run while those loads are in flight -- the gathered rows come back one
+        // every ~400 cycles per warp -- and then tile j is written out.  The conversion waits for the SCAN of tile j only, never
+        // for its output (that would close a loop scan -> output -> convert -> MMA -> scan over two tiles).
         if (my_tiles > 0) issue_tile_load(0);
         if (my_tiles > 1) issue_tile_load(1);
         if (my_tiles > 0) convert_rows(0);
         if (my_tiles > 1) convert_rows(1);
         if (my_tiles > 2) issue_tile_load(2);
         for (int j = 0; j < my_tiles; ++j) {
+            float4 ev[kRowsPerLane], xo[kRowsPerLane];
+#if WM_VQ_TUNE & 4
+#if WM_VQ_TUNE & 8
+            load_rows(j, xo);                              // re-read of tile j (L2 hit)
+#endif
+            output_decide(j, ev);
             if (j + 2 < my_tiles) convert_rows(j + 2);
             if (j + 3 < my_tiles) issue_tile_load(j + 3);
-            float4 xo[kRowsPerLane];
-            load_rows(j, xo);                              // re-read of tile j for its output (L2 hit)
-            output_rows(j, xo);
+#if !(WM_VQ_TUNE & 8)
+            load_rows(j, xo);                              // re-read of tile j (L2 hit)
+#endif
+#else
+            if (j + 2 < my_tiles) convert_rows(j + 2);
+            if (j + 3 < my_tiles) issue_tile_load(j + 3);
+            load_rows(j, xo);                              // re-read of tile j (L2 hit)
+            output_decide(j, ev);
+#endif
+            output_write(j, ev, xo);
         }
     }
     tc_fence_before();
@@ -676,7 +756,7 @@ static size_t smem_bytes(int K, int D) {
 
 #if WM_VQ_EXP & 32
 extern "C" __attribute__((visibility("default"))) int wm_vq_debug_read(unsigned long long* out) {
-    return (int)cudaMemcpyFromSymbol(out, vq::g_vq_dbg, sizeof(unsigned long long) * 64 * 16);
+    return (int)cudaMemcpyFromSymbol(out, vq::g_vq_dbg, sizeof(unsigned long long) * 64 * 24);
 }
 #endif
 
@@ -691,7 +771,7 @@ int vq_nearest_tc(const void* x, const void* cb, int64_t* idx, void* quantized, 
                   int D, cudaStream_t st) {
     using namespace vq;
     Params prm{static_cast<const float*>(x), static_cast<const float*>(cb), idx, static_cast<float*>(quantized), sq_err,
-               N, L, K, D, (int)((N + kTileM - 1) / kTileM)};
+               N, L, K, D, (int)((N + kTileM - 1) / kTileM), 16u};
     const size_t smem = smem_bytes(K, D);
     const int sms = sm_count();
     int ctas = prm.tiles < sms ? prm.tiles : sms;
@@ -700,8 +780,9 @@ int vq_nearest_tc(const void* x, const void* cb, int64_t* idx, void* quantized, 
     WM_CUDA_CHECK(cudaFuncSetAttribute(vq_nearest_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     vq_nearest_tc_kernel<64><<<grid, kThreads, smem, st>>>(prm);
     WM_CUDA_CHECK(cudaGetLastError());
-    const long items = N * L;
-    vq_settle_kernel<64><<<(unsigned)((items + 255) / 256), 256, 0, st>>>(prm);
+    const long rounds = (N * L + kSettleRound - 1) / kSettleRound;
+    const long wave = 4L * sms;                            // 64 registers x 256 threads: four blocks per SM
+    vq_settle_kernel<64><<<(unsigned)(rounds < wave ? rounds : wave), kSettleThreads, 0, st>>>(prm);
     WM_CUDA_CHECK(cudaGetLastError());
     return WM_OK;
 }
