@@ -119,7 +119,7 @@ WM_API int wm_l3d_attn_bwd_ld(const void* q, const void* k, const void* v, const
  *                                     x + (e_idx - x) in fp32 (vq.py:70)
  *   sq_err    [N, L]    fp32 or NULL  sum_d (e_idx - x)^2 (vq.py:35)
  * The winner is decided on distances accumulated in fp64 from the fp32 inputs, so the
- * index equals the exact-arithmetic argmin.  For D = 64 and K <= 512 (multiple of 32) a
+ * index equals the exact-arithmetic argmin.  For D = 64 and K <= 512 (multiple of 64) a
  * split-bf16 (hi + lo, three products) tcgen05 distance GEMM is the filter and only codes
  * inside its error window are re-checked exactly; other shapes (or WM_FLAG_SIMT) use the
  * fp32 SIMT filter.  Same indices either way. */

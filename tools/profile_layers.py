@@ -29,6 +29,14 @@ def bwd():
 def colsum():
     check(L.wm_colsum(dy.data_ptr(), db.data_ptr(), ws.data_ptr(), rows, dim, 0, _stream()), 'colsum')
 
+hid, bias_h = rnd(rows, dim), rnd(dim)
+gy, gdh, gdb = torch.empty_like(hid), torch.empty_like(hid), torch.empty_like(bias_h)
+def gelu_fwd():
+    check(L.wm_bias_gelu_fwd(hid.data_ptr(), bias_h.data_ptr(), gy.data_ptr(), rows, dim, 0, _stream()), 'gelu fwd')
+def gelu_bwd():
+    check(L.wm_bias_gelu_bwd(dy.data_ptr(), hid.data_ptr(), bias_h.data_ptr(), gdh.data_ptr(), gdb.data_ptr(), ws.data_ptr(), rows, dim, 0,
+                             _stream()), 'gelu bwd')
+
 def timeit(fn, n=10):
     fn(); torch.cuda.synchronize()
     tot = 0.0
@@ -41,6 +49,7 @@ def timeit(fn, n=10):
 
 fwd()
 t = rows * dim * 2
-for name, fn, nbytes in (('add_layernorm_fwd', fwd, 4 * t), ('add_layernorm_bwd (+reduce)', bwd, 4 * t), ('colsum (+reduce)', colsum, t)):
+for name, fn, nbytes in (('add_layernorm_fwd', fwd, 4 * t), ('add_layernorm_bwd (+reduce)', bwd, 4 * t), ('colsum (+reduce)', colsum, t),
+                        ('bias_gelu_fwd', gelu_fwd, 2 * t), ('bias_gelu_bwd (+reduce)', gelu_bwd, 3 * t)):
     ms = timeit(fn)
     print(f'{name:30s} {ms * 1e3:7.1f} us   {nbytes / ms / 1e6:7.0f} GB/s algorithmic')

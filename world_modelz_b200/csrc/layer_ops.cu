@@ -345,25 +345,73 @@ colsum_partial_kernel(const T* __restrict__ a, float* __restrict__ part, long ro
 // erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7): one exponential, one reciprocal, five FMAs.  The exponential
 // exp(-v^2/2) is also the Gaussian of gelu', so the backward needs no second one.  (erff + __expf made these kernels
 // instruction-bound: ~45 instructions per element against 6 bytes of traffic.)
-struct GeluTerms { float cdf, pdf_v; };        // Phi(v) and v * phi(v)
-__device__ __forceinline__ GeluTerms gelu_terms(float v) {
-    const float x = fabsf(v) * 0.70710678118654752f;
-    const float t = __fdividef(1.f, fmaf(0.3275911f, x, 1.f));
-    const float e = __expf(-x * x);
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float erf_abs = fmaf(-p * t, e, 1.f);
-    GeluTerms r;
-    r.cdf = 0.5f * (1.f + copysignf(erf_abs, v));
-    r.pdf_v = v * 0.3989422804014327f * e;
+// Two elements per instruction: sm_100 issues fp32 add / mul / fma on 64-bit register pairs (FADD2 / FMUL2 / FFMA2).  The scalar
+// form cost ~25 issue slots per element against 4-6 bytes of traffic, i.e. these kernels were issue-bound, not HBM-bound.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
     return r;
 }
-__device__ __forceinline__ float gelu_f(float v) { return v * gelu_terms(v).cdf; }
-__device__ __forceinline__ float gelu_grad_f(float v) {
-    const GeluTerms g = gelu_terms(v);
-    return g.cdf + g.pdf_v;
+__device__ __forceinline__ f32x2 pk2c(float c) { return pk2(c, c); }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+struct GeluTerms2 { f32x2 cdf, pdf_v; };      // Phi(v) and v * phi(v) for a pair of values
+template <bool kWantPdf>
+__device__ __forceinline__ GeluTerms2 gelu_terms2(float v0, float v1) {
+    const f32x2 x = pk2(fabsf(v0) * 0.70710678118654752f, fabsf(v1) * 0.70710678118654752f);
+    float d0, d1;
+    upk2(ffma2(pk2c(0.3275911f), x, pk2c(1.f)), d0, d1);
+    const f32x2 t = pk2(rcp_approx(d0), rcp_approx(d1));
+    float a0, a1;
+    upk2(fmul2(x, fmul2(x, pk2c(-1.4426950408889634f))), a0, a1);      // -x^2 log2(e)
+    const f32x2 e = pk2(ex2_approx(a0), ex2_approx(a1));                // exp(-x^2) = exp(-v^2 / 2)
+    f32x2 p = ffma2(pk2c(1.061405429f), t, pk2c(-1.453152027f));
+    p = ffma2(p, t, pk2c(1.421413741f));
+    p = ffma2(p, t, pk2c(-0.284496736f));
+    p = ffma2(p, t, pk2c(0.254829592f));
+    float e0, e1;
+    upk2(ffma2(fmul2(fmul2(p, t), e), pk2c(-1.f), pk2c(1.f)), e0, e1);  // erf(|x|)
+    GeluTerms2 r;
+    r.cdf = ffma2(pk2(copysignf(e0, v0), copysignf(e1, v1)), pk2c(0.5f), pk2c(0.5f));
+    r.pdf_v = kWantPdf ? fmul2(fmul2(pk2(v0, v1), e), pk2c(0.3989422804014327f)) : 0ull;
+    return r;
+}
+// in place on 8 values: v <- gelu(v + b)
+__device__ __forceinline__ void gelu8(float (&v)[8], const float (&b)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        const float v0 = v[i] + b[i], v1 = v[i + 1] + b[i + 1];
+        upk2(fmul2(pk2(v0, v1), gelu_terms2<false>(v0, v1).cdf), v[i], v[i + 1]);
+    }
+}
+// g <- g * gelu'(v + b)
+__device__ __forceinline__ void gelu_grad8(float (&g)[8], const float (&v)[8], const float (&b)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        const float v0 = v[i] + b[i], v1 = v[i + 1] + b[i + 1];
+        const GeluTerms2 t = gelu_terms2<true>(v0, v1);
+        upk2(fmul2(pk2(g[i], g[i + 1]), ffma2(t.pdf_v, pk2c(1.f), t.cdf)), g[i], g[i + 1]);
+    }
 }
 
 // thread = (column group of 8, row lane); four rows in flight per thread
@@ -384,23 +432,21 @@ bias_gelu_fwd_kernel(const T* __restrict__ h, const T* __restrict__ bias, T* __r
         for (int u = 0; u < 4; ++u) load8(h + (row + u * stride) * C + grp * 8, v[u]);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[u][i] = gelu_f(v[u][i] + b[i]);
+            gelu8(v[u], b);
             store8(y + (row + u * stride) * C + grp * 8, v[u]);
         }
     }
     for (; row < rows; row += stride) {
         float v[8];
         load8(h + row * C + grp * 8, v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = gelu_f(v[i] + b[i]);
+        gelu8(v, b);
         store8(y + row * C + grp * 8, v);
     }
 }
 
 // same thread layout as colsum_partial_kernel; per-block column sums of dh go to `part`
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)       // 64 registers: the packed-math form compiled to 73 and lost a resident block per SM
 bias_gelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ h, const T* __restrict__ bias, T* __restrict__ dh,
                      float* __restrict__ part, long rows, int C) {
     extern __shared__ float red[];          // [row lanes][C]
@@ -423,9 +469,10 @@ bias_gelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ h, const T*
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
+                gelu_grad8(g[u], v[u], b);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    g[u][i] = round_to(g[u][i] * gelu_grad_f(v[u][i] + b[i]), dh);   // the value the GEMMs and the column sum both see
+                    g[u][i] = round_to(g[u][i], dh);       // the value the GEMMs and the column sum both see
                     acc[i] += g[u][i];
                 }
                 store8(dh + (row + u * stride) * C + grp * 8, g[u]);
@@ -435,9 +482,10 @@ bias_gelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ h, const T*
             float g[8], v[8];
             load8(dy + row * C + grp * 8, g);
             load8(h + row * C + grp * 8, v);
+            gelu_grad8(g, v, b);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                g[i] = round_to(g[i] * gelu_grad_f(v[i] + b[i]), dh);
+                g[i] = round_to(g[i], dh);
                 acc[i] += g[i];
             }
             store8(dh + row * C + grp * 8, g);

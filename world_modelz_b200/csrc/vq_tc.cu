@@ -174,25 +174,21 @@ __device__ __forceinline__ void split3_bf16(float v, uint16_t (&out)[3]) {
     out[2] = *reinterpret_cast<const uint16_t*>(&l);
 }
 
-// exact squared distance (fp64 accumulation of fp32 differences) between a latent row and a code, both in global memory;
-// all loads are issued before the first use (one memory round trip)
+// exact squared distance (fp64 accumulation of fp32 differences) between a latent row (staged in shared memory: every lane of
+// the warp reads the same values, a broadcast) and a code in global memory; all 16 loads of the code are issued before the
+// first use -- ONE memory round trip per candidate
 template <int D>
-__device__ __noinline__ double exact_dist(const float* __restrict__ xr, const float* __restrict__ er) {
+__device__ __forceinline__ double exact_dist(const float* __restrict__ xs, const float* __restrict__ er) {
+    float4 ev[D / 4];
+#pragma unroll
+    for (int c = 0; c < D / 4; ++c) ev[c] = __ldg(reinterpret_cast<const float4*>(er) + c);
     double a = 0.0;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {                          // two halves: 16 + 16 loads in flight at D = 64
-        float4 xv[D / 8], ev[D / 8];
-#pragma unroll
-        for (int c = 0; c < D / 8; ++c) {
-            xv[c] = __ldg(reinterpret_cast<const float4*>(xr) + h * (D / 8) + c);
-            ev[c] = __ldg(reinterpret_cast<const float4*>(er) + h * (D / 8) + c);
-        }
-#pragma unroll
-        for (int c = 0; c < D / 8; ++c) {
-            const double d0 = (double)xv[c].x - (double)ev[c].x, d1 = (double)xv[c].y - (double)ev[c].y;
-            const double d2 = (double)xv[c].z - (double)ev[c].z, d3 = (double)xv[c].w - (double)ev[c].w;
-            a = fma(d0, d0, a); a = fma(d1, d1, a); a = fma(d2, d2, a); a = fma(d3, d3, a);
-        }
+    for (int c = 0; c < D / 4; ++c) {
+        const float4 xv = reinterpret_cast<const float4*>(xs)[c];
+        const double d0 = (double)xv.x - (double)ev[c].x, d1 = (double)xv.y - (double)ev[c].y;
+        const double d2 = (double)xv.z - (double)ev[c].z, d3 = (double)xv.w - (double)ev[c].w;
+        a = fma(d0, d0, a); a = fma(d1, d1, a); a = fma(d2, d2, a); a = fma(d3, d3, a);
     }
     return a;
 }
@@ -218,10 +214,13 @@ constexpr int kSettleThreads = 256;
 constexpr int kSettleRound = kSettleThreads * 8;
 
 template <int D>
-__device__ __forceinline__ void settle_row(const Params& prm, long item, int lane) {
+__device__ __forceinline__ void settle_row(const Params& prm, long item, int lane, float* xs) {
     const uint64_t m = (uint64_t)prm.idx[item];
     const int l = (int)(item % prm.L);
     const float* xr = prm.x + item * (long)D;
+    __syncwarp();                                         // the previous row's distances are done with xs
+    if (lane < D / 4) reinterpret_cast<float4*>(xs)[lane] = __ldg(reinterpret_cast<const float4*>(xr) + lane);
+    __syncwarp();
     const float* cbl = prm.cb + (long)l * prm.K * D;
     // candidates: per code half its best code, its runner-up (w == 1) or the whole half (w == 2)
     const int KH = prm.K >> 1;
@@ -235,7 +234,7 @@ __device__ __forceinline__ void settle_row(const Params& prm, long item, int lan
         int k;
         if (c < nA) k = wa == 2u ? c : (c == 0 ? (int)k1a : (int)k2a);
         else k = wb == 2u ? KH + (c - nA) : (c == nA ? (int)k1b : (int)k2b);
-        const double dd = exact_dist<D>(xr, cbl + (long)k * D);
+        const double dd = exact_dist<D>(xs, cbl + (long)k * D);
         if (dd < bd || (dd == bd && k < bk)) { bd = dd; bk = k; }
     }
 #pragma unroll
@@ -265,6 +264,7 @@ __global__ void __launch_bounds__(kSettleThreads)
 vq_settle_kernel(const Params prm) {
     __shared__ unsigned short queue[kSettleRound];
     __shared__ unsigned queued;
+    __shared__ __align__(16) float xrow[kSettleThreads / 32][D];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long items = prm.N * prm.L;
     const long rounds = (items + kSettleRound - 1) / kSettleRound;
@@ -279,7 +279,7 @@ vq_settle_kernel(const Params prm) {
         }
         __syncthreads();
         const unsigned n = queued;
-        for (unsigned e = warp; e < n; e += kSettleThreads / 32) settle_row<D>(prm, base + queue[e], lane);
+        for (unsigned e = warp; e < n; e += kSettleThreads / 32) settle_row<D>(prm, base + queue[e], lane, xrow[warp]);
         __syncthreads();
     }
 }

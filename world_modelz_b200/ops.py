@@ -176,7 +176,7 @@ def vq_nearest(x: torch.Tensor, codebook: torch.Tensor, want_quantized: bool = T
                                    ste.data_ptr() if ste is not None else None,
                                    err.data_ptr() if err is not None else None,
                                    N, L, K, D, DTYPE_FP32, flags, _stream()), 'wm_vq_nearest')
-    tensor_core = D == 64 and K % 32 == 0 and 32 <= K <= 512 and not (flags & FLAG_SIMT) and N >= 1
+    tensor_core = D == 64 and K % 64 == 0 and 64 <= K <= 512 and not (flags & FLAG_SIMT) and N >= 1
     _count(2 if tensor_core else 1)          # tcgen05 filter + the exact settlement of its undecided rows
     return idx, ste, err
 
