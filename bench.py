@@ -516,7 +516,7 @@ def run_b200(args):
                 line['roofline']['traffic_commit'] = tr.get('commit')
             if 'vq_dram_bytes' in tr:
                 micro['roofline_vq']['traffic'] = tr['vq_dram_bytes']
-                micro['roofline_vq']['traffic_commit'] = tr.get('commit')
+                micro['roofline_vq']['traffic_commit'] = tr.get('vq_commit', tr.get('commit'))
         line.update(micro)
         line['sampling_config5'] = samp
         line['receptive_field_cone'] = {'train_step': pruned, 'sampling_config5': samp_pruned}
