@@ -25,8 +25,9 @@
 //                quarter: the scanners never wait for the tensor pipe.
 //                One thread per row: distance keys (the score's fp32 bits times 16, the code's position inside its
 //                16-column chunk below them: one IMAD per score -- with the factor passed as a kernel parameter, or ptxas
-//                turns it into an LEA on the ALU pipe that the min / max instructions already saturate) reduced with
-//                3-input integer min / max to the two smallest keys.  |x|^2 + |e_k|^2 + 2 arrive WITH the score: a
+//                turns it into an LEA on the ALU pipe that the min / max instructions already saturate).  Smallest key by a
+//                3-input min tree per chunk; the runner-up exactly from two partitions of the keys (chunk minima and the
+//                minima of the 16 position classes: 1.3 ALU instructions per score instead of 3.25 for a running top-2).  |x|^2 + |e_k|^2 + 2 arrive WITH the score: a
 //                thirteenth K = 16 MMA step multiplies [1 1 1 | split3(|x|^2 + 2)] with [split3(|e_k|^2) | 1 1 1] (three bf16
 //                terms carry an fp32 value exactly), so the scanners add nothing and read no shared memory.  A runner-up
 //                inside the error window marks the whole half for the exact settlement (the scores are gone by then)
@@ -60,7 +61,8 @@ __device__ unsigned long long g_vq_dbg[64 * 24];
 #endif
 
 #ifndef WM_VQ_TUNE
-#define WM_VQ_TUNE 3          // bit 0: the issuer warp sleeps between barrier probes; bit 1: keys by IMAD (FMA pipe) instead of LEA (ALU pipe);
+#define WM_VQ_TUNE 19         // bit 0: the issuer warp sleeps between barrier probes; bit 1: keys by IMAD (FMA pipe) instead of LEA (ALU pipe);
+                              // bit 4: runner-up from two partitions of the keys (chunks and position classes) instead of a running top-2;
                               // bit 2: the gather of a tile's winners is in flight across the conversion of the tile two ahead (measured: 0.285 vs
                               // 0.279 ms -- the re-read of x then waits behind the conversion); bit 3: with bit 2, re-read x first (spills)
 #endif
@@ -467,9 +469,37 @@ vq_nearest_tc_kernel(const Params prm) {
         for (int j = 0; j < my_tiles; ++j) {
             const int b = j & 1;
             const long n = ((long)(first_tile + j * stride)) * kTileM + row;
-            // two smallest keys of this half and the 16-column chunks they came from.  A score t = |x - e|^2 + 2 (>= 1, so
-            // its fp32 bits order like integers) becomes the key (bits(t) - bits(1)) * 16 + position-in-chunk: one IMAD,
-            // no bits dropped; t < 2^32 is the writer's business (kHugeNorm)
+            // Smallest key of this half (with the 16-column chunk it came from) and the second smallest.  A score t = |x - e|^2 + 2
+            // (>= 1, so its fp32 bits order like integers) becomes the key (bits(t) - bits(1)) * 16 + position-in-chunk: one
+            // IMAD, no bits dropped; t < 2^32 is the writer's business (kHugeNorm).
+            // The runner-up costs ONE min per key instead of the 2.5 min / max of a running top-2: the keys are covered by two
+            // partitions -- the chunks (min by a 3-input tree, 8 instructions per 16 keys, then a top-2 of the chunk minima) and the
+            // 16 position classes (b[i] = smallest key seen at position i of any chunk).  Winner w and runner-up r differ in chunk
+            // or in position; every chunk / class minimum other than w is >= r, and r is the minimum of its chunk (if the chunks
+            // differ) or of its class (if the positions do).  So min(second chunk minimum, second class minimum) = r exactly.
+#if WM_VQ_TUNE & 16
+            uint32_t m1 = 0xffffffffu, m2 = 0xffffffffu;
+            int c1 = 0;
+            uint32_t cls[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) cls[i] = 0xffffffffu;
+            uint32_t r0[16], r1[16];
+            const uint32_t sixteen = prm.key_mul;          // opaque to the compiler: the key stays an IMAD (FMA pipe), not an LEA (ALU pipe)
+            auto scan16 = [&](const uint32_t (&r)[16], int c) {
+                uint32_t k[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    k[i] = r[i] * sixteen + (kKeyBase + (uint32_t)i);
+                    cls[i] = min(cls[i], k[i]);
+                }
+                const uint32_t t0 = vmin3(k[0], k[1], k[2]), t1 = vmin3(k[3], k[4], k[5]), t2 = vmin3(k[6], k[7], k[8]);
+                const uint32_t t3 = vmin3(k[9], k[10], k[11]), t4 = vmin3(k[12], k[13], k[14]);
+                const uint32_t a1 = min(vmin3(t0, t1, t2), vmin3(t3, t4, k[15]));
+                m2 = min(m2, max(m1, a1));                 // second smallest chunk minimum (== m1 for an equal key in another chunk)
+                if (a1 < m1) c1 = c;
+                m1 = min(m1, a1);
+            };
+#else
             uint32_t m1 = 0xffffffffu, m2 = 0xffffffffu;
             int c1 = 0, c2 = 0;
             uint32_t r0[16], r1[16];
@@ -500,6 +530,7 @@ vq_nearest_tc_kernel(const Params prm) {
                 c2 = l2 ? loser_c : rest_c;
                 if (first) { m1 = a1; c1 = c; }
             };
+#endif
 #pragma unroll 1
             for (int qq = 0; qq < 2; ++qq) {
                 const int q = half * 2 + qq;
@@ -544,6 +575,18 @@ vq_nearest_tc_kernel(const Params prm) {
             }
             if (quad == 0) VQ_TL(j, half ? 13 : 8);
             const float xn2 = sXn2[(j % 3) * kTileM + row];
+#if WM_VQ_TUNE & 16
+            {   // second smallest class minimum: the winner's own class wraps to 2^32 - 1 under  - (m1 + 1)
+                const uint32_t sub = m1 + 1u;
+                uint32_t d[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) d[i] = cls[i] - sub;
+                const uint32_t t0 = vmin3(d[0], d[1], d[2]), t1b = vmin3(d[3], d[4], d[5]), t2 = vmin3(d[6], d[7], d[8]);
+                const uint32_t t3 = vmin3(d[9], d[10], d[11]), t4 = vmin3(d[12], d[13], d[14]);
+                m2 = min(m2, min(vmin3(t0, t1b, t2), vmin3(t3, t4, d[15])) + sub);
+            }
+            const int c2 = c1;
+#endif
             const float t1 = __uint_as_float((m1 >> 4) + 0x3f800000u), t2nd = __uint_as_float((m2 >> 4) + 0x3f800000u);
             const int k1 = half * KH + c1 * 16 + (int)(m1 & 15u), k2 = half * KH + c2 * 16 + (int)(m2 & 15u);
             const float win = filter_window(xn2, emax);
