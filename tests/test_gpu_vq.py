@@ -147,6 +147,28 @@ def test_tensor_core_filter_matches_exact_simt_kernel(N, L, K, D):
     assert np.array_equal(a[0].cpu().numpy(), OV.encode(x.numpy(), cb.numpy()))
 
 
+def test_runner_up_partitions_see_every_near_tie():
+    """The filter's scanners find the runner-up as min(second chunk minimum, second position-class minimum).  Plant the
+    second-best code in every relation to the best one -- same 16-code chunk, another chunk at the SAME position, the
+    other quarter, the other half, the last code -- as an exact duplicate or a hair away, under latents that sit on the
+    planted pair: every such row has to come out as the exact-arithmetic argmin (lowest index on exact ties)."""
+    g = torch.Generator().manual_seed(77)
+    K, D = 512, 64
+    base = torch.randn(1, K, D, generator=g)
+    pairs = [(37, 41), (37, 37 + 16), (37, 37 + 128), (37, 37 + 256), (200, 200 + 48), (300, 511), (5, 4), (130, 129)]
+    for eps in (0.0, 3e-7, 2e-5):
+        for a, b in pairs:
+            cb = base.clone()
+            cb[0, b] = cb[0, a] + eps * torch.randn(D, generator=g).sign()
+            x = torch.randn(640, 1, D, generator=g)
+            x[:512] = cb[0, a] + 0.05 * torch.randn(512, 1, D, generator=g)      # a and b are the two nearest codes, almost tied
+            idx, ste, err = ops.vq_nearest(x.to(DEV), cb.to(DEV))
+            ref = OV.encode(x.numpy(), cb.numpy())
+            assert np.array_equal(idx.cpu().numpy(), ref), (a, b, eps)
+            codes = OV.decode(ref, cb.numpy()).reshape(640, 1, D)
+            assert np.array_equal(ste.cpu().numpy(), x.numpy() + (codes - x.numpy())), (a, b, eps)
+
+
 def test_fused_statistics_and_onehot_kernels():
     """wm_vq_stats / wm_vq_onehot against index_add / scatter on random assignments (multi-latent, K not a power of 2)."""
     g = torch.Generator().manual_seed(3)
