@@ -316,3 +316,31 @@ def test_last_frame_cone_is_the_reference_models_dependency_cone():
         live = tokens.clone()
         live[:, cone[0]] = (live[:, cone[0]] + 3) % 10
         assert not torch.equal(O.denoiser_forward(p, live, cfg), base)
+
+
+def test_runner_up_from_two_partitions_is_exact():
+    """The argument behind the VQ scanners (csrc/vq_tc.cu): keys that are unique within a 16-key chunk (the position sits
+    in their low 4 bits) are covered by two partitions, the chunks and the 16 position classes; then
+    min(second smallest chunk minimum, second smallest class minimum) is the second smallest key.  Checked in numpy on
+    random key sets, with planted near-ties in the same chunk, at the same position of another chunk, and exact duplicates
+    of the (score, position) pair in another chunk."""
+    rng = np.random.default_rng(0)
+    for trial in range(400):
+        nchunk = int(rng.integers(1, 17))
+        score = rng.integers(0, 1 << 20, size=(nchunk, 16), dtype=np.int64)
+        if trial % 4 == 1 and nchunk > 1:                        # runner-up at the winner's position in another chunk
+            c, p = np.unravel_index(np.argmin(score), score.shape)
+            score[(c + 1) % nchunk, p] = score[c, p] + (trial % 3)
+        if trial % 4 == 2:                                       # runner-up in the winner's own chunk
+            c, p = np.unravel_index(np.argmin(score), score.shape)
+            score[c, (p + 5) % 16] = score[c, p] + (trial % 2)
+        keys = score * 16 + np.arange(16)[None, :]               # (bits - bits(1.0)) * 16 + position
+        flat = np.sort(keys.reshape(-1))
+        truth = flat[1] if flat.size > 1 else None
+        chunk_min = np.sort(keys.min(axis=1))
+        class_min = keys.min(axis=0)
+        m1 = chunk_min[0]
+        second_chunk = chunk_min[1] if nchunk > 1 else np.iinfo(np.int64).max
+        wrapped = (class_min - (m1 + 1)) % (1 << 40)             # the winner's class wraps to the top, as in the kernel
+        second_class = wrapped.min() + m1 + 1
+        assert min(second_chunk, second_class) == truth, (trial, nchunk)
